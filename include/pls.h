@@ -1,0 +1,135 @@
+/* pls.h -- C ABI of libpls_cuda.so, the B200 (sm_100a) solver core behind PartitionedLS.jl's
+ * fit(Opt, X, y, P; eta).
+ *
+ * The reference has no FFI today: the seam is the Julia method
+ *   fit(::Type{Opt}, X, y, P; eta, nnlsalg, returnAllSolutions)     src/PartitionedLSOpt.jl:73-104
+ * and this library replaces its body between argument validation and cleanupResult
+ * (Opt.jl:79-97): homogeneousCoords (src/PartitionedLS.jl:76-81), regularizeProblem (:108-123),
+ * the 2^(K+1) orthant loop with one NNLS each (Opt.jl:85-94) and the argmin (Opt.jl:96).
+ * The host keeps cleanupResult (Opt.jl:34-44), PartLSFitResult (PartitionedLS.jl:29-49) and
+ * predict (:132-134).  INTEGRATION.md shows the Julia ccall stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all matrices column-major exactly as Julia stores them
+ *     (X: N x M Float64, P: M x K Int64 0/1, y: N Float64);
+ *   - host pointers are owned by the caller and never retained past return; "resident" entry
+ *     points work on the device copy made by pls_load;
+ *   - every function returns PLS_OK (0) or a negative PLS_E* code; pls_last_error() gives the
+ *     thread-local message.  No exceptions, aborts or stdout output cross this boundary;
+ *   - there is no CPU fallback: without a usable B200-class GPU pls_create fails with PLS_ECUDA.
+ */
+#ifndef PLS_H_
+#define PLS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLS_VERSION 100 /* 0.1.0 */
+
+enum {
+  PLS_OK = 0,
+  PLS_EINVAL = -1,       /* bad argument (shape, null pointer, non-binary P, eta < 0, K too large) */
+  PLS_ECUDA = -2,        /* CUDA runtime/driver error, or no device */
+  PLS_ENCCL = -3,        /* reserved for the in-library multi-GPU path */
+  PLS_ENOMEM = -4,       /* host or device allocation failed */
+  PLS_ENUMERIC = -5,     /* NaN/Inf in inputs or results, or the solver hit its iteration cap */
+  PLS_EUNSUPPORTED = -6  /* valid request this build does not implement */
+};
+
+/* flags for pls_opt_* */
+#define PLS_FLAG_DEFAULT 0u
+#define PLS_FLAG_NO_RECOMPUTE 1u /* skip the data-space recompute of the winner's objective (K4) */
+
+typedef struct pls_ctx pls_ctx;
+
+/* Timings (CUDA events, ms) and solver work counters of the last fit on this context. */
+typedef struct pls_stats {
+  double ms_upload;      /* host -> device copy of X, y, P (0 for resident fits) */
+  double ms_gram;        /* K1: Gram build + finalize */
+  double ms_nnls;        /* K2: batched orthant NNLS */
+  double ms_select;      /* K3: argmin over orthants */
+  double ms_recompute;   /* K4: data-space objective of the winner */
+  double ms_total;       /* wall time of the call (host clock) */
+  int64_t orthants;      /* NNLS problems solved */
+  int64_t pivots;        /* variables moved in/out of passive sets (rank-1 inverse updates) */
+  int64_t grad_evals;    /* gradient evaluations r = c - G[:,F] w_F */
+  int64_t sum_p;         /* sum of passive-set sizes over gradient evaluations */
+  int64_t sum_p2;        /* sum of squared passive-set sizes over pivots */
+  int64_t bpp_iters;     /* block-pivoting iterations */
+  int64_t spills;        /* chains whose inverse outgrew shared memory (global-memory slow path) */
+  int64_t rebuilds;      /* inverses rebuilt from scratch after a failed refinement */
+  int64_t blocked;       /* variables refused as numerically dependent */
+  int64_t kernel_launches; /* kernels launched by the call */
+  double gram_flops;     /* algorithmic: N*M'(M'+1) + 2*N*M' + 2*N    */
+  double nnls_flops;     /* model: 2*M'*sum_p + 4*sum_p2 (+ refinement 2*p^2 per grad eval) */
+  double nnls_l2_bytes;  /* model: 8*M'*sum_p  (columns of G streamed by gradient evaluations) */
+} pls_stats;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int pls_version(void);
+const char *pls_last_error(void);
+/* device_ids == NULL or n_dev == 0: device 0.  n_dev > 1: PLS_EUNSUPPORTED in this build (multi-GPU
+ * runs are one process per GPU, see pls_gram_raw / pls_opt_solve_range). */
+int pls_create(pls_ctx **out, const int *device_ids, int n_dev);
+void pls_destroy(pls_ctx *ctx);
+int pls_device_count(void);
+
+/* ---- the hot path, one call, host pointers ------------------------------------------------------
+ * Replaces the body of fit(::Type{Opt}, ...) (src/PartitionedLSOpt.jl:79-97).
+ *   alpha_raw[M+1]  raw NNLS solution of the winning orthant (Opt.jl:92: alpha incl. intercept slot)
+ *   b_best          winning orthant index, beta_k = 2*bit_k(b) - 1, LSB first (Opt.jl:4-20)
+ *   obj_best        norm(Xo*(Po.*alpha)*beta - yo) of the winner (Opt.jl:90), data-space recompute
+ *   all_obj         nullable, 2^(K+1) objectives (Gram-space) for returnAllSolutions (Opt.jl:99-100)
+ *   all_alpha       nullable, (M+1) x 2^(K+1) column-major raw alphas
+ *   stats           nullable */
+int pls_opt_fit(pls_ctx *ctx, const double *X, int64_t N, int64_t M, const double *y,
+                const int64_t *P, int64_t K, double eta, uint32_t flags, double *alpha_raw,
+                int64_t *b_best, double *obj_best, double *all_obj, double *all_alpha,
+                pls_stats *stats);
+
+/* ---- resident data set: upload once, fit many times -------------------------------------------
+ * pls_load copies rows [0, N) of X (leading dimension ldx >= N), y and P to the device in the
+ * library's augmented layout Z = [X | 1 | y] (zero padded).  In a multi-process run each rank loads
+ * its own row shard; n_total is the global row count (only used for reporting). */
+int pls_load(pls_ctx *ctx, const double *X, int64_t N, int64_t ldx, int64_t M, const double *y,
+             const int64_t *P, int64_t K, double eta);
+int pls_opt_fit_resident(pls_ctx *ctx, uint32_t flags, double *alpha_raw, int64_t *b_best,
+                         double *obj_best, double *all_obj, double *all_alpha, pls_stats *stats);
+
+/* ---- stage-wise entry points (one process per GPU; the caller owns the collectives) ----------
+ * K1 on the loaded rows.  pls_gram_raw exposes the device buffer of raw sums S = Z'Z
+ * ((M+2) x (M+2) doubles, column-major, lower triangle valid) so the caller can all-reduce it in
+ * place across ranks (e.g. torch.distributed / NCCL) before pls_gram_finalize adds eta*Po*Po'
+ * and mirrors it into G, c = Xo'y, yy. */
+int pls_gram_build(pls_ctx *ctx);
+int pls_gram_raw(pls_ctx *ctx, void **dev_ptr, int64_t *count);
+int pls_gram_finalize(pls_ctx *ctx);
+/* K2+K3 on orthants [b_begin, b_begin + b_count): b_count must be a power of two and b_begin a
+ * multiple of it (or the full range).  Outputs the local winner. */
+int pls_opt_solve_range(pls_ctx *ctx, int64_t b_begin, int64_t b_count, double *alpha_raw,
+                        int64_t *b_best, double *obj_best, double *all_obj, double *all_alpha);
+/* K4 on the loaded rows: sum over local rows of (Xo*(d.*alpha) - y)^2 for orthant b.  The caller
+ * sums over ranks and calls pls_opt_objective_finish to add the eta rows and take the root. */
+int pls_opt_residual_partial(pls_ctx *ctx, const double *alpha_raw, int64_t b, double *ssq_out);
+int pls_opt_objective_finish(pls_ctx *ctx, const double *alpha_raw, int64_t b, double ssq_total,
+                             double *obj_out);
+int pls_get_stats(pls_ctx *ctx, pls_stats *stats);
+
+/* ---- test / bench hooks ------------------------------------------------------------------------
+ * pls_gram: K1 + finalize from host pointers; G is (M+1) x (M+1) column-major, c has M+1 entries.
+ * pls_nnls_batch: K2 only, on a caller-supplied Gram (host pointers), gmask[m] = bit set of the
+ * groups variable m belongs to (intercept included); outputs per-orthant objective^2-consistent
+ * objective and raw alpha for b in [b_begin, b_begin + b_count). */
+int pls_gram(pls_ctx *ctx, const double *X, int64_t N, int64_t M, const double *y, const int64_t *P,
+             int64_t K, double eta, double *G, double *c, double *yy);
+int pls_nnls_batch(pls_ctx *ctx, const double *G, const double *c, double yy, int64_t Mp,
+                   const uint64_t *gmask, int64_t Kp, int64_t b_begin, int64_t b_count,
+                   double *obj_out, double *alpha_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLS_H_ */

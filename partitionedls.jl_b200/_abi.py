@@ -1,0 +1,207 @@
+"""ctypes binding of libpls_cuda.so (include/pls.h).  This is what a Julia ``ccall`` stub does,
+written in Python because Julia is not available in this image.
+
+There is no CPU fallback: if the shared library is missing this module raises at import time,
+and if no B200 is visible ``pls_create`` fails with PLS_ECUDA."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpls_cuda.so")
+
+PLS_OK, PLS_EINVAL, PLS_ECUDA, PLS_ENCCL, PLS_ENOMEM, PLS_ENUMERIC, PLS_EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
+PLS_FLAG_DEFAULT, PLS_FLAG_NO_RECOMPUTE = 0, 1
+_ERRNAMES = {-1: "PLS_EINVAL", -2: "PLS_ECUDA", -3: "PLS_ENCCL", -4: "PLS_ENOMEM",
+             -5: "PLS_ENUMERIC", -6: "PLS_EUNSUPPORTED"}
+
+
+class PlsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{_ERRNAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+class PlsStats(C.Structure):
+    _fields_ = [(n, C.c_double) for n in
+                ("ms_upload", "ms_gram", "ms_nnls", "ms_select", "ms_recompute", "ms_total")] + \
+               [(n, C.c_int64) for n in
+                ("orthants", "pivots", "grad_evals", "sum_p", "sum_p2", "bpp_iters", "spills",
+                 "rebuilds", "blocked", "kernel_launches")] + \
+               [(n, C.c_double) for n in ("gram_flops", "nnls_flops", "nnls_l2_bytes")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(nvcc, sm_100a).  There is no CPU fallback.")
+
+lib = C.CDLL(LIB_PATH)
+_dp, _ip, _vp = C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_void_p
+
+lib.pls_version.restype = C.c_int
+lib.pls_last_error.restype = C.c_char_p
+lib.pls_device_count.restype = C.c_int
+lib.pls_create.argtypes = [C.POINTER(_vp), C.POINTER(C.c_int), C.c_int]
+lib.pls_destroy.argtypes = [_vp]
+lib.pls_destroy.restype = None
+lib.pls_opt_fit.argtypes = [_vp, _dp, C.c_int64, C.c_int64, _dp, _ip, C.c_int64, C.c_double, C.c_uint32,
+                            _dp, _ip, _dp, _dp, _dp, C.POINTER(PlsStats)]
+lib.pls_load.argtypes = [_vp, _dp, C.c_int64, C.c_int64, C.c_int64, _dp, _ip, C.c_int64, C.c_double]
+lib.pls_opt_fit_resident.argtypes = [_vp, C.c_uint32, _dp, _ip, _dp, _dp, _dp, C.POINTER(PlsStats)]
+lib.pls_gram_build.argtypes = [_vp]
+lib.pls_gram_raw.argtypes = [_vp, C.POINTER(_vp), _ip]
+lib.pls_gram_finalize.argtypes = [_vp]
+lib.pls_opt_solve_range.argtypes = [_vp, C.c_int64, C.c_int64, _dp, _ip, _dp, _dp, _dp]
+lib.pls_opt_residual_partial.argtypes = [_vp, _dp, C.c_int64, _dp]
+lib.pls_opt_objective_finish.argtypes = [_vp, _dp, C.c_int64, C.c_double, _dp]
+lib.pls_get_stats.argtypes = [_vp, C.POINTER(PlsStats)]
+lib.pls_gram.argtypes = [_vp, _dp, C.c_int64, C.c_int64, _dp, _ip, C.c_int64, C.c_double, _dp, _dp, _dp]
+lib.pls_nnls_batch.argtypes = [_vp, _dp, _dp, C.c_double, C.c_int64, C.POINTER(C.c_uint64), C.c_int64,
+                               C.c_int64, C.c_int64, _dp, _dp]
+for _n in ("pls_create", "pls_opt_fit", "pls_load", "pls_opt_fit_resident", "pls_gram_build", "pls_gram_raw",
+           "pls_gram_finalize", "pls_opt_solve_range", "pls_opt_residual_partial", "pls_opt_objective_finish",
+           "pls_get_stats", "pls_gram", "pls_nnls_batch"):
+    getattr(lib, _n).restype = C.c_int
+
+
+def _check(rc):
+    if rc != 0:
+        raise PlsError(rc, (lib.pls_last_error() or b"").decode())
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+def _as_inputs(X, y, P):
+    """Julia's layout: column-major Float64 X, Float64 y, column-major Int64 P (Float32 upcast)."""
+    X = np.asarray(X)
+    if X.ndim != 2:
+        raise ValueError("X must be a matrix")
+    X = np.asfortranarray(X, dtype=np.float64)
+    y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
+    P = np.asfortranarray(np.asarray(P), dtype=np.int64)
+    if P.ndim != 2 or P.shape[0] != X.shape[1] or y.shape[0] != X.shape[0]:
+        raise ValueError(f"shape mismatch: X {X.shape}, y {y.shape}, P {P.shape}")
+    return X, y, P
+
+
+class Context:
+    """Owns one pls_ctx (one GPU)."""
+
+    def __init__(self, device: int = 0):
+        self._h = _vp()
+        dev = (C.c_int * 1)(device)
+        _check(lib.pls_create(C.byref(self._h), dev, 1))
+        self.device = device
+        self._shape = None
+
+    def close(self):
+        if self._h:
+            lib.pls_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- one-call path -------------------------------------------------------------------------
+    def opt_fit(self, X, y, P, eta=0.0, flags=0, return_all=False, prepared=False):
+        if not prepared:
+            X, y, P = _as_inputs(X, y, P)
+        N, M = X.shape
+        K = P.shape[1]
+        Mp, nb = M + 1, 1 << (K + 1)
+        alpha = np.zeros(Mp)
+        b = C.c_int64()
+        obj = C.c_double()
+        all_obj = np.zeros(nb) if return_all else None
+        all_alpha = np.zeros((nb, Mp)) if return_all else None
+        st = PlsStats()
+        _check(lib.pls_opt_fit(self._h, _d(X), N, M, _d(y), P.ctypes.data_as(_ip), K, float(eta), flags,
+                               _d(alpha), C.byref(b), C.byref(obj), _d(all_obj), _d(all_alpha), C.byref(st)))
+        return dict(alpha_raw=alpha, b_best=b.value, opt=obj.value, objs=all_obj, alphas=all_alpha,
+                    stats=st.as_dict())
+
+    # -- resident / stage-wise path ----------------------------------------------------------
+    def load(self, X, y, P, eta=0.0, prepared=False):
+        if not prepared:
+            X, y, P = _as_inputs(X, y, P)
+        N, M = X.shape
+        _check(lib.pls_load(self._h, _d(X), N, N, M, _d(y), P.ctypes.data_as(_ip), P.shape[1], float(eta)))
+        self._shape = (N, M, P.shape[1])
+
+    def opt_fit_resident(self, flags=0, return_all=False):
+        N, M, K = self._shape
+        Mp, nb = M + 1, 1 << (K + 1)
+        alpha = np.zeros(Mp); b = C.c_int64(); obj = C.c_double(); st = PlsStats()
+        all_obj = np.zeros(nb) if return_all else None
+        all_alpha = np.zeros((nb, Mp)) if return_all else None
+        _check(lib.pls_opt_fit_resident(self._h, flags, _d(alpha), C.byref(b), C.byref(obj), _d(all_obj),
+                                        _d(all_alpha), C.byref(st)))
+        return dict(alpha_raw=alpha, b_best=b.value, opt=obj.value, objs=all_obj, alphas=all_alpha,
+                    stats=st.as_dict())
+
+    def gram_build(self):
+        _check(lib.pls_gram_build(self._h))
+
+    def gram_raw(self):
+        p = _vp(); n = C.c_int64()
+        _check(lib.pls_gram_raw(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def gram_finalize(self):
+        _check(lib.pls_gram_finalize(self._h))
+
+    def opt_solve_range(self, b_begin, b_count, return_all=False):
+        N, M, K = self._shape
+        Mp = M + 1
+        alpha = np.zeros(Mp); b = C.c_int64(); obj = C.c_double()
+        all_obj = np.zeros(b_count) if return_all else None
+        all_alpha = np.zeros((b_count, Mp)) if return_all else None
+        _check(lib.pls_opt_solve_range(self._h, b_begin, b_count, _d(alpha), C.byref(b), C.byref(obj),
+                                       _d(all_obj), _d(all_alpha)))
+        return dict(alpha_raw=alpha, b_best=b.value, obj_gram=obj.value, objs=all_obj, alphas=all_alpha)
+
+    def residual_partial(self, alpha_raw, b):
+        a = np.ascontiguousarray(alpha_raw, dtype=np.float64); s = C.c_double()
+        _check(lib.pls_opt_residual_partial(self._h, _d(a), int(b), C.byref(s)))
+        return s.value
+
+    def objective_finish(self, alpha_raw, b, ssq_total):
+        a = np.ascontiguousarray(alpha_raw, dtype=np.float64); o = C.c_double()
+        _check(lib.pls_opt_objective_finish(self._h, _d(a), int(b), float(ssq_total), C.byref(o)))
+        return o.value
+
+    def stats(self):
+        st = PlsStats()
+        _check(lib.pls_get_stats(self._h, C.byref(st)))
+        return st.as_dict()
+
+    # -- hooks -----------------------------------------------------------------------------------
+    def gram(self, X, y, P, eta=0.0):
+        X, y, P = _as_inputs(X, y, P)
+        N, M = X.shape
+        Mp = M + 1
+        G = np.zeros((Mp, Mp), order="F"); c = np.zeros(Mp); yy = C.c_double()
+        _check(lib.pls_gram(self._h, _d(X), N, M, _d(y), P.ctypes.data_as(_ip), P.shape[1], float(eta),
+                            _d(G), _d(c), C.byref(yy)))
+        return G, c, yy.value
+
+    def nnls_batch(self, G, c, yy, gmask, Kp, b_begin, b_count, want_alpha=True):
+        G = np.asfortranarray(G, dtype=np.float64); c = np.ascontiguousarray(c, dtype=np.float64)
+        gm = np.ascontiguousarray(gmask, dtype=np.uint64)
+        Mp = len(c)
+        obj = np.zeros(b_count); al = np.zeros((b_count, Mp)) if want_alpha else None
+        _check(lib.pls_nnls_batch(self._h, _d(G), _d(c), float(yy), Mp, gm.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                  Kp, b_begin, b_count, _d(obj), _d(al)))
+        return obj, al

@@ -1,0 +1,491 @@
+// C ABI of libpls_cuda.so (declared in include/pls.h): context, resident data set, and the
+// orchestration of K1 (Gram) -> K2 (orthant NNLS) -> K3 (argmin) -> K4 (winner recompute) that
+// replaces the body of fit(::Type{Opt}, ...) (src/PartitionedLSOpt.jl:79-97).
+#include <stdarg.h>
+#include <string.h>
+#include <chrono>
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace pls {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+__global__ void fill_ones(double *p, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 1.0;
+}
+
+// w = d .* alpha for orthant b, from the K3 winner record (alpha[Mp], obj, b bits)
+__global__ void winner_weights(const double *win, const uint64_t *gmask, int Mp, double *w) {
+  const long long b = __double_as_longlong(win[Mp + 1]);
+  for (int m = threadIdx.x; m < Mp; m += blockDim.x) {
+    const uint64_t gm = gmask[m];
+    const int d = 2 * __popcll(gm & (uint64_t)b) - __popcll(gm);
+    w[m] = (double)d * win[m];
+  }
+}
+
+double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+}  // namespace pls
+
+using namespace pls;
+
+struct pls_ctx {
+  int dev = 0, sm_count = 0;
+  cudaStream_t stream = nullptr;
+  Problem pb;
+  SolveWs ws;
+  std::vector<uint64_t> h_gmask;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  pls_stats stats;
+  double *d_w = nullptr, *d_ssq = nullptr;
+  double *h_pin = nullptr;   // pinned: winner record + ssq
+  size_t z_bytes = 0;
+  int launches = 0;
+};
+
+namespace {
+
+void free_problem(pls_ctx *c) {
+  Problem &pb = c->pb;
+  cudaFree(pb.Z); cudaFree(pb.gmask); cudaFree(pb.S); cudaFree(pb.part); cudaFree(pb.G);
+  cudaFree(pb.c); cudaFree(pb.scal);
+  pb = Problem();
+  c->z_bytes = 0;
+}
+
+void free_ws(pls_ctx *c) {
+  SolveWs &ws = c->ws;
+  cudaFree(ws.cta_obj); cudaFree(ws.cta_b); cudaFree(ws.cta_w); cudaFree(ws.hspill);
+  cudaFree(ws.counters); cudaFree(ws.win); cudaFree(ws.all_obj); cudaFree(ws.all_alpha);
+  cudaFree(ws.resid_part);
+  ws = SolveWs();
+}
+
+int check_ctx(pls_ctx *c) {
+  if (!c) { set_error("null context"); return PLS_EINVAL; }
+  PLS_CUDA_TRY(cudaSetDevice(c->dev));
+  return PLS_OK;
+}
+
+int host_d(const std::vector<uint64_t> &gm, int m, int64_t b) {
+  return 2 * __builtin_popcountll(gm[m] & (uint64_t)b) - __builtin_popcountll(gm[m]);
+}
+
+int ensure_all_buffers(pls_ctx *c, int64_t count, bool want_obj, bool want_alpha) {
+  SolveWs &ws = c->ws;
+  const int Mp = c->pb.Mp;
+  if (want_obj && ws.all_obj_n < (size_t)count) {
+    cudaFree(ws.all_obj); ws.all_obj = nullptr; ws.all_obj_n = 0;
+    PLS_CUDA_TRY(cudaMalloc(&ws.all_obj, sizeof(double) * (size_t)count));
+    ws.all_obj_n = (size_t)count;
+  }
+  if (want_alpha) {
+    const size_t need = (size_t)count * Mp;
+    if (need * sizeof(double) > ((size_t)16 << 30)) {
+      set_error("all_alpha would need %.1f GB of device staging", need * 8.0 / 1e9);
+      return PLS_EUNSUPPORTED;
+    }
+    if (ws.all_alpha_n < need) {
+      cudaFree(ws.all_alpha); ws.all_alpha = nullptr; ws.all_alpha_n = 0;
+      PLS_CUDA_TRY(cudaMalloc(&ws.all_alpha, sizeof(double) * need));
+      ws.all_alpha_n = need;
+    }
+  }
+  return PLS_OK;
+}
+
+void read_counters(pls_ctx *c, const unsigned long long *h) {
+  pls_stats &s = c->stats;
+  s.pivots = (int64_t)h[CNT_PIVOTS]; s.grad_evals = (int64_t)h[CNT_GRAD];
+  s.sum_p = (int64_t)h[CNT_SUMP]; s.sum_p2 = (int64_t)h[CNT_SUMP2];
+  s.bpp_iters = (int64_t)h[CNT_ITERS]; s.spills = (int64_t)h[CNT_SPILLS];
+  s.rebuilds = (int64_t)h[CNT_REBUILDS]; s.blocked = (int64_t)h[CNT_BLOCKED];
+  const double Mp = c->pb.Mp;
+  s.nnls_flops = 2.0 * Mp * (double)s.sum_p + 4.0 * (double)s.sum_p2;
+  s.nnls_l2_bytes = 8.0 * Mp * (double)s.sum_p;
+}
+
+// K2 + K3 over a range, winner record left in ws.win.  Caller holds the device.
+int solve_range_dev(pls_ctx *c, int64_t b_begin, int64_t b_count, bool want_obj, bool want_alpha) {
+  Problem &pb = c->pb;
+  if (!pb.gram_ready) { set_error("Gram matrix not built (call pls_gram_build / pls_gram_finalize)"); return PLS_EINVAL; }
+  const int64_t total = (int64_t)1 << pb.Kp;
+  if (b_begin < 0 || b_count <= 0 || b_begin + b_count > total) { set_error("orthant range out of bounds"); return PLS_EINVAL; }
+  int rc = ensure_all_buffers(c, b_count, want_obj, want_alpha);
+  if (rc) return rc;
+  if (c->ws.Mp != pb.Mp && c->ws.win) { cudaFree(c->ws.win); c->ws.win = nullptr; }
+  if (c->ws.counters)
+    PLS_CUDA_TRY(cudaMemsetAsync(c->ws.counters, 0, sizeof(unsigned long long) * (CNT_NUM + 1), c->stream));
+  return k2_solve_range(pb, pb.G, pb.ldg, pb.c, pb.scal, pb.gmask, pb.Mp, pb.Kp, c->ws, b_begin, b_count,
+                        want_obj ? c->ws.all_obj : nullptr, want_alpha ? c->ws.all_alpha : nullptr,
+                        c->sm_count, c->stream, &c->launches);
+}
+
+double eta_term(const pls_ctx *c, const double *alpha_raw, int64_t b) {
+  // the eta rows of regularizeProblem (PartitionedLS.jl:115-118): eta * sum_k (sum_{m in k} w_m)^2
+  const Problem &pb = c->pb;
+  if (pb.eta == 0.0) return 0.0;
+  double tot = 0.0;
+  for (int k = 0; k < pb.Kp; ++k) {
+    double s = 0.0;
+    for (int m = 0; m < pb.Mp; ++m)
+      if (c->h_gmask[m] >> k & 1ull) s += (double)host_d(c->h_gmask, m, b) * alpha_raw[m];
+    tot += s * s;
+  }
+  return pb.eta * tot;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pls_version(void) { return PLS_VERSION; }
+
+const char *pls_last_error(void) { return g_err; }
+
+int pls_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int pls_create(pls_ctx **out, const int *device_ids, int n_dev) {
+  if (!out) { set_error("out is null"); return PLS_EINVAL; }
+  *out = nullptr;
+  if (n_dev > 1) { set_error("n_dev > 1: run one process per GPU and use the stage-wise entry points"); return PLS_EUNSUPPORTED; }
+  const int dev = (device_ids && n_dev == 1) ? device_ids[0] : 0;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available (%s); libpls_cuda has no CPU fallback",
+              e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    return PLS_ECUDA;
+  }
+  if (dev < 0 || dev >= n) { set_error("device %d out of range (0..%d)", dev, n - 1); return PLS_EINVAL; }
+  cudaDeviceProp prop;
+  PLS_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, prop.major, prop.minor);
+    return PLS_ECUDA;
+  }
+  pls_ctx *c = new (std::nothrow) pls_ctx();
+  if (!c) { set_error("out of host memory"); return PLS_ENOMEM; }
+  c->dev = dev; c->sm_count = prop.multiProcessorCount;
+  memset(&c->stats, 0, sizeof(c->stats));
+  PLS_CUDA_TRY(cudaSetDevice(dev));
+  PLS_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (auto &ev : c->ev) PLS_CUDA_TRY(cudaEventCreate(&ev));
+  PLS_CUDA_TRY(cudaMalloc(&c->d_ssq, sizeof(double) * 2));
+  *out = c;
+  return PLS_OK;
+}
+
+void pls_destroy(pls_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->dev);
+  cudaStreamSynchronize(c->stream);
+  free_problem(c); free_ws(c);
+  cudaFree(c->d_w); cudaFree(c->d_ssq);
+  if (c->h_pin) cudaFreeHost(c->h_pin);
+  for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int pls_load(pls_ctx *c, const double *X, int64_t N, int64_t ldx, int64_t M, const double *y,
+             const int64_t *P, int64_t K, double eta) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!X || !y || !P) { set_error("null input pointer"); return PLS_EINVAL; }
+  if (N < 1 || M < 1 || K < 1 || ldx < N) { set_error("bad shape N=%lld M=%lld K=%lld ldx=%lld", (long long)N, (long long)M, (long long)K, (long long)ldx); return PLS_EINVAL; }
+  if (K + 1 > 40) { set_error("K = %lld: 2^(K+1) orthants cannot be enumerated (limit K <= 39)", (long long)K); return PLS_EINVAL; }
+  if (M + 2 > 4096) { set_error("M = %lld exceeds this build's limit (4094)", (long long)M); return PLS_EUNSUPPORTED; }
+  if (!(eta >= 0.0) || !std::isfinite(eta)) { set_error("eta must be finite and >= 0"); return PLS_EINVAL; }
+  std::vector<uint64_t> gm((size_t)M + 1, 0);
+  for (int64_t k = 0; k < K; ++k)
+    for (int64_t m = 0; m < M; ++m) {
+      const int64_t v = P[k * M + m];
+      if (v != 0 && v != 1) { set_error("P must be binary (P[%lld,%lld] = %lld)", (long long)m, (long long)k, (long long)v); return PLS_EINVAL; }
+      if (v) gm[(size_t)m] |= 1ull << k;
+    }
+  gm[(size_t)M] = 1ull << K;     // the intercept is its own group (PartitionedLS.jl:78)
+
+  Problem &pb = c->pb;
+  const int Mp = (int)M + 1, zc = (int)M + 2;
+  const int zcp = (int)round_up(zc, 64);
+  const int64_t ldz = round_up(N, 32);
+  const size_t zb = (size_t)ldz * zcp * sizeof(double);
+  if (pb.M != (int)M || pb.K != (int)K || zb > c->z_bytes) {
+    free_problem(c);
+    PLS_CUDA_TRY(cudaMalloc(&pb.Z, zb));
+    c->z_bytes = zb;
+    PLS_CUDA_TRY(cudaMalloc(&pb.gmask, sizeof(uint64_t) * Mp));
+    PLS_CUDA_TRY(cudaMalloc(&pb.S, sizeof(double) * (size_t)zc * zc));
+    pb.ldg = (int)round_up(Mp, 4);
+    PLS_CUDA_TRY(cudaMalloc(&pb.G, sizeof(double) * (size_t)pb.ldg * Mp));
+    PLS_CUDA_TRY(cudaMalloc(&pb.c, sizeof(double) * Mp));
+    PLS_CUDA_TRY(cudaMalloc(&pb.scal, sizeof(double) * 4));
+    cudaFree(c->d_w); c->d_w = nullptr;
+    PLS_CUDA_TRY(cudaMalloc(&c->d_w, sizeof(double) * Mp));
+    if (c->h_pin) { cudaFreeHost(c->h_pin); c->h_pin = nullptr; }
+    PLS_CUDA_TRY(cudaMallocHost(&c->h_pin, sizeof(double) * (Mp + 4 + CNT_NUM + 1)));
+  }
+  pb.N = N; pb.ldz = ldz; pb.M = (int)M; pb.K = (int)K; pb.Mp = Mp; pb.Kp = (int)K + 1;
+  pb.zcols = zc; pb.zcols_pad = zcp; pb.eta = eta;
+  pb.loaded = false; pb.gram_ready = false;
+  c->h_gmask = gm;
+  cudaStream_t st = c->stream;
+  // zero the pad columns and pad rows, then X, ones, y
+  if (zcp > zc) PLS_CUDA_TRY(cudaMemsetAsync(pb.Z + (size_t)ldz * zc, 0, sizeof(double) * (size_t)ldz * (zcp - zc), st));
+  if (ldz > N) PLS_CUDA_TRY(cudaMemset2DAsync(pb.Z + N, sizeof(double) * ldz, 0, sizeof(double) * (ldz - N), zc, st));
+  PLS_CUDA_TRY(cudaMemcpy2DAsync(pb.Z, sizeof(double) * ldz, X, sizeof(double) * ldx, sizeof(double) * N, M,
+                                 cudaMemcpyHostToDevice, st));
+  fill_ones<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(pb.Z + (size_t)ldz * M, N);
+  PLS_CUDA_TRY(cudaGetLastError());
+  ++c->launches;
+  PLS_CUDA_TRY(cudaMemcpyAsync(pb.Z + (size_t)ldz * (M + 1), y, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+  PLS_CUDA_TRY(cudaMemcpyAsync(pb.gmask, gm.data(), sizeof(uint64_t) * Mp, cudaMemcpyHostToDevice, st));
+  PLS_CUDA_TRY(cudaStreamSynchronize(st));   // gm / caller buffers may go away after return
+  pb.loaded = true;
+  return PLS_OK;
+}
+
+int pls_gram_build(pls_ctx *c) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!c->pb.loaded) { set_error("no data set loaded"); return PLS_EINVAL; }
+  c->pb.gram_ready = false;
+  return k1_gram_build(c->pb, c->stream, &c->launches);
+}
+
+int pls_gram_raw(pls_ctx *c, void **dev_ptr, int64_t *count) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!c->pb.loaded || !dev_ptr || !count) { set_error("no data set loaded or null output"); return PLS_EINVAL; }
+  PLS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  *dev_ptr = c->pb.S;
+  *count = (int64_t)c->pb.zcols * c->pb.zcols;
+  return PLS_OK;
+}
+
+int pls_gram_finalize(pls_ctx *c) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!c->pb.loaded) { set_error("no data set loaded"); return PLS_EINVAL; }
+  rc = k1_gram_finalize(c->pb, c->stream, &c->launches);
+  if (rc) return rc;
+  PLS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return PLS_OK;
+}
+
+int pls_opt_solve_range(pls_ctx *c, int64_t b_begin, int64_t b_count, double *alpha_raw,
+                        int64_t *b_best, double *obj_best, double *all_obj, double *all_alpha) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!alpha_raw || !b_best || !obj_best) { set_error("null output pointer"); return PLS_EINVAL; }
+  cudaStream_t st = c->stream;
+  PLS_CUDA_TRY(cudaEventRecord(c->ev[2], st));
+  rc = solve_range_dev(c, b_begin, b_count, all_obj != nullptr, all_alpha != nullptr);
+  if (rc) return rc;
+  PLS_CUDA_TRY(cudaEventRecord(c->ev[3], st));
+  const int Mp = c->pb.Mp;
+  PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin, c->ws.win, sizeof(double) * (Mp + 2), cudaMemcpyDeviceToHost, st));
+  PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin + Mp + 4, c->ws.counters, sizeof(unsigned long long) * CNT_NUM, cudaMemcpyDeviceToHost, st));
+  if (all_obj) PLS_CUDA_TRY(cudaMemcpyAsync(all_obj, c->ws.all_obj, sizeof(double) * (size_t)b_count, cudaMemcpyDeviceToHost, st));
+  if (all_alpha) PLS_CUDA_TRY(cudaMemcpyAsync(all_alpha, c->ws.all_alpha, sizeof(double) * (size_t)b_count * Mp, cudaMemcpyDeviceToHost, st));
+  PLS_CUDA_TRY(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
+  c->stats.ms_nnls = ms;
+  c->stats.orthants = b_count;
+  const unsigned long long *cnt = reinterpret_cast<const unsigned long long *>(c->h_pin + Mp + 4);
+  read_counters(c, cnt);
+  memcpy(alpha_raw, c->h_pin, sizeof(double) * Mp);
+  *obj_best = c->h_pin[Mp];
+  long long bb; memcpy(&bb, &c->h_pin[Mp + 1], sizeof(bb));
+  *b_best = bb;
+  c->stats.kernel_launches = c->launches;
+  if (cnt[CNT_NOCONV]) { set_error("%llu orthant solves hit the iteration cap", cnt[CNT_NOCONV]); return PLS_ENUMERIC; }
+  if (*obj_best != *obj_best) { set_error("NaN objective (non-finite input?)"); return PLS_ENUMERIC; }
+  return PLS_OK;
+}
+
+int pls_opt_residual_partial(pls_ctx *c, const double *alpha_raw, int64_t b, double *ssq_out) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!c->pb.loaded || !alpha_raw || !ssq_out) { set_error("no data set loaded or null pointer"); return PLS_EINVAL; }
+  const int Mp = c->pb.Mp;
+  for (int m = 0; m < Mp; ++m) c->h_pin[m] = (double)host_d(c->h_gmask, m, b) * alpha_raw[m];
+  cudaStream_t st = c->stream;
+  PLS_CUDA_TRY(cudaMemcpyAsync(c->d_w, c->h_pin, sizeof(double) * Mp, cudaMemcpyHostToDevice, st));
+  rc = k4_residual(c->pb, c->ws, c->d_w, c->d_ssq, c->sm_count, st, &c->launches);
+  if (rc) return rc;
+  PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin + Mp, c->d_ssq, sizeof(double), cudaMemcpyDeviceToHost, st));
+  PLS_CUDA_TRY(cudaStreamSynchronize(st));
+  *ssq_out = c->h_pin[Mp];
+  return PLS_OK;
+}
+
+int pls_opt_objective_finish(pls_ctx *c, const double *alpha_raw, int64_t b, double ssq_total, double *obj_out) {
+  if (!c || !alpha_raw || !obj_out) { set_error("null pointer"); return PLS_EINVAL; }
+  *obj_out = std::sqrt(ssq_total + eta_term(c, alpha_raw, b));
+  return PLS_OK;
+}
+
+int pls_opt_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_raw, int64_t *b_best, double *obj_best,
+                         double *all_obj, double *all_alpha, pls_stats *stats) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!c->pb.loaded) { set_error("no data set loaded"); return PLS_EINVAL; }
+  if (!alpha_raw || !b_best || !obj_best) { set_error("null output pointer"); return PLS_EINVAL; }
+  const double t0 = now_ms();
+  const double keep_upload = c->stats.ms_upload;
+  memset(&c->stats, 0, sizeof(c->stats));
+  c->stats.ms_upload = keep_upload;
+  const int launches0 = c->launches;
+  Problem &pb = c->pb;
+  cudaStream_t st = c->stream;
+  const int Mp = pb.Mp;
+  const int64_t total = (int64_t)1 << pb.Kp;
+  PLS_CUDA_TRY(cudaEventRecord(c->ev[0], st));
+  rc = k1_gram_build(pb, st, &c->launches); if (rc) return rc;
+  rc = k1_gram_finalize(pb, st, &c->launches); if (rc) return rc;
+  PLS_CUDA_TRY(cudaEventRecord(c->ev[1], st));
+  rc = solve_range_dev(c, 0, total, all_obj != nullptr, all_alpha != nullptr); if (rc) return rc;
+  PLS_CUDA_TRY(cudaEventRecord(c->ev[2], st));
+  const bool recompute = !(flags & PLS_FLAG_NO_RECOMPUTE);
+  if (recompute) {
+    winner_weights<<<1, 256, 0, st>>>(c->ws.win, pb.gmask, Mp, c->d_w);
+    PLS_CUDA_TRY(cudaGetLastError());
+    ++c->launches;
+    rc = k4_residual(pb, c->ws, c->d_w, c->d_ssq, c->sm_count, st, &c->launches); if (rc) return rc;
+  }
+  PLS_CUDA_TRY(cudaEventRecord(c->ev[3], st));
+  PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin, c->ws.win, sizeof(double) * (Mp + 2), cudaMemcpyDeviceToHost, st));
+  if (recompute) PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin + Mp + 2, c->d_ssq, sizeof(double), cudaMemcpyDeviceToHost, st));
+  PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin + Mp + 4, c->ws.counters, sizeof(unsigned long long) * CNT_NUM, cudaMemcpyDeviceToHost, st));
+  if (all_obj) PLS_CUDA_TRY(cudaMemcpyAsync(all_obj, c->ws.all_obj, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost, st));
+  if (all_alpha) PLS_CUDA_TRY(cudaMemcpyAsync(all_alpha, c->ws.all_alpha, sizeof(double) * (size_t)total * Mp, cudaMemcpyDeviceToHost, st));
+  PLS_CUDA_TRY(cudaStreamSynchronize(st));
+
+  memcpy(alpha_raw, c->h_pin, sizeof(double) * Mp);
+  long long bb; memcpy(&bb, &c->h_pin[Mp + 1], sizeof(bb));
+  *b_best = bb;
+  double obj = c->h_pin[Mp];
+  if (recompute && obj == obj) obj = std::sqrt(c->h_pin[Mp + 2] + eta_term(c, alpha_raw, bb));
+  *obj_best = obj;
+
+  float ms = 0.f;
+  pls_stats &s = c->stats;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); s.ms_gram = ms;
+  cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); s.ms_nnls = ms;
+  cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); s.ms_recompute = ms;
+  s.ms_select = 0.0;   // K3 is timed with K2 (same stream, ~microseconds)
+  s.orthants = total;
+  const unsigned long long *cnt = reinterpret_cast<const unsigned long long *>(c->h_pin + Mp + 4);
+  read_counters(c, cnt);
+  const double Nd = (double)pb.N, Md = (double)Mp;
+  s.gram_flops = Nd * Md * (Md + 1.0) + 2.0 * Nd * Md + 2.0 * Nd;
+  s.kernel_launches = c->launches - launches0;
+  s.ms_total = now_ms() - t0 + s.ms_upload;
+  if (stats) *stats = s;
+  if (cnt[CNT_NOCONV]) { set_error("%llu orthant solves hit the iteration cap", cnt[CNT_NOCONV]); return PLS_ENUMERIC; }
+  if (obj != obj) { set_error("NaN objective (non-finite input?)"); return PLS_ENUMERIC; }
+  return PLS_OK;
+}
+
+int pls_opt_fit(pls_ctx *c, const double *X, int64_t N, int64_t M, const double *y, const int64_t *P,
+                int64_t K, double eta, uint32_t flags, double *alpha_raw, int64_t *b_best, double *obj_best,
+                double *all_obj, double *all_alpha, pls_stats *stats) {
+  const double t0 = now_ms();
+  int rc = pls_load(c, X, N, N, M, y, P, K, eta);
+  if (rc) return rc;
+  c->stats.ms_upload = now_ms() - t0;
+  rc = pls_opt_fit_resident(c, flags, alpha_raw, b_best, obj_best, all_obj, all_alpha, stats);
+  c->stats.ms_upload = 0.0;
+  return rc;
+}
+
+int pls_get_stats(pls_ctx *c, pls_stats *stats) {
+  if (!c || !stats) { set_error("null pointer"); return PLS_EINVAL; }
+  *stats = c->stats;
+  return PLS_OK;
+}
+
+int pls_gram(pls_ctx *c, const double *X, int64_t N, int64_t M, const double *y, const int64_t *P,
+             int64_t K, double eta, double *G, double *cv, double *yy) {
+  if (!G || !cv || !yy) { set_error("null output pointer"); return PLS_EINVAL; }
+  int rc = pls_load(c, X, N, N, M, y, P, K, eta);
+  if (rc) return rc;
+  rc = pls_gram_build(c); if (rc) return rc;
+  rc = pls_gram_finalize(c); if (rc) return rc;
+  const Problem &pb = c->pb;
+  PLS_CUDA_TRY(cudaMemcpy2D(G, sizeof(double) * pb.Mp, pb.G, sizeof(double) * pb.ldg, sizeof(double) * pb.Mp, pb.Mp, cudaMemcpyDeviceToHost));
+  PLS_CUDA_TRY(cudaMemcpy(cv, pb.c, sizeof(double) * pb.Mp, cudaMemcpyDeviceToHost));
+  PLS_CUDA_TRY(cudaMemcpy(yy, pb.scal, sizeof(double), cudaMemcpyDeviceToHost));
+  return PLS_OK;
+}
+
+int pls_nnls_batch(pls_ctx *c, const double *G, const double *cv, double yy, int64_t Mp, const uint64_t *gmask,
+                   int64_t Kp, int64_t b_begin, int64_t b_count, double *obj_out, double *alpha_out) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!G || !cv || !gmask) { set_error("null input pointer"); return PLS_EINVAL; }
+  if (Mp < 1 || Mp > 4095 || Kp < 1 || Kp > 40 || b_count < 1 || b_begin < 0 || b_begin + b_count > ((int64_t)1 << Kp)) {
+    set_error("bad shape / range"); return PLS_EINVAL;
+  }
+  // build a throw-away device problem holding only the Gram side
+  free_problem(c);
+  Problem &pb = c->pb;
+  pb.Mp = (int)Mp; pb.Kp = (int)Kp; pb.M = (int)Mp - 1; pb.K = (int)Kp - 1;
+  pb.ldg = (int)round_up(Mp, 4);
+  PLS_CUDA_TRY(cudaMalloc(&pb.G, sizeof(double) * (size_t)pb.ldg * Mp));
+  PLS_CUDA_TRY(cudaMemset(pb.G, 0, sizeof(double) * (size_t)pb.ldg * Mp));
+  PLS_CUDA_TRY(cudaMalloc(&pb.c, sizeof(double) * Mp));
+  PLS_CUDA_TRY(cudaMalloc(&pb.scal, sizeof(double) * 4));
+  PLS_CUDA_TRY(cudaMalloc(&pb.gmask, sizeof(uint64_t) * Mp));
+  PLS_CUDA_TRY(cudaMemcpy2D(pb.G, sizeof(double) * pb.ldg, G, sizeof(double) * Mp, sizeof(double) * Mp, Mp, cudaMemcpyHostToDevice));
+  PLS_CUDA_TRY(cudaMemcpy(pb.c, cv, sizeof(double) * Mp, cudaMemcpyHostToDevice));
+  double sc[4] = {yy, 0.0, 0.0, 0.0};
+  for (int64_t m = 0; m < Mp; ++m) { sc[1] = std::fmax(sc[1], std::fabs(cv[m])); sc[2] = std::fmax(sc[2], std::fabs(G[m * Mp + m])); }
+  PLS_CUDA_TRY(cudaMemcpy(pb.scal, sc, sizeof(sc), cudaMemcpyHostToDevice));
+  PLS_CUDA_TRY(cudaMemcpy(pb.gmask, gmask, sizeof(uint64_t) * Mp, cudaMemcpyHostToDevice));
+  c->h_gmask.assign(gmask, gmask + Mp);
+  if (c->h_pin) { cudaFreeHost(c->h_pin); c->h_pin = nullptr; }
+  PLS_CUDA_TRY(cudaMallocHost(&c->h_pin, sizeof(double) * (Mp + 4 + CNT_NUM + 1)));
+  pb.gram_ready = true;
+  rc = solve_range_dev(c, b_begin, b_count, obj_out != nullptr, alpha_out != nullptr);
+  if (rc) return rc;
+  cudaStream_t st = c->stream;
+  if (obj_out) PLS_CUDA_TRY(cudaMemcpyAsync(obj_out, c->ws.all_obj, sizeof(double) * (size_t)b_count, cudaMemcpyDeviceToHost, st));
+  if (alpha_out) PLS_CUDA_TRY(cudaMemcpyAsync(alpha_out, c->ws.all_alpha, sizeof(double) * (size_t)b_count * Mp, cudaMemcpyDeviceToHost, st));
+  PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin + Mp + 4, c->ws.counters, sizeof(unsigned long long) * CNT_NUM, cudaMemcpyDeviceToHost, st));
+  PLS_CUDA_TRY(cudaStreamSynchronize(st));
+  const unsigned long long *cnt = reinterpret_cast<const unsigned long long *>(c->h_pin + Mp + 4);
+  c->stats.orthants = b_count;
+  read_counters(c, cnt);
+  if (cnt[CNT_NOCONV]) { set_error("%llu orthant solves hit the iteration cap", cnt[CNT_NOCONV]); return PLS_ENUMERIC; }
+  return PLS_OK;
+}
+
+}  // extern "C"

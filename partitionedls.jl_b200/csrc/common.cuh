@@ -1,0 +1,76 @@
+// Internal declarations shared by the kernels and the C ABI of libpls_cuda.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/pls.h"
+
+namespace pls {
+
+void set_error(const char *fmt, ...);
+
+#define PLS_CUDA_TRY(expr)                                                              \
+  do {                                                                                  \
+    cudaError_t e_ = (expr);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      ::pls::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, \
+                       __LINE__);                                                       \
+      return e_ == cudaErrorMemoryAllocation ? PLS_ENOMEM : PLS_ECUDA;                  \
+    }                                                                                   \
+  } while (0)
+
+static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// Solver work counters accumulated by K2 (device side, unsigned long long each).
+enum Counter {
+  CNT_PIVOTS = 0, CNT_GRAD, CNT_SUMP, CNT_SUMP2, CNT_ITERS, CNT_SPILLS, CNT_REBUILDS, CNT_BLOCKED,
+  CNT_NOCONV, CNT_NUM
+};
+
+// Device-resident problem (one GPU).
+struct Problem {
+  // data, augmented layout Z = [X | 1 | y | 0-pad], column-major, ldz rows per column
+  double *Z = nullptr;
+  int64_t N = 0, ldz = 0;
+  int M = 0, K = 0, Mp = 0, Kp = 0, zcols = 0, zcols_pad = 0;
+  double eta = 0.0;
+  uint64_t *gmask = nullptr;  // [Mp] group membership bits of each variable (intercept included)
+  // Gram
+  double *S = nullptr;        // raw sums Z'Z, (M+2)^2 column-major (lower triangle valid)
+  double *part = nullptr;     // split-K partial tiles
+  size_t part_bytes = 0;
+  double *G = nullptr;        // [ldg * Mp] full symmetric, eta folded in
+  int ldg = 0;
+  double *c = nullptr;        // [Mp]
+  double *scal = nullptr;     // [4]: yy, cmax, gdiag_max, unused
+  bool loaded = false, gram_ready = false;
+};
+
+// K2 outputs / workspaces
+struct SolveWs {
+  double *cta_obj = nullptr;      // [max_ctas]
+  long long *cta_b = nullptr;     // [max_ctas]
+  double *cta_w = nullptr;        // [max_ctas * Mp]
+  double *hspill = nullptr;       // [max_ctas * Mp * Mp] (only when the inverse may outgrow smem)
+  unsigned long long *counters = nullptr;  // [CNT_NUM]
+  double *win = nullptr;          // [Mp + 2]: winner alpha_raw, obj, b (as double bits)
+  double *all_obj = nullptr;      // device staging for per-orthant outputs
+  double *all_alpha = nullptr;
+  size_t all_obj_n = 0, all_alpha_n = 0;
+  int max_ctas = 0, Mp = 0;
+  size_t hspill_bytes = 0;
+  double *resid_part = nullptr;   // K4 block partials
+  int resid_blocks = 0;
+};
+
+// ---- kernel launchers (defined in gram.cu / nnls.cu / resid.cu) -----------------------------
+int k1_gram_build(Problem &pb, cudaStream_t st, int *launches);
+int k1_gram_finalize(Problem &pb, cudaStream_t st, int *launches);
+int k2_solve_range(const Problem &pb, const double *G, int ldg, const double *c, const double *scal,
+                   const uint64_t *gmask, int Mp, int Kp, SolveWs &ws, int64_t b_begin,
+                   int64_t b_count, double *d_all_obj, double *d_all_alpha, int sm_count,
+                   cudaStream_t st, int *launches);
+int k4_residual(const Problem &pb, SolveWs &ws, const double *d_w, double *d_ssq, int sm_count,
+                cudaStream_t st, int *launches);
+
+}  // namespace pls

@@ -1,0 +1,553 @@
+// K2: batched orthant NNLS in Gram space, and K3: argmin over orthants.
+//
+// Replaces the body of the reference loop  for b = 0:2^K'-1  (src/PartitionedLSOpt.jl:85-94):
+//   beta = indextobeta(b, K)            (Opt.jl:4-20)   -> sign bits of b, LSB first
+//   Xb   = bmatrix(Xo, Po, beta)        (Opt.jl:22-31)  -> never materialised: D_b G D_b on the fly
+//   alpha = nonneg_lsq(Xb, yo)          (Opt.jl:89)     -> active-set solve on the Gram matrix
+//   optval = norm(Xo*(Po.*alpha)*beta - yo) (Opt.jl:90) -> sqrt(yy - c_F' w_F)
+// and  argmin(first.(results))          (Opt.jl:96)     -> lexicographic (objective, b) reduction.
+//
+// Formulation.  In signed-weight space w = d .* alpha (d = Po*beta) every orthant minimises the
+// SAME quadratic  w'Gw - 2c'w + yy  under sign constraints  sigma_m w_m >= 0, sigma = sign(d).
+// For a passive set F the minimiser is w_F = inv(G_FF) c_F regardless of the orthant; the orthant
+// only decides which F is KKT-feasible.  One CTA therefore walks a Gray-code chain of orthants
+// (consecutive orthants differ in one group's sign) and carries H = inv(G_FF) in shared memory
+// from one orthant to the next, moving variables in/out of F with rank-1 bordering / deletion
+// updates of H (block principal pivoting with Murty's backup rule guarantees termination at the
+// unique KKT point of each strictly convex subproblem).  Each accepted solution is polished by one
+// step of iterative refinement against G itself, so the returned alpha does not depend on how H
+// was reached.
+#include "common.cuh"
+
+namespace pls {
+namespace {
+
+constexpr int T2 = 256;
+constexpr int NW2 = T2 / 32;
+
+struct K2Args {
+  const double *G; int ldg;
+  const double *c;
+  const double *scal;            // [0] = yy, [1] = max |c|
+  const uint64_t *gmask;
+  int Mp, Kp;
+  long long b_begin;
+  int chain_log2;
+  long long n_chains;
+  unsigned long long *chain_counter;   // dynamic chain scheduler (zeroed before launch)
+  int cap;                       // slots of H that fit in shared memory
+  double *hspill;                // [grid][Mp*Mp] or null
+  double *cta_obj; long long *cta_b; double *cta_w;
+  double *all_obj; double *all_alpha;   // nullable, indexed by (b - b_begin)
+  unsigned long long *counters;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Sum of (a, b) over the block, result to every thread.  red: 2*NW2 doubles.  Two barriers.
+__device__ __forceinline__ void block_sum2(double &a, double &b, double *red) {
+  a = warp_sum(a); b = warp_sum(b);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { red[wid] = a; red[NW2 + wid] = b; }
+  __syncthreads();
+  double x = 0.0, y = 0.0;
+#pragma unroll
+  for (int i = 0; i < NW2; ++i) { x += red[i]; y += red[NW2 + i]; }
+  __syncthreads();
+  a = x; b = y;
+}
+__device__ __forceinline__ double block_max1(double a, double *red) {
+  a = warp_max(a);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) red[wid] = a;
+  __syncthreads();
+  double x = red[0];
+#pragma unroll
+  for (int i = 1; i < NW2; ++i) x = fmax(x, red[i]);
+  __syncthreads();
+  return x;
+}
+
+// (objective, b) ordering of Opt.jl:96: first minimum wins, NaN sorts first; b < 0 = empty.
+__device__ __forceinline__ bool lex_better(double oa, long long ba, double ob, long long bb) {
+  if (bb < 0) return ba >= 0;
+  if (ba < 0) return false;
+  const bool na = oa != oa, nb = ob != ob;
+  if (na != nb) return na;
+  if (na) return ba < bb;
+  return oa < ob || (oa == ob && ba < bb);
+}
+
+struct Cta {
+  // problem
+  const double *G; int ldg; const double *c; int Mp;
+  // inverse of the passive block
+  double *H; int hp; int capcur; int p;
+  double *Hs; int cap_s; double *Hg;      // shared-memory home, and global spill area
+  // shared vectors
+  double *w, *r, *wF, *u, *v, *part, *red;
+  int *F, *pos, *sg, *dd, *vflag, *lst;
+  int *ctl;                               // [0]=n_remove [1]=n_add [2]=max index in V
+  // counters (uniform across the block)
+  unsigned long long n_piv, n_grad, n_sump, n_sump2, n_iter, n_spill, n_rebuild, n_blocked, n_noconv;
+};
+
+// u = H v on the leading p x p block (H symmetric).  Column-per-thread, rows split into parts.
+__device__ void matvec(const Cta &s, const double *vin, double *uout) {
+  const int tid = threadIdx.x, p = s.p, hp = s.hp;
+  const double *H = s.H;
+  const int pr = (p + 31) & ~31;
+  const int W = pr < T2 ? pr : T2;
+  const int nparts = T2 / W;
+  const int part_id = tid / W, i0 = tid - part_id * W;
+  if (part_id < nparts) {
+    for (int i = i0; i < p; i += W) {
+      double a0 = 0.0, a1 = 0.0;
+      int k = part_id;
+      for (; k + nparts < p; k += 2 * nparts) {
+        a0 = fma(H[(size_t)k * hp + i], vin[k], a0);
+        a1 = fma(H[(size_t)(k + nparts) * hp + i], vin[k + nparts], a1);
+      }
+      if (k < p) a0 = fma(H[(size_t)k * hp + i], vin[k], a0);
+      const double a = a0 + a1;
+      if (nparts == 1) uout[i] = a; else s.part[part_id * W + i] = a;
+    }
+  }
+  __syncthreads();
+  if (nparts > 1) {
+    for (int i = tid; i < p; i += T2) {
+      double a = 0.0;
+      for (int q = 0; q < nparts; ++q) a += s.part[q * W + i];
+      uout[i] = a;
+    }
+    __syncthreads();
+  }
+}
+
+// Move H from shared memory to this CTA's global spill area (pitch Mp) -- the slow path taken
+// when a passive set outgrows the shared-memory capacity.
+__device__ void spill(Cta &s) {
+  const int p = s.p;
+  for (int idx = threadIdx.x; idx < p * p; idx += T2) {
+    const int a = idx / p, b = idx - a * p;
+    s.Hg[(size_t)a * s.Mp + b] = s.Hs[(size_t)a * s.hp + b];
+  }
+  __syncthreads();
+  s.H = s.Hg; s.hp = s.Mp; s.capcur = s.Mp;
+  s.n_spill++;
+}
+
+// F <- F + {j}: bordering update of H and incremental update of w.  Returns false (and leaves the
+// state untouched) when column j is numerically dependent on the passive columns.
+__device__ bool add_var(Cta &s, int j) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int p = s.p;
+  for (int t = tid; t < p; t += T2) s.v[t] = s.G[(size_t)s.ldg * j + s.F[t]];
+  __syncthreads();
+  if (p > 0) matvec(s, s.v, s.u);
+  double a = 0.0, b = 0.0;
+  for (int t = tid; t < p; t += T2) { a = fma(s.v[t], s.u[t], a); b = fma(s.v[t], s.w[s.F[t]], b); }
+  block_sum2(a, b, s.red);
+  const double gjj = s.G[(size_t)s.ldg * j + j];
+  const double delta = gjj - a;
+  if (!(delta > 1e-13 * gjj)) { s.n_blocked++; return false; }
+  if (p == s.capcur) {
+    if (s.Hg == nullptr || s.H == s.Hg) { s.n_blocked++; return false; }
+    spill(s);
+  }
+  double *H = s.H; const int hp = s.hp;
+  const double inv = 1.0 / delta;
+  const double theta = (s.c[j] - b) * inv;
+  for (int q = wid; q < p; q += NW2) {
+    const double uq = s.u[q] * inv;
+    double *row = H + (size_t)q * hp;
+    for (int t = lane; t < p; t += 32) row[t] = fma(uq, s.u[t], row[t]);
+  }
+  for (int t = tid; t < p; t += T2) {
+    const double val = -s.u[t] * inv;
+    H[(size_t)p * hp + t] = val;
+    H[(size_t)t * hp + p] = val;
+    s.w[s.F[t]] -= theta * s.u[t];
+  }
+  if (tid == 0) { H[(size_t)p * hp + p] = inv; s.w[j] = theta; s.F[p] = j; s.pos[j] = p; }
+  __syncthreads();
+  s.n_piv++; s.n_sump2 += (unsigned long long)p * p;
+  s.p = p + 1;
+  return true;
+}
+
+// F <- F \ {F[slot]}: deletion update of H, w; the last slot is moved into the hole.
+__device__ void remove_slot(Cta &s, int slot) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int p = s.p, hp = s.hp;
+  double *H = s.H;
+  for (int t = tid; t < p; t += T2) s.u[t] = H[(size_t)t * hp + slot];
+  __syncthreads();
+  const double hss = s.u[slot];
+  const int j = s.F[slot];
+  const double inv = 1.0 / hss;
+  const double f = s.w[j] * inv;
+  for (int q = wid; q < p; q += NW2) {
+    const double uq = s.u[q] * inv;
+    double *row = H + (size_t)q * hp;
+    for (int t = lane; t < p; t += 32) row[t] = fma(-uq, s.u[t], row[t]);
+  }
+  for (int t = tid; t < p; t += T2) if (t != slot) s.w[s.F[t]] -= s.u[t] * f;
+  __syncthreads();
+  const int last = p - 1;
+  if (slot != last) {
+    for (int t = tid; t < last; t += T2) {
+      if (t == slot) H[(size_t)slot * hp + slot] = H[(size_t)last * hp + last];
+      else {
+        const double x = H[(size_t)last * hp + t];
+        H[(size_t)slot * hp + t] = x;
+        H[(size_t)t * hp + slot] = x;
+      }
+    }
+  }
+  if (tid == 0) {
+    s.w[j] = 0.0; s.pos[j] = -1;
+    if (slot != last) { const int jl = s.F[last]; s.F[slot] = jl; s.pos[jl] = slot; }
+  }
+  __syncthreads();
+  s.n_piv++; s.n_sump2 += (unsigned long long)p * p;
+  s.p = last;
+}
+
+// r = c - G[:,F] w_F for every variable (entries in F are the normal-equation residuals).
+__device__ void grad_eval(Cta &s) {
+  const int tid = threadIdx.x, p = s.p;
+  for (int t = tid; t < p; t += T2) s.wF[t] = s.w[s.F[t]];
+  __syncthreads();
+  for (int m = tid; m < s.Mp; m += T2) {
+    double a0 = s.c[m], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int t = 0;
+    for (; t + 3 < p; t += 4) {
+      const double g0 = s.G[(size_t)s.ldg * s.F[t] + m];
+      const double g1 = s.G[(size_t)s.ldg * s.F[t + 1] + m];
+      const double g2 = s.G[(size_t)s.ldg * s.F[t + 2] + m];
+      const double g3 = s.G[(size_t)s.ldg * s.F[t + 3] + m];
+      a0 = fma(-g0, s.wF[t], a0); a1 = fma(-g1, s.wF[t + 1], a1);
+      a2 = fma(-g2, s.wF[t + 2], a2); a3 = fma(-g3, s.wF[t + 3], a3);
+    }
+    for (; t < p; ++t) a0 = fma(-s.G[(size_t)s.ldg * s.F[t] + m], s.wF[t], a0);
+    s.r[m] = (a0 + a1) + (a2 + a3);
+  }
+  __syncthreads();
+  s.n_grad++; s.n_sump += (unsigned long long)p;
+}
+
+// One refinement step  w_F += H r_F.  Returns max |r_F| (before the step), same on all threads.
+__device__ double refine(Cta &s) {
+  const int tid = threadIdx.x, p = s.p;
+  double mx = 0.0;
+  for (int t = tid; t < p; t += T2) { const double x = s.r[s.F[t]]; s.v[t] = x; mx = fmax(mx, fabs(x)); }
+  mx = block_max1(mx, s.red);          // barriers inside also publish v
+  if (p == 0) return 0.0;
+  matvec(s, s.v, s.u);
+  for (int t = tid; t < p; t += T2) s.w[s.F[t]] += s.u[t];
+  __syncthreads();
+  return mx;
+}
+
+__global__ void __launch_bounds__(T2, 1) k2_orthant_chains(const K2Args A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int Mp = A.Mp, cap = A.cap;
+  const int MpP = (Mp + 3) & ~3;
+  Cta s;
+  s.G = A.G; s.ldg = A.ldg; s.c = A.c; s.Mp = Mp;
+  // ---- carve shared memory
+  double *dptr = reinterpret_cast<double *>(smem_raw);
+  s.Hs = dptr; dptr += (size_t)cap * cap;
+  s.w = dptr; dptr += MpP;
+  s.r = dptr; dptr += MpP;
+  s.wF = dptr; dptr += MpP;
+  s.u = dptr; dptr += MpP;
+  s.v = dptr; dptr += MpP;
+  s.part = dptr; dptr += (MpP > T2 ? MpP : T2);
+  s.red = dptr; dptr += 2 * NW2;
+  int *iptr = reinterpret_cast<int *>(dptr);
+  s.F = iptr; iptr += MpP;
+  s.pos = iptr; iptr += MpP;
+  s.sg = iptr; iptr += MpP;
+  s.dd = iptr; iptr += MpP;
+  s.vflag = iptr; iptr += MpP;
+  s.lst = iptr; iptr += MpP;
+  s.ctl = iptr; iptr += 4;
+  s.cap_s = cap;
+  s.Hg = A.hspill ? A.hspill + (size_t)blockIdx.x * Mp * Mp : nullptr;
+  s.n_piv = s.n_grad = s.n_sump = s.n_sump2 = s.n_iter = s.n_spill = s.n_rebuild = s.n_blocked =
+      s.n_noconv = 0;
+
+  const double yy = A.scal[0], cmax = A.scal[1];
+  const double told = 1e-12 * cmax;
+  const long long L = 1ll << A.chain_log2;
+  double best_obj = 0.0; long long best_b = -1;
+  __shared__ unsigned long long s_chain;
+
+  for (;;) {   // persistent CTA: fetch chains until the range is exhausted
+  if (tid == 0) s_chain = atomicAdd(A.chain_counter, 1ull);
+  __syncthreads();
+  const unsigned long long chain = s_chain;
+  __syncthreads();
+  if (chain >= (unsigned long long)A.n_chains) break;
+  const long long base = A.b_begin + (long long)chain * L;
+
+  // chain start: empty passive set, w = 0, r = c
+  s.H = s.Hs; s.hp = cap; s.capcur = cap; s.p = 0;
+  for (int m = tid; m < Mp; m += T2) { s.w[m] = 0.0; s.r[m] = A.c[m]; s.pos[m] = -1; }
+  __syncthreads();
+  bool r_valid = true;
+
+  for (long long i = 0; i < L; ++i) {
+    const long long b = base + (i ^ (i >> 1));
+    // sigma / d of this orthant:  d_m = sum_k Po[m,k] * (2 bit_k(b) - 1)   (Opt.jl:28-29)
+    for (int m = tid; m < Mp; m += T2) {
+      const uint64_t gm = A.gmask[m];
+      const int d = 2 * __popcll(gm & (uint64_t)b) - __popcll(gm);
+      s.dd[m] = d; s.sg[m] = (d > 0) - (d < 0);
+      s.vflag[m] = 0;
+    }
+    __syncthreads();
+
+    int t_best = Mp + 1, pbar = 3, iters = 0;
+    bool ok = true;
+    for (;;) {
+      if (!r_valid) {
+        int rep = 0;
+        for (;;) {
+          grad_eval(s);
+          const double rf = refine(s);
+          if (rf <= 1e-9 * cmax) break;
+          if (++rep >= 4) {
+            // the carried inverse has degraded: rebuild it by re-adding the passive set
+            const int pn = s.p;
+            for (int t = tid; t < pn; t += T2) s.lst[t] = s.F[t];
+            __syncthreads();
+            for (int t = tid; t < pn; t += T2) { s.pos[s.lst[t]] = -1; s.w[s.lst[t]] = 0.0; }
+            __syncthreads();
+            s.p = 0;
+            for (int t = 0; t < pn; ++t) add_var(s, s.lst[t]);
+            s.n_rebuild++;
+            if (rep >= 6) { ok = false; break; }
+          }
+        }
+        if (!ok) break;
+      }
+      r_valid = false;
+      // ---- infeasibility sets: passive variables with the wrong sign, active ones with a
+      //      positive (sign-adjusted) gradient
+      for (int m = tid; m < Mp; m += T2) {
+        const int sl = s.pos[m], sg = s.sg[m];
+        int f = 0;
+        if (sl >= 0) { if (sg == 0 || (double)sg * s.w[m] < 0.0) f = 1; }
+        else if (sg != 0 && s.vflag[m] != 3 && (double)sg * s.r[m] > told) f = 2;
+        if (s.vflag[m] != 3) s.vflag[m] = f;
+      }
+      __syncthreads();
+      if (wid == 0) {   // deterministic compaction in index order: removals then additions
+        int nr = 0, na = 0, mxi = -1;
+        for (int m0 = 0; m0 < Mp; m0 += 32) {
+          const int m = m0 + lane;
+          const int f = (m < Mp) ? s.vflag[m] : 0;
+          const unsigned br = __ballot_sync(0xffffffffu, f == 1);
+          const unsigned ba = __ballot_sync(0xffffffffu, f == 2);
+          if (f == 1) s.lst[nr + __popc(br & ((1u << lane) - 1))] = m;
+          if (f == 2) s.lst[Mp - 1 - (na + __popc(ba & ((1u << lane) - 1)))] = m;
+          nr += __popc(br); na += __popc(ba);
+          const unsigned any = br | ba;
+          if (any) mxi = m0 + 31 - __clz(any);
+        }
+        if (lane == 0) { s.ctl[0] = nr; s.ctl[1] = na; s.ctl[2] = mxi; }
+      }
+      __syncthreads();
+      int nr = s.ctl[0], na = s.ctl[1];
+      const int nv = nr + na;
+      if (nv == 0) { r_valid = true; break; }   // KKT point reached; r stays valid for the next orthant
+      bool single = false;
+      if (nv < t_best) { t_best = nv; pbar = 3; }
+      else if (pbar >= 1) { --pbar; }
+      else single = true;                       // Murty's rule: only the highest index moves
+      if (single) {
+        const int m = s.ctl[2];
+        if (s.pos[m] >= 0) remove_slot(s, s.pos[m]);
+        else if (!add_var(s, m)) { if (tid == 0) s.vflag[m] = 3; __syncthreads(); }
+      } else {
+        for (int q = 0; q < nr; ++q) remove_slot(s, s.pos[s.lst[q]]);
+        for (int q = 0; q < na; ++q) {
+          const int m = s.lst[Mp - 1 - q];
+          if (!add_var(s, m)) { if (tid == 0) s.vflag[m] = 3; __syncthreads(); }
+        }
+      }
+      s.n_iter++;
+      if (++iters > 60 + 6 * Mp) { ok = false; break; }
+    }
+    if (!ok) s.n_noconv++;
+
+    // ---- objective  sqrt(yy - c_F' w_F)   (= norm(Xa w - ya) at the KKT point, Opt.jl:90)
+    double a = 0.0, dummy = 0.0;
+    for (int t = tid; t < s.p; t += T2) { const int m = s.F[t]; a = fma(A.c[m], s.w[m], a); }
+    block_sum2(a, dummy, s.red);
+    double obj2 = yy - a;
+    double obj = ok ? sqrt(fmax(obj2, 0.0)) : __longlong_as_double(0x7ff8000000000000ll);
+    const long long rel = b - A.b_begin;
+    if (A.all_obj && tid == 0) A.all_obj[rel] = obj;
+    if (A.all_alpha) {
+      for (int m = tid; m < Mp; m += T2) {
+        const int d = s.dd[m];
+        A.all_alpha[(size_t)rel * Mp + m] = (s.pos[m] >= 0 && d != 0) ? fmax(s.w[m] / (double)d, 0.0) : 0.0;
+      }
+    }
+    const bool better = lex_better(obj, b, best_obj, best_b);
+    if (better) {
+      best_obj = obj; best_b = b;
+      for (int m = tid; m < Mp; m += T2) {
+        const int d = s.dd[m];
+        A.cta_w[(size_t)blockIdx.x * Mp + m] =
+            (s.pos[m] >= 0 && d != 0) ? fmax(s.w[m] / (double)d, 0.0) : 0.0;
+      }
+    }
+    __syncthreads();
+  }
+  }  // chains
+  if (tid == 0) {
+    A.cta_obj[blockIdx.x] = best_obj;
+    A.cta_b[blockIdx.x] = best_b;
+    atomicAdd(&A.counters[CNT_PIVOTS], s.n_piv);
+    atomicAdd(&A.counters[CNT_GRAD], s.n_grad);
+    atomicAdd(&A.counters[CNT_SUMP], s.n_sump);
+    atomicAdd(&A.counters[CNT_SUMP2], s.n_sump2);
+    atomicAdd(&A.counters[CNT_ITERS], s.n_iter);
+    atomicAdd(&A.counters[CNT_SPILLS], s.n_spill);
+    atomicAdd(&A.counters[CNT_REBUILDS], s.n_rebuild);
+    atomicAdd(&A.counters[CNT_BLOCKED], s.n_blocked);
+    atomicAdd(&A.counters[CNT_NOCONV], s.n_noconv);
+  }
+}
+
+// K3: lexicographic (objective, b) minimum over the per-CTA winners; NaN sorts first (Julia
+// argmin semantics, Opt.jl:96).  One block.
+__global__ void __launch_bounds__(256) k3_select_winner(const double *cta_obj, const long long *cta_b,
+                                                        const double *cta_w, int n, int Mp, double *win) {
+  __shared__ double so[256];
+  __shared__ long long sb[256];
+  __shared__ int si[256];
+  const int tid = threadIdx.x;
+  double o = 0.0; long long b = -1; int idx = -1;
+  for (int i = tid; i < n; i += 256)
+    if (lex_better(cta_obj[i], cta_b[i], o, b)) { o = cta_obj[i]; b = cta_b[i]; idx = i; }
+  so[tid] = o; sb[tid] = b; si[tid] = idx;
+  __syncthreads();
+  for (int st = 128; st; st >>= 1) {
+    if (tid < st && lex_better(so[tid + st], sb[tid + st], so[tid], sb[tid])) {
+      so[tid] = so[tid + st]; sb[tid] = sb[tid + st]; si[tid] = si[tid + st];
+    }
+    __syncthreads();
+  }
+  const int wi = si[0];
+  for (int m = tid; m < Mp; m += 256) win[m] = wi >= 0 ? cta_w[(size_t)wi * Mp + m] : 0.0;
+  if (tid == 0) { win[Mp] = so[0]; win[Mp + 1] = __longlong_as_double(sb[0]); }
+}
+
+size_t k2_smem_bytes(int Mp, int cap) {
+  const int MpP = (Mp + 3) & ~3;
+  size_t d = (size_t)cap * cap + 5 * (size_t)MpP + (MpP > T2 ? MpP : T2) + 2 * NW2;
+  size_t i = 6 * (size_t)MpP + 4;
+  return d * sizeof(double) + i * sizeof(int);
+}
+
+}  // namespace
+
+int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, const double *scal,
+                   const uint64_t *gmask, int Mp, int Kp, SolveWs &ws, int64_t b_begin,
+                   int64_t b_count, double *d_all_obj, double *d_all_alpha, int sm_count,
+                   cudaStream_t st, int *launches) {
+  if (b_count <= 0) { set_error("k2: empty orthant range"); return PLS_EINVAL; }
+  // shared-memory capacity for the inverse
+  int dev = 0, max_smem = 0;
+  PLS_CUDA_TRY(cudaGetDevice(&dev));
+  PLS_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  int cap = Mp;
+  while (cap > 8 && k2_smem_bytes(Mp, cap) > (size_t)max_smem) --cap;
+  cap &= ~1;
+  if (cap < 2) cap = 2;
+  if (cap > Mp) cap = Mp;
+  if (k2_smem_bytes(Mp, cap) > (size_t)max_smem) {
+    set_error("k2: M' = %d too large for this build", Mp);
+    return PLS_EUNSUPPORTED;
+  }
+  const size_t smem = k2_smem_bytes(Mp, cap);
+  PLS_CUDA_TRY(cudaFuncSetAttribute(k2_orthant_chains, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+  int occ = 1;
+  PLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_orthant_chains, T2, smem));
+  if (occ < 1) occ = 1;
+  long long grid = (long long)sm_count * occ;
+
+  // Gray chains: aligned power-of-two blocks of orthants.  Long enough to amortise the cold
+  // start, short enough that every CTA gets >= ~8 chains from the dynamic scheduler.
+  int align_log2 = 0;
+  while (align_log2 < 62 && (((uint64_t)b_begin | (uint64_t)b_count) >> align_log2 & 1ull) == 0) ++align_log2;
+  int chain_log2 = 0;
+  while (chain_log2 < 8 && (b_count >> (chain_log2 + 1)) >= grid * 8) ++chain_log2;
+  if (chain_log2 > align_log2) chain_log2 = align_log2;
+  if (chain_log2 > Kp) chain_log2 = Kp;
+  const long long n_chains = b_count >> chain_log2;
+  if (grid > n_chains) grid = n_chains;
+
+  // per-CTA workspaces
+  if (grid > ws.max_ctas || Mp != ws.Mp) {
+    if (ws.cta_obj) cudaFree(ws.cta_obj);
+    if (ws.cta_b) cudaFree(ws.cta_b);
+    if (ws.cta_w) cudaFree(ws.cta_w);
+    ws.cta_obj = nullptr; ws.cta_b = nullptr; ws.cta_w = nullptr; ws.max_ctas = 0;
+    const long long n = (long long)sm_count * occ;
+    PLS_CUDA_TRY(cudaMalloc(&ws.cta_obj, sizeof(double) * n));
+    PLS_CUDA_TRY(cudaMalloc(&ws.cta_b, sizeof(long long) * n));
+    PLS_CUDA_TRY(cudaMalloc(&ws.cta_w, sizeof(double) * n * Mp));
+    ws.max_ctas = (int)n; ws.Mp = Mp;
+  }
+  if (cap < Mp) {
+    const size_t need = (size_t)ws.max_ctas * Mp * Mp * sizeof(double);
+    if (need > ws.hspill_bytes) {
+      if (ws.hspill) cudaFree(ws.hspill);
+      ws.hspill = nullptr; ws.hspill_bytes = 0;
+      PLS_CUDA_TRY(cudaMalloc(&ws.hspill, need));
+      ws.hspill_bytes = need;
+    }
+  }
+  if (!ws.counters) {
+    PLS_CUDA_TRY(cudaMalloc(&ws.counters, sizeof(unsigned long long) * (CNT_NUM + 1)));
+    PLS_CUDA_TRY(cudaMemsetAsync(ws.counters, 0, sizeof(unsigned long long) * (CNT_NUM + 1), st));
+  }
+  if (!ws.win) PLS_CUDA_TRY(cudaMalloc(&ws.win, sizeof(double) * (Mp + 2)));
+  PLS_CUDA_TRY(cudaMemsetAsync(ws.counters + CNT_NUM, 0, sizeof(unsigned long long), st));
+
+  K2Args A;
+  A.G = G; A.ldg = ldg; A.c = c; A.scal = scal; A.gmask = gmask; A.Mp = Mp; A.Kp = Kp;
+  A.b_begin = b_begin; A.chain_log2 = chain_log2; A.n_chains = n_chains;
+  A.chain_counter = ws.counters + CNT_NUM;
+  A.cap = cap;
+  A.hspill = (cap < Mp) ? ws.hspill : nullptr;
+  A.cta_obj = ws.cta_obj; A.cta_b = ws.cta_b; A.cta_w = ws.cta_w;
+  A.all_obj = d_all_obj; A.all_alpha = d_all_alpha; A.counters = ws.counters;
+  k2_orthant_chains<<<(unsigned)grid, T2, smem, st>>>(A);
+  PLS_CUDA_TRY(cudaGetLastError());
+  ++*launches;
+  k3_select_winner<<<1, 256, 0, st>>>(ws.cta_obj, ws.cta_b, ws.cta_w, (int)grid, Mp, ws.win);
+  PLS_CUDA_TRY(cudaGetLastError());
+  ++*launches;
+  return PLS_OK;
+}
+
+}  // namespace pls

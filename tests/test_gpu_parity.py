@@ -1,0 +1,200 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle / golden vectors.
+
+Tolerances (BASELINE.json north_star): same selected sign pattern; objective, alpha, beta within
+1e-9 relative (FP64).  Per-orthant objectives returned for returnAllSolutions are Gram-space values
+sqrt(yy - c'w): when the residual is << ||y|| they carry an absolute error ~ sqrt(eps * yy), so they
+are compared with atol = 1e-6 * sqrt(yy) (the reference's own tests use atol = 1e-6 on opt)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+CASES = ["rand_a", "rand_b", "rand_c_corr", "rand_d_overlap"]
+RTOL = 1e-9
+
+
+def _close(a, b, scale=None):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    s = np.abs(b).max() if scale is None else scale
+    return np.all(np.abs(a - b) <= RTOL * max(s, 1e-300))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_toy_native_interface(pkg, oracle, dtype):
+    """test/runtests.jl:8-39 and :123-146 (Float32 inputs)."""
+    o, _ = oracle
+    X, y = o.TOY_X.astype(dtype), o.TOY_Y.astype(dtype)
+    model, cache, rep = pkg.fit(pkg.Opt, X, y, o.TOY_P, η=0.0)
+    assert cache is None
+    assert abs(rep.opt) < 1e-6
+    yp = pkg.predict(model, o.TOY_X)
+    assert abs(np.sum(yp - o.TOY_Y) ** 2) < 1e-6
+    assert rep.b == 5
+    assert _close(model.α, [5 / 11, 6 / 11, 1.0]) and _close(model.β, [11 / 29, -16 / 29])
+    assert abs(model.t - 60 / 29) < 1e-9
+    assert rep.stats["kernel_launches"] >= 5
+
+
+def test_toy_eta_and_all_solutions(pkg, oracle):
+    o, _ = oracle
+    g = np.load(os.path.join(GOLD, "toy.npz"))
+    model, _, rep = pkg.fit(pkg.Opt, o.TOY_X, o.TOY_Y, o.TOY_P, η=1e-3)
+    assert rep.b == int(g["eta3_b_best"]) and abs(rep.opt - float(g["eta3_opt"])) < 1e-9 * float(g["eta3_opt"])
+    assert _close(model.α, g["eta3_alpha"]) and _close(model.β, g["eta3_beta"]) and abs(model.t - float(g["eta3_t"])) < 1e-9
+    model, _, rep = pkg.fit(pkg.Opt, o.TOY_X, o.TOY_Y, o.TOY_P, η=0.0, returnAllSolutions=True)
+    assert len(rep.solutions) == 8
+    objs = np.array([s[0] for s in rep.solutions])
+    assert np.allclose(objs, g["objs"], rtol=1e-9, atol=1e-6 * np.linalg.norm(o.TOY_Y))
+    ref = o.fit_opt(o.TOY_X, o.TOY_Y, o.TOY_P, 0.0, return_all=True)
+    for (og, mg), (orf, a, b, t) in zip(rep.solutions, ref["solutions"]):
+        assert _close(mg.α, a, 1.0) and _close(mg.β, b, 1.0) and abs(mg.t - t) < 1e-9
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_cases_all_orthants(ctx, pkg, oracle, name):
+    o, _ = oracle
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    X, y, P, eta = g["X"], g["y"], g["P"], float(g["eta"])
+    r = ctx.opt_fit(X, y, P, eta=eta, return_all=True)
+    assert r["b_best"] == int(g["b_best"])
+    assert abs(r["opt"] - float(g["opt"])) <= RTOL * float(g["opt"])
+    assert np.allclose(r["objs"], g["objs"], rtol=RTOL, atol=1e-6 * np.linalg.norm(y))
+    scale = np.abs(g["alphas"]).max(axis=1, keepdims=True)
+    assert np.all(np.abs(r["alphas"] - g["alphas"]) <= RTOL * scale + 1e-300)
+    model, _, rep = pkg.fit(pkg.Opt, X, y, P, η=eta, ctx=ctx)
+    assert _close(model.α, g["alpha"]) and _close(model.β, g["beta"]) and abs(model.t - float(g["t"])) <= RTOL * max(1, abs(float(g["t"])))
+    assert r["stats"]["spills"] == 0 and r["stats"]["rebuilds"] == 0
+
+
+@pytest.mark.parametrize("shape", [(1500, 40, 6, 0.0, False, 0.0), (2000, 64, 8, 1e-3, True, 0.0),
+                                   (800, 30, 5, 1e-2, True, 0.8), (64, 20, 4, 1e-3, True, 0.0),
+                                   (33, 7, 2, 0.0, False, 0.0)])
+def test_random_against_c_oracle(ctx, oracle, shape):
+    """Seeded random problems (incl. odd N, strongly correlated columns that force removals, N ~ M)."""
+    o, oc = oracle
+    N, M, K, eta, mixed, rho = shape
+    X, y, P = o.make_synthetic(N, M, K, seed=1000 + N + M, mixed_sign=mixed, rho=rho)
+    ref = oc.opt_fit(X, y, P, eta)
+    r = ctx.opt_fit(X, y, P, eta=eta, return_all=True)
+    assert r["b_best"] == ref["b_best"]
+    assert abs(r["opt"] - ref["obj_best"]) <= RTOL * ref["obj_best"]
+    assert np.allclose(r["objs"], ref["objs"], rtol=RTOL, atol=1e-6 * np.linalg.norm(y))
+    scale = np.abs(ref["alphas"]).max(axis=1, keepdims=True)
+    assert np.all(np.abs(r["alphas"] - ref["alphas"]) <= RTOL * scale + 1e-300)
+    st = r["stats"]
+    assert st["orthants"] == 2 ** (K + 1) and st["pivots"] > 0 and st["grad_evals"] > 0
+
+
+def test_gram_hook_identity(ctx, oracle):
+    """K1 alone: G = Xa'Xa (eta rows included), c = Xo'y, yy = y'y."""
+    o, _ = oracle
+    for (N, M, K, eta) in [(1000, 37, 5, 0.25), (4097, 130, 7, 0.0), (31, 5, 2, 1e-3)]:
+        X, y, P = o.make_synthetic(N, M, K, seed=N)
+        P[0, K - 1] = 1
+        G, c, yy = ctx.gram(X, y, P, eta)
+        Xo, Po = o.homogeneous_coords(X, P)
+        Xa, ya = o.regularize_problem(Xo, y, Po, eta)
+        Gr = Xa.T @ Xa
+        assert np.all(np.abs(G - Gr) <= 1e-12 * np.abs(Gr).max())
+        assert np.array_equal(G, G.T)
+        assert np.all(np.abs(c - Xa.T @ ya) <= 1e-12 * np.abs(c).max())
+        assert abs(yy - y @ y) <= 1e-12 * yy
+
+
+def test_nnls_batch_hook_unaligned_range(ctx, oracle):
+    """K2 alone on a caller-supplied Gram, on a range that is not chain-aligned."""
+    o, oc = oracle
+    X, y, P = o.make_synthetic(700, 22, 5, seed=77, mixed_sign=True, rho=0.4)
+    Xo, Po = o.homogeneous_coords(X, P)
+    G = Xo.T @ Xo; c = Xo.T @ y; yy = float(y @ y)
+    gmask = np.array([sum(1 << k for k in range(Po.shape[1]) if Po[m, k]) for m in range(Po.shape[0])], dtype=np.uint64)
+    ref = oc.opt_fit(X, y, P, 0.0)
+    for (b0, nb) in [(0, 64), (5, 13), (40, 24), (63, 1)]:
+        obj, al = ctx.nnls_batch(G, c, yy, gmask, Po.shape[1], b0, nb)
+        assert np.allclose(obj, ref["objs"][b0:b0 + nb], rtol=RTOL, atol=1e-6 * np.sqrt(yy))
+        sc = np.abs(ref["alphas"][b0:b0 + nb]).max(axis=1, keepdims=True)
+        assert np.all(np.abs(al - ref["alphas"][b0:b0 + nb]) <= RTOL * sc + 1e-300)
+
+
+def test_inverse_spills_to_global_memory(ctx, oracle):
+    """M' large enough that a passive set outgrows the shared-memory inverse: slow path parity."""
+    o, oc = oracle
+    N, M, K = 1200, 190, 2
+    X, y, P = o.make_synthetic(N, M, K, seed=4242, mixed_sign=False)
+    ref = oc.opt_fit(X, y, P, 1e-3, want_alpha=True)
+    r = ctx.opt_fit(X, y, P, eta=1e-3, return_all=True)
+    assert r["b_best"] == ref["b_best"] and abs(r["opt"] - ref["obj_best"]) <= RTOL * ref["obj_best"]
+    scale = np.abs(ref["alphas"]).max(axis=1, keepdims=True)
+    assert np.all(np.abs(r["alphas"] - ref["alphas"]) <= RTOL * scale + 1e-300)
+    assert (np.count_nonzero(r["alphas"], axis=1).max() > 160) == (r["stats"]["spills"] > 0)
+
+
+def test_stagewise_equals_one_call_and_two_rank_split(ctx, oracle):
+    """The stage-wise entry points used by the multi-process path give the one-call answer, and
+    splitting the orthant range in two (as two ranks would) selects the same winner."""
+    o, oc = oracle
+    X, y, P = o.make_synthetic(3000, 48, 7, seed=99, mixed_sign=True)
+    one = ctx.opt_fit(X, y, P, eta=1e-3)
+    ctx.load(X, y, P, eta=1e-3)
+    ctx.gram_build(); ctx.gram_finalize()
+    total = 2 ** (P.shape[1] + 1)
+    halves = [ctx.opt_solve_range(0, total // 2), ctx.opt_solve_range(total // 2, total // 2)]
+    win = min(halves, key=lambda h: (h["obj_gram"], h["b_best"]))
+    assert win["b_best"] == one["b_best"]
+    assert np.array_equal(win["alpha_raw"], one["alpha_raw"])
+    ssq = ctx.residual_partial(win["alpha_raw"], win["b_best"])
+    obj = ctx.objective_finish(win["alpha_raw"], win["b_best"], ssq)
+    assert abs(obj - one["opt"]) <= 1e-12 * one["opt"]
+    ref = oc.opt_fit(X, y, P, 1e-3, b_list=[one["b_best"]])
+    assert abs(obj - ref["objs"][0]) <= RTOL * ref["objs"][0]
+    res = ctx.opt_fit_resident()
+    assert res["b_best"] == one["b_best"] and np.array_equal(res["alpha_raw"], one["alpha_raw"])
+
+
+def test_error_behaviour(ctx, pkg, oracle):
+    o, _ = oracle
+    X, y, P = o.make_synthetic(50, 6, 2, seed=1)
+    bad = P.copy(); bad[0, 0] = 2
+    with pytest.raises(pkg.PlsError) as e:
+        ctx.opt_fit(X, y, bad)
+    assert e.value.code == pkg._abi.PLS_EINVAL and "binary" in str(e.value)
+    with pytest.raises(pkg.PlsError) as e:
+        ctx.opt_fit(X, y, P, eta=-1.0)
+    assert e.value.code == pkg._abi.PLS_EINVAL
+    with pytest.raises(ValueError):
+        ctx.opt_fit(X, y[:-1], P)
+    Xn = X.copy(); Xn[3, 2] = np.nan
+    with pytest.raises(pkg.PlsError) as e:
+        ctx.opt_fit(Xn, y, P)
+    assert e.value.code == pkg._abi.PLS_ENUMERIC
+    r = ctx.opt_fit(X, y, P)            # the context is still usable afterwards
+    assert r["opt"] > 0
+
+
+def test_full_size_config2_properties(ctx, oracle):
+    """BASELINE.json configs[1] (N=100k, M=200, K=16, eta=1e-3; 2^17 orthants): size-independent
+    checks -- KKT conditions of the winner on a numpy Gram, winner objective vs a data-space
+    recompute, and one sampled orthant against the C oracle's data-space Lawson-Hanson."""
+    o, oc = oracle
+    X, y, P = o.make_synthetic(100_000, 200, 16, seed=20240416)
+    eta = 1e-3
+    r = ctx.opt_fit(X, y, P, eta=eta)
+    st = r["stats"]
+    assert st["orthants"] == 2 ** 17 and st["rebuilds"] == 0
+    Xo, Po = o.homogeneous_coords(X, P)
+    G = Xo.T @ Xo + eta * (Po @ Po.T); c = Xo.T @ y
+    beta = o.index_to_beta(r["b_best"], 17)
+    d = Po @ beta
+    w = d * r["alpha_raw"]
+    grad = c - G @ w
+    passive = r["alpha_raw"] > 0
+    assert np.all(r["alpha_raw"] >= 0)
+    assert np.abs(grad[passive]).max() <= 1e-9 * np.abs(c).max()
+    assert np.all((d * grad)[~passive] <= 1e-9 * np.abs(c).max())
+    obj = np.sqrt(np.sum((Xo @ w - y) ** 2) + eta * np.sum((Po.T @ w) ** 2))
+    assert abs(r["opt"] - obj) <= RTOL * obj
+    ref = oc.opt_fit(X, y, P, eta, b_list=[r["b_best"]], nthreads=1)
+    assert abs(ref["objs"][0] - r["opt"]) <= RTOL * r["opt"]
+    assert np.all(np.abs(ref["alphas"][0] - r["alpha_raw"]) <= RTOL * np.abs(ref["alphas"][0]).max())
