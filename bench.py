@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- Opt fit (orthant NNLS enumeration) throughput on B200, one process per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload NAME]
+
+A "step" is one complete Opt fit of the workload: Gram build (K1) -> 2^(K+1) orthant NNLS solves
+(K2) -> argmin (K3) -> data-space recompute of the winner (K4).  `value` = orthant NNLS solves per
+second with the data set already resident in HBM; `e2e` = the same through pls_opt_fit /
+pls_load with HOST (pinned) buffers, host->device copy of X, y, P and the device->host read of the
+result inside the timed region.
+
+N = 1: BASELINE.json configs[1] (N=100k, M=200, K=16, eta=1e-3; the reference enumerates 2^(K+1) =
+131072 orthants, intercept sign included).  N > 1 (weak scaling): K = 16 + log2(N) so every GPU
+keeps 2^17 orthants; rows of X are sharded for K1/K4 (one all-reduce of the raw Gram sums, one of
+the winner's residual), orthant ranges are sharded for K2, winners are all-gathered.
+
+--impl reference: the reference's own CPU algorithm (oracle/pls_oracle.c: per-orthant
+materialised column scaling + data-space Lawson-Hanson + residual norm, i.e. Opt.jl:85-94) on all
+host threads, on a bounded sample of the same workload's orthants.  Julia is not in this image, so
+this is the C restatement ("port"), not the Julia package itself.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+METRIC = "opt_fit_orthant_nnls_solves_per_sec"
+UNIT = "solves/s"
+
+
+def load_peaks():
+    peaks = {"hbm_gbs": 6650.0, "source": "fallback"}
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            peaks.update(json.load(open(p)))
+            peaks["source"] = "measured"
+        except Exception:
+            pass
+    # FP64 peaks are not in MEASURED_PEAKS.json: measured by tools/fp64_peak.cu on this pool's B200
+    p64 = os.path.join(ROOT, "profiles", "fp64_peaks_r01.json")
+    if os.path.exists(p64):
+        peaks["fp64"] = json.load(open(p64))
+    else:
+        peaks["fp64"] = {"dfma_tflops": 36.4, "dmma_m8n8k4_tflops": 37.1}
+    return peaks
+
+
+class ClockSampler:
+    """Samples SM clocks and throttle reasons during the timed region (pynvml)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80, "sync_boost": 0x10}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr:
+            self._stop.set()
+            self._thr.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def cpu_reference_sample(o, oc, X, y, P, eta, n_orthants, nthreads, seed=0):
+    """Times the C restatement of the reference loop on `n_orthants` seeded random orthants at
+    full N, M.  Returns (solves_per_sec, seconds)."""
+    rng = np.random.default_rng(seed)
+    bl = rng.integers(0, 1 << (P.shape[1] + 1), size=n_orthants).astype(np.int64)
+    t0 = time.perf_counter()
+    oc.opt_fit(X, y, P, eta, b_list=bl, nthreads=nthreads, want_alpha=False)
+    dt = time.perf_counter() - t0
+    return n_orthants / dt, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    o, oc = entry.load_oracle()
+    oc.build()
+    X, y, P, eta, wl = make_workload(args, world)
+    cores = oc.num_threads()
+    per_step = cores                      # one orthant per host thread per step (~5-10 s)
+    for i in range(args.warmup):
+        cpu_reference_sample(o, oc, X, y, P, eta, max(1, per_step // 4), cores, seed=100 + i)
+    t_tot, n_tot = 0.0, 0
+    for i in range(args.steps):
+        _, dt = cpu_reference_sample(o, oc, X, y, P, eta, per_step, cores, seed=i)
+        t_tot += dt
+        n_tot += per_step
+    val = n_tot / t_tot
+    sample = f"{per_step} seeded random orthants per step at full N, M (of {1 << (P.shape[1] + 1)}); C restatement of Opt.jl:85-94 (Julia not installed)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": wl,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def make_workload(args, world):
+    pkg = entry.load_package()
+    from importlib import import_module
+    synth = import_module(entry.PKG_NAME + ".synth")
+    if args.workload:
+        name = args.workload
+    else:
+        name = {1: "cfg2", 2: "cfg2_k17", 4: "cfg2_k18", 8: "cfg2_k19"}.get(world, "cfg2")
+    N, M, K, eta, seed, mixed = synth.CONFIGS[name]
+    X, y, P = synth.make_synthetic(N, M, K, seed, mixed_sign=mixed)
+    wl = {"workload": f"{name}: synthetic N={N} M={M} K={K} eta={eta} fit(Opt); 2^(K+1)={1 << (K + 1)} orthant NNLS "
+                      f"(reference count, intercept sign enumerated)",
+          "N": N, "M": M, "K": K, "eta": eta, "orthants": 1 << (K + 1), "seed": seed,
+          "l2": "inputs larger than L2 (Z = %.0f MB) and an L2 flush (256 MB memset) before every timed step" % (N * (M + 2) * 8 / 1e6)}
+    return X, y, P, eta, wl
+
+
+class _DevBuf:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+
+def run_native(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    pkg = entry.load_package()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    X, y, P, eta, wl = make_workload(args, world)
+    N, M = X.shape
+    K = P.shape[1]
+    Mp, total = M + 1, 1 << (K + 1)
+    ctx = pkg.Context(local_rank)
+    # row shard for K1/K4, orthant shard for K2
+    r0, r1 = (N * rank) // world, (N * (rank + 1)) // world
+    Xs = np.asfortranarray(X[r0:r1]); ys = np.ascontiguousarray(y[r0:r1]); Pc = np.asfortranarray(P)
+    cudart = torch.cuda.cudart()
+    for a in (Xs, ys, Pc):
+        cudart.cudaHostRegister(a.ctypes.data, a.nbytes, 0)
+    b0, bn = (total // world) * rank, total // world
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        """One Opt fit on the resident data set.  Returns (b*, obj, alpha_raw, stats)."""
+        if world == 1:
+            r = ctx.opt_fit_resident()
+            return r["b_best"], r["opt"], r["alpha_raw"], r["stats"]
+        ctx.gram_build()
+        ptr, n = ctx.gram_raw()
+        S = torch.as_tensor(_DevBuf(ptr, n), device=dev)
+        dist.all_reduce(S)
+        torch.cuda.synchronize()
+        ctx.gram_finalize()
+        loc = ctx.opt_solve_range(b0, bn)
+        st = ctx.stats()
+        rec = torch.empty(Mp + 2, dtype=torch.float64)
+        rec[:Mp] = torch.from_numpy(loc["alpha_raw"]); rec[Mp] = loc["obj_gram"]; rec[Mp + 1] = float(loc["b_best"])
+        rec = rec.to(dev)
+        allrec = [torch.empty_like(rec) for _ in range(world)]
+        dist.all_gather(allrec, rec)
+        allrec = torch.stack(allrec).cpu().numpy()
+        win = min(range(world), key=lambda i: (allrec[i, Mp], allrec[i, Mp + 1]))
+        alpha, bb = allrec[win, :Mp].copy(), int(allrec[win, Mp + 1])
+        ssq = torch.tensor([ctx.residual_partial(alpha, bb)], dtype=torch.float64, device=dev)
+        dist.all_reduce(ssq)
+        obj = ctx.objective_finish(alpha, bb, float(ssq.item()))
+        return bb, obj, alpha, st
+
+    def step_e2e():
+        if world == 1:
+            r = ctx.opt_fit(Xs, ys, Pc, eta=eta, prepared=True)
+            return r["b_best"], r["opt"], r["alpha_raw"], r["stats"]
+        ctx.load(Xs, ys, Pc, eta=eta, prepared=True)
+        return step_resident()
+
+    def timed(fn, steps, warmup, sample_clocks):
+        for _ in range(warmup):
+            fn()
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        per_step, last = [], None
+        barrier()
+        if sampler:
+            sampler.start()
+        for _ in range(steps):
+            flush.zero_()                  # L2 flush, outside the timed step
+            barrier()
+            t0 = time.perf_counter()
+            last = fn()
+            torch.cuda.synchronize()
+            per_step.append(time.perf_counter() - t0)
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        tt = torch.tensor([sum(per_step)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item()), last, clocks
+
+    ctx.load(Xs, ys, Pc, eta=eta, prepared=True)
+    t_res, last, clocks = timed(step_resident, args.steps, args.warmup, True)
+    bb, obj, alpha, st = last
+    t_e2e, last_e, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2), False)
+    assert last_e[0] == bb, "e2e and resident paths disagree on the winner"
+
+    if rank != 0:
+        return
+    peaks = load_peaks()
+    value = total * args.steps / t_res
+    e2e_val = total * args.steps / t_e2e
+    k2_ms = st["ms_nnls"]
+    fp64_peak = float(peaks["fp64"].get("dfma_tflops", 36.4))
+    k2_tflops = st["nnls_flops"] / (k2_ms * 1e-3) / 1e12 if k2_ms > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": wl,
+        "clocks": clocks,
+        "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": 1e3 * t_e2e / args.steps,
+                "h2d_bytes_per_step": int((Xs.nbytes + ys.nbytes + Pc.nbytes) * world),
+                "d2h_bytes_per_step": int((Mp + 4 + 10) * 8 * world)},
+        "gpu_launches": int(st["kernel_launches"] * args.steps * world),
+        "roofline": {
+            "kernel": "k2_orthant_chains (batched orthant NNLS, FP64 FMA pipe; tcgen05 has no f64 kind)",
+            "bound": "tensor", "achieved": k2_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": k2_tflops / fp64_peak if fp64_peak else None, "traffic": None,
+            "peak_source": "FP64 DFMA peak measured by tools/fp64_peak.cu on this pool (profiles/fp64_peaks_r01.json); MEASURED_PEAKS.json holds no FP64 figure",
+            "algorithmic_flops_per_launch": st["nnls_flops"], "launch_ms": k2_ms,
+            "l2_model_gbs": st["nnls_l2_bytes"] / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else None,
+        },
+        "stages_ms": {"gram_k1": st["ms_gram"], "nnls_k2_k3": st["ms_nnls"], "recompute_k4": st["ms_recompute"]},
+        "k1_gram": {"tflops": st["gram_flops"] / (st["ms_gram"] * 1e-3) / 1e12 if st["ms_gram"] > 0 else None,
+                    "peak_tflops": float(peaks["fp64"].get("dmma_m8n8k4_tflops", 37.1))},
+        "solver_counters": {k: st[k] for k in ("pivots", "grad_evals", "sum_p", "sum_p2", "bpp_iters", "spills", "rebuilds", "blocked")},
+        "result": {"b_best": int(bb), "opt": float(obj)},
+        "time_to_solution_ms": {"resident": 1e3 * t_res / args.steps, "from_host": 1e3 * t_e2e / args.steps},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        o, oc = entry.load_oracle()
+        oc.build()
+        n_s = 4
+        v, dt = cpu_reference_sample(o, oc, X, y, P, eta, n_s, 1, seed=0)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"{n_s} seeded random orthants at full N, M, single thread (the reference loop is serial), {dt:.1f} s; C restatement of Opt.jl:85-94"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_native(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

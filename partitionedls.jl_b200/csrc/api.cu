@@ -383,11 +383,13 @@ int pls_opt_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_raw, int64_t 
   PLS_CUDA_TRY(cudaEventRecord(c->ev[3], st));
   PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin, c->ws.win, sizeof(double) * (Mp + 2), cudaMemcpyDeviceToHost, st));
   if (recompute) PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin + Mp + 2, c->d_ssq, sizeof(double), cudaMemcpyDeviceToHost, st));
+  PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin + Mp + 3, pb.scal + 3, sizeof(double), cudaMemcpyDeviceToHost, st));
   PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin + Mp + 4, c->ws.counters, sizeof(unsigned long long) * CNT_NUM, cudaMemcpyDeviceToHost, st));
   if (all_obj) PLS_CUDA_TRY(cudaMemcpyAsync(all_obj, c->ws.all_obj, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost, st));
   if (all_alpha) PLS_CUDA_TRY(cudaMemcpyAsync(all_alpha, c->ws.all_alpha, sizeof(double) * (size_t)total * Mp, cudaMemcpyDeviceToHost, st));
   PLS_CUDA_TRY(cudaStreamSynchronize(st));
 
+  if (c->h_pin[Mp + 3] != 0.0) { set_error("non-finite values in X or y"); return PLS_ENUMERIC; }
   memcpy(alpha_raw, c->h_pin, sizeof(double) * Mp);
   long long bb; memcpy(&bb, &c->h_pin[Mp + 1], sizeof(bb));
   *b_best = bb;

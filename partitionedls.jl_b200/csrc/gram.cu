@@ -137,11 +137,19 @@ __global__ void k1_finalize(const double *__restrict__ S, int zc, int Mp, double
 __global__ void k1_scalars(const double *__restrict__ S, int zc, int Mp, const double *__restrict__ c,
                            const double *__restrict__ G, int ldg, double *__restrict__ scal) {
   __shared__ double sm[256], sd[256];
+  __shared__ int bad;
+  if (threadIdx.x == 0) bad = 0;
+  __syncthreads();
   double mx = 0.0, md = 0.0;
+  int nonfinite = 0;
   for (int i = threadIdx.x; i < Mp; i += 256) {
     mx = fmax(mx, fabs(c[i]));
     md = fmax(md, fabs(G[(size_t)i * ldg + i]));
+    if (!isfinite(c[i])) nonfinite = 1;
   }
+  for (long long idx = threadIdx.x; idx < (long long)Mp * Mp; idx += 256)
+    if (!isfinite(G[(size_t)(idx / Mp) * ldg + idx % Mp])) nonfinite = 1;
+  if (nonfinite) bad = 1;
   sm[threadIdx.x] = mx; sd[threadIdx.x] = md;
   __syncthreads();
   for (int st = 128; st; st >>= 1) {
@@ -155,7 +163,7 @@ __global__ void k1_scalars(const double *__restrict__ S, int zc, int Mp, const d
     scal[0] = S[(size_t)Mp * zc + Mp];
     scal[1] = sm[0];
     scal[2] = sd[0];
-    scal[3] = 0.0;
+    scal[3] = (bad || !isfinite(scal[0])) ? 1.0 : 0.0;   // non-finite input flag
   }
 }
 

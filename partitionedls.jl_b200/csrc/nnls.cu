@@ -479,7 +479,7 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   PLS_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   int cap = Mp;
   while (cap > 8 && k2_smem_bytes(Mp, cap) > (size_t)max_smem) --cap;
-  cap &= ~1;
+  if (cap < Mp) cap &= ~1;
   if (cap < 2) cap = 2;
   if (cap > Mp) cap = Mp;
   if (k2_smem_bytes(Mp, cap) > (size_t)max_smem) {
