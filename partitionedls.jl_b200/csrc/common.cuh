@@ -63,6 +63,24 @@ struct SolveWs {
   int resid_blocks = 0;
 };
 
+// Arguments of the K2 kernels (both variants).
+struct K2Args {
+  const double *G; int ldg;
+  const double *c;
+  const double *scal;            // [0] = yy, [1] = max |c|
+  const uint64_t *gmask;
+  int Mp, Kp;
+  long long b_begin;
+  int chain_log2;
+  long long n_chains;
+  unsigned long long *chain_counter;   // dynamic chain scheduler (zeroed before launch)
+  int cap;                       // slots of H that fit in shared memory
+  double *hspill;                // [grid][Mp*Mp] or null
+  double *cta_obj; long long *cta_b; double *cta_w;
+  double *all_obj; double *all_alpha;   // nullable, indexed by (b - b_begin)
+  unsigned long long *counters;
+};
+
 // ---- kernel launchers (defined in gram.cu / nnls.cu / resid.cu) -----------------------------
 int k1_gram_build(Problem &pb, cudaStream_t st, int *launches);
 int k1_gram_finalize(Problem &pb, cudaStream_t st, int *launches);
@@ -70,6 +88,10 @@ int k2_solve_range(const Problem &pb, const double *G, int ldg, const double *c,
                    const uint64_t *gmask, int Mp, int Kp, SolveWs &ws, int64_t b_begin,
                    int64_t b_count, double *d_all_obj, double *d_all_alpha, int sm_count,
                    cudaStream_t st, int *launches);
+// K2 variants: v2 = block pivoting with DMMA rank-8 updates on a tile-packed symmetric inverse
+// (M' <= 208); v1 = rank-1 updates on a dense inverse with a global-memory spill path (any M').
+int k2v2_launch(const K2Args &A, int grid, cudaStream_t st);
+int k2v2_config(int Mp, int *cap, size_t *smem, int *occ);
 int k4_residual(const Problem &pb, SolveWs &ws, const double *d_w, double *d_ssq, int sm_count,
                 cudaStream_t st, int *launches);
 

@@ -17,6 +17,9 @@
 // unique KKT point of each strictly convex subproblem).  Each accepted solution is polished by one
 // step of iterative refinement against G itself, so the returned alpha does not depend on how H
 // was reached.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace pls {
@@ -25,22 +28,6 @@ namespace {
 constexpr int T2 = 256;
 constexpr int NW2 = T2 / 32;
 
-struct K2Args {
-  const double *G; int ldg;
-  const double *c;
-  const double *scal;            // [0] = yy, [1] = max |c|
-  const uint64_t *gmask;
-  int Mp, Kp;
-  long long b_begin;
-  int chain_log2;
-  long long n_chains;
-  unsigned long long *chain_counter;   // dynamic chain scheduler (zeroed before launch)
-  int cap;                       // slots of H that fit in shared memory
-  double *hspill;                // [grid][Mp*Mp] or null
-  double *cta_obj; long long *cta_b; double *cta_w;
-  double *all_obj; double *all_alpha;   // nullable, indexed by (b - b_begin)
-  unsigned long long *counters;
-};
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -473,25 +460,31 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
                    int64_t b_count, double *d_all_obj, double *d_all_alpha, int sm_count,
                    cudaStream_t st, int *launches) {
   if (b_count <= 0) { set_error("k2: empty orthant range"); return PLS_EINVAL; }
-  // shared-memory capacity for the inverse
-  int dev = 0, max_smem = 0;
-  PLS_CUDA_TRY(cudaGetDevice(&dev));
-  PLS_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  int cap = Mp;
-  while (cap > 8 && k2_smem_bytes(Mp, cap) > (size_t)max_smem) --cap;
-  if (cap < Mp) cap &= ~1;
-  if (cap < 2) cap = 2;
-  if (cap > Mp) cap = Mp;
-  if (k2_smem_bytes(Mp, cap) > (size_t)max_smem) {
-    set_error("k2: M' = %d too large for this build", Mp);
-    return PLS_EUNSUPPORTED;
+  // variant: v2 (block pivoting, DMMA, tile-packed inverse) for M' <= 208, else v1
+  const char *impl = getenv("PLS_K2_IMPL");
+  bool use_v2 = !(impl && strcmp(impl, "v1") == 0);
+  int cap = Mp, occ = 1;
+  size_t smem = 0;
+  if (use_v2 && k2v2_config(Mp, &cap, &smem, &occ) != PLS_OK) use_v2 = false;
+  if (!use_v2) {
+    int dev = 0, max_smem = 0;
+    PLS_CUDA_TRY(cudaGetDevice(&dev));
+    PLS_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    cap = Mp;
+    while (cap > 8 && k2_smem_bytes(Mp, cap) > (size_t)max_smem) --cap;
+    if (cap < Mp) cap &= ~1;
+    if (cap < 2) cap = 2;
+    if (cap > Mp) cap = Mp;
+    if (k2_smem_bytes(Mp, cap) > (size_t)max_smem) {
+      set_error("k2: M' = %d too large for this build", Mp);
+      return PLS_EUNSUPPORTED;
+    }
+    smem = k2_smem_bytes(Mp, cap);
+    PLS_CUDA_TRY(cudaFuncSetAttribute(k2_orthant_chains, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    PLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_orthant_chains, T2, smem));
+    if (occ < 1) occ = 1;
   }
-  const size_t smem = k2_smem_bytes(Mp, cap);
-  PLS_CUDA_TRY(cudaFuncSetAttribute(k2_orthant_chains, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem));
-  int occ = 1;
-  PLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_orthant_chains, T2, smem));
-  if (occ < 1) occ = 1;
   long long grid = (long long)sm_count * occ;
 
   // Gray chains: aligned power-of-two blocks of orthants.  Long enough to amortise the cold
@@ -517,7 +510,7 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
     PLS_CUDA_TRY(cudaMalloc(&ws.cta_w, sizeof(double) * n * Mp));
     ws.max_ctas = (int)n; ws.Mp = Mp;
   }
-  if (cap < Mp) {
+  if (!use_v2 && cap < Mp) {
     const size_t need = (size_t)ws.max_ctas * Mp * Mp * sizeof(double);
     if (need > ws.hspill_bytes) {
       if (ws.hspill) cudaFree(ws.hspill);
@@ -538,11 +531,16 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   A.b_begin = b_begin; A.chain_log2 = chain_log2; A.n_chains = n_chains;
   A.chain_counter = ws.counters + CNT_NUM;
   A.cap = cap;
-  A.hspill = (cap < Mp) ? ws.hspill : nullptr;
+  A.hspill = (!use_v2 && cap < Mp) ? ws.hspill : nullptr;
   A.cta_obj = ws.cta_obj; A.cta_b = ws.cta_b; A.cta_w = ws.cta_w;
   A.all_obj = d_all_obj; A.all_alpha = d_all_alpha; A.counters = ws.counters;
-  k2_orthant_chains<<<(unsigned)grid, T2, smem, st>>>(A);
-  PLS_CUDA_TRY(cudaGetLastError());
+  if (use_v2) {
+    const int rc = k2v2_launch(A, (int)grid, st);
+    if (rc) return rc;
+  } else {
+    k2_orthant_chains<<<(unsigned)grid, T2, smem, st>>>(A);
+    PLS_CUDA_TRY(cudaGetLastError());
+  }
   ++*launches;
   k3_select_winner<<<1, 256, 0, st>>>(ws.cta_obj, ws.cta_b, ws.cta_w, (int)grid, Mp, ws.win);
   PLS_CUDA_TRY(cudaGetLastError());
