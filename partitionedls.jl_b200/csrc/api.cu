@@ -2,6 +2,7 @@
 // orchestration of K1 (Gram) -> K2 (orthant NNLS) -> K3 (argmin) -> K4 (winner recompute) that
 // replaces the body of fit(::Type{Opt}, ...) (src/PartitionedLSOpt.jl:79-97).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <chrono>
 #include <cmath>
@@ -115,6 +116,11 @@ int ensure_all_buffers(pls_ctx *c, int64_t count, bool want_obj, bool want_alpha
 
 void read_counters(pls_ctx *c, const unsigned long long *h) {
   pls_stats &s = c->stats;
+  if (getenv("PLS_K2_PHASES")) {
+    static const char *nm[] = {"start", "plan", "remove", "add", "grad", "refine", "out", "n_remove_blocks", "n_add_blocks",
+                               "r_gather", "r_panel", "r_rank", "r_zero", "a_gather", "a_hmul", "a_spart", "a_inv", "a_panel", "a_rank", "a_rows", "a_inv1_load", "a_inv2_gj", "a_inv3_theta"};
+    for (int i = 0; i < 23; ++i) fprintf(stderr, "k2 phase %-16s %llu\n", nm[i], h[CNT_NUM + 1 + i]);
+  }
   s.pivots = (int64_t)h[CNT_PIVOTS]; s.grad_evals = (int64_t)h[CNT_GRAD];
   s.sum_p = (int64_t)h[CNT_SUMP]; s.sum_p2 = (int64_t)h[CNT_SUMP2];
   s.bpp_iters = (int64_t)h[CNT_ITERS]; s.spills = (int64_t)h[CNT_SPILLS];
@@ -134,7 +140,7 @@ int solve_range_dev(pls_ctx *c, int64_t b_begin, int64_t b_count, bool want_obj,
   if (rc) return rc;
   if (c->ws.Mp != pb.Mp && c->ws.win) { cudaFree(c->ws.win); c->ws.win = nullptr; }
   if (c->ws.counters)
-    PLS_CUDA_TRY(cudaMemsetAsync(c->ws.counters, 0, sizeof(unsigned long long) * (CNT_NUM + 1), c->stream));
+    PLS_CUDA_TRY(cudaMemsetAsync(c->ws.counters, 0, sizeof(unsigned long long) * (CNT_NUM + 1 + 24), c->stream));
   return k2_solve_range(pb, pb.G, pb.ldg, pb.c, pb.scal, pb.gmask, pb.Mp, pb.Kp, c->ws, b_begin, b_count,
                         want_obj ? c->ws.all_obj : nullptr, want_alpha ? c->ws.all_alpha : nullptr,
                         c->sm_count, c->stream, &c->launches);
@@ -248,7 +254,7 @@ int pls_load(pls_ctx *c, const double *X, int64_t N, int64_t ldx, int64_t M, con
     cudaFree(c->d_w); c->d_w = nullptr;
     PLS_CUDA_TRY(cudaMalloc(&c->d_w, sizeof(double) * Mp));
     if (c->h_pin) { cudaFreeHost(c->h_pin); c->h_pin = nullptr; }
-    PLS_CUDA_TRY(cudaMallocHost(&c->h_pin, sizeof(double) * (Mp + 4 + CNT_NUM + 1)));
+    PLS_CUDA_TRY(cudaMallocHost(&c->h_pin, sizeof(double) * (Mp + 4 + CNT_NUM + 1 + 24)));
   }
   pb.N = N; pb.ldz = ldz; pb.M = (int)M; pb.K = (int)K; pb.Mp = Mp; pb.Kp = (int)K + 1;
   pb.zcols = zc; pb.zcols_pad = zcp; pb.eta = eta;
@@ -310,7 +316,7 @@ int pls_opt_solve_range(pls_ctx *c, int64_t b_begin, int64_t b_count, double *al
   PLS_CUDA_TRY(cudaEventRecord(c->ev[3], st));
   const int Mp = c->pb.Mp;
   PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin, c->ws.win, sizeof(double) * (Mp + 2), cudaMemcpyDeviceToHost, st));
-  PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin + Mp + 4, c->ws.counters, sizeof(unsigned long long) * CNT_NUM, cudaMemcpyDeviceToHost, st));
+  PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin + Mp + 4, c->ws.counters, sizeof(unsigned long long) * (CNT_NUM + 1 + 24), cudaMemcpyDeviceToHost, st));
   if (all_obj) PLS_CUDA_TRY(cudaMemcpyAsync(all_obj, c->ws.all_obj, sizeof(double) * (size_t)b_count, cudaMemcpyDeviceToHost, st));
   if (all_alpha) PLS_CUDA_TRY(cudaMemcpyAsync(all_alpha, c->ws.all_alpha, sizeof(double) * (size_t)b_count * Mp, cudaMemcpyDeviceToHost, st));
   PLS_CUDA_TRY(cudaStreamSynchronize(st));
@@ -384,7 +390,7 @@ int pls_opt_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_raw, int64_t 
   PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin, c->ws.win, sizeof(double) * (Mp + 2), cudaMemcpyDeviceToHost, st));
   if (recompute) PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin + Mp + 2, c->d_ssq, sizeof(double), cudaMemcpyDeviceToHost, st));
   PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin + Mp + 3, pb.scal + 3, sizeof(double), cudaMemcpyDeviceToHost, st));
-  PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin + Mp + 4, c->ws.counters, sizeof(unsigned long long) * CNT_NUM, cudaMemcpyDeviceToHost, st));
+  PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin + Mp + 4, c->ws.counters, sizeof(unsigned long long) * (CNT_NUM + 1 + 24), cudaMemcpyDeviceToHost, st));
   if (all_obj) PLS_CUDA_TRY(cudaMemcpyAsync(all_obj, c->ws.all_obj, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost, st));
   if (all_alpha) PLS_CUDA_TRY(cudaMemcpyAsync(all_alpha, c->ws.all_alpha, sizeof(double) * (size_t)total * Mp, cudaMemcpyDeviceToHost, st));
   PLS_CUDA_TRY(cudaStreamSynchronize(st));
@@ -474,14 +480,14 @@ int pls_nnls_batch(pls_ctx *c, const double *G, const double *cv, double yy, int
   PLS_CUDA_TRY(cudaMemcpy(pb.gmask, gmask, sizeof(uint64_t) * Mp, cudaMemcpyHostToDevice));
   c->h_gmask.assign(gmask, gmask + Mp);
   if (c->h_pin) { cudaFreeHost(c->h_pin); c->h_pin = nullptr; }
-  PLS_CUDA_TRY(cudaMallocHost(&c->h_pin, sizeof(double) * (Mp + 4 + CNT_NUM + 1)));
+  PLS_CUDA_TRY(cudaMallocHost(&c->h_pin, sizeof(double) * (Mp + 4 + CNT_NUM + 1 + 24)));
   pb.gram_ready = true;
   rc = solve_range_dev(c, b_begin, b_count, obj_out != nullptr, alpha_out != nullptr);
   if (rc) return rc;
   cudaStream_t st = c->stream;
   if (obj_out) PLS_CUDA_TRY(cudaMemcpyAsync(obj_out, c->ws.all_obj, sizeof(double) * (size_t)b_count, cudaMemcpyDeviceToHost, st));
   if (alpha_out) PLS_CUDA_TRY(cudaMemcpyAsync(alpha_out, c->ws.all_alpha, sizeof(double) * (size_t)b_count * Mp, cudaMemcpyDeviceToHost, st));
-  PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin + Mp + 4, c->ws.counters, sizeof(unsigned long long) * CNT_NUM, cudaMemcpyDeviceToHost, st));
+  PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin + Mp + 4, c->ws.counters, sizeof(unsigned long long) * (CNT_NUM + 1 + 24), cudaMemcpyDeviceToHost, st));
   PLS_CUDA_TRY(cudaStreamSynchronize(st));
   const unsigned long long *cnt = reinterpret_cast<const unsigned long long *>(c->h_pin + Mp + 4);
   c->stats.orthants = b_count;

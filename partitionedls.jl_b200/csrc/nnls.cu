@@ -520,8 +520,8 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
     }
   }
   if (!ws.counters) {
-    PLS_CUDA_TRY(cudaMalloc(&ws.counters, sizeof(unsigned long long) * (CNT_NUM + 1)));
-    PLS_CUDA_TRY(cudaMemsetAsync(ws.counters, 0, sizeof(unsigned long long) * (CNT_NUM + 1), st));
+    PLS_CUDA_TRY(cudaMalloc(&ws.counters, sizeof(unsigned long long) * (CNT_NUM + 1 + 24)));
+    PLS_CUDA_TRY(cudaMemsetAsync(ws.counters, 0, sizeof(unsigned long long) * (CNT_NUM + 1 + 24), st));
   }
   if (!ws.win) PLS_CUDA_TRY(cudaMalloc(&ws.win, sizeof(double) * (Mp + 2)));
   PLS_CUDA_TRY(cudaMemsetAsync(ws.counters + CNT_NUM, 0, sizeof(unsigned long long), st));

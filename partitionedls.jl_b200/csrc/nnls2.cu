@@ -22,7 +22,7 @@ constexpr int NW = T / 32;
 constexpr int CAPMAX = 208;
 
 __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 __device__ __forceinline__ double warp_sum(double v) {
@@ -61,21 +61,75 @@ __device__ __forceinline__ void h_set(double *H, int i, int j, double v) {
 __device__ __forceinline__ int pan(int row, int col) { return (row << 3) + (col ^ ((row & 2) << 1)); }
 
 struct Sh {
-  double *H, *Pa, *Pb, *w, *r, *wF, *rpart, *Sinv, *Gaa, *Spart, *rho, *theta, *cA, *red;
-  int *F, *pos, *lst, *Rs, *As, *Av, *ctl;
-  signed char *sg, *dd, *vflag;
+  double *H, *Pa, *Pb, *w, *r, *wF, *rpart, *Sinv, *Gaa, *Spart, *rho, *theta, *cA, *red, *cs;
+  unsigned long long *gms;        // smem copies of c and the group masks
+  long long *stat, *prof;
+  int *F, *pos, *lst, *asl, *ctl, *pl;
+  unsigned short *tmap;           // tile index -> (ti << 8) | tj
+  signed char *sg, *dd, *vflag, *smark;
 };
 
+enum Phase { PH_START = 0, PH_PLAN, PH_REMOVE, PH_ADD, PH_GRAD, PH_REFINE, PH_OUT, PH_NREM, PH_NADD,
+             PH_R_GATHER, PH_R_PANEL, PH_R_RANK, PH_R_ZERO, PH_A_GATHER, PH_A_HMUL, PH_A_SPART, PH_A_INV, PH_A_PANEL,
+             PH_A_RANK, PH_A_ROWS, PH_A_INV1, PH_A_INV2, PH_A_INV3, PH_NUM };
+#define SUBTICK(which) do { if (threadIdx.x == 0) { const long long now_ = clock64(); s.prof[which] += now_ - s.stat[ST_TSUB]; s.stat[ST_TSUB] = now_; } } while (0)
+
+// statistics / phase timers live in shared memory and are touched by thread 0 only
+enum Stat { ST_P = 0, ST_PIV, ST_GRAD, ST_SUMP, ST_SUMP2, ST_ITER, ST_REBUILD, ST_BLOCKED, ST_NOCONV, ST_TMARK, ST_TSUB, ST_NUM };
+#define STAT_ADD(which, v) do { if (threadIdx.x == 0) s.stat[which] += (long long)(v); } while (0)
+
+// Carves the dynamic shared memory; called (and fully inlined) in every device function so the
+// pointers live in registers instead of a struct in local memory.
+__device__ __forceinline__ Sh make_sh(int cap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int ntc = cap >> 3;
+  const int ntiles_cap = (ntc * (ntc + 1)) >> 1;
+  Sh s;
+  double *dp = reinterpret_cast<double *>(smem_raw);
+  s.H = dp; dp += (ntiles_cap << 6);
+  s.Pa = dp; dp += cap * 8;
+  s.Pb = dp; dp += cap * 8;
+  s.w = dp; dp += cap;
+  s.r = dp; dp += cap;
+  s.wF = dp; dp += cap;
+  s.Sinv = dp; dp += 64;
+  s.Gaa = dp; dp += 64;
+  s.Spart = dp; dp += 256;
+  s.rho = dp; dp += 8;
+  s.theta = dp; dp += 8;
+  s.cA = dp; dp += 8;
+  s.red = dp; dp += NW;
+  s.cs = dp; dp += cap;
+  s.gms = reinterpret_cast<unsigned long long *>(dp); dp += cap;
+  s.stat = reinterpret_cast<long long *>(dp); dp += ST_NUM;
+  s.prof = reinterpret_cast<long long *>(dp); dp += PH_NUM;
+  s.rpart = nullptr;
+  int *ip = reinterpret_cast<int *>(dp);
+  s.F = ip; ip += cap;
+  s.pos = ip; ip += cap;
+  s.lst = ip; ip += cap;
+  s.asl = ip; ip += cap;
+  s.ctl = ip; ip += 8;
+  s.pl = ip; ip += 32;
+  s.tmap = reinterpret_cast<unsigned short *>(ip); ip += (ntiles_cap + 1) / 2;
+  signed char *cp = reinterpret_cast<signed char *>(ip);
+  s.sg = cp; cp += cap;
+  s.dd = cp; cp += cap;
+  s.vflag = cp; cp += cap;
+  s.smark = cp; cp += cap;
+
+  return s;
+}
+
 // H(lower tiles) += Pa * Pb'   over the leading nt x nt tiles
-__device__ __forceinline__ void rank_update(double *H, const double *Pa, const double *Pb, int nt) {
+__device__ __noinline__ void rank_update(double *H, const double *Pa, const double *Pb, int nt,
+                                            const unsigned short *tmap) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int fr = lane >> 2, fk = lane & 3;
   const int ntiles = (nt * (nt + 1)) >> 1;
   for (int q = wid; q < ntiles; q += NW) {
-    int ti = (int)((sqrtf(8.f * (float)q + 1.f) - 1.f) * 0.5f);
-    while (((ti + 1) * (ti + 2)) / 2 <= q) ++ti;
-    while ((ti * (ti + 1)) / 2 > q) --ti;
-    const int tj = q - (ti * (ti + 1)) / 2;
+    const int tt = tmap[q];
+    const int ti = tt >> 8, tj = tt & 255;
     const double a0 = Pa[pan(ti * 8 + fr, fk)], a1 = Pa[pan(ti * 8 + fr, 4 + fk)];
     const double b0 = Pb[pan(tj * 8 + fr, fk)], b1 = Pb[pan(tj * 8 + fr, 4 + fk)];
     double2 *cp = reinterpret_cast<double2 *>(H + (q << 6) + swz8(fr, fk * 2));
@@ -87,7 +141,7 @@ __device__ __forceinline__ void rank_update(double *H, const double *Pa, const d
 }
 
 // Pout = H * Pin  (H symmetric, nt x nt tiles; panels nt*8 x 8)
-__device__ __forceinline__ void hmul(const double *H, const double *Pin, double *Pout, int nt) {
+__device__ __noinline__ void hmul(const double *H, const double *Pin, double *Pout, int nt) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int fr = lane >> 2, fk = lane & 3;
   for (int ti = wid; ti < nt; ti += NW) {
@@ -112,75 +166,76 @@ __device__ __forceinline__ void hmul(const double *H, const double *Pin, double 
 // In-place Gauss-Jordan inverse of an SPD 8x8 held by one warp: lane owns S[i][j0], S[i][j0+1]
 // with i = lane >> 2, j0 = 2 * (lane & 3).  Only the leading n x n block is eliminated (the rest must
 // be the identity).  Returns false if a pivot is not safely positive (relative to dref[k]).
-__device__ __forceinline__ bool warp_inv8(double &e0, double &e1, int n, const double *dref, double tol) {
+__device__ __forceinline__ bool warp_inv8(double &e0, double &e1, int n, const double *dref, double tol,
+                                          double *Ssm) {
+  // Gauss-Jordan through a 64-double shared scratch (one warp): every step publishes the current
+  // matrix, then each lane reads pivot row / column / pivot.  Ssm doubles as the output (inverse).
   const int lane = threadIdx.x & 31;
   const int i = lane >> 2, j0 = (lane & 3) << 1, j1 = j0 + 1;
   bool ok = true;
   for (int k = 0; k < n; ++k) {
-    const int srow = (k << 2) + (lane & 3);
-    const double pk0 = __shfl_sync(0xffffffffu, e0, srow), pk1 = __shfl_sync(0xffffffffu, e1, srow);
-    const int scol = (lane & ~3) + (k >> 1);
-    const double ca = __shfl_sync(0xffffffffu, e0, scol), cb = __shfl_sync(0xffffffffu, e1, scol);
-    const double cik = (k & 1) ? cb : ca;
-    const int sp = (k << 2) + (k >> 1);
-    const double pa = __shfl_sync(0xffffffffu, e0, sp), pb = __shfl_sync(0xffffffffu, e1, sp);
-    const double pkk = (k & 1) ? pb : pa;
-    if (!(pkk > tol * dref[k])) ok = false;
+    *reinterpret_cast<double2 *>(Ssm + i * 8 + j0) = make_double2(e0, e1);
+    __syncwarp();
+    const double2 pk = *reinterpret_cast<const double2 *>(Ssm + k * 8 + j0);   // S[k][j0], S[k][j1]
+    const double cik = Ssm[i * 8 + k];                                            // S[i][k]
+    const double pkk = Ssm[k * 8 + k];
+    __syncwarp();
+    ok = ok && (pkk > tol * dref[k]);
     const double d = 1.0 / pkk;
-    if (i == k) {
-      e0 = (j0 == k) ? d : pk0 * d;
-      e1 = (j1 == k) ? d : pk1 * d;
-    } else {
-      const double f = cik * d;
-      e0 = (j0 == k) ? -f : fma(-f, pk0, e0);
-      e1 = (j1 == k) ? -f : fma(-f, pk1, e1);
-    }
+    const bool rowk = (i == k);
+    const double f = cik * d;
+    double n0 = rowk ? pk.x * d : fma(-f, pk.x, e0);
+    double n1 = rowk ? pk.y * d : fma(-f, pk.y, e1);
+    if (j0 == k) n0 = rowk ? d : -f;
+    if (j1 == k) n1 = rowk ? d : -f;
+    e0 = n0; e1 = n1;
   }
   return ok;
 }
 
-// Pout[row][q] = sign * sum_j Pin[row][j] * Sinv[j][q];   w[F[row]] -= sum_j Pin[row][j] * coef[j]
+// Pout = sign * Pin * Sinv  (one 8x8x8 DMMA product per row tile);  w[F[row]] -= Pin[row,:] . coef
 __device__ __forceinline__ void panel_small(const Sh &s, const double *Pin, double *Pout, const double *coef,
                                             double sign, int nrows) {
-  for (int item = threadIdx.x; item < nrows * 8; item += T) {
-    const int row = item >> 3, q = item & 7;
-    double acc = 0.0, z = 0.0;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  // B fragments of Sinv: B[k][n] = Sinv[kk*4 + k][n]
+  const double b0 = sign * s.Sinv[fk * 8 + fr], b1 = sign * s.Sinv[(4 + fk) * 8 + fr];
+  for (int ti = wid; ti < (nrows >> 3); ti += NW) {
+    double c0 = 0.0, c1 = 0.0;
+    dmma(c0, c1, Pin[pan(ti * 8 + fr, fk)], b0);
+    dmma(c0, c1, Pin[pan(ti * 8 + fr, 4 + fk)], b1);
+    *reinterpret_cast<double2 *>(Pout + pan(ti * 8 + fr, fk * 2)) = make_double2(c0, c1);
+  }
+  for (int row = threadIdx.x; row < nrows; row += T) {
+    const int var = s.F[row];
+    if (var >= 0) {
+      double z = 0.0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const double x = Pin[pan(row, j)];
-      acc = fma(x, s.Sinv[j * 8 + q], acc);
-      z = fma(x, coef[j], z);
+      for (int j = 0; j < 8; ++j) z = fma(Pin[pan(row, j)], coef[j], z);
+      s.w[var] -= z;
     }
-    Pout[pan(row, q)] = sign * acc;
-    if (q == 0) { const int var = s.F[row]; if (var >= 0) s.w[var] -= z; }
   }
 }
 
-struct State {
-  int hwm, nt, p;
-  unsigned long long n_piv, n_grad, n_sump, n_sump2, n_iter, n_rebuild, n_blocked, n_noconv;
-};
-
-// Remove the r <= 8 slots listed in s.Rs.
-__device__ void block_remove(const Sh &s, State &st, int r) {
+// Remove the r <= 8 slots Rs[0..r).  nt covers every slot in use.
+__device__ __noinline__ void block_remove(int cap, const int *Rs, int r, int nt) {
+  const Sh s = make_sh(cap);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int nrows = st.nt * 8;
-  for (int item = tid; item < nrows * 8; item += T) {
-    const int q = item / nrows, row = item - q * nrows;
-    s.Pb[pan(row, q)] = (q < r) ? h_get(s.H, row, s.Rs[q]) : 0.0;
-  }
-  __syncthreads();
-  if (wid == 0) {
+  const int nrows = nt * 8;
+  const int row = tid & 255;
+  if (tid == 0) s.stat[ST_TSUB] = clock64();
+  if (row < nrows)
+    for (int q = tid >> 8; q < 8; q += 2) s.Pb[pan(row, q)] = (q < r) ? h_get(s.H, row, Rs[q]) : 0.0;
+  if (wid == 15) {                              // S = H[R,R] straight from the tiles, then invert
     const int i = lane >> 2, j0 = (lane & 3) << 1;
-    double e0 = (i < r && j0 < r) ? s.Pb[pan(s.Rs[i], j0)] : (i == j0 ? 1.0 : 0.0);
-    double e1 = (i < r && j0 + 1 < r) ? s.Pb[pan(s.Rs[i], j0 + 1)] : (i == j0 + 1 ? 1.0 : 0.0);
-    if (lane < 8) s.rho[lane] = (lane < r) ? s.w[s.F[s.Rs[lane]]] : 0.0;    // w_R
-    if (lane < 8) s.cA[lane] = 0.0;
+    double e0 = (i < r && j0 < r) ? h_get(s.H, Rs[i], Rs[j0]) : (i == j0 ? 1.0 : 0.0);
+    double e1 = (i < r && j0 + 1 < r) ? h_get(s.H, Rs[i], Rs[j0 + 1]) : (i == j0 + 1 ? 1.0 : 0.0);
+    if (lane < 8) { s.rho[lane] = (lane < r) ? s.w[s.F[Rs[lane]]] : 0.0; s.cA[lane] = 0.0; }   // w_R
     __syncwarp();
-    warp_inv8(e0, e1, r, s.cA, -1.0);      // H[R,R] is SPD; no pivot test (tol < 0 with dref = 0)
+    warp_inv8(e0, e1, r, s.cA, -1.0, s.Sinv);   // H[R,R] is SPD: no pivot test
     s.Sinv[i * 8 + j0] = e0; s.Sinv[i * 8 + j0 + 1] = e1;
     __syncwarp();
-    if (lane < 8) {      // phi = inv(S) w_R
+    if (lane < 8) {                             // phi = inv(S) w_R
       double a = 0.0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) a = fma(s.Sinv[lane * 8 + j], s.rho[j], a);
@@ -188,61 +243,71 @@ __device__ void block_remove(const Sh &s, State &st, int r) {
     }
   }
   __syncthreads();
-  panel_small(s, s.Pb, s.Pa, s.theta, -1.0, nrows);
+  SUBTICK(PH_R_GATHER);
+  panel_small(s, s.Pb, s.Pa, s.theta, -1.0, nrows);      // Pa = -B inv(S);  w -= B phi
   __syncthreads();
-  rank_update(s.H, s.Pa, s.Pb, st.nt);
+  SUBTICK(PH_R_PANEL);
+  rank_update(s.H, s.Pa, s.Pb, nt, s.tmap);              // H -= B inv(S) B'
   __syncthreads();
-  for (int item = tid; item < nrows * 8; item += T) {
-    const int q = item / nrows, row = item - q * nrows;
-    if (q < r) h_set(s.H, s.Rs[q], row, 0.0);
-  }
+  SUBTICK(PH_R_RANK);
+  if (row < nrows)
+    for (int q = tid >> 8; q < r; q += 2) h_set(s.H, Rs[q], row, 0.0);
   if (tid < r) {
-    const int sl = s.Rs[tid], var = s.F[sl];
+    const int sl = Rs[tid], var = s.F[sl];
     s.w[var] = 0.0; s.pos[var] = -1; s.F[sl] = -1;
   }
   __syncthreads();
-  st.p -= r;
-  st.n_piv += r; st.n_sump2 += (unsigned long long)r * st.p * st.p;
+  SUBTICK(PH_R_ZERO);
+  if (tid == 0) { const long long p = s.stat[ST_P]; s.stat[ST_PIV] += r; s.stat[ST_SUMP2] += r * p * p; s.stat[ST_P] = p - r; }
 }
 
-// Add the a <= 8 variables listed in s.Av into the free slots s.As.  Returns false (state
-// untouched) if the Schur complement is not safely positive definite.
-__device__ bool block_add(const Sh &s, State &st, const K2Args &A, int a) {
+// Add the a <= 8 variables Av[-k] (k = 0..a-1, stored downwards) into the free slots As[k].
+// Returns false (state untouched) if the Schur complement is not safely positive definite.
+__device__ __noinline__ bool block_add(int cap, const double *G, int ldg, const int *Av, const int *As, int a, int nt) {
+  const Sh s = make_sh(cap);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  int hw = st.hwm;
-  for (int q = 0; q < a; ++q) hw = max(hw, s.As[q] + 1);
-  const int nt = (hw + 7) >> 3, nrows = nt * 8;
-  for (int item = tid; item < nrows * 8; item += T) {
-    const int q = item / nrows, row = item - q * nrows;
+  const int nrows = nt * 8;
+  const int row = tid & 255;
+  if (tid == 0) s.stat[ST_TSUB] = clock64();
+  if (row < nrows) {
     const int var = s.F[row];
-    s.Pa[pan(row, q)] = (q < a && var >= 0) ? A.G[(size_t)A.ldg * s.Av[q] + var] : 0.0;
-    if (q == 0) s.wF[row] = var >= 0 ? s.w[var] : 0.0;
+    for (int q = tid >> 8; q < 8; q += 2)
+      s.Pa[pan(row, q)] = (q < a && var >= 0) ? G[(size_t)ldg * Av[-q] + var] : 0.0;
+    if (tid < 256) s.wF[row] = var >= 0 ? s.w[var] : 0.0;
   }
-  if (tid < 64) {
-    const int i = tid >> 3, j = tid & 7;
-    s.Gaa[tid] = (i < a && j < a) ? A.G[(size_t)A.ldg * s.Av[j] + s.Av[i]] : (i == j ? 1.0 : 0.0);
+  if (tid >= 256 + 208 && tid < 256 + 208 + 8) {
+    const int q = tid - (256 + 208);
+    s.cA[q] = (q < a) ? s.cs[Av[-q]] : 0.0;
   }
-  if (tid >= 64 && tid < 72) s.cA[tid - 64] = (tid - 64 < a) ? A.c[s.Av[tid - 64]] : 0.0;
+  if (wid == 15) {                              // warp 15's rows are >= 224 > cap: free for G[A,A]
+    for (int e = lane; e < 64; e += 32) {
+      const int i = e >> 3, j = e & 7;
+      s.Gaa[e] = (i < a && j < a) ? G[(size_t)ldg * Av[-j] + Av[-i]] : (i == j ? 1.0 : 0.0);
+    }
+  }
   __syncthreads();
-  hmul(s.H, s.Pa, s.Pb, nt);                        // U = H V
+  SUBTICK(PH_A_GATHER);
+  hmul(s.H, s.Pa, s.Pb, nt);                    // U = H V
   __syncthreads();
-  if (wid < 4) {                                    // S partials = V' U over interleaved k-steps
+  SUBTICK(PH_A_HMUL);
+  if (wid < 4) {                                // S partials = V' U over interleaved k-steps
     const int fr = lane >> 2, fk = lane & 3;
     double c0 = 0.0, c1 = 0.0;
     for (int ks = wid; ks < nt * 2; ks += 4) {
-      const int row = ks * 4 + fk;
-      dmma(c0, c1, s.Pa[pan(row, fr)], s.Pb[pan(row, fr)]);
+      const int rw = ks * 4 + fk;
+      dmma(c0, c1, s.Pa[pan(rw, fr)], s.Pb[pan(rw, fr)]);
     }
     s.Spart[wid * 64 + fr * 8 + fk * 2] = c0;
     s.Spart[wid * 64 + fr * 8 + fk * 2 + 1] = c1;
-  } else if (wid < 12) {                            // rho_i = c_i - V[:,i]' w
+  } else if (wid < 12) {                        // rho_i = c_i - V[:,i]' w
     const int i = wid - 4;
     double acc = 0.0;
-    for (int row = lane; row < nrows; row += 32) acc = fma(s.Pa[pan(row, i)], s.wF[row], acc);
+    for (int rw = lane; rw < nrows; rw += 32) acc = fma(s.Pa[pan(rw, i)], s.wF[rw], acc);
     acc = warp_sum(acc);
     if (lane == 0) s.rho[i] = s.cA[i] - acc;
   }
   __syncthreads();
+  SUBTICK(PH_A_SPART);
   if (wid == 0) {
     const int i = lane >> 2, j0 = (lane & 3) << 1;
     double e0 = s.Gaa[i * 8 + j0], e1 = s.Gaa[i * 8 + j0 + 1];
@@ -254,8 +319,10 @@ __device__ bool block_add(const Sh &s, State &st, const K2Args &A, int a) {
     }
     if (lane < 8) s.theta[lane] = s.Gaa[lane * 8 + lane];     // pivot reference: G_jj
     __syncwarp();
-    const bool ok = warp_inv8(e0, e1, a, s.theta, 1e-13);
+    SUBTICK(PH_A_INV1);
+    const bool ok = warp_inv8(e0, e1, a, s.theta, 1e-13, s.Sinv);
     const bool all_ok = __all_sync(0xffffffffu, ok);
+    SUBTICK(PH_A_INV2);
     s.Sinv[i * 8 + j0] = e0; s.Sinv[i * 8 + j0 + 1] = e1;
     __syncwarp();
     double th = 0.0;
@@ -266,64 +333,79 @@ __device__ bool block_add(const Sh &s, State &st, const K2Args &A, int a) {
     __syncwarp();
     if (lane < 8) s.theta[lane] = (lane < a) ? th : 0.0;
     if (lane == 0) s.ctl[4] = all_ok ? 1 : 0;
+    SUBTICK(PH_A_INV3);
   }
   __syncthreads();
+  SUBTICK(PH_A_INV);
   if (!s.ctl[4]) { __syncthreads(); return false; }
-  panel_small(s, s.Pb, s.Pa, s.theta, 1.0, nrows);  // T = U inv(S) -> Pa;  w_F -= U theta
+  panel_small(s, s.Pb, s.Pa, s.theta, 1.0, nrows);       // T = U inv(S) -> Pa;  w_F -= U theta
   __syncthreads();
-  rank_update(s.H, s.Pa, s.Pb, nt);                 // H += T U'
+  SUBTICK(PH_A_PANEL);
+  rank_update(s.H, s.Pa, s.Pb, nt, s.tmap);              // H += T U'
   __syncthreads();
-  for (int item = tid; item < nrows * 8; item += T) {   // new rows / columns: -T
-    const int q = item / nrows, row = item - q * nrows;
-    if (q < a && s.F[row] >= 0) h_set(s.H, s.As[q], row, -s.Pa[pan(row, q)]);
-  }
+  SUBTICK(PH_A_RANK);
+  if (row < nrows && s.F[row] >= 0)                      // new rows / columns: -T
+    for (int q = tid >> 8; q < a; q += 2) h_set(s.H, As[q], row, -s.Pa[pan(row, q)]);
   __syncthreads();
   if (tid < 64) {
     const int i = tid >> 3, j = tid & 7;
-    if (i < a && j <= i) h_set(s.H, s.As[i], s.As[j], s.Sinv[i * 8 + j]);
+    if (i < a && j <= i) h_set(s.H, As[i], As[j], s.Sinv[i * 8 + j]);
   }
-  if (tid < a) {
-    const int var = s.Av[tid], sl = s.As[tid];
-    s.w[var] = s.theta[tid]; s.F[sl] = var; s.pos[var] = sl;
+  if (tid >= 64 && tid < 64 + a) {
+    const int q = tid - 64;
+    const int var = Av[-q], sl = As[q];
+    s.w[var] = s.theta[q]; s.F[sl] = var; s.pos[var] = sl;
   }
   __syncthreads();
-  st.n_piv += a; st.n_sump2 += (unsigned long long)a * st.p * st.p;
-  st.hwm = hw; st.nt = nt; st.p += a;
+  SUBTICK(PH_A_ROWS);
+  if (tid == 0) { const long long p = s.stat[ST_P]; s.stat[ST_PIV] += a; s.stat[ST_SUMP2] += a * p * p; s.stat[ST_P] = p + a; }
   return true;
 }
 
-// r = c - G[:,F] w_F for all variables.  Threads 0..255 take the even half of the slots, 256..511
-// the odd half.  Returns max |r_F| (normal-equation residual), same on all threads.
-__device__ double grad_eval(const Sh &s, State &st, const K2Args &A) {
+// r = c - G[:,F] w_F for all variables; the passive columns of G stream from L2 as double2 row
+// pairs, the slot range is split over nsl thread slices.  Returns max |r_F| (normal-equation
+// residual), same on all threads.  Uses Pb as scratch.
+__device__ __noinline__ double grad_eval(int cap, const double *G, int ldg, int Mp, int hw) {
+  const Sh s = make_sh(cap);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int hw = st.hwm, Mp = A.Mp;
   for (int t = tid; t < hw; t += T) { const int var = s.F[t]; s.wF[t] = var >= 0 ? s.w[var] : 0.0; }
   __syncthreads();
-  const int half = tid >> 8, m = tid & 255;
-  const int mid = ((hw + 1) >> 1);
-  const int t0 = half ? mid : 0, t1 = half ? hw : mid;
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-  if (m < Mp) {
-    int t = t0;
-    for (; t + 3 < t1; t += 4) {
-      const int v0 = s.F[t], v1 = s.F[t + 1], v2 = s.F[t + 2], v3 = s.F[t + 3];
-      const double g0 = v0 >= 0 ? A.G[(size_t)A.ldg * v0 + m] : 0.0;
-      const double g1 = v1 >= 0 ? A.G[(size_t)A.ldg * v1 + m] : 0.0;
-      const double g2 = v2 >= 0 ? A.G[(size_t)A.ldg * v2 + m] : 0.0;
-      const double g3 = v3 >= 0 ? A.G[(size_t)A.ldg * v3 + m] : 0.0;
-      a0 = fma(g0, s.wF[t], a0); a1 = fma(g1, s.wF[t + 1], a1);
-      a2 = fma(g2, s.wF[t + 2], a2); a3 = fma(g3, s.wF[t + 3], a3);
+  const int npairs = (Mp + 1) >> 1;
+  int nsl = T / npairs;
+  if (nsl > 8) nsl = 8;
+  const int sl = tid / npairs, pr = tid - sl * npairs;
+  double *part = s.Pb;                            // [nsl][2 * npairs]
+  if (sl < nsl) {
+    const int t0 = (hw * sl) / nsl, t1 = (hw * (sl + 1)) / nsl;
+    const double *Gp = G + 2 * pr;
+    double2 acc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = make_double2(0.0, 0.0);
+    for (int t = t0; t < t1; t += 8) {           // predicated batches of 8 loads: no serial tail
+      double2 g[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int v = (t + i < t1) ? s.F[t + i] : -1;
+        g[i] = v >= 0 ? *reinterpret_cast<const double2 *>(Gp + (size_t)ldg * v) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const double ww = (t + i < t1) ? s.wF[t + i] : 0.0;
+        acc[i & 3].x = fma(g[i].x, ww, acc[i & 3].x);
+        acc[i & 3].y = fma(g[i].y, ww, acc[i & 3].y);
+      }
     }
-    for (; t < t1; ++t) { const int v0 = s.F[t]; if (v0 >= 0) a0 = fma(A.G[(size_t)A.ldg * v0 + m], s.wF[t], a0); }
+    *reinterpret_cast<double2 *>(part + sl * 2 * npairs + 2 * pr) =
+        make_double2((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x), (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y));
   }
-  const double part = (a0 + a1) + (a2 + a3);
-  if (half) s.rpart[m] = part;
   __syncthreads();
   double mx = 0.0;
-  if (!half && m < Mp) {
-    const double rv = A.c[m] - (part + s.rpart[m]);
-    s.r[m] = rv;
-    if (s.pos[m] >= 0) mx = fabs(rv);
+  if (tid < Mp) {
+    double sum = 0.0;
+    for (int q = 0; q < nsl; ++q) sum += part[q * 2 * npairs + tid];
+    const double rv = s.cs[tid] - sum;
+    s.r[tid] = rv;
+    if (s.pos[tid] >= 0) mx = fabs(rv);
   }
   mx = warp_max(mx);
   if (lane == 0) s.red[wid] = mx;
@@ -332,72 +414,54 @@ __device__ double grad_eval(const Sh &s, State &st, const K2Args &A) {
 #pragma unroll
   for (int i = 1; i < NW; ++i) x = fmax(x, s.red[i]);
   __syncthreads();
-  st.n_grad++; st.n_sump += (unsigned long long)st.p;
+  if (tid == 0) { s.stat[ST_GRAD] += 1; s.stat[ST_SUMP] += s.stat[ST_P]; }
   return x;
 }
 
 // w_F += H r_F   (one DMMA product with a single live column)
-__device__ void refine(const Sh &s, State &st) {
-  const int nrows = st.nt * 8;
-  for (int item = threadIdx.x; item < nrows * 8; item += T) {
-    const int q = item / nrows, row = item - q * nrows;
+__device__ __noinline__ void refine(int cap, int nt) {
+  const Sh s = make_sh(cap);
+  const int nrows = nt * 8;
+  const int row = threadIdx.x & 255;
+  if (row < nrows) {
     const int var = s.F[row];
-    s.Pa[pan(row, q)] = (q == 0 && var >= 0) ? s.r[var] : 0.0;
+    for (int q = threadIdx.x >> 8; q < 8; q += 2) s.Pa[pan(row, q)] = (q == 0 && var >= 0) ? s.r[var] : 0.0;
   }
   __syncthreads();
-  hmul(s.H, s.Pa, s.Pb, st.nt);
+  hmul(s.H, s.Pa, s.Pb, nt);
   __syncthreads();
-  for (int row = threadIdx.x; row < nrows; row += T) {
-    const int var = s.F[row];
-    if (var >= 0) s.w[var] += s.Pb[pan(row, 0)];
+  for (int rw = threadIdx.x; rw < nrows; rw += T) {
+    const int var = s.F[rw];
+    if (var >= 0) s.w[var] += s.Pb[pan(rw, 0)];
   }
   __syncthreads();
 }
 
-__device__ void clear_state(const Sh &s, State &st, const K2Args &A, int cap) {
+__device__ __noinline__ void clear_state(int cap) {
+  const Sh s = make_sh(cap);
   const int ntc = cap >> 3;
   const int words = ((ntc * (ntc + 1)) >> 1) << 6;
   for (int i = threadIdx.x; i < words; i += T) s.H[i] = 0.0;
-  for (int t = threadIdx.x; t < cap; t += T) s.F[t] = -1;
-  st.hwm = 0; st.nt = 0; st.p = 0;
+  for (int t = threadIdx.x; t < cap; t += T) { s.F[t] = -1; s.smark[t] = 0; }
+  if (threadIdx.x == 0) s.stat[ST_P] = 0;
 }
 
 __global__ void __launch_bounds__(T, 1) k2v2_orthant_chains(const K2Args A) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int Mp = A.Mp, cap = A.cap;            // cap % 8 == 0, cap >= Mp
   const int ntc = cap >> 3;
-  Sh s;
-  double *dp = reinterpret_cast<double *>(smem_raw);
-  s.H = dp; dp += (((ntc * (ntc + 1)) >> 1) << 6);
-  s.Pa = dp; dp += cap * 8;
-  s.Pb = dp; dp += cap * 8;
-  s.w = dp; dp += cap;
-  s.r = dp; dp += cap;
-  s.wF = dp; dp += cap;
-  s.rpart = dp; dp += 256;
-  s.Sinv = dp; dp += 64;
-  s.Gaa = dp; dp += 64;
-  s.Spart = dp; dp += 256;
-  s.rho = dp; dp += 8;
-  s.theta = dp; dp += 8;
-  s.cA = dp; dp += 8;
-  s.red = dp; dp += NW;
-  int *ip = reinterpret_cast<int *>(dp);
-  s.F = ip; ip += cap;
-  s.pos = ip; ip += cap;
-  s.lst = ip; ip += cap;
-  s.Rs = ip; ip += 8;
-  s.As = ip; ip += 8;
-  s.Av = ip; ip += 8;
-  s.ctl = ip; ip += 8;
-  signed char *cp = reinterpret_cast<signed char *>(ip);
-  s.sg = cp; cp += cap;
-  s.dd = cp; cp += cap;
-  s.vflag = cp; cp += cap;
+  const Sh s = make_sh(cap);
+  for (int m = tid; m < cap; m += T) { s.cs[m] = m < Mp ? A.c[m] : 0.0; s.gms[m] = m < Mp ? A.gmask[m] : 0ull; }
+  for (int ti = tid; ti < ntc; ti += T)
+    for (int tj = 0; tj <= ti; ++tj) s.tmap[((ti * (ti + 1)) >> 1) + tj] = (unsigned short)((ti << 8) | tj);
 
-  State st;
-  st.n_piv = st.n_grad = st.n_sump = st.n_sump2 = st.n_iter = st.n_rebuild = st.n_blocked = st.n_noconv = 0;
+  int hwm = 0, nt_cur = 0;
+  if (tid == 0) {
+    for (int i = 0; i < PH_NUM; ++i) s.prof[i] = 0;
+    for (int i = 0; i < ST_NUM; ++i) s.stat[i] = 0;
+    s.stat[ST_TMARK] = clock64();
+  }
+#define PH_TICK(which) do { if (tid == 0) { const long long now_ = clock64(); s.prof[which] += now_ - s.stat[ST_TMARK]; s.stat[ST_TMARK] = now_; } } while (0)
   const double yy = A.scal[0], cmax = A.scal[1];
   const double told = 1e-12 * cmax;
   const long long L = 1ll << A.chain_log2;
@@ -412,15 +476,17 @@ __global__ void __launch_bounds__(T, 1) k2v2_orthant_chains(const K2Args A) {
     if (chain >= (unsigned long long)A.n_chains) break;
     const long long base = A.b_begin + (long long)chain * L;
 
-    clear_state(s, st, A, cap);
-    for (int m = tid; m < Mp; m += T) { s.w[m] = 0.0; s.r[m] = A.c[m]; s.pos[m] = -1; }
+    clear_state(cap);
+    hwm = 0; nt_cur = 0;
+    for (int m = tid; m < Mp; m += T) { s.w[m] = 0.0; s.r[m] = s.cs[m]; s.pos[m] = -1; }
     __syncthreads();
     bool r_valid = true;
+    PH_TICK(PH_START);
 
     for (long long i = 0; i < L; ++i) {
       const long long b = base + (i ^ (i >> 1));
       for (int m = tid; m < Mp; m += T) {   // d_m = sum_k Po[m,k] (2 bit_k(b) - 1)   (Opt.jl:28-29)
-        const uint64_t gm = A.gmask[m];
+        const uint64_t gm = s.gms[m];
         const int d = 2 * __popcll(gm & (uint64_t)b) - __popcll(gm);
         s.dd[m] = (signed char)d; s.sg[m] = (signed char)((d > 0) - (d < 0));
         s.vflag[m] = 0;
@@ -433,36 +499,37 @@ __global__ void __launch_bounds__(T, 1) k2v2_orthant_chains(const K2Args A) {
         if (!r_valid) {
           int rep = 0;
           for (;;) {
-            const double rf = grad_eval(s, st, A);
-            if (rf <= 1e-12 * cmax) break;          // carried solution is already exact to working accuracy
-            refine(s, st);
+            PH_TICK(PH_OUT);
+            const double rf = grad_eval(cap, A.G, A.ldg, Mp, hwm);
+            PH_TICK(PH_GRAD);
+            if (rf <= 1e-12 * cmax) break;          // carried solution already exact to working accuracy
+            refine(cap, nt_cur);
+            PH_TICK(PH_REFINE);
             if (rf <= 1e-9 * cmax) break;
             if (++rep >= 4) {                       // inverse degraded: rebuild by re-adding the passive set
-              int pn = 0;
               if (tid == 0) {
                 int n = 0;
-                for (int t = 0; t < st.hwm; ++t) if (s.F[t] >= 0) s.lst[n++] = s.F[t];
+                for (int t = 0; t < hwm; ++t) if (s.F[t] >= 0) { s.lst[cap - 1 - n] = s.F[t]; s.asl[n] = n; ++n; }
                 s.ctl[5] = n;
               }
               __syncthreads();
-              pn = s.ctl[5];
-              clear_state(s, st, A, cap);
+              const int pn = s.ctl[5];
+              clear_state(cap);
               for (int m = tid; m < Mp; m += T) { s.w[m] = 0.0; s.pos[m] = -1; }
               __syncthreads();
-              for (int q0 = 0; q0 < pn; q0 += 8) {
-                const int a = min(8, pn - q0);
-                if (tid < a) { s.Av[tid] = s.lst[q0 + tid]; s.As[tid] = st.p + tid; }
-                __syncthreads();
-                block_add(s, st, A, a);
-              }
-              st.n_rebuild++;
+              const int ntr = (pn + 7) >> 3;
+              for (int q0 = 0; q0 < pn; q0 += 8)
+                block_add(cap, A.G, A.ldg, s.lst + (cap - 1 - q0), s.asl + q0, min(8, pn - q0), ntr);
+              hwm = pn; nt_cur = ntr;
+              STAT_ADD(ST_REBUILD, 1);
               if (rep >= 6) { ok = false; break; }
             }
           }
           if (!ok) break;
         }
         r_valid = false;
-        // ---- infeasibility sets
+        // ---- infeasibility flags: passive variables with the wrong sign, active ones whose
+        //      sign-adjusted gradient is positive
         for (int m = tid; m < Mp; m += T) {
           const int sl = s.pos[m], sg = s.sg[m];
           int f = 0;
@@ -471,103 +538,92 @@ __global__ void __launch_bounds__(T, 1) k2v2_orthant_chains(const K2Args A) {
           if (s.vflag[m] != 3) s.vflag[m] = (signed char)f;
         }
         __syncthreads();
-        if (wid == 0) {   // deterministic compaction in index order: removals from the front, additions from the back
-          int nr = 0, na = 0, mxi = -1;
-          for (int m0 = 0; m0 < Mp; m0 += 32) {
-            const int m = m0 + lane;
-            const int f = (m < Mp) ? s.vflag[m] : 0;
-            const unsigned br = __ballot_sync(0xffffffffu, f == 1);
-            const unsigned ba = __ballot_sync(0xffffffffu, f == 2);
-            if (f == 1) s.lst[nr + __popc(br & ((1u << lane) - 1))] = m;
-            if (f == 2) s.lst[cap - 1 - (na + __popc(ba & ((1u << lane) - 1)))] = m;
-            nr += __popc(br); na += __popc(ba);
-            const unsigned any = br | ba;
-            if (any) mxi = m0 + 31 - __clz(any);
-          }
-          if (lane == 0) { s.ctl[0] = nr; s.ctl[1] = na; s.ctl[2] = mxi; }
+        // ---- plan: ordered lists (index order), pivoting rule, slots for the additions, new high-water
+        //      mark.  One warp per 32 variables / 32 slots; four short barrier-separated steps.
+        const int nvw = (Mp + 31) >> 5, nsw = cap >> 5 ? (cap + 31) >> 5 : 1;
+        int f_my = 0, rank_r = 0, rank_a = 0;
+        if (wid < nvw) {
+          const int m = (wid << 5) + lane;
+          f_my = (m < Mp) ? s.vflag[m] : 0;
+          const unsigned br = __ballot_sync(0xffffffffu, f_my == 1);
+          const unsigned ba = __ballot_sync(0xffffffffu, f_my == 2);
+          rank_r = __popc(br & ((1u << lane) - 1)); rank_a = __popc(ba & ((1u << lane) - 1));
+          const unsigned any = br | ba;
+          if (lane == 0) { s.pl[wid] = __popc(br) | (__popc(ba) << 16); s.pl[8 + wid] = any ? (wid << 5) + 31 - __clz(any) : -1; }
         }
         __syncthreads();
-        int nr = s.ctl[0], na = s.ctl[1];
+        int nr = 0, na = 0, mxi = -1, pref_r = 0, pref_a = 0;
+        for (int q = 0; q < nvw; ++q) {
+          const int cnt = s.pl[q];
+          if (q < wid) { pref_r += cnt & 0xffff; pref_a += cnt >> 16; }
+          nr += cnt & 0xffff; na += cnt >> 16;
+          mxi = max(mxi, s.pl[8 + q]);
+        }
         const int nv = nr + na;
-        if (nv == 0) { r_valid = true; break; }
-        bool single = false;
+        const bool single = nv > 0 && !(nv < t_best) && pbar < 1;    // Murty's rule: only the highest index moves
+        if (!single) {
+          if (f_my == 1) { const int sl = s.pos[(wid << 5) + lane]; s.lst[pref_r + rank_r] = sl; s.smark[sl] = 1; }
+          if (f_my == 2) s.lst[cap - 1 - (pref_a + rank_a)] = (wid << 5) + lane;
+        } else {
+          if (s.pos[mxi] >= 0) { nr = 1; na = 0; if (tid == 0) { const int sl = s.pos[mxi]; s.lst[0] = sl; s.smark[sl] = 1; } }
+          else { nr = 0; na = 1; if (tid == 0) s.lst[cap - 1] = mxi; }
+        }
+        __syncthreads();
+        bool fr_my = false, used_my = false;
+        int rank_f = 0;
+        if (wid < nsw) {
+          const int sl = (wid << 5) + lane;
+          used_my = sl < cap && s.F[sl] >= 0 && !s.smark[sl];
+          fr_my = sl < cap && !used_my;
+          const unsigned bal = __ballot_sync(0xffffffffu, fr_my);
+          rank_f = __popc(bal & ((1u << lane) - 1));
+          if (lane == 0) s.pl[16 + wid] = __popc(bal);
+        }
+        __syncthreads();
+        if (wid < nsw) {
+          const int sl = (wid << 5) + lane;
+          int pref_f = 0;
+          for (int q = 0; q < wid; ++q) pref_f += s.pl[16 + q];
+          const bool take = fr_my && (pref_f + rank_f) < na;
+          if (take) s.asl[pref_f + rank_f] = sl;
+          if (sl < cap && s.smark[sl]) s.smark[sl] = 0;
+          const unsigned after = __ballot_sync(0xffffffffu, used_my || take);
+          if (lane == 0) s.pl[24 + wid] = after ? (wid << 5) + 32 - __clz(after) : 0;
+        }
+        __syncthreads();
+        int hw_after = 0;
+        for (int q = 0; q < nsw; ++q) hw_after = max(hw_after, s.pl[24 + q]);
+        if (nv == 0) { r_valid = true; PH_TICK(PH_PLAN); break; }   // KKT point; r stays valid for the next orthant
         if (nv < t_best) { t_best = nv; pbar = 3; }
         else if (pbar >= 1) { --pbar; }
-        else single = true;                         // Murty's rule: only the highest index moves
-        if (single) {
-          const int m = s.ctl[2];
-          if (s.pos[m] >= 0) { nr = 1; na = 0; if (tid == 0) s.lst[0] = m; }
-          else { nr = 0; na = 1; if (tid == 0) s.lst[cap - 1] = m; }
-          __syncthreads();
-        }
-        // ---- removals, 8 at a time
-        for (int q0 = 0; q0 < nr; q0 += 8) {
-          const int r = min(8, nr - q0);
-          if (tid < r) s.Rs[tid] = s.pos[s.lst[q0 + tid]];
-          __syncthreads();
-          block_remove(s, st, r);
-        }
-        // ---- additions, 8 at a time, into the lowest free slots
+        const int nt_op = (max(hwm, hw_after) + 7) >> 3;
+        PH_TICK(PH_PLAN);
+        for (int q0 = 0; q0 < nr; q0 += 8) { block_remove(cap, s.lst + q0, min(8, nr - q0), nt_op); if (tid == 0) s.prof[PH_NREM]++; }
+        PH_TICK(PH_REMOVE);
         for (int q0 = 0; q0 < na; q0 += 8) {
+          if (tid == 0) s.prof[PH_NADD]++;
           const int a = min(8, na - q0);
-          if (wid == 0) {
-            if (lane < a) s.Av[lane] = s.lst[cap - 1 - (q0 + lane)];
-            int found = 0;
-            for (int s0 = 0; s0 < cap && found < a; s0 += 32) {
-              const int sl = s0 + lane;
-              const bool fr = sl < cap && s.F[sl] < 0;
-              const unsigned bal = __ballot_sync(0xffffffffu, fr);
-              const int rank = found + __popc(bal & ((1u << lane) - 1));
-              if (fr && rank < a) s.As[rank] = sl;
-              found += __popc(bal);
-            }
-          }
-          __syncthreads();
-          if (!block_add(s, st, A, a)) {
+          if (!block_add(cap, A.G, A.ldg, s.lst + (cap - 1 - q0), s.asl + q0, a, nt_op)) {
             // numerically dependent column in the block: retry one variable at a time
             for (int q = 0; q < a; ++q) {
-              __syncthreads();
-              if (wid == 0) {
-                const int var = s.lst[cap - 1 - (q0 + q)];
-                int found = 0;
-                for (int s0 = 0; s0 < cap && found < 1; s0 += 32) {
-                  const int sl = s0 + lane;
-                  const bool fr = sl < cap && s.F[sl] < 0;
-                  const unsigned bal = __ballot_sync(0xffffffffu, fr);
-                  if (fr && __popc(bal & ((1u << lane) - 1)) == 0 && found == 0) s.As[0] = sl;
-                  found += __popc(bal);
-                }
-                if (lane == 0) s.Av[0] = var;
-              }
-              __syncthreads();
-              if (!block_add(s, st, A, 1)) {
-                if (tid == 0) s.vflag[s.Av[0]] = 3;
-                st.n_blocked++;
+              if (!block_add(cap, A.G, A.ldg, s.lst + (cap - 1 - q0 - q), s.asl + q0 + q, 1, nt_op)) {
+                if (tid == 0) s.vflag[s.lst[cap - 1 - q0 - q]] = 3;
+                STAT_ADD(ST_BLOCKED, 1);
                 __syncthreads();
               }
             }
           }
         }
-        // high-water mark may have dropped
-        if (wid == 0) {
-          int hw = 0;
-          for (int s0 = 0; s0 < cap; s0 += 32) {
-            const int sl = s0 + lane;
-            const unsigned bal = __ballot_sync(0xffffffffu, sl < cap && s.F[sl] >= 0);
-            if (bal) hw = s0 + 32 - __clz(bal);
-          }
-          if (lane == 0) s.ctl[3] = hw;
-        }
-        __syncthreads();
-        st.hwm = s.ctl[3]; st.nt = (st.hwm + 7) >> 3;
-        st.n_iter++;
+        PH_TICK(PH_ADD);
+        hwm = hw_after; nt_cur = (hw_after + 7) >> 3;
+        STAT_ADD(ST_ITER, 1);
         if (++iters > 60 + 6 * Mp) { ok = false; break; }
       }
-      if (!ok) st.n_noconv++;
+      if (!ok) STAT_ADD(ST_NOCONV, 1);
 
       // ---- objective  sqrt(yy - c_F' w_F)   (= norm(Xa w - ya) at the KKT point, Opt.jl:90)
       double acc = 0.0;
-      for (int m = tid; m < Mp; m += T) if (s.pos[m] >= 0) acc = fma(A.c[m], s.w[m], acc);
+      for (int m = tid; m < Mp; m += T) if (s.pos[m] >= 0) acc = fma(s.cs[m], s.w[m], acc);
       acc = warp_sum(acc);
       if (lane == 0) s.red[wid] = acc;
       __syncthreads();
@@ -596,22 +652,25 @@ __global__ void __launch_bounds__(T, 1) k2v2_orthant_chains(const K2Args A) {
   if (tid == 0) {
     A.cta_obj[blockIdx.x] = best_obj;
     A.cta_b[blockIdx.x] = best_b;
-    atomicAdd(&A.counters[CNT_PIVOTS], st.n_piv);
-    atomicAdd(&A.counters[CNT_GRAD], st.n_grad);
-    atomicAdd(&A.counters[CNT_SUMP], st.n_sump);
-    atomicAdd(&A.counters[CNT_SUMP2], st.n_sump2);
-    atomicAdd(&A.counters[CNT_ITERS], st.n_iter);
-    atomicAdd(&A.counters[CNT_REBUILDS], st.n_rebuild);
-    atomicAdd(&A.counters[CNT_BLOCKED], st.n_blocked);
-    atomicAdd(&A.counters[CNT_NOCONV], st.n_noconv);
+    atomicAdd(&A.counters[CNT_PIVOTS], (unsigned long long)s.stat[ST_PIV]);
+    atomicAdd(&A.counters[CNT_GRAD], (unsigned long long)s.stat[ST_GRAD]);
+    atomicAdd(&A.counters[CNT_SUMP], (unsigned long long)s.stat[ST_SUMP]);
+    atomicAdd(&A.counters[CNT_SUMP2], (unsigned long long)s.stat[ST_SUMP2]);
+    atomicAdd(&A.counters[CNT_ITERS], (unsigned long long)s.stat[ST_ITER]);
+    atomicAdd(&A.counters[CNT_REBUILDS], (unsigned long long)s.stat[ST_REBUILD]);
+    atomicAdd(&A.counters[CNT_BLOCKED], (unsigned long long)s.stat[ST_BLOCKED]);
+    atomicAdd(&A.counters[CNT_NOCONV], (unsigned long long)s.stat[ST_NOCONV]);
+    PH_TICK(PH_OUT);
+    for (int i = 0; i < PH_NUM; ++i) atomicAdd(&A.counters[CNT_NUM + 1 + i], (unsigned long long)s.prof[i]);
   }
 }
 
 size_t v2_smem_bytes(int cap) {
   const int ntc = cap >> 3;
-  size_t d = ((size_t)(ntc * (ntc + 1) / 2) << 6) + 2 * (size_t)cap * 8 + 3 * (size_t)cap + 256 + 64 + 64 + 256 + 24 + NW;
-  size_t i = 3 * (size_t)cap + 32;
-  size_t c = 3 * (size_t)cap;
+  const size_t ntiles = (size_t)(ntc * (ntc + 1) / 2);
+  size_t d = (ntiles << 6) + 2 * (size_t)cap * 8 + 5 * (size_t)cap + 64 + 64 + 256 + 24 + NW + ST_NUM + PH_NUM;
+  size_t i = 4 * (size_t)cap + 8 + 32 + (ntiles + 1) / 2;
+  size_t c = 4 * (size_t)cap;
   return d * sizeof(double) + i * sizeof(int) + c + 16;
 }
 
