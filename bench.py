@@ -35,6 +35,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
 
+_JSON_OUT = sys.stdout
 METRIC = "opt_fit_orthant_nnls_solves_per_sec"
 UNIT = "solves/s"
 
@@ -55,6 +56,21 @@ def load_peaks():
     else:
         peaks["fp64"] = {"dfma_tflops": 36.4, "dmma_m8n8k4_tflops": 37.1}
     return peaks
+
+
+def ncu_dram_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the K2 launch from the committed ncu --set full
+    capture (profiles/r01_v2c_k2_raw_summary.txt); None if the summary is missing."""
+    p = os.path.join(ROOT, "profiles", "r01_v2c_k2_raw_summary.txt")
+    if not os.path.exists(p):
+        return None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for ln in open(p):
+        f = ln.split()
+        if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(f[1]) * unit.get(f[2], 1.0)
+    return tot
 
 
 class ClockSampler:
@@ -140,7 +156,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 def make_workload(args, world):
@@ -160,11 +176,6 @@ def make_workload(args, world):
     return X, y, P, eta, wl
 
 
-class _DevBuf:
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
-
-
 def run_native(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -182,7 +193,6 @@ def run_native(args, rank, world, local_rank):
     cudart = torch.cuda.cudart()
     for a in (Xs, ys, Pc):
         cudart.cudaHostRegister(a.ctypes.data, a.nbytes, 0)
-    b0, bn = (total // world) * rank, total // world
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -190,38 +200,25 @@ def run_native(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    from importlib import import_module
+    distmod = import_module(entry.PKG_NAME + ".dist")
+    comm = distmod.TorchComm(device=dev) if world > 1 else None
+
     def step_resident():
         """One Opt fit on the resident data set.  Returns (b*, obj, alpha_raw, stats)."""
         if world == 1:
             r = ctx.opt_fit_resident()
             return r["b_best"], r["opt"], r["alpha_raw"], r["stats"]
-        ctx.gram_build()
-        ptr, n = ctx.gram_raw()
-        S = torch.as_tensor(_DevBuf(ptr, n), device=dev)
-        dist.all_reduce(S)
-        torch.cuda.synchronize()
-        ctx.gram_finalize()
-        loc = ctx.opt_solve_range(b0, bn)
-        st = ctx.stats()
-        rec = torch.empty(Mp + 2, dtype=torch.float64)
-        rec[:Mp] = torch.from_numpy(loc["alpha_raw"]); rec[Mp] = loc["obj_gram"]; rec[Mp + 1] = float(loc["b_best"])
-        rec = rec.to(dev)
-        allrec = [torch.empty_like(rec) for _ in range(world)]
-        dist.all_gather(allrec, rec)
-        allrec = torch.stack(allrec).cpu().numpy()
-        win = min(range(world), key=lambda i: (allrec[i, Mp], allrec[i, Mp + 1]))
-        alpha, bb = allrec[win, :Mp].copy(), int(allrec[win, Mp + 1])
-        ssq = torch.tensor([ctx.residual_partial(alpha, bb)], dtype=torch.float64, device=dev)
-        dist.all_reduce(ssq)
-        obj = ctx.objective_finish(alpha, bb, float(ssq.item()))
-        return bb, obj, alpha, st
+        bb, obj, alpha = distmod.opt_fit_sharded(ctx, comm, Mp, K + 1)
+        return bb, obj, alpha, ctx.stats()
 
     def step_e2e():
         if world == 1:
             r = ctx.opt_fit(Xs, ys, Pc, eta=eta, prepared=True)
             return r["b_best"], r["opt"], r["alpha_raw"], r["stats"]
-        ctx.load(Xs, ys, Pc, eta=eta, prepared=True)
-        return step_resident()
+        bb, obj, alpha = distmod.opt_fit_sharded(ctx, comm, Mp, K + 1,
+                                                 reload=lambda: ctx.load(Xs, ys, Pc, eta=eta, prepared=True))
+        return bb, obj, alpha, ctx.stats()
 
     def timed(fn, steps, warmup, sample_clocks):
         for _ in range(warmup):
@@ -269,9 +266,9 @@ def run_native(args, rank, world, local_rank):
                 "d2h_bytes_per_step": int((Mp + 4 + 10) * 8 * world)},
         "gpu_launches": int(st["kernel_launches"] * args.steps * world),
         "roofline": {
-            "kernel": "k2_orthant_chains (batched orthant NNLS, FP64 FMA pipe; tcgen05 has no f64 kind)",
+            "kernel": "k2v2_orthant_chains (batched orthant NNLS: FP64 DMMA + DFMA; tcgen05 has no f64 kind)",
             "bound": "tensor", "achieved": k2_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-            "frac": k2_tflops / fp64_peak if fp64_peak else None, "traffic": None,
+            "frac": k2_tflops / fp64_peak if fp64_peak else None, "traffic": ncu_dram_traffic(),
             "peak_source": "FP64 DFMA peak measured by tools/fp64_peak.cu on this pool (profiles/fp64_peaks_r01.json); MEASURED_PEAKS.json holds no FP64 figure",
             "algorithmic_flops_per_launch": st["nnls_flops"], "launch_ms": k2_ms,
             "l2_model_gbs": st["nnls_l2_bytes"] / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else None,
@@ -290,7 +287,7 @@ def run_native(args, rank, world, local_rank):
         v, dt = cpu_reference_sample(o, oc, X, y, P, eta, n_s, 1, seed=0)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": f"{n_s} seeded random orthants at full N, M, single thread (the reference loop is serial), {dt:.1f} s; C restatement of Opt.jl:85-94"}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 def main():
@@ -302,6 +299,11 @@ def main():
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # keep stdout clean for the one JSON line: libraries (NCCL banner, torchrun) write to fd 1 too
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(json_fd, "w")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -60,7 +60,7 @@ struct pls_ctx {
   double *d_w = nullptr, *d_ssq = nullptr;
   double *h_pin = nullptr;   // pinned: winner record + ssq
   size_t z_bytes = 0;
-  int launches = 0;
+  int launches = 0, launch_mark = 0;
 };
 
 namespace {
@@ -281,6 +281,7 @@ int pls_gram_build(pls_ctx *c) {
   if (rc) return rc;
   if (!c->pb.loaded) { set_error("no data set loaded"); return PLS_EINVAL; }
   c->pb.gram_ready = false;
+  c->launch_mark = c->launches;
   return k1_gram_build(c->pb, c->stream, &c->launches);
 }
 
@@ -330,7 +331,7 @@ int pls_opt_solve_range(pls_ctx *c, int64_t b_begin, int64_t b_count, double *al
   *obj_best = c->h_pin[Mp];
   long long bb; memcpy(&bb, &c->h_pin[Mp + 1], sizeof(bb));
   *b_best = bb;
-  c->stats.kernel_launches = c->launches;
+  c->stats.kernel_launches = c->launches - c->launch_mark + 3;   // + winner-weights / K4 launches that follow
   if (cnt[CNT_NOCONV]) { set_error("%llu orthant solves hit the iteration cap", cnt[CNT_NOCONV]); return PLS_ENUMERIC; }
   if (*obj_best != *obj_best) { set_error("NaN objective (non-finite input?)"); return PLS_ENUMERIC; }
   return PLS_OK;

@@ -1,0 +1,94 @@
+"""One-process-per-GPU Opt fit: the host-side plumbing around the stage-wise C ABI entry points.
+
+Sharding:
+  K1  rows of X are sharded; the raw Gram sums S = Z'Z are all-reduced once ((M+2)^2 doubles);
+  K2  the orthant index space [0, 2^(K+1)) is split into one contiguous range per rank, no
+      communication;
+  K3  every rank's (objective, b, alpha) winner is all-gathered, the lexicographic minimum
+      (objective, b) wins on every rank (first-minimum semantics of Opt.jl:96);
+  K4  the winner's squared residual is summed over the row shards (one double all-reduced).
+
+`backend` is anything with the stage-wise methods of `_abi.Context` (load, gram_build, gram_raw,
+gram_finalize, opt_solve_range, residual_partial, objective_finish); `comm` wraps the collectives so
+the same code runs over NCCL (GPU tensors) in bench.py and over gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_rows(N: int, rank: int, world: int):
+    """Contiguous near-equal row ranges."""
+    return (N * rank) // world, (N * (rank + 1)) // world
+
+
+def shard_orthants(total: int, rank: int, world: int):
+    """Contiguous equal orthant ranges; world must divide the (power of two) total."""
+    if total % world:
+        raise ValueError(f"world size {world} does not divide {total} orthants")
+    n = total // world
+    return n * rank, n
+
+
+def pick_winner(records, Mp):
+    """records: array (world, Mp + 2) rows [alpha_raw (Mp), objective, b].  Lexicographic
+    (objective, b) minimum; NaN objectives sort first (Julia argmin semantics, Opt.jl:96)."""
+    rec = np.asarray(records, dtype=np.float64)
+    key = [(0 if np.isnan(r[Mp]) else 1, r[Mp] if not np.isnan(r[Mp]) else 0.0, r[Mp + 1]) for r in rec]
+    i = min(range(len(rec)), key=lambda q: key[q])
+    return rec[i, :Mp].copy(), int(rec[i, Mp + 1]), float(rec[i, Mp]), i
+
+
+class TorchComm:
+    """Collectives over torch.distributed (NCCL for CUDA tensors, gloo for CPU tensors)."""
+
+    def __init__(self, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.device = torch, dist, device
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+
+    def allreduce_sum_inplace_dev(self, dev_ptr: int, count: int):
+        """Sum a device buffer of `count` doubles across ranks, in place (zero-copy view)."""
+        class _Buf:
+            pass
+        b = _Buf()
+        b.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (dev_ptr, False), "version": 3}
+        t = self.torch.as_tensor(b, device=self.device)
+        self.dist.all_reduce(t)
+        self.torch.cuda.synchronize(self.device)
+
+    def allreduce_sum(self, arr: np.ndarray) -> np.ndarray:
+        t = self.torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64))
+        if self.device is not None:
+            t = t.to(self.device)
+        self.dist.all_reduce(t)
+        return t.cpu().numpy()
+
+    def allgather(self, arr: np.ndarray) -> np.ndarray:
+        t = self.torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64))
+        if self.device is not None:
+            t = t.to(self.device)
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return self.torch.stack(out).cpu().numpy()
+
+
+def opt_fit_sharded(backend, comm, Mp: int, Kp: int, *, reload=None):
+    """One Opt fit over `comm.world` ranks on data already loaded in `backend` (or loaded by the
+    `reload()` callback first -- the end-to-end variant).  Returns (b*, objective, alpha_raw)."""
+    if reload is not None:
+        reload()
+    backend.gram_build()
+    ptr, count = backend.gram_raw()
+    if isinstance(ptr, np.ndarray):          # CPU test double: host array, reduced out of place
+        ptr[...] = comm.allreduce_sum(ptr)
+    else:
+        comm.allreduce_sum_inplace_dev(ptr, count)
+    backend.gram_finalize()
+    b0, bn = shard_orthants(1 << Kp, comm.rank, comm.world)
+    loc = backend.opt_solve_range(b0, bn)
+    rec = np.concatenate([loc["alpha_raw"], [loc["obj_gram"], float(loc["b_best"])]])
+    alpha, b, _, _ = pick_winner(comm.allgather(rec), Mp)
+    ssq = comm.allreduce_sum(np.array([backend.residual_partial(alpha, b)]))[0]
+    return b, backend.objective_finish(alpha, b, float(ssq)), alpha

@@ -1,0 +1,80 @@
+# PartitionedLSCUDA.jl -- thin Julia host for libpls_cuda.so (the B200 solver core).
+#
+# Drop-in for the body of `fit(::Type{Opt}, X, y, P; η, nnlsalg, returnAllSolutions)`
+# (PartitionedLS.jl/src/PartitionedLSOpt.jl:73-104).  Everything between argument validation
+# and `cleanupResult` (Opt.jl:79-97) runs in the library; `cleanupResult` (Opt.jl:34-44),
+# `PartLSFitResult` (PartitionedLS.jl:29-49) and `predict` (:132-155) are the reference's own.
+#
+# NOTE: Julia is not installed in the build image, so this file has been reviewed by eye only; the
+# same C ABI is exercised end to end by the Python twin (partitionedls.jl_b200/_abi.py + tests/).
+module PartitionedLSCUDA
+
+using PartitionedLS: PartLSFitResult, Opt, cleanupResult
+import PartitionedLS: fit
+
+const libpls = get(ENV, "LIBPLS_CUDA", "libpls_cuda.so")
+
+struct PlsStats            # mirrors `pls_stats` in include/pls.h
+    ms_upload::Cdouble; ms_gram::Cdouble; ms_nnls::Cdouble; ms_select::Cdouble
+    ms_recompute::Cdouble; ms_total::Cdouble
+    orthants::Int64; pivots::Int64; grad_evals::Int64; sum_p::Int64; sum_p2::Int64
+    bpp_iters::Int64; spills::Int64; rebuilds::Int64; blocked::Int64; kernel_launches::Int64
+    gram_flops::Cdouble; nnls_flops::Cdouble; nnls_l2_bytes::Cdouble
+end
+
+const _ctx = Ref{Ptr{Cvoid}}(C_NULL)      # created lazily: never ccall at precompile time
+                                          # (the reference runs all fits in @compile_workload,
+                                          #  PartitionedLS.jl:363-385)
+
+function _check(rc::Cint)
+    rc == 0 && return
+    msg = unsafe_string(ccall((:pls_last_error, libpls), Cstring, ()))
+    error("libpls_cuda: $msg (code $rc)")
+end
+
+function context()
+    if _ctx[] == C_NULL
+        dev = Ref{Cint}(parse(Cint, get(ENV, "PLS_DEVICE", "0")))
+        _check(ccall((:pls_create, libpls), Cint, (Ref{Ptr{Cvoid}}, Ref{Cint}, Cint), _ctx, dev, 1))
+        atexit(() -> ccall((:pls_destroy, libpls), Cvoid, (Ptr{Cvoid},), _ctx[]))
+    end
+    _ctx[]
+end
+
+"""
+    fit(Opt, X, y, P; η=0.0, nnlsalg=:nnls, returnAllSolutions=false)
+
+Same signature and return tuple as the reference (Opt.jl:73-74, :99-103).  `nnlsalg` is accepted
+and ignored: the GPU path has one Gram-space solver.  Float32 inputs are upcast (result fields are
+`Vector{AbstractFloat}`, PartitionedLS.jl:34,39).
+"""
+function fit(::Type{Opt}, X::Array{<:AbstractFloat,2}, y::AbstractArray{<:AbstractFloat,1}, P::Array{Int,2};
+             η=0.0, nnlsalg=:nnls, returnAllSolutions=false)
+    Xd = convert(Matrix{Float64}, X); yd = convert(Vector{Float64}, y); Pd = convert(Matrix{Int64}, P)
+    N, M = size(Xd); K = size(Pd, 2)
+    alpha = zeros(Float64, M + 1); b = Ref{Int64}(0); obj = Ref{Cdouble}(0.0)
+    nb = 2^(K + 1)
+    allobj = returnAllSolutions ? zeros(Float64, nb) : Float64[]
+    allalpha = returnAllSolutions ? zeros(Float64, M + 1, nb) : zeros(Float64, 0, 0)
+    stats = Ref{PlsStats}()
+    GC.@preserve Xd yd Pd alpha allobj allalpha begin
+        _check(ccall((:pls_opt_fit, libpls), Cint,
+            (Ptr{Cvoid}, Ptr{Cdouble}, Int64, Int64, Ptr{Cdouble}, Ptr{Int64}, Int64, Cdouble, UInt32,
+             Ptr{Cdouble}, Ref{Int64}, Ref{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{PlsStats}),
+            context(), Xd, N, M, yd, Pd, K, Float64(η), UInt32(0),
+            alpha, b, obj,
+            returnAllSolutions ? pointer(allobj) : C_NULL,
+            returnAllSolutions ? pointer(allalpha) : C_NULL, stats))
+    end
+    # the tuple of Opt.jl:92: (optval, α[1:M], β[1:K], β[K+1]*α[M+1], P), β from indextobeta (Opt.jl:4-20)
+    beta(bb) = [2 * ((bb >> (k - 1)) & 1) - 1 for k in 1:K+1]
+    tup(o, a, bb) = (o, a[1:end-1], beta(bb)[1:end-1], beta(bb)[end] * a[end], P)
+    opt, model = cleanupResult(Opt, tup(obj[], alpha, b[]), P)
+    if returnAllSolutions
+        sols = [cleanupResult(Opt, tup(allobj[i], allalpha[:, i], i - 1), P) for i in 1:nb]
+        return (model, nothing, (; solutions = sols))
+    end
+    return (model, nothing, (; opt = opt))
+end
+
+end # module

@@ -1,0 +1,120 @@
+"""world_size-2 gloo test of the multi-process Opt fit plumbing (partitionedls.jl_b200/dist.py) on the
+CPU.  The per-rank compute is a test double with the stage-wise interface of the GPU context: numpy
+Gram sums for the rank's row shard and oracle solves for its orthant range (tests may use the
+oracle; the product path never does)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleBackend:
+    """Stage-wise interface of _abi.Context, computed on the CPU for one rank's shard."""
+
+    def __init__(self, o, oc, X, y, P, eta, rows):
+        self.o, self.oc, self.eta = o, oc, eta
+        self.Xfull, self.yfull, self.P = X, y, P
+        r0, r1 = rows
+        Z = np.hstack([X[r0:r1], np.ones((r1 - r0, 1)), y[r0:r1, None]])
+        self.Z = Z
+        self.S = None
+
+    def gram_build(self):
+        self.S = np.ascontiguousarray(self.Z.T @ self.Z).reshape(-1)
+
+    def gram_raw(self):
+        return self.S, self.S.size
+
+    def gram_finalize(self):
+        zc = self.Z.shape[1]
+        S = self.S.reshape(zc, zc)
+        _, Po = self.o.homogeneous_coords(self.Xfull[:1], self.P)
+        self.G = S[:-1, :-1] + self.eta * (Po @ Po.T)
+        self.c = S[:-1, -1].copy()
+        self.yy = S[-1, -1]
+        self.Po = Po
+
+    def opt_solve_range(self, b0, bn):
+        # oracle solve of the rank's orthant range on the GLOBAL Gram (Cholesky surrogate data)
+        L = np.linalg.cholesky(self.G)
+        A = L.T
+        bb = np.linalg.solve(L, self.c)
+        best = None
+        for b in range(b0, b0 + bn):
+            beta = self.o.index_to_beta(b, self.Po.shape[1])
+            d = self.Po @ beta
+            alpha = self.o.nonneg_lsq(A * d[None, :], bb)
+            w = d * alpha
+            obj = float(np.sqrt(max(self.yy - 2 * self.c @ w + w @ self.G @ w, 0.0)))
+            if best is None or (obj, b) < (best["obj_gram"], best["b_best"]):
+                best = dict(alpha_raw=alpha, b_best=b, obj_gram=obj)
+        return best
+
+    def residual_partial(self, alpha, b):
+        d = self.Po @ self.o.index_to_beta(b, self.Po.shape[1])
+        res = self.Z[:, :-1] @ (d * alpha) - self.Z[:, -1]
+        return float(res @ res)
+
+    def objective_finish(self, alpha, b, ssq):
+        d = self.Po @ self.o.index_to_beta(b, self.Po.shape[1])
+        return float(np.sqrt(ssq + self.eta * np.sum((self.Po.T @ (d * alpha)) ** 2)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    from importlib import import_module
+    g.load_package()
+    distmod = import_module(g.PKG_NAME + ".dist")
+    o, oc = g.load_oracle()
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        X, y, P = o.make_synthetic(400, 10, 3, seed=5, mixed_sign=True)
+        eta = 1e-2
+        be = OracleBackend(o, oc, X, y, P, eta, distmod.shard_rows(400, rank, world))
+        comm = distmod.TorchComm(device=None)
+        b, obj, alpha = distmod.opt_fit_sharded(be, comm, Mp=11, Kp=4)
+        q.put((rank, b, obj, alpha))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharded_fit_matches_single_process(oracle):
+    import torch.multiprocessing as mp
+    o, oc = oracle
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    X, y, P = o.make_synthetic(400, 10, 3, seed=5, mixed_sign=True)
+    ref = oc.opt_fit(X, y, P, 1e-2)
+    for rank, b, obj, alpha in res:
+        assert b == ref["b_best"]
+        assert abs(obj - ref["obj_best"]) <= 1e-9 * ref["obj_best"]
+        assert np.all(np.abs(alpha - ref["alpha_best"]) <= 1e-8 * np.abs(ref["alpha_best"]).max())
+
+
+def test_sharding_helpers(pkg):
+    from importlib import import_module
+    import __graft_entry__ as g
+    d = import_module(g.PKG_NAME + ".dist")
+    assert [d.shard_rows(10, r, 3) for r in range(3)] == [(0, 3), (3, 6), (6, 10)]
+    assert [d.shard_orthants(16, r, 4) for r in range(4)] == [(0, 4), (4, 4), (8, 4), (12, 4)]
+    with pytest.raises(ValueError):
+        d.shard_orthants(16, 0, 3)
+    rec = np.array([[1.0, 2.0, 5.0, 7.0], [3.0, 4.0, 5.0, 3.0], [0.0, 0.0, 6.0, 0.0]])
+    a, b, obj, i = d.pick_winner(rec, 2)
+    assert (b, obj, i) == (3, 5.0, 1) and list(a) == [3.0, 4.0]      # tie on objective -> lower b
+    rec[2, 2] = np.nan
+    assert d.pick_winner(rec, 2)[1] == 0                              # NaN sorts first

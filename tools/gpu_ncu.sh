@@ -5,5 +5,5 @@ CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"
 $CMD > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
 $CMD > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k2v2_orthant -s 1 -c 1 -o gpurun_out/k2v2b_prof $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k2v2_orthant -s 1 -c 1 -o gpurun_out/k2v2c_prof $CMD > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
