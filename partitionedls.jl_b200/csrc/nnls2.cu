@@ -123,20 +123,31 @@ __device__ __forceinline__ Sh make_sh(int cap) {
 
 // H(lower tiles) += Pa * Pb'   over the leading nt x nt tiles
 __device__ __noinline__ void rank_update(double *H, const double *Pa, const double *Pb, int nt,
-                                            const unsigned short *tmap) {
+                                         const unsigned short *tmap) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int fr = lane >> 2, fk = lane & 3;
   const int ntiles = (nt * (nt + 1)) >> 1;
-  for (int q = wid; q < ntiles; q += NW) {
-    const int tt = tmap[q];
-    const int ti = tt >> 8, tj = tt & 255;
-    const double a0 = Pa[pan(ti * 8 + fr, fk)], a1 = Pa[pan(ti * 8 + fr, 4 + fk)];
-    const double b0 = Pb[pan(tj * 8 + fr, fk)], b1 = Pb[pan(tj * 8 + fr, 4 + fk)];
-    double2 *cp = reinterpret_cast<double2 *>(H + (q << 6) + swz8(fr, fk * 2));
-    double2 c = *cp;
-    dmma(c.x, c.y, a0, b0);
-    dmma(c.x, c.y, a1, b1);
-    *cp = c;
+  const int coff = swz8(fr, fk * 2);
+  // three tiles in flight per warp: loads of all three first, then their (independent) DMMA chains
+  for (int q = wid; q < ntiles; q += 3 * NW) {
+    const int q1 = q + NW, q2 = q + 2 * NW;
+    const bool h1 = q1 < ntiles, h2 = q2 < ntiles;
+    const int t0 = tmap[q], t1 = tmap[h1 ? q1 : q], t2 = tmap[h2 ? q2 : q];
+    double2 *cp0 = reinterpret_cast<double2 *>(H + (q << 6) + coff);
+    double2 *cp1 = reinterpret_cast<double2 *>(H + ((h1 ? q1 : q) << 6) + coff);
+    double2 *cp2 = reinterpret_cast<double2 *>(H + ((h2 ? q2 : q) << 6) + coff);
+    const int ra0 = ((t0 >> 8) << 3) + fr, rb0 = ((t0 & 255) << 3) + fr;
+    const int ra1 = ((t1 >> 8) << 3) + fr, rb1 = ((t1 & 255) << 3) + fr;
+    const int ra2 = ((t2 >> 8) << 3) + fr, rb2 = ((t2 & 255) << 3) + fr;
+    const double a00 = Pa[pan(ra0, fk)], a01 = Pa[pan(ra0, 4 + fk)], b00 = Pb[pan(rb0, fk)], b01 = Pb[pan(rb0, 4 + fk)];
+    const double a10 = Pa[pan(ra1, fk)], a11 = Pa[pan(ra1, 4 + fk)], b10 = Pb[pan(rb1, fk)], b11 = Pb[pan(rb1, 4 + fk)];
+    const double a20 = Pa[pan(ra2, fk)], a21 = Pa[pan(ra2, 4 + fk)], b20 = Pb[pan(rb2, fk)], b21 = Pb[pan(rb2, 4 + fk)];
+    double2 c0 = *cp0, c1 = *cp1, c2 = *cp2;
+    dmma(c0.x, c0.y, a00, b00); dmma(c1.x, c1.y, a10, b10); dmma(c2.x, c2.y, a20, b20);
+    dmma(c0.x, c0.y, a01, b01); dmma(c1.x, c1.y, a11, b11); dmma(c2.x, c2.y, a21, b21);
+    *cp0 = c0;
+    if (h1) *cp1 = c1;
+    if (h2) *cp2 = c2;
   }
 }
 
@@ -144,22 +155,33 @@ __device__ __noinline__ void rank_update(double *H, const double *Pa, const doub
 __device__ __noinline__ void hmul(const double *H, const double *Pin, double *Pout, int nt) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int fr = lane >> 2, fk = lane & 3;
+  const int off_d0 = swz8(fr, fk), off_d1 = swz8(fr, 4 + fk);      // direct tile (tj <= ti)
+  const int off_t0 = swz8(fk, fr), off_t1 = swz8(4 + fk, fr);      // transposed tile (tj > ti)
   for (int ti = wid; ti < nt; ti += NW) {
-    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
-    for (int tj = 0; tj < nt; ++tj) {
-      double a0, a1;
-      if (tj <= ti) {
-        const int base = tile_base(ti, tj);
-        a0 = H[base + swz8(fr, fk)]; a1 = H[base + swz8(fr, 4 + fk)];
-      } else {
-        const int base = tile_base(tj, ti);
-        a0 = H[base + swz8(fk, fr)]; a1 = H[base + swz8(4 + fk, fr)];
-      }
-      const double b0 = Pin[pan(tj * 8 + fk, fr)], b1 = Pin[pan(tj * 8 + 4 + fk, fr)];
-      if (tj & 1) { dmma(e0, e1, a0, b0); dmma(e0, e1, a1, b1); }
-      else { dmma(c0, c1, a0, b0); dmma(c0, c1, a1, b1); }
+    // four independent accumulator pairs: (tile parity) x (k-step) -> short DMMA dependency chains
+    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0, e00 = 0.0, e01 = 0.0, e10 = 0.0, e11 = 0.0;
+    const int rowbase = (ti * (ti + 1)) >> 1;
+    int tj = 0;
+    for (; tj + 1 < nt; tj += 2) {
+      const int tk = tj + 1;
+      const bool dj = tj <= ti, dk = tk <= ti;
+      const int bj = dj ? ((rowbase + tj) << 6) : (tile_base(tj, ti));
+      const int bk = dk ? ((rowbase + tk) << 6) : (tile_base(tk, ti));
+      const double aj0 = H[bj + (dj ? off_d0 : off_t0)], aj1 = H[bj + (dj ? off_d1 : off_t1)];
+      const double ak0 = H[bk + (dk ? off_d0 : off_t0)], ak1 = H[bk + (dk ? off_d1 : off_t1)];
+      const double pj0 = Pin[pan(tj * 8 + fk, fr)], pj1 = Pin[pan(tj * 8 + 4 + fk, fr)];
+      const double pk0 = Pin[pan(tk * 8 + fk, fr)], pk1 = Pin[pan(tk * 8 + 4 + fk, fr)];
+      dmma(c00, c01, aj0, pj0); dmma(c10, c11, aj1, pj1);
+      dmma(e00, e01, ak0, pk0); dmma(e10, e11, ak1, pk1);
     }
-    *reinterpret_cast<double2 *>(Pout + pan(ti * 8 + fr, fk * 2)) = make_double2(c0 + e0, c1 + e1);
+    if (tj < nt) {
+      const bool dj = tj <= ti;
+      const int bj = dj ? ((rowbase + tj) << 6) : (tile_base(tj, ti));
+      const double aj0 = H[bj + (dj ? off_d0 : off_t0)], aj1 = H[bj + (dj ? off_d1 : off_t1)];
+      dmma(c00, c01, aj0, Pin[pan(tj * 8 + fk, fr)]); dmma(c10, c11, aj1, Pin[pan(tj * 8 + 4 + fk, fr)]);
+    }
+    *reinterpret_cast<double2 *>(Pout + pan(ti * 8 + fr, fk * 2)) =
+        make_double2((c00 + c10) + (e00 + e10), (c01 + c11) + (e01 + e11));
   }
 }
 
@@ -292,13 +314,16 @@ __device__ __noinline__ bool block_add(int cap, const double *G, int ldg, const 
   SUBTICK(PH_A_HMUL);
   if (wid < 4) {                                // S partials = V' U over interleaved k-steps
     const int fr = lane >> 2, fk = lane & 3;
-    double c0 = 0.0, c1 = 0.0;
-    for (int ks = wid; ks < nt * 2; ks += 4) {
-      const int rw = ks * 4 + fk;
+    double c0 = 0.0, c1 = 0.0, g0 = 0.0, g1 = 0.0;
+    int ks = wid;
+    for (; ks + 4 < nt * 2; ks += 8) {
+      const int rw = ks * 4 + fk, rx = (ks + 4) * 4 + fk;
       dmma(c0, c1, s.Pa[pan(rw, fr)], s.Pb[pan(rw, fr)]);
+      dmma(g0, g1, s.Pa[pan(rx, fr)], s.Pb[pan(rx, fr)]);
     }
-    s.Spart[wid * 64 + fr * 8 + fk * 2] = c0;
-    s.Spart[wid * 64 + fr * 8 + fk * 2 + 1] = c1;
+    if (ks < nt * 2) { const int rw = ks * 4 + fk; dmma(c0, c1, s.Pa[pan(rw, fr)], s.Pb[pan(rw, fr)]); }
+    s.Spart[wid * 64 + fr * 8 + fk * 2] = c0 + g0;
+    s.Spart[wid * 64 + fr * 8 + fk * 2 + 1] = c1 + g1;
   } else if (wid < 12) {                        // rho_i = c_i - V[:,i]' w
     const int i = wid - 4;
     double acc = 0.0;
@@ -528,28 +553,30 @@ __global__ void __launch_bounds__(T, 1) k2v2_orthant_chains(const K2Args A) {
           if (!ok) break;
         }
         r_valid = false;
-        // ---- infeasibility flags: passive variables with the wrong sign, active ones whose
-        //      sign-adjusted gradient is positive
-        for (int m = tid; m < Mp; m += T) {
-          const int sl = s.pos[m], sg = s.sg[m];
-          int f = 0;
-          if (sl >= 0) { if (sg == 0 || (double)sg * s.w[m] < 0.0) f = 1; }
-          else if (sg != 0 && s.vflag[m] != 3 && (double)sg * s.r[m] > told) f = 2;
-          if (s.vflag[m] != 3) s.vflag[m] = (signed char)f;
-        }
-        __syncthreads();
-        // ---- plan: ordered lists (index order), pivoting rule, slots for the additions, new high-water
-        //      mark.  One warp per 32 variables / 32 slots; four short barrier-separated steps.
+        // ---- plan: infeasibility flags (passive variables with the wrong sign; active ones whose
+        //      sign-adjusted gradient is positive), ordered lists in index order, pivoting rule, slots for
+        //      the additions, new high-water mark.  One warp per 32 variables / 32 slots.  The first step
+        //      also reduces c_F' w_F, so a converged orthant costs a single barrier here.
         const int nvw = (Mp + 31) >> 5, nsw = cap >> 5 ? (cap + 31) >> 5 : 1;
         int f_my = 0, rank_r = 0, rank_a = 0;
         if (wid < nvw) {
           const int m = (wid << 5) + lane;
-          f_my = (m < Mp) ? s.vflag[m] : 0;
+          double cw = 0.0;
+          if (m < Mp) {
+            const int sl = s.pos[m], sg = s.sg[m];
+            if (sl >= 0) { cw = s.cs[m] * s.w[m]; if (sg == 0 || (double)sg * s.w[m] < 0.0) f_my = 1; }
+            else if (sg != 0 && s.vflag[m] != 3 && (double)sg * s.r[m] > told) f_my = 2;
+          }
           const unsigned br = __ballot_sync(0xffffffffu, f_my == 1);
           const unsigned ba = __ballot_sync(0xffffffffu, f_my == 2);
           rank_r = __popc(br & ((1u << lane) - 1)); rank_a = __popc(ba & ((1u << lane) - 1));
           const unsigned any = br | ba;
-          if (lane == 0) { s.pl[wid] = __popc(br) | (__popc(ba) << 16); s.pl[8 + wid] = any ? (wid << 5) + 31 - __clz(any) : -1; }
+          cw = warp_sum(cw);
+          if (lane == 0) {
+            s.pl[wid] = __popc(br) | (__popc(ba) << 16);
+            s.pl[8 + wid] = any ? (wid << 5) + 31 - __clz(any) : -1;
+            s.red[wid] = cw;
+          }
         }
         __syncthreads();
         int nr = 0, na = 0, mxi = -1, pref_r = 0, pref_a = 0;
@@ -560,6 +587,7 @@ __global__ void __launch_bounds__(T, 1) k2v2_orthant_chains(const K2Args A) {
           mxi = max(mxi, s.pl[8 + q]);
         }
         const int nv = nr + na;
+        if (nv == 0) { r_valid = true; PH_TICK(PH_PLAN); break; }   // KKT point; r stays valid for the next orthant
         const bool single = nv > 0 && !(nv < t_best) && pbar < 1;    // Murty's rule: only the highest index moves
         if (!single) {
           if (f_my == 1) { const int sl = s.pos[(wid << 5) + lane]; s.lst[pref_r + rank_r] = sl; s.smark[sl] = 1; }
@@ -593,7 +621,6 @@ __global__ void __launch_bounds__(T, 1) k2v2_orthant_chains(const K2Args A) {
         __syncthreads();
         int hw_after = 0;
         for (int q = 0; q < nsw; ++q) hw_after = max(hw_after, s.pl[24 + q]);
-        if (nv == 0) { r_valid = true; PH_TICK(PH_PLAN); break; }   // KKT point; r stays valid for the next orthant
         if (nv < t_best) { t_best = nv; pbar = 3; }
         else if (pbar >= 1) { --pbar; }
         const int nt_op = (max(hwm, hw_after) + 7) >> 3;
@@ -621,15 +648,10 @@ __global__ void __launch_bounds__(T, 1) k2v2_orthant_chains(const K2Args A) {
       }
       if (!ok) STAT_ADD(ST_NOCONV, 1);
 
-      // ---- objective  sqrt(yy - c_F' w_F)   (= norm(Xa w - ya) at the KKT point, Opt.jl:90)
-      double acc = 0.0;
-      for (int m = tid; m < Mp; m += T) if (s.pos[m] >= 0) acc = fma(s.cs[m], s.w[m], acc);
-      acc = warp_sum(acc);
-      if (lane == 0) s.red[wid] = acc;
-      __syncthreads();
+      // ---- objective  sqrt(yy - c_F' w_F)   (= norm(Xa w - ya) at the KKT point, Opt.jl:90); the
+      //      partial sums were left in s.red by the plan step that found no violation
       double tot = 0.0;
-#pragma unroll
-      for (int q = 0; q < NW; ++q) tot += s.red[q];
+      for (int q = 0; q < ((Mp + 31) >> 5); ++q) tot += s.red[q];
       const double obj = ok ? sqrt(fmax(yy - tot, 0.0)) : __longlong_as_double(0x7ff8000000000000ll);
       const long long rel = b - A.b_begin;
       if (A.all_obj && tid == 0) A.all_obj[rel] = obj;
