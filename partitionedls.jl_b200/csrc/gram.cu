@@ -10,6 +10,10 @@
 // Layout: Z is column-major with ldz % 16 == 0, rows [N, ldz) and columns [M+2, zcols_pad) are zero,
 // so tiles never need bounds checks.  Only lower-triangle 64x64 tiles are computed; the row range is
 // split into chunks (split-K) whose partial tiles are summed in a fixed order by the reduce kernel.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace pls {
@@ -104,6 +108,223 @@ __global__ void __launch_bounds__(T1) k1_gram_tiles(const double *__restrict__ Z
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K1 v2: TMA-fed.  One producer warp streams 16-row x 64-column boxes of Z (128 B inner dimension,
+// SWIZZLE_128B) through a 3-stage mbarrier ring; four consumer warps run the DMMA tiles straight
+// from the swizzled boxes.  Within every 8-column block the MMA row r reads column perm(r) =
+// (r < 4 ? 2r : 2(r-4)+1): under the 128 B swizzle that makes each half-warp's fragment load hit
+// all 16 banks exactly once.  MMA tiles that lie entirely in the zero padding or strictly above
+// the diagonal are skipped (warp-uniform predicates).
+// ------------------------------------------------------------------------------------------------
+constexpr int KS = 16;            // rows per TMA box (128 B)
+constexpr int BOXES = 2;          // boxes per stage and side -> 32 rows per stage
+constexpr int STAGES = 2;
+constexpr int T1B = 160;          // 4 consumer warps + 1 producer warp
+constexpr int BOX_DOUBLES = BT * KS;                  // 1024 doubles = 8 KB
+constexpr int STAGE_DOUBLES = 2 * BOXES * BOX_DOUBLES; // A boxes then B boxes: 32 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+// element (column c of the 64-column box, row k of the 16-row box) under SWIZZLE_128B
+__device__ __forceinline__ int box_off(int c, int k) { return c * KS + ((((k >> 1) ^ (c & 7)) << 1) | (k & 1)); }
+__device__ __forceinline__ int perm8(int r) { return r < 4 ? 2 * r : 2 * (r - 4) + 1; }
+
+__global__ void __launch_bounds__(T1B) k1_gram_tiles_tma(const __grid_constant__ CUtensorMap zmap,
+                                                         long long rows_per_chunk, long long n_rows_pad,
+                                                         int n_tiles, int zcols, double *__restrict__ part) {
+  extern __shared__ __align__(1024) unsigned char smem_k1[];
+  double *stage_mem = reinterpret_cast<double *>(smem_k1);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_k1 + (size_t)STAGES * STAGE_DOUBLES * sizeof(double));
+  uint64_t *empty = full + STAGES;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  int tile = blockIdx.x, ti = 0;
+  while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
+  const int tj = tile - ti * (ti + 1) / 2;
+  const bool diag = (ti == tj);
+  const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+  long long r1 = r0 + rows_per_chunk;
+  if (r1 > n_rows_pad) r1 = n_rows_pad;
+  const int n_stages = (int)((r1 - r0) / (KS * BOXES));
+
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (wid == 4) {
+    // ---------------- producer ----------------
+    if (lane == 0) {
+      const uint32_t bytes = (diag ? 1 : 2) * BOXES * BOX_DOUBLES * sizeof(double);
+      for (int it = 0; it < n_stages; ++it) {
+        const int st = it % STAGES;
+        if (it >= STAGES) mbar_wait(&empty[st], ((it / STAGES) - 1) & 1);
+        mbar_expect_tx(&full[st], bytes);
+        double *base = stage_mem + (size_t)st * STAGE_DOUBLES;
+        const int row = (int)(r0 + (long long)it * KS * BOXES);
+#pragma unroll
+        for (int bx = 0; bx < BOXES; ++bx) {
+          tma_load_2d(base + bx * BOX_DOUBLES, &zmap, row + bx * KS, ti * BT, &full[st]);
+          if (!diag) tma_load_2d(base + (BOXES + bx) * BOX_DOUBLES, &zmap, row + bx * KS, tj * BT, &full[st]);
+        }
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers ----------------
+  const int fr = lane >> 2, fk = lane & 3;
+  const int pc = perm8(fr);
+  double *out = part + ((size_t)blockIdx.y * n_tiles + tile) * (BT * BT);
+  if (diag) {
+    // Diagonal tile: only the 36 MMA tiles on or below the diagonal are needed.  Warp w takes MMA
+    // rows 7-w and w (8-w + w+1 = 9 tiles each): perfectly balanced, no wasted tensor work.
+    const int ra = 7 - wid, rb = wid;
+    const bool live_a = (ti * BT + ra * 8) < zcols, live_b = (ti * BT + rb * 8) < zcols;
+    double accA[8][2], accB[4][2];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) accA[c][0] = accA[c][1] = 0.0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) accB[c][0] = accB[c][1] = 0.0;
+    for (int it = 0; it < n_stages; ++it) {
+      const int st = it % STAGES;
+      mbar_wait(&full[st], (it / STAGES) & 1);
+      const double *As = stage_mem + (size_t)st * STAGE_DOUBLES;
+      if (live_a || live_b) {
+#pragma unroll
+        for (int bx = 0; bx < BOXES; ++bx) {
+#pragma unroll
+          for (int kk = 0; kk < KS / 4; ++kk) {
+            const double a_ra = As[bx * BOX_DOUBLES + box_off(ra * 8 + pc, kk * 4 + fk)];
+            const double a_rb = As[bx * BOX_DOUBLES + box_off(rb * 8 + pc, kk * 4 + fk)];
+            double bq[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) if (c <= ra) bq[c] = As[bx * BOX_DOUBLES + box_off(c * 8 + pc, kk * 4 + fk)];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) if (c <= ra && live_a) dmma(accA[c][0], accA[c][1], a_ra, bq[c]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if (c <= rb && live_b) dmma(accB[c][0], accB[c][1], a_rb, bq[c]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[st]);
+    }
+    const int p0 = perm8(fk * 2), p1 = perm8(fk * 2 + 1);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) if (c <= ra) {
+      out[(size_t)(c * 8 + p0) * BT + ra * 8 + pc] = accA[c][0];
+      out[(size_t)(c * 8 + p1) * BT + ra * 8 + pc] = accA[c][1];
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) if (c <= rb) {
+      out[(size_t)(c * 8 + p0) * BT + rb * 8 + pc] = accB[c][0];
+      out[(size_t)(c * 8 + p1) * BT + rb * 8 + pc] = accB[c][1];
+    }
+    return;
+  }
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  const int wi = (wid >> 1) * 32, wj = (wid & 1) * 32;
+  // warp-uniform activity of the 4 x 4 MMA tiles: inside the live columns
+  unsigned act = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if ((ti * BT + wi + i * 8) < zcols && (tj * BT + wj + j * 8) < zcols) act |= 1u << (i * 4 + j);
+
+  for (int it = 0; it < n_stages; ++it) {
+    const int st = it % STAGES;
+    mbar_wait(&full[st], (it / STAGES) & 1);
+    const double *As = stage_mem + (size_t)st * STAGE_DOUBLES;
+    const double *Bs = As + BOXES * BOX_DOUBLES;
+    if (act) {
+#pragma unroll
+      for (int bx = 0; bx < BOXES; ++bx) {
+#pragma unroll
+        for (int kk = 0; kk < KS / 4; ++kk) {
+          double a[4], b[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) a[i] = As[bx * BOX_DOUBLES + box_off(wi + i * 8 + pc, kk * 4 + fk)];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) b[j] = Bs[bx * BOX_DOUBLES + box_off(wj + j * 8 + pc, kk * 4 + fk)];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (act & (1u << (i * 4 + j))) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int row = wi + i * 8 + pc;                    // permuted MMA row -> column of tile ti
+      const int c0 = wj + j * 8 + perm8(fk * 2), c1 = wj + j * 8 + perm8(fk * 2 + 1);
+      out[(size_t)c0 * BT + row] = acc[i][j][0];
+      out[(size_t)c1 * BT + row] = acc[i][j][1];
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+bool make_zmap(const Problem &pb, CUtensorMap *map) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess ||
+        qr != cudaDriverEntryPointSuccess || !p) {
+      cudaGetLastError();
+      return false;
+    }
+    fn = (EncodeTiledFn)p;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)pb.ldz, (cuuint64_t)pb.zcols_pad};
+  const cuuint64_t gstr[1] = {(cuuint64_t)pb.ldz * sizeof(double)};
+  const cuuint32_t box[2] = {KS, BT};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, pb.Z, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // S[i + j*zc] (i >= j) = sum over chunks of the partial tiles, fixed order.
 __global__ void k1_reduce(const double *__restrict__ part, int n_tiles, int n_chunks, int zc,
                           double *__restrict__ S) {
@@ -119,51 +340,48 @@ __global__ void k1_reduce(const double *__restrict__ part, int n_tiles, int n_ch
   S[idx] = s;
 }
 
-// G = S (mirrored) + eta * |groups(i) & groups(j)|;  c = S[y row];  scal = {yy, max|c|, max diag}
+// G = S (mirrored) + eta * |groups(i) & groups(j)|;  c = S[y row];
+// scal = {yy, max|c|, max diag, non-finite flag} (scal[1..3] zeroed before launch; max via
+// atomicMax on the bit pattern, valid for non-negative doubles)
 __global__ void k1_finalize(const double *__restrict__ S, int zc, int Mp, double eta,
                             const uint64_t *__restrict__ gmask, double *__restrict__ G, int ldg,
-                            double *__restrict__ c) {
+                            double *__restrict__ c, double *__restrict__ scal) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)ldg * Mp) return;
-  const int i = (int)(idx % ldg), j = (int)(idx / ldg);
-  if (i >= Mp) { G[idx] = 0.0; return; }
-  const int hi = i > j ? i : j, lo = i > j ? j : i;
-  double g = S[(size_t)lo * zc + hi];
-  if (eta != 0.0) g += eta * (double)__popcll(gmask[i] & gmask[j]);
-  G[idx] = g;
-  if (j == 0) c[i] = S[(size_t)i * zc + (Mp)];   // row index of y in Z'Z is Mp = M+1
-}
-
-__global__ void k1_scalars(const double *__restrict__ S, int zc, int Mp, const double *__restrict__ c,
-                           const double *__restrict__ G, int ldg, double *__restrict__ scal) {
-  __shared__ double sm[256], sd[256];
-  __shared__ int bad;
-  if (threadIdx.x == 0) bad = 0;
-  __syncthreads();
-  double mx = 0.0, md = 0.0;
-  int nonfinite = 0;
-  for (int i = threadIdx.x; i < Mp; i += 256) {
-    mx = fmax(mx, fabs(c[i]));
-    md = fmax(md, fabs(G[(size_t)i * ldg + i]));
-    if (!isfinite(c[i])) nonfinite = 1;
-  }
-  for (long long idx = threadIdx.x; idx < (long long)Mp * Mp; idx += 256)
-    if (!isfinite(G[(size_t)(idx / Mp) * ldg + idx % Mp])) nonfinite = 1;
-  if (nonfinite) bad = 1;
-  sm[threadIdx.x] = mx; sd[threadIdx.x] = md;
-  __syncthreads();
-  for (int st = 128; st; st >>= 1) {
-    if (threadIdx.x < st) {
-      sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + st]);
-      sd[threadIdx.x] = fmax(sd[threadIdx.x], sd[threadIdx.x + st]);
+  double mc = 0.0, md = 0.0;
+  int bad = 0;
+  if (idx < (long long)ldg * Mp) {
+    const int i = (int)(idx % ldg), j = (int)(idx / ldg);
+    if (i >= Mp) G[idx] = 0.0;
+    else {
+      const int hi = i > j ? i : j, lo = i > j ? j : i;
+      double g = S[(size_t)lo * zc + hi];
+      if (eta != 0.0) g += eta * (double)__popcll(gmask[i] & gmask[j]);
+      G[idx] = g;
+      if (!isfinite(g)) bad = 1;
+      if (i == j) md = fabs(g);
+      if (j == 0) {
+        const double ci = S[(size_t)i * zc + Mp];     // row index of y in Z'Z is Mp = M+1
+        c[i] = ci;
+        mc = fabs(ci);
+        if (!isfinite(ci)) bad = 1;
+      }
     }
-    __syncthreads();
+    if (idx == 0) {
+      const double yy = S[(size_t)Mp * zc + Mp];
+      scal[0] = yy;
+      if (!isfinite(yy)) bad = 1;
+    }
   }
-  if (threadIdx.x == 0) {
-    scal[0] = S[(size_t)Mp * zc + Mp];
-    scal[1] = sm[0];
-    scal[2] = sd[0];
-    scal[3] = (bad || !isfinite(scal[0])) ? 1.0 : 0.0;   // non-finite input flag
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    mc = fmax(mc, __shfl_xor_sync(0xffffffffu, mc, o));
+    md = fmax(md, __shfl_xor_sync(0xffffffffu, md, o));
+    bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (mc > 0.0 && isfinite(mc)) atomicMax(reinterpret_cast<unsigned long long *>(scal + 1), (unsigned long long)__double_as_longlong(mc));
+    if (md > 0.0 && isfinite(md)) atomicMax(reinterpret_cast<unsigned long long *>(scal + 2), (unsigned long long)__double_as_longlong(md));
+    if (bad) atomicMax(reinterpret_cast<unsigned long long *>(scal + 3), (unsigned long long)__double_as_longlong(1.0));
   }
 }
 
@@ -177,7 +395,7 @@ int k1_gram_build(Problem &pb, cudaStream_t st, int *launches) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   // ~4 waves of CTAs (several CTAs fit per SM), chunks of whole stages
-  long long want_chunks = (4ll * 4 * sms + n_tiles - 1) / n_tiles;
+  long long want_chunks = (2ll * 3 * sms + n_tiles - 1) / n_tiles;
   long long max_chunks = n_rows_pad / (KB * 8);
   if (max_chunks < 1) max_chunks = 1;
   if (want_chunks > max_chunks) want_chunks = max_chunks;
@@ -192,7 +410,15 @@ int k1_gram_build(Problem &pb, cudaStream_t st, int *launches) {
     pb.part_bytes = need;
   }
   dim3 grid(n_tiles, n_chunks);
-  k1_gram_tiles<<<grid, T1, 0, st>>>(pb.Z, pb.ldz, rows_per_chunk, n_rows_pad, n_tiles, pb.part);
+  const char *impl = getenv("PLS_K1_IMPL");
+  CUtensorMap zmap;
+  if (!(impl && strcmp(impl, "v1") == 0) && make_zmap(pb, &zmap)) {
+    const size_t smem = (size_t)STAGES * STAGE_DOUBLES * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
+    PLS_CUDA_TRY(cudaFuncSetAttribute(k1_gram_tiles_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k1_gram_tiles_tma<<<grid, T1B, smem, st>>>(zmap, rows_per_chunk, n_rows_pad, n_tiles, pb.zcols, pb.part);
+  } else {
+    k1_gram_tiles<<<grid, T1, 0, st>>>(pb.Z, pb.ldz, rows_per_chunk, n_rows_pad, n_tiles, pb.part);
+  }
   PLS_CUDA_TRY(cudaGetLastError());
   ++*launches;
   const int zc = pb.zcols;
@@ -205,11 +431,9 @@ int k1_gram_build(Problem &pb, cudaStream_t st, int *launches) {
 
 int k1_gram_finalize(Problem &pb, cudaStream_t st, int *launches) {
   const long long tot = (long long)pb.ldg * pb.Mp;
+  PLS_CUDA_TRY(cudaMemsetAsync(pb.scal, 0, sizeof(double) * 4, st));
   k1_finalize<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(pb.S, pb.zcols, pb.Mp, pb.eta, pb.gmask,
-                                                            pb.G, pb.ldg, pb.c);
-  PLS_CUDA_TRY(cudaGetLastError());
-  ++*launches;
-  k1_scalars<<<1, 256, 0, st>>>(pb.S, pb.zcols, pb.Mp, pb.c, pb.G, pb.ldg, pb.scal);
+                                                            pb.G, pb.ldg, pb.c, pb.scal);
   PLS_CUDA_TRY(cudaGetLastError());
   ++*launches;
   pb.gram_ready = true;
