@@ -76,6 +76,9 @@ struct K2Args {
   unsigned long long *chain_counter;   // dynamic chain scheduler (zeroed before launch)
   int cap;                       // slots of H that fit in shared memory
   double *hspill;                // [grid][Mp*Mp] or null
+  int qs;                        // v3: tiles of the packed inverse kept in shared memory
+  double *hglob;                 // v3: [grid][hstride] global tiles (L2-resident), or null
+  size_t hstride;
   double *cta_obj; long long *cta_b; double *cta_w;
   double *all_obj; double *all_alpha;   // nullable, indexed by (b - b_begin)
   unsigned long long *counters;
@@ -92,6 +95,11 @@ int k2_solve_range(const Problem &pb, const double *G, int ldg, const double *c,
 // (M' <= 208); v1 = rank-1 updates on a dense inverse with a global-memory spill path (any M').
 int k2v2_launch(const K2Args &A, int grid, cudaStream_t st);
 int k2v2_config(int Mp, int *cap, size_t *smem, int *occ);
+// v3 = v2's algorithm with the inverse split between shared memory and an L2-resident global slice,
+// any thread count, M' <= 1024 (nnls3.cu)
+struct K3Plan { int cap, qs, T, mode, occ, variant; size_t smem, hstride; };
+int k2v3_plan(int Mp, K3Plan *pl);
+int k2v3_launch(const K2Args &A, const K3Plan &pl, int grid, cudaStream_t st);
 int k4_residual(const Problem &pb, SolveWs &ws, const double *d_w, double *d_ssq, int sm_count,
                 cudaStream_t st, int *launches);
 

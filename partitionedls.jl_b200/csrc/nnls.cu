@@ -460,13 +460,25 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
                    int64_t b_count, double *d_all_obj, double *d_all_alpha, int sm_count,
                    cudaStream_t st, int *launches) {
   if (b_count <= 0) { set_error("k2: empty orthant range"); return PLS_EINVAL; }
-  // variant: v2 (block pivoting, DMMA, tile-packed inverse) for M' <= 208, else v1
+  // variant (PLS_K2_IMPL = v1 | v2 | v3 overrides):
+  //   v2  block pivoting, DMMA, tile-packed inverse entirely in shared memory   (M' <= 208)
+  //   v3  same algorithm, inverse split between shared memory and L2           (M' <= 1024)
+  //   v1  rank-1 updates on a dense inverse with a global spill path           (any M')
   const char *impl = getenv("PLS_K2_IMPL");
-  bool use_v2 = !(impl && strcmp(impl, "v1") == 0);
+  int variant = Mp <= 208 ? 2 : (Mp <= 1024 ? 3 : 1);
+  if (impl && strcmp(impl, "v1") == 0) variant = 1;
+  if (impl && strcmp(impl, "v2") == 0 && Mp <= 208) variant = 2;
+  if (impl && strcmp(impl, "v3") == 0 && Mp <= 1024) variant = 3;
   int cap = Mp, occ = 1;
   size_t smem = 0;
-  if (use_v2 && k2v2_config(Mp, &cap, &smem, &occ) != PLS_OK) use_v2 = false;
-  if (!use_v2) {
+  K3Plan plan3;
+  if (variant == 2 && k2v2_config(Mp, &cap, &smem, &occ) != PLS_OK) variant = 3;
+  if (variant == 3) {
+    const int rc = k2v3_plan(Mp, &plan3);
+    if (rc == PLS_EUNSUPPORTED) variant = 1; else if (rc) return rc;
+    else { cap = plan3.cap; occ = plan3.occ; smem = plan3.smem; }
+  }
+  if (variant == 1) {
     int dev = 0, max_smem = 0;
     PLS_CUDA_TRY(cudaGetDevice(&dev));
     PLS_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -485,7 +497,8 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
     PLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_orthant_chains, T2, smem));
     if (occ < 1) occ = 1;
   }
-  long long grid = (long long)sm_count * occ;
+  const long long max_grid = (long long)sm_count * occ;
+  long long grid = max_grid;
 
   // Gray chains: aligned power-of-two blocks of orthants.  Long enough to amortise the cold
   // start, short enough that every CTA gets >= ~8 chains from the dynamic scheduler.
@@ -499,25 +512,24 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   if (grid > n_chains) grid = n_chains;
 
   // per-CTA workspaces
-  if (grid > ws.max_ctas || Mp != ws.Mp) {
+  if (max_grid > ws.max_ctas || Mp != ws.Mp) {
     if (ws.cta_obj) cudaFree(ws.cta_obj);
     if (ws.cta_b) cudaFree(ws.cta_b);
     if (ws.cta_w) cudaFree(ws.cta_w);
     ws.cta_obj = nullptr; ws.cta_b = nullptr; ws.cta_w = nullptr; ws.max_ctas = 0;
-    const long long n = (long long)sm_count * occ;
-    PLS_CUDA_TRY(cudaMalloc(&ws.cta_obj, sizeof(double) * n));
-    PLS_CUDA_TRY(cudaMalloc(&ws.cta_b, sizeof(long long) * n));
-    PLS_CUDA_TRY(cudaMalloc(&ws.cta_w, sizeof(double) * n * Mp));
-    ws.max_ctas = (int)n; ws.Mp = Mp;
+    PLS_CUDA_TRY(cudaMalloc(&ws.cta_obj, sizeof(double) * max_grid));
+    PLS_CUDA_TRY(cudaMalloc(&ws.cta_b, sizeof(long long) * max_grid));
+    PLS_CUDA_TRY(cudaMalloc(&ws.cta_w, sizeof(double) * max_grid * Mp));
+    ws.max_ctas = (int)max_grid; ws.Mp = Mp;
   }
-  if (!use_v2 && cap < Mp) {
-    const size_t need = (size_t)ws.max_ctas * Mp * Mp * sizeof(double);
-    if (need > ws.hspill_bytes) {
-      if (ws.hspill) cudaFree(ws.hspill);
-      ws.hspill = nullptr; ws.hspill_bytes = 0;
-      PLS_CUDA_TRY(cudaMalloc(&ws.hspill, need));
-      ws.hspill_bytes = need;
-    }
+  size_t hneed = 0;
+  if (variant == 1 && cap < Mp) hneed = (size_t)max_grid * Mp * Mp * sizeof(double);
+  if (variant == 3) hneed = (size_t)max_grid * plan3.hstride * sizeof(double);
+  if (hneed > ws.hspill_bytes) {
+    if (ws.hspill) cudaFree(ws.hspill);
+    ws.hspill = nullptr; ws.hspill_bytes = 0;
+    PLS_CUDA_TRY(cudaMalloc(&ws.hspill, hneed));
+    ws.hspill_bytes = hneed;
   }
   if (!ws.counters) {
     PLS_CUDA_TRY(cudaMalloc(&ws.counters, sizeof(unsigned long long) * (CNT_NUM + 1 + 24)));
@@ -531,11 +543,16 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   A.b_begin = b_begin; A.chain_log2 = chain_log2; A.n_chains = n_chains;
   A.chain_counter = ws.counters + CNT_NUM;
   A.cap = cap;
-  A.hspill = (!use_v2 && cap < Mp) ? ws.hspill : nullptr;
+  A.hspill = (variant == 1 && cap < Mp) ? ws.hspill : nullptr;
+  A.qs = 0; A.hglob = nullptr; A.hstride = 0;
   A.cta_obj = ws.cta_obj; A.cta_b = ws.cta_b; A.cta_w = ws.cta_w;
   A.all_obj = d_all_obj; A.all_alpha = d_all_alpha; A.counters = ws.counters;
-  if (use_v2) {
+  if (variant == 2) {
     const int rc = k2v2_launch(A, (int)grid, st);
+    if (rc) return rc;
+  } else if (variant == 3) {
+    A.qs = plan3.qs; A.hglob = plan3.hstride ? ws.hspill : nullptr; A.hstride = plan3.hstride;
+    const int rc = k2v3_launch(A, plan3, (int)grid, st);
     if (rc) return rc;
   } else {
     k2_orthant_chains<<<(unsigned)grid, T2, smem, st>>>(A);

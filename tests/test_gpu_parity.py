@@ -15,16 +15,30 @@ CASES = ["rand_a", "rand_b", "rand_c_corr", "rand_d_overlap"]
 RTOL = 1e-9
 
 
-@pytest.fixture(params=["v2", "v1"])
+K2_VARIANTS = {
+    # name: environment of the K2 dispatcher (nnls.cu: k2_solve_range, nnls3.cu: k2v3_plan)
+    "v2": {"PLS_K2_IMPL": "v2"},                                        # inverse in shared memory, M' <= 208
+    "v1": {"PLS_K2_IMPL": "v1"},                                        # rank-1 updates (any M')
+    "v3g": {"PLS_K2_IMPL": "v3", "PLS_K3_QS": "0"},                     # inverse in L2 (global), T = 256
+    "v3h": {"PLS_K2_IMPL": "v3", "PLS_K3_QS": "10"},                    # first 10 tiles shared, rest global
+    "v3s512": {"PLS_K2_IMPL": "v3", "PLS_K3_QS": "-1", "PLS_K3_T": "512"},  # as much as fits shared, T = 512
+}
+_K2_KEYS = ("PLS_K2_IMPL", "PLS_K3_QS", "PLS_K3_T", "PLS_K3_MINB")
+
+
+@pytest.fixture(params=list(K2_VARIANTS))
 def k2impl(request):
-    """Both K2 variants: v2 = block pivoting with DMMA updates (M' <= 208), v1 = rank-1 updates."""
-    old = os.environ.get("PLS_K2_IMPL")
-    os.environ["PLS_K2_IMPL"] = request.param
+    """Every K2 variant must give the same answers."""
+    old = {k: os.environ.get(k) for k in _K2_KEYS}
+    for k in _K2_KEYS:
+        os.environ.pop(k, None)
+    os.environ.update(K2_VARIANTS[request.param])
     yield request.param
-    if old is None:
-        os.environ.pop("PLS_K2_IMPL", None)
-    else:
-        os.environ["PLS_K2_IMPL"] = old
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
 
 
 def _close(a, b, scale=None):
@@ -144,6 +158,22 @@ def test_large_passive_sets(ctx, oracle, M, k2impl):
     assert np.all(np.abs(r["alphas"] - ref["alphas"]) <= RTOL * scale + 1e-300)
     if k2impl == "v1":
         assert (np.count_nonzero(r["alphas"], axis=1).max() > 160) == (r["stats"]["spills"] > 0)
+
+
+@pytest.mark.parametrize("shape", [(1500, 512, 3, 0.0), (900, 300, 4, 1e-3)])
+def test_wide_problems_default_path(ctx, oracle, shape):
+    """M' = 513 (BASELINE configs[2]'s width) and M' = 301: beyond the all-shared-memory kernel, the
+    default dispatch takes the L2-resident inverse (v3)."""
+    o, oc = oracle
+    N, M, K, eta = shape
+    X, y, P = o.make_synthetic(N, M, K, seed=555 + M, mixed_sign=True)
+    ref = oc.opt_fit(X, y, P, eta, want_alpha=True)
+    r = ctx.opt_fit(X, y, P, eta=eta, return_all=True)
+    assert r["b_best"] == ref["b_best"] and abs(r["opt"] - ref["obj_best"]) <= RTOL * ref["obj_best"]
+    assert np.allclose(r["objs"], ref["objs"], rtol=RTOL, atol=1e-6 * np.linalg.norm(y))
+    scale = np.abs(ref["alphas"]).max(axis=1, keepdims=True)
+    assert np.all(np.abs(r["alphas"] - ref["alphas"]) <= RTOL * scale + 1e-300)
+    assert r["stats"]["spills"] == 0
 
 
 def test_stagewise_equals_one_call_and_two_rank_split(ctx, oracle):
