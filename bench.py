@@ -60,8 +60,8 @@ def load_peaks():
 
 def ncu_dram_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the K2 launch from the committed ncu --set full
-    capture (profiles/r01_v2c_k2_raw_summary.txt); None if the summary is missing."""
-    p = os.path.join(ROOT, "profiles", "r01_v2c_k2_raw_summary.txt")
+    capture (profiles/r01_v3_k2_raw_summary.txt); None if the summary is missing."""
+    p = os.path.join(ROOT, "profiles", "r01_v3_k2_raw_summary.txt")
     if not os.path.exists(p):
         return None
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -266,7 +266,7 @@ def run_native(args, rank, world, local_rank):
                 "d2h_bytes_per_step": int((Mp + 4 + 10) * 8 * world)},
         "gpu_launches": int(st["kernel_launches"] * args.steps * world),
         "roofline": {
-            "kernel": "k2v2_orthant_chains (batched orthant NNLS: FP64 DMMA + DFMA; tcgen05 has no f64 kind)",
+            "kernel": "k2v3_orthant_chains (batched orthant NNLS, block pivoting: FP64 DMMA rank-8 updates + DFMA gradient; tcgen05 has no f64 kind)",
             "bound": "tensor", "achieved": k2_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": k2_tflops / fp64_peak if fp64_peak else None, "traffic": ncu_dram_traffic(),
             "peak_source": "FP64 DFMA peak measured by tools/fp64_peak.cu on this pool (profiles/fp64_peaks_r01.json); MEASURED_PEAKS.json holds no FP64 figure",

@@ -465,7 +465,7 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   //   v3  same algorithm, inverse split between shared memory and L2           (M' <= 1024)
   //   v1  rank-1 updates on a dense inverse with a global spill path           (any M')
   const char *impl = getenv("PLS_K2_IMPL");
-  int variant = Mp <= 208 ? 2 : (Mp <= 1024 ? 3 : 1);
+  int variant = Mp <= 1024 ? 3 : 1;
   if (impl && strcmp(impl, "v1") == 0) variant = 1;
   if (impl && strcmp(impl, "v2") == 0 && Mp <= 208) variant = 2;
   if (impl && strcmp(impl, "v3") == 0 && Mp <= 1024) variant = 3;
@@ -505,7 +505,8 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   int align_log2 = 0;
   while (align_log2 < 62 && (((uint64_t)b_begin | (uint64_t)b_count) >> align_log2 & 1ull) == 0) ++align_log2;
   int chain_log2 = 0;
-  while (chain_log2 < 8 && (b_count >> (chain_log2 + 1)) >= grid * 8) ++chain_log2;
+  while (chain_log2 < 8 && (b_count >> (chain_log2 + 1)) >= grid * (variant == 3 ? 4 : 8)) ++chain_log2;
+  if (const char *ec = getenv("PLS_K3_CHAIN")) chain_log2 = atoi(ec);
   if (chain_log2 > align_log2) chain_log2 = align_log2;
   if (chain_log2 > Kp) chain_log2 = Kp;
   const long long n_chains = b_count >> chain_log2;

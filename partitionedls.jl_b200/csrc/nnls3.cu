@@ -356,12 +356,13 @@ __device__ __noinline__ bool block_add3(const Cfg3 cf, const double *G, int ldg,
   hmul3<T, MODE>(cf, s.Pa, s.Pb, nt);           // U = H V
   __syncthreads();
   SUBTICK3(PH_A_HMUL);
-  if (wid < 4) {                                // S partials = V' U over interleaved k-steps
+  constexpr int NSP = NW >= 8 ? 4 : (NW >= 4 ? 2 : 1);   // warps on the S partials; the rest on rho
+  if (wid < NSP) {                              // S partials = V' U over interleaved k-steps
     const int fr = lane >> 2, fk = lane & 3;
     double c0 = 0.0, c1 = 0.0, g0 = 0.0, g1 = 0.0;
     int ks = wid;
-    for (; ks + 4 < nt * 2; ks += 8) {
-      const int rw = ks * 4 + fk, rx = (ks + 4) * 4 + fk;
+    for (; ks + NSP < nt * 2; ks += 2 * NSP) {
+      const int rw = ks * 4 + fk, rx = (ks + NSP) * 4 + fk;
       dmma(c0, c1, s.Pa[pan(rw, fr)], s.Pb[pan(rw, fr)]);
       dmma(g0, g1, s.Pa[pan(rx, fr)], s.Pb[pan(rx, fr)]);
     }
@@ -369,7 +370,7 @@ __device__ __noinline__ bool block_add3(const Cfg3 cf, const double *G, int ldg,
     s.Spart[wid * 64 + fr * 8 + fk * 2] = c0 + g0;
     s.Spart[wid * 64 + fr * 8 + fk * 2 + 1] = c1 + g1;
   } else {                                      // rho_i = c_i - V[:,i]' w
-    for (int i = wid - 4; i < 8; i += NW - 4) {
+    for (int i = wid - NSP; i < 8; i += NW - NSP) {
       double acc = 0.0;
       for (int rw = lane; rw < nrows; rw += 32) acc = fma(s.Pa[pan(rw, i)], s.wF[rw], acc);
       acc = warp_sum(acc);
@@ -383,7 +384,7 @@ __device__ __noinline__ bool block_add3(const Cfg3 cf, const double *G, int ldg,
     double e0 = s.Gaa[i * 8 + j0], e1 = s.Gaa[i * 8 + j0 + 1];
     if (i < a) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { e0 -= s.Spart[q * 64 + i * 8 + j0]; e1 -= s.Spart[q * 64 + i * 8 + j0 + 1]; }
+      for (int q = 0; q < NSP; ++q) { e0 -= s.Spart[q * 64 + i * 8 + j0]; e1 -= s.Spart[q * 64 + i * 8 + j0 + 1]; }
       if (j0 >= a) e0 = 0.0;
       if (j0 + 1 >= a) e1 = 0.0;
     }
@@ -779,6 +780,9 @@ const Variant kVariants[] = {
     {256, 2, 2, k2v3_orthant_chains<256, 2, 2>}, {256, 1, 3, k2v3_orthant_chains<256, 1, 3>},
     {512, 0, 1, k2v3_orthant_chains<512, 0, 1>}, {512, 1, 1, k2v3_orthant_chains<512, 1, 1>},
     {512, 2, 1, k2v3_orthant_chains<512, 2, 1>},
+    {128, 1, 4, k2v3_orthant_chains<128, 1, 4>}, {128, 1, 5, k2v3_orthant_chains<128, 1, 5>},
+    {128, 1, 6, k2v3_orthant_chains<128, 1, 6>}, {128, 2, 4, k2v3_orthant_chains<128, 2, 4>},
+    {256, 1, 4, k2v3_orthant_chains<256, 1, 4>}, {256, 2, 3, k2v3_orthant_chains<256, 2, 3>},
 };
 
 }  // namespace
@@ -793,15 +797,15 @@ int k2v3_plan(int Mp, K3Plan *pl) {
   PLS_CUDA_TRY(cudaGetDevice(&dev));
   PLS_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   const char *eT = getenv("PLS_K3_T"), *eQ = getenv("PLS_K3_QS"), *eB = getenv("PLS_K3_MINB");
-  int T = eT ? atoi(eT) : 256;
-  if (T != 256 && T != 512) T = 256;
-  if (Mp > 4 * T) T = 512;
+  int T = eT ? atoi(eT) : (Mp <= 256 ? 128 : 256);   // measured: cfg2 16.1 ms at 5 x 128, M'=513 166 ms at 2 x 256
+  if (T != 128 && T != 256 && T != 512) T = 256;
+  while (Mp > 4 * T) T *= 2;
   int qs = eQ ? atoi(eQ) : 0;
   if (qs < 0 || qs > ntiles) qs = ntiles;
   while (qs > 0 && v3_smem_bytes(cap, qs) > (size_t)max_smem) --qs;
   if (v3_smem_bytes(cap, qs) > (size_t)max_smem) { set_error("k2v3: M' = %d needs more shared memory than one SM has", Mp); return PLS_EUNSUPPORTED; }
   const int mode = qs == 0 ? 1 : (qs == ntiles ? 0 : 2);
-  int minb = eB ? atoi(eB) : (T == 256 ? 2 : 1);
+  int minb = eB ? atoi(eB) : (T == 128 ? 5 : (T == 256 ? (Mp <= 256 ? 3 : 2) : 1));
   const Variant *best = nullptr;
   for (const Variant &v : kVariants)
     if (v.T == T && v.mode == mode && (!best || abs(v.minb - minb) < abs(best->minb - minb))) best = &v;
