@@ -66,6 +66,8 @@ typedef struct pls_stats {
   double gram_flops;     /* algorithmic: N*M'(M'+1) + 2*N*M' + 2*N    */
   double nnls_flops;     /* model: 2*M'*sum_p + 4*sum_p2 (+ refinement 2*p^2 per grad eval) */
   double nnls_l2_bytes;  /* model: 8*M'*sum_p  (columns of G streamed by gradient evaluations) */
+  int64_t waves;         /* BnB: frontier batches launched; Alt: alternating iterations of the longest restart */
+  int64_t max_open;      /* BnB: largest number of open nodes (= live pooled states) */
 } pls_stats;
 
 /* ---- context ------------------------------------------------------------------------------ */
@@ -89,6 +91,21 @@ int pls_opt_fit(pls_ctx *ctx, const double *X, int64_t N, int64_t M, const doubl
                 const int64_t *P, int64_t K, double eta, uint32_t flags, double *alpha_raw,
                 int64_t *b_best, double *obj_best, double *all_obj, double *all_alpha,
                 pls_stats *stats);
+
+/* ---- fit(::Type{BnB}, ...)  (src/PartitionedLSBnB.jl:30-40; fit_BnB :94-132) -------------------
+ * Branch and bound over group signs with batched frontier expansion: every node relaxation
+ * (lower_bound, BnB.jl:69-92) is solved on the GPU by the same Gram-space solver as the Opt orthants,
+ * warm-started from its parent's pooled state; nodes are expanded in waves with bound pruning.
+ *   alpha_signed[M+1]  the signed weights alpha = alpha_p - alpha_n of the best feasible leaf
+ *                      (BnB.jl:84-89), intercept last; the host applies BnB.jl:36-39 to get alpha/beta/t
+ *   obj                norm(X*alpha - y) of that leaf (BnB.jl:111), data-space recompute
+ *   nopen              number of nodes visited by THIS traversal (traversal-order dependent: it is not
+ *                      the reference's depth-first count) */
+int pls_bnb_fit(pls_ctx *ctx, const double *X, int64_t N, int64_t M, const double *y,
+                const int64_t *P, int64_t K, double eta, uint32_t flags, double *alpha_signed,
+                double *obj, int64_t *nopen, pls_stats *stats);
+int pls_bnb_fit_resident(pls_ctx *ctx, uint32_t flags, double *alpha_signed, double *obj,
+                         int64_t *nopen, pls_stats *stats);
 
 /* ---- resident data set: upload once, fit many times -------------------------------------------
  * pls_load copies rows [0, N) of X (leading dimension ldx >= N), y and P to the device in the

@@ -109,6 +109,21 @@ def _cleanup_result(opt, alpha_raw, b, P):
     return opt, PartLSFitResult(aa, bb, t, P)
 
 
+def _bnb_postprocess(alpha_signed, P):
+    """src/PartitionedLSBnB.jl:36-39 on the signed weights of the best leaf: beta_k = signed group
+    sums, alpha = alpha ./ beta (no zero guard upstream: a group summing to 0 gives NaN),
+    t = beta[end]."""
+    P = np.asarray(P, dtype=np.int64)
+    Po = np.zeros((P.shape[0] + 1, P.shape[1] + 1))
+    Po[:-1, :-1] = P
+    Po[-1, -1] = 1
+    a = np.asarray(alpha_signed, dtype=np.float64)
+    beta = (Po * a[:, None]).sum(axis=0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        alpha = (Po * a[:, None] / beta[None, :]).sum(axis=1)
+    return PartLSFitResult(alpha[:-1], beta[:-1], float(beta[-1]), P)
+
+
 def fit(alg, X, y, P, *, η=0.0, eta=None, nnlsalg="nnls", returnAllSolutions=False, ctx=None, **kw):
     """fit(Opt, X, y, P; η, nnlsalg, returnAllSolutions) -- src/PartitionedLSOpt.jl:73-104.
 
@@ -124,8 +139,13 @@ def fit(alg, X, y, P, *, η=0.0, eta=None, nnlsalg="nnls", returnAllSolutions=Fa
             sols = [_cleanup_result(r["objs"][b], r["alphas"][b], b, P) for b in range(len(r["objs"]))]
             return model, None, SimpleNamespace(solutions=sols, stats=r["stats"])
         return model, None, SimpleNamespace(opt=opt, b=r["b_best"], stats=r["stats"])
-    if alg in (Alt, BnB) or isinstance(alg, (Alt, BnB)):
-        raise NotImplementedError("fit(Alt|BnB) is not part of this round's GPU hot path (SURVEY.md 8f)")
+    if alg is BnB or isinstance(alg, BnB):
+        c = ctx or default_context()
+        r = c.bnb_fit(X, y, P, eta=float(η))
+        model = _bnb_postprocess(r["alpha_signed"], P)
+        return model, None, SimpleNamespace(opt=r["opt"], nopen=r["nopen"], stats=r["stats"])
+    if alg is Alt or isinstance(alg, Alt):
+        raise NotImplementedError("fit(Alt) is not part of this round's GPU hot path (SURVEY.md 8f)")
     raise TypeError(f"unknown algorithm {alg!r}")
 
 

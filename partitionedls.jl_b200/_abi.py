@@ -31,7 +31,8 @@ class PlsStats(C.Structure):
                [(n, C.c_int64) for n in
                 ("orthants", "pivots", "grad_evals", "sum_p", "sum_p2", "bpp_iters", "spills",
                  "rebuilds", "blocked", "kernel_launches")] + \
-               [(n, C.c_double) for n in ("gram_flops", "nnls_flops", "nnls_l2_bytes")]
+               [(n, C.c_double) for n in ("gram_flops", "nnls_flops", "nnls_l2_bytes")] + \
+               [(n, C.c_int64) for n in ("waves", "max_open")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -53,6 +54,9 @@ lib.pls_destroy.argtypes = [_vp]
 lib.pls_destroy.restype = None
 lib.pls_opt_fit.argtypes = [_vp, _dp, C.c_int64, C.c_int64, _dp, _ip, C.c_int64, C.c_double, C.c_uint32,
                             _dp, _ip, _dp, _dp, _dp, C.POINTER(PlsStats)]
+lib.pls_bnb_fit.argtypes = [_vp, _dp, C.c_int64, C.c_int64, _dp, _ip, C.c_int64, C.c_double, C.c_uint32,
+                            _dp, _dp, _ip, C.POINTER(PlsStats)]
+lib.pls_bnb_fit_resident.argtypes = [_vp, C.c_uint32, _dp, _dp, _ip, C.POINTER(PlsStats)]
 lib.pls_load.argtypes = [_vp, _dp, C.c_int64, C.c_int64, C.c_int64, _dp, _ip, C.c_int64, C.c_double]
 lib.pls_opt_fit_resident.argtypes = [_vp, C.c_uint32, _dp, _ip, _dp, _dp, _dp, C.POINTER(PlsStats)]
 lib.pls_gram_build.argtypes = [_vp]
@@ -65,7 +69,7 @@ lib.pls_get_stats.argtypes = [_vp, C.POINTER(PlsStats)]
 lib.pls_gram.argtypes = [_vp, _dp, C.c_int64, C.c_int64, _dp, _ip, C.c_int64, C.c_double, _dp, _dp, _dp]
 lib.pls_nnls_batch.argtypes = [_vp, _dp, _dp, C.c_double, C.c_int64, C.POINTER(C.c_uint64), C.c_int64,
                                C.c_int64, C.c_int64, _dp, _dp]
-for _n in ("pls_create", "pls_opt_fit", "pls_load", "pls_opt_fit_resident", "pls_gram_build", "pls_gram_raw",
+for _n in ("pls_create", "pls_opt_fit", "pls_bnb_fit", "pls_bnb_fit_resident", "pls_load", "pls_opt_fit_resident", "pls_gram_build", "pls_gram_raw",
            "pls_gram_finalize", "pls_opt_solve_range", "pls_opt_residual_partial", "pls_opt_objective_finish",
            "pls_get_stats", "pls_gram", "pls_nnls_batch"):
     getattr(lib, _n).restype = C.c_int
@@ -131,6 +135,24 @@ class Context:
                                _d(alpha), C.byref(b), C.byref(obj), _d(all_obj), _d(all_alpha), C.byref(st)))
         return dict(alpha_raw=alpha, b_best=b.value, opt=obj.value, objs=all_obj, alphas=all_alpha,
                     stats=st.as_dict())
+
+    def bnb_fit(self, X, y, P, eta=0.0, flags=0, prepared=False):
+        """pls_bnb_fit: signed weights of the best feasible leaf, its objective, nodes visited."""
+        if not prepared:
+            X, y, P = _as_inputs(X, y, P)
+        N, M = X.shape
+        K = P.shape[1]
+        a = np.zeros(M + 1); obj = C.c_double(); nopen = C.c_int64(); st = PlsStats()
+        _check(lib.pls_bnb_fit(self._h, _d(X), N, M, _d(y), P.ctypes.data_as(_ip), K, float(eta), flags,
+                               _d(a), C.byref(obj), C.byref(nopen), C.byref(st)))
+        self._shape = (N, M, K)
+        return dict(alpha_signed=a, opt=obj.value, nopen=nopen.value, stats=st.as_dict())
+
+    def bnb_fit_resident(self, flags=0):
+        N, M, K = self._shape
+        a = np.zeros(M + 1); obj = C.c_double(); nopen = C.c_int64(); st = PlsStats()
+        _check(lib.pls_bnb_fit_resident(self._h, flags, _d(a), C.byref(obj), C.byref(nopen), C.byref(st)))
+        return dict(alpha_signed=a, opt=obj.value, nopen=nopen.value, stats=st.as_dict())
 
     # -- resident / stage-wise path ----------------------------------------------------------
     def load(self, X, y, P, eta=0.0, prepared=False):

@@ -160,6 +160,20 @@ double eta_term(const pls_ctx *c, const double *alpha_raw, int64_t b) {
   return pb.eta * tot;
 }
 
+// the eta rows for signed weights w (BnB / Alt): eta * sum_k (sum_{m in k} w_m)^2
+double eta_term_w(const pls_ctx *c, const double *w) {
+  const Problem &pb = c->pb;
+  if (pb.eta == 0.0) return 0.0;
+  double tot = 0.0;
+  for (int k = 0; k < pb.Kp; ++k) {
+    double s = 0.0;
+    for (int m = 0; m < pb.Mp; ++m)
+      if (c->h_gmask[m] >> k & 1ull) s += w[m];
+    tot += s * s;
+  }
+  return pb.eta * tot;
+}
+
 }  // namespace
 
 extern "C" {
@@ -431,6 +445,77 @@ int pls_opt_fit(pls_ctx *c, const double *X, int64_t N, int64_t M, const double 
   if (rc) return rc;
   c->stats.ms_upload = now_ms() - t0;
   rc = pls_opt_fit_resident(c, flags, alpha_raw, b_best, obj_best, all_obj, all_alpha, stats);
+  c->stats.ms_upload = 0.0;
+  return rc;
+}
+
+int pls_bnb_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_signed, double *obj_out, int64_t *nopen,
+                         pls_stats *stats) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!c->pb.loaded) { set_error("no data set loaded"); return PLS_EINVAL; }
+  if (!alpha_signed || !obj_out || !nopen) { set_error("null output pointer"); return PLS_EINVAL; }
+  const double t0 = now_ms();
+  const double keep_upload = c->stats.ms_upload;
+  memset(&c->stats, 0, sizeof(c->stats));
+  c->stats.ms_upload = keep_upload;
+  const int launches0 = c->launches;
+  Problem &pb = c->pb;
+  cudaStream_t st = c->stream;
+  const int Mp = pb.Mp;
+  PLS_CUDA_TRY(cudaEventRecord(c->ev[0], st));
+  rc = k1_gram_build(pb, st, &c->launches); if (rc) return rc;
+  rc = k1_gram_finalize(pb, st, &c->launches); if (rc) return rc;
+  PLS_CUDA_TRY(cudaEventRecord(c->ev[1], st));
+  if (c->ws.Mp != pb.Mp && c->ws.win) { cudaFree(c->ws.win); c->ws.win = nullptr; }
+  BnbReport rep;
+  rc = k5_bnb_run(pb, c->ws, c->sm_count, st, &c->launches, &rep); if (rc) return rc;
+  PLS_CUDA_TRY(cudaEventRecord(c->ev[2], st));
+  const bool recompute = !(flags & PLS_FLAG_NO_RECOMPUTE);
+  if (recompute) {
+    PLS_CUDA_TRY(cudaMemcpyAsync(c->d_w, c->ws.win, sizeof(double) * Mp, cudaMemcpyDeviceToDevice, st));
+    rc = k4_residual(pb, c->ws, c->d_w, c->d_ssq, c->sm_count, st, &c->launches); if (rc) return rc;
+  }
+  PLS_CUDA_TRY(cudaEventRecord(c->ev[3], st));
+  PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin, c->ws.win, sizeof(double) * (Mp + 2), cudaMemcpyDeviceToHost, st));
+  if (recompute) PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin + Mp + 2, c->d_ssq, sizeof(double), cudaMemcpyDeviceToHost, st));
+  PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin + Mp + 3, pb.scal + 3, sizeof(double), cudaMemcpyDeviceToHost, st));
+  PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin + Mp + 4, c->ws.counters, sizeof(unsigned long long) * (CNT_NUM + 1 + 24), cudaMemcpyDeviceToHost, st));
+  PLS_CUDA_TRY(cudaStreamSynchronize(st));
+  if (c->h_pin[Mp + 3] != 0.0) { set_error("non-finite values in X or y"); return PLS_ENUMERIC; }
+  long long seq; memcpy(&seq, &c->h_pin[Mp + 1], sizeof(seq));
+  if (seq < 0) { set_error("bnb: no feasible leaf found"); return PLS_ENUMERIC; }
+  memcpy(alpha_signed, c->h_pin, sizeof(double) * Mp);
+  double obj = c->h_pin[Mp];
+  if (recompute && obj == obj) obj = std::sqrt(c->h_pin[Mp + 2] + eta_term_w(c, alpha_signed));
+  *obj_out = obj;
+  *nopen = rep.visited;
+  float ms = 0.f;
+  pls_stats &s = c->stats;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); s.ms_gram = ms;
+  cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); s.ms_nnls = ms;
+  cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); s.ms_recompute = ms;
+  const unsigned long long *cnt = reinterpret_cast<const unsigned long long *>(c->h_pin + Mp + 4);
+  read_counters(c, cnt);
+  s.spills = 0;
+  s.orthants = rep.visited; s.waves = rep.waves; s.max_open = rep.max_open;
+  const double Nd = (double)pb.N, Md = (double)Mp;
+  s.gram_flops = Nd * Md * (Md + 1.0) + 2.0 * Nd * Md + 2.0 * Nd;
+  s.kernel_launches = c->launches - launches0;
+  s.ms_total = now_ms() - t0 + s.ms_upload;
+  if (stats) *stats = s;
+  if (obj != obj) { set_error("NaN objective (non-finite input?)"); return PLS_ENUMERIC; }
+  return PLS_OK;
+}
+
+int pls_bnb_fit(pls_ctx *c, const double *X, int64_t N, int64_t M, const double *y, const int64_t *P,
+                int64_t K, double eta, uint32_t flags, double *alpha_signed, double *obj, int64_t *nopen,
+                pls_stats *stats) {
+  const double t0 = now_ms();
+  int rc = pls_load(c, X, N, N, M, y, P, K, eta);
+  if (rc) return rc;
+  c->stats.ms_upload = now_ms() - t0;
+  rc = pls_bnb_fit_resident(c, flags, alpha_signed, obj, nopen, stats);
   c->stats.ms_upload = 0.0;
   return rc;
 }

@@ -100,6 +100,9 @@ int k2v2_config(int Mp, int *cap, size_t *smem, int *occ);
 struct K3Plan { int cap, qs, T, mode, occ, variant; size_t smem, hstride; };
 int k2v3_plan(int Mp, K3Plan *pl);
 int k2v3_launch(const K2Args &A, const K3Plan &pl, int grid, cudaStream_t st);
+// K5: branch and bound with batched frontier expansion (bnb.cu); winner left in ws.win
+struct BnbReport { long long visited, waves, max_open, pool_slots; double mu; };
+int k5_bnb_run(const Problem &pb, SolveWs &ws, int sm_count, cudaStream_t st, int *launches, BnbReport *rep);
 int k4_residual(const Problem &pb, SolveWs &ws, const double *d_w, double *d_ssq, int sm_count,
                 cudaStream_t st, int *launches);
 

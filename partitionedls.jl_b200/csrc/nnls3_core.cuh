@@ -1,0 +1,699 @@
+// Device-side core of the block-pivoting NNLS solver shared by the Opt (nnls3.cu), BnB (bnb.cu) and
+// Alt (alt.cu) kernels: tile-packed symmetric inverse split between shared memory and an
+// L2-resident global slice, rank-8 DMMA block updates, gradient evaluation, and the pivoting loop.
+// Everything lives in an anonymous namespace: each translation unit gets its own copy.
+#pragma once
+#include "common.cuh"
+
+namespace pls {
+namespace {
+
+constexpr int CAP3MAX = 1024;
+
+__device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_max_i(int v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_incl_scan(int v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+  return v;
+}
+__device__ __forceinline__ bool lex_better(double oa, long long ba, double ob, long long bb) {
+  if (bb < 0) return ba >= 0;
+  if (ba < 0) return false;
+  const bool na = oa != oa, nb = ob != ob;
+  if (na != nb) return na;
+  if (na) return ba < bb;
+  return oa < ob || (oa == ob && ba < bb);
+}
+
+// ---- tile-packed symmetric storage --------------------------------------------------------------
+__device__ __forceinline__ int tile_q(int ti, int tj) { return ((ti * (ti + 1)) >> 1) + tj; }
+__device__ __forceinline__ int swz8(int r, int c) { return (r << 3) + (c ^ ((r & 2) << 1)); }
+__device__ __forceinline__ int pan(int row, int col) { return (row << 3) + (col ^ ((row & 2) << 1)); }
+
+struct Cfg3 {
+  int cap;        // slots (multiple of 8)
+  int qs;         // tiles [0, qs) live in shared memory
+  double *hg;     // this CTA's global tiles: tile q >= qs at hg + (q - qs) * 64
+};
+
+struct Sh3 {
+  double *Hs, *Hg;
+  int qs;
+  double *Pa, *Pb, *w, *r, *wF, *cs, *Sinv, *Gaa, *Spart, *rho, *theta, *cA, *red;
+  unsigned long long *gms;
+  long long *stat, *prof;
+  int *F, *pos, *lst, *asl, *ctl, *pl;
+  unsigned short *tmap;
+  signed char *sg, *dd, *vflag, *smark, *fl;
+};
+
+enum Phase3 { PH_START = 0, PH_PLAN, PH_REMOVE, PH_ADD, PH_GRAD, PH_REFINE, PH_OUT, PH_NREM, PH_NADD,
+              PH_R_GATHER, PH_R_PANEL, PH_R_RANK, PH_R_ZERO, PH_A_GATHER, PH_A_HMUL, PH_A_SPART, PH_A_INV, PH_A_PANEL,
+              PH_A_RANK, PH_A_ROWS, PH_A_INV1, PH_A_INV2, PH_A_INV3, PH_NUM };
+enum Stat3 { ST_P = 0, ST_PIV, ST_GRAD, ST_SUMP, ST_SUMP2, ST_ITER, ST_REBUILD, ST_BLOCKED, ST_NOCONV, ST_TMARK, ST_TSUB, ST_NUM };
+#define SUBTICK3(which) do { if (threadIdx.x == 0) { const long long now_ = clock64(); s.prof[which] += now_ - s.stat[ST_TSUB]; s.stat[ST_TSUB] = now_; } } while (0)
+#define STAT_ADD3(which, v) do { if (threadIdx.x == 0) s.stat[which] += (long long)(v); } while (0)
+
+__host__ __device__ inline size_t sh3_doubles(int cap) {
+  return 2 * (size_t)cap * 8 + 4 * (size_t)cap + 64 + 64 + 256 + 24 + 32 + (size_t)cap /*gms*/ + ST_NUM + PH_NUM;
+}
+__host__ __device__ inline size_t sh3_ints(int cap) {
+  const int ntc = cap >> 3;
+  return 4 * (size_t)cap + 8 + 128 + ((size_t)(ntc * (ntc + 1) / 2) + 1) / 2;
+}
+
+__device__ __forceinline__ Sh3 make_sh3(const Cfg3 &cf) {
+  extern __shared__ __align__(16) unsigned char smem_raw3[];
+  const int cap = cf.cap;
+  const int ntc = cap >> 3;
+  const int ntiles_cap = (ntc * (ntc + 1)) >> 1;
+  Sh3 s;
+  double *dp = reinterpret_cast<double *>(smem_raw3);
+  s.Hs = dp; dp += ((size_t)cf.qs << 6);
+  s.Hg = cf.hg; s.qs = cf.qs;
+  s.Pa = dp; dp += cap * 8;
+  s.Pb = dp; dp += cap * 8;
+  s.w = dp; dp += cap;
+  s.r = dp; dp += cap;
+  s.wF = dp; dp += cap;
+  s.cs = dp; dp += cap;
+  s.Sinv = dp; dp += 64;
+  s.Gaa = dp; dp += 64;
+  s.Spart = dp; dp += 256;
+  s.rho = dp; dp += 8;
+  s.theta = dp; dp += 8;
+  s.cA = dp; dp += 8;
+  s.red = dp; dp += 32;
+  s.gms = reinterpret_cast<unsigned long long *>(dp); dp += cap;
+  s.stat = reinterpret_cast<long long *>(dp); dp += ST_NUM;
+  s.prof = reinterpret_cast<long long *>(dp); dp += PH_NUM;
+  int *ip = reinterpret_cast<int *>(dp);
+  s.F = ip; ip += cap;
+  s.pos = ip; ip += cap;
+  s.lst = ip; ip += cap;
+  s.asl = ip; ip += cap;
+  s.ctl = ip; ip += 8;
+  s.pl = ip; ip += 128;
+  s.tmap = reinterpret_cast<unsigned short *>(ip); ip += (ntiles_cap + 1) / 2;
+  signed char *cp = reinterpret_cast<signed char *>(ip);
+  s.sg = cp; cp += cap;
+  s.dd = cp; cp += cap;
+  s.vflag = cp; cp += cap;
+  s.smark = cp; cp += cap;
+  s.fl = cp; cp += cap;
+  return s;
+}
+
+template <int MODE>
+__device__ __forceinline__ double *tptr(const Sh3 &s, int q) {
+  if (MODE == 0) return s.Hs + ((size_t)q << 6);
+  if (MODE == 1) return s.Hg + ((size_t)q << 6);
+  return q < s.qs ? s.Hs + ((size_t)q << 6) : s.Hg + ((size_t)(q - s.qs) << 6);
+}
+template <int MODE>
+__device__ __forceinline__ double h_get(const Sh3 &s, int i, int j) {
+  const int a = i > j ? i : j, b = i > j ? j : i;
+  return tptr<MODE>(s, tile_q(a >> 3, b >> 3))[swz8(a & 7, b & 7)];
+}
+template <int MODE>
+__device__ __forceinline__ void h_set(const Sh3 &s, int i, int j, double v) {
+  const int a = i > j ? i : j, b = i > j ? j : i;
+  double *t = tptr<MODE>(s, tile_q(a >> 3, b >> 3));
+  t[swz8(a & 7, b & 7)] = v;
+  if ((a >> 3) == (b >> 3)) t[swz8(b & 7, a & 7)] = v;   // diagonal tiles hold both halves
+}
+
+// H(lower tiles) += Pa * Pb'   over the leading nt x nt tiles; four tiles in flight per warp
+template <int T, int MODE>
+__device__ __noinline__ void rank_update3(const Cfg3 cf, int nt) {
+  const Sh3 s = make_sh3(cf);
+  constexpr int NW = T / 32;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int ntiles = (nt * (nt + 1)) >> 1;
+  const int coff = swz8(fr, fk * 2);
+  const double *Pa = s.Pa, *Pb = s.Pb;
+  for (int q = wid; q < ntiles; q += 4 * NW) {
+    int qq[4]; bool hv[4]; double2 *cp[4]; double2 c[4]; double a0[4], a1[4], b0[4], b1[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      hv[u] = q + u * NW < ntiles;
+      qq[u] = hv[u] ? q + u * NW : q;
+      cp[u] = reinterpret_cast<double2 *>(tptr<MODE>(s, qq[u]) + coff);
+      c[u] = *cp[u];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = s.tmap[qq[u]];
+      const int ra = ((t >> 8) << 3) + fr, rb = ((t & 255) << 3) + fr;
+      a0[u] = Pa[pan(ra, fk)]; a1[u] = Pa[pan(ra, 4 + fk)];
+      b0[u] = Pb[pan(rb, fk)]; b1[u] = Pb[pan(rb, 4 + fk)];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) dmma(c[u].x, c[u].y, a0[u], b0[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) dmma(c[u].x, c[u].y, a1[u], b1[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) if (hv[u]) *cp[u] = c[u];
+  }
+}
+
+// Pout = H * Pin  (H symmetric, nt x nt tiles; panels nt*8 x 8).  One warp per tile row.
+template <int T, int MODE>
+__device__ __noinline__ void hmul3(const Cfg3 cf, const double *Pin, double *Pout, int nt) {
+  const Sh3 s = make_sh3(cf);
+  constexpr int NW = T / 32;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int off_d0 = swz8(fr, fk), off_d1 = swz8(fr, 4 + fk);      // direct tile (tj <= ti)
+  const int off_t0 = swz8(fk, fr), off_t1 = swz8(4 + fk, fr);      // transposed tile (tj > ti)
+  for (int ti = wid; ti < nt; ti += NW) {
+    double acc[2][2][2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) acc[u][0][0] = acc[u][0][1] = acc[u][1][0] = acc[u][1][1] = 0.0;
+    const int rowbase = (ti * (ti + 1)) >> 1;
+    for (int tj = 0; tj < nt; tj += 4) {
+      double h0[4], h1[4], p0[4], p1[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int tk = tj + u;
+        const bool live = tk < nt;
+        const int tkk = live ? tk : ti;
+        const bool dj = tkk <= ti;
+        const double *tp = tptr<MODE>(s, dj ? rowbase + tkk : tile_q(tkk, ti));
+        h0[u] = tp[dj ? off_d0 : off_t0]; h1[u] = tp[dj ? off_d1 : off_t1];
+        p0[u] = live ? Pin[pan(tkk * 8 + fk, fr)] : 0.0;
+        p1[u] = live ? Pin[pan(tkk * 8 + 4 + fk, fr)] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { dmma(acc[u & 1][0][0], acc[u & 1][0][1], h0[u], p0[u]); dmma(acc[u & 1][1][0], acc[u & 1][1][1], h1[u], p1[u]); }
+    }
+    *reinterpret_cast<double2 *>(Pout + pan(ti * 8 + fr, fk * 2)) =
+        make_double2((acc[0][0][0] + acc[0][1][0]) + (acc[1][0][0] + acc[1][1][0]),
+                     (acc[0][0][1] + acc[0][1][1]) + (acc[1][0][1] + acc[1][1][1]));
+  }
+}
+
+// In-place Gauss-Jordan inverse of an SPD 8x8 held by one warp (lane owns S[i][j0], S[i][j0+1],
+// i = lane >> 2, j0 = 2 * (lane & 3)) through a 64-double shared scratch.  Only the leading n x n
+// block is eliminated (the rest must be the identity).  Returns false if a pivot is not safely
+// positive relative to dref[k].
+__device__ __forceinline__ bool warp_inv8(double &e0, double &e1, int n, const double *dref, double tol, double *Ssm) {
+  const int lane = threadIdx.x & 31;
+  const int i = lane >> 2, j0 = (lane & 3) << 1, j1 = j0 + 1;
+  bool ok = true;
+  for (int k = 0; k < n; ++k) {
+    *reinterpret_cast<double2 *>(Ssm + i * 8 + j0) = make_double2(e0, e1);
+    __syncwarp();
+    const double2 pk = *reinterpret_cast<const double2 *>(Ssm + k * 8 + j0);
+    const double cik = Ssm[i * 8 + k];
+    const double pkk = Ssm[k * 8 + k];
+    __syncwarp();
+    ok = ok && (pkk > tol * dref[k]);
+    const double d = 1.0 / pkk;
+    const bool rowk = (i == k);
+    const double f = cik * d;
+    double n0 = rowk ? pk.x * d : fma(-f, pk.x, e0);
+    double n1 = rowk ? pk.y * d : fma(-f, pk.y, e1);
+    if (j0 == k) n0 = rowk ? d : -f;
+    if (j1 == k) n1 = rowk ? d : -f;
+    e0 = n0; e1 = n1;
+  }
+  return ok;
+}
+
+// Pout = sign * Pin * Sinv  (one 8x8x8 DMMA product per row tile);  w[F[row]] -= Pin[row,:] . coef
+template <int T>
+__device__ __forceinline__ void panel_small3(const Sh3 &s, const double *Pin, double *Pout, const double *coef,
+                                             double sign, int nrows) {
+  constexpr int NW = T / 32;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  const double b0 = sign * s.Sinv[fk * 8 + fr], b1 = sign * s.Sinv[(4 + fk) * 8 + fr];
+  for (int ti = wid; ti < (nrows >> 3); ti += NW) {
+    double c0 = 0.0, c1 = 0.0;
+    dmma(c0, c1, Pin[pan(ti * 8 + fr, fk)], b0);
+    dmma(c0, c1, Pin[pan(ti * 8 + fr, 4 + fk)], b1);
+    *reinterpret_cast<double2 *>(Pout + pan(ti * 8 + fr, fk * 2)) = make_double2(c0, c1);
+  }
+  for (int row = threadIdx.x; row < nrows; row += T) {
+    const int var = s.F[row];
+    if (var >= 0) {
+      double z = 0.0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) z = fma(Pin[pan(row, j)], coef[j], z);
+      s.w[var] -= z;
+    }
+  }
+}
+
+// Remove the r <= 8 slots Rs[0..r).  nt covers every slot in use.
+template <int T, int MODE>
+__device__ __noinline__ void block_remove3(const Cfg3 cf, const int *Rs, int r, int nt) {
+  const Sh3 s = make_sh3(cf);
+  constexpr int NW = T / 32;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nrows = nt * 8;
+  if (tid == 0) s.stat[ST_TSUB] = clock64();
+  if (wid < NW - 1) {                           // B = H[:, R]
+    for (int idx = tid; idx < nrows * 8; idx += T - 32) {
+      const int q = idx / nrows, row = idx - q * nrows;
+      s.Pb[pan(row, q)] = (q < r) ? h_get<MODE>(s, row, Rs[q]) : 0.0;
+    }
+  } else {                                      // S = H[R,R] straight from the tiles, then invert
+    const int i = lane >> 2, j0 = (lane & 3) << 1;
+    double e0 = (i < r && j0 < r) ? h_get<MODE>(s, Rs[i], Rs[j0]) : (i == j0 ? 1.0 : 0.0);
+    double e1 = (i < r && j0 + 1 < r) ? h_get<MODE>(s, Rs[i], Rs[j0 + 1]) : (i == j0 + 1 ? 1.0 : 0.0);
+    if (lane < 8) { s.rho[lane] = (lane < r) ? s.w[s.F[Rs[lane]]] : 0.0; s.cA[lane] = 0.0; }   // w_R
+    __syncwarp();
+    warp_inv8(e0, e1, r, s.cA, -1.0, s.Sinv);   // H[R,R] is SPD: no pivot test
+    s.Sinv[i * 8 + j0] = e0; s.Sinv[i * 8 + j0 + 1] = e1;
+    __syncwarp();
+    if (lane < 8) {                             // phi = inv(S) w_R
+      double a = 0.0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a = fma(s.Sinv[lane * 8 + j], s.rho[j], a);
+      s.theta[lane] = a;
+    }
+  }
+  __syncthreads();
+  SUBTICK3(PH_R_GATHER);
+  panel_small3<T>(s, s.Pb, s.Pa, s.theta, -1.0, nrows);   // Pa = -B inv(S);  w -= B phi
+  __syncthreads();
+  SUBTICK3(PH_R_PANEL);
+  rank_update3<T, MODE>(cf, nt);                          // H -= B inv(S) B'
+  __syncthreads();
+  SUBTICK3(PH_R_RANK);
+  for (int idx = tid; idx < nrows * r; idx += T) {        // rows / columns R become exact zeros
+    const int q = idx / nrows, row = idx - q * nrows;
+    h_set<MODE>(s, Rs[q], row, 0.0);
+  }
+  if (tid < r) {
+    const int sl = Rs[tid], var = s.F[sl];
+    s.w[var] = 0.0; s.pos[var] = -1; s.F[sl] = -1;
+  }
+  __syncthreads();
+  SUBTICK3(PH_R_ZERO);
+  if (tid == 0) { const long long p = s.stat[ST_P]; s.stat[ST_PIV] += r; s.stat[ST_SUMP2] += r * p * p; s.stat[ST_P] = p - r; }
+}
+
+// Add the a <= 8 variables Av[-k] (k = 0..a-1, stored downwards) into the free slots As[k].
+// Returns false (state untouched) if the Schur complement is not safely positive definite.
+template <int T, int MODE>
+__device__ __noinline__ bool block_add3(const Cfg3 cf, const double *G, int ldg, const int *Av, const int *As, int a, int nt) {
+  const Sh3 s = make_sh3(cf);
+  constexpr int NW = T / 32;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nrows = nt * 8;
+  if (tid == 0) s.stat[ST_TSUB] = clock64();
+  if (wid < NW - 1) {                           // V = G[F, A]  (free slots: zero rows)
+    for (int idx = tid; idx < nrows * 8; idx += T - 32) {
+      const int q = idx / nrows, row = idx - q * nrows;
+      const int var = s.F[row];
+      s.Pa[pan(row, q)] = (q < a && var >= 0) ? G[(size_t)ldg * Av[-q] + var] : 0.0;
+      if (q == 0) s.wF[row] = var >= 0 ? s.w[var] : 0.0;
+    }
+  } else {
+    for (int e = lane; e < 64; e += 32) {
+      const int i = e >> 3, j = e & 7;
+      s.Gaa[e] = (i < a && j < a) ? G[(size_t)ldg * Av[-j] + Av[-i]] : (i == j ? 1.0 : 0.0);
+    }
+    if (lane < 8) s.cA[lane] = (lane < a) ? s.cs[Av[-lane]] : 0.0;
+  }
+  __syncthreads();
+  SUBTICK3(PH_A_GATHER);
+  hmul3<T, MODE>(cf, s.Pa, s.Pb, nt);           // U = H V
+  __syncthreads();
+  SUBTICK3(PH_A_HMUL);
+  constexpr int NSP = NW >= 8 ? 4 : (NW >= 4 ? 2 : 1);   // warps on the S partials; the rest on rho
+  if (wid < NSP) {                              // S partials = V' U over interleaved k-steps
+    const int fr = lane >> 2, fk = lane & 3;
+    double c0 = 0.0, c1 = 0.0, g0 = 0.0, g1 = 0.0;
+    int ks = wid;
+    for (; ks + NSP < nt * 2; ks += 2 * NSP) {
+      const int rw = ks * 4 + fk, rx = (ks + NSP) * 4 + fk;
+      dmma(c0, c1, s.Pa[pan(rw, fr)], s.Pb[pan(rw, fr)]);
+      dmma(g0, g1, s.Pa[pan(rx, fr)], s.Pb[pan(rx, fr)]);
+    }
+    if (ks < nt * 2) { const int rw = ks * 4 + fk; dmma(c0, c1, s.Pa[pan(rw, fr)], s.Pb[pan(rw, fr)]); }
+    s.Spart[wid * 64 + fr * 8 + fk * 2] = c0 + g0;
+    s.Spart[wid * 64 + fr * 8 + fk * 2 + 1] = c1 + g1;
+  } else {                                      // rho_i = c_i - V[:,i]' w
+    for (int i = wid - NSP; i < 8; i += NW - NSP) {
+      double acc = 0.0;
+      for (int rw = lane; rw < nrows; rw += 32) acc = fma(s.Pa[pan(rw, i)], s.wF[rw], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) s.rho[i] = s.cA[i] - acc;
+    }
+  }
+  __syncthreads();
+  SUBTICK3(PH_A_SPART);
+  if (wid == 0) {
+    const int i = lane >> 2, j0 = (lane & 3) << 1;
+    double e0 = s.Gaa[i * 8 + j0], e1 = s.Gaa[i * 8 + j0 + 1];
+    if (i < a) {
+#pragma unroll
+      for (int q = 0; q < NSP; ++q) { e0 -= s.Spart[q * 64 + i * 8 + j0]; e1 -= s.Spart[q * 64 + i * 8 + j0 + 1]; }
+      if (j0 >= a) e0 = 0.0;
+      if (j0 + 1 >= a) e1 = 0.0;
+    }
+    if (lane < 8) s.theta[lane] = s.Gaa[lane * 8 + lane];     // pivot reference: G_jj
+    __syncwarp();
+    const bool ok = warp_inv8(e0, e1, a, s.theta, 1e-13, s.Sinv);
+    const bool all_ok = __all_sync(0xffffffffu, ok);
+    s.Sinv[i * 8 + j0] = e0; s.Sinv[i * 8 + j0 + 1] = e1;
+    __syncwarp();
+    double th = 0.0;
+    if (lane < 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) th = fma(s.Sinv[lane * 8 + j], s.rho[j], th);
+    }
+    __syncwarp();
+    if (lane < 8) s.theta[lane] = (lane < a) ? th : 0.0;
+    if (lane == 0) s.ctl[4] = all_ok ? 1 : 0;
+  }
+  __syncthreads();
+  SUBTICK3(PH_A_INV);
+  if (!s.ctl[4]) { __syncthreads(); return false; }
+  panel_small3<T>(s, s.Pb, s.Pa, s.theta, 1.0, nrows);    // T = U inv(S) -> Pa;  w_F -= U theta
+  __syncthreads();
+  SUBTICK3(PH_A_PANEL);
+  rank_update3<T, MODE>(cf, nt);                          // H += T U'
+  __syncthreads();
+  SUBTICK3(PH_A_RANK);
+  for (int idx = tid; idx < nrows * a; idx += T) {        // new rows / columns: -T
+    const int q = idx / nrows, row = idx - q * nrows;
+    if (s.F[row] >= 0) h_set<MODE>(s, As[q], row, -s.Pa[pan(row, q)]);
+  }
+  __syncthreads();
+  if (tid < 64) {
+    const int i = tid >> 3, j = tid & 7;
+    if (i < a && j <= i) h_set<MODE>(s, As[i], As[j], s.Sinv[i * 8 + j]);
+  }
+  if (tid >= 64 && tid < 64 + a) {
+    const int q = tid - 64;
+    const int var = Av[-q], sl = As[q];
+    s.w[var] = s.theta[q]; s.F[sl] = var; s.pos[var] = sl;
+  }
+  __syncthreads();
+  SUBTICK3(PH_A_ROWS);
+  if (tid == 0) { const long long p = s.stat[ST_P]; s.stat[ST_PIV] += a; s.stat[ST_SUMP2] += a * p * p; s.stat[ST_P] = p + a; }
+  return true;
+}
+
+// r = c - G[:,F] w_F for all variables; the passive columns of G stream from L2 as double2 row
+// pairs (M' <= T*2 rows) or two row pairs per thread (larger M'), the slot range is split over nsl
+// thread slices.  Returns max |r_F| (normal-equation residual), same on all threads.  Pb = scratch.
+template <int T, int RPT>
+__device__ __noinline__ double grad_eval3(const Cfg3 cf, const double *G, int ldg, int Mp, int hw) {
+  const Sh3 s = make_sh3(cf);
+  constexpr int NW = T / 32;
+  constexpr int NP = RPT / 2;                      // double2 loads per thread and column
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int t = tid; t < hw; t += T) { const int var = s.F[t]; s.wF[t] = var >= 0 ? s.w[var] : 0.0; }
+  __syncthreads();
+  const int nunits = (Mp + RPT - 1) / RPT;         // <= T by construction
+  int nsl = T / nunits;
+  if (nsl > 8) nsl = 8;
+  const int sl = tid / nunits, un = tid - sl * nunits;
+  double *part = s.Pb;                             // [nsl][nunits * RPT]
+  const int pstride = nunits * RPT;
+  if (sl < nsl) {
+    const int t0 = (hw * sl) / nsl, t1 = (hw * (sl + 1)) / nsl;
+    const double *Gp = G + RPT * un;
+    double2 acc[2][NP];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int k = 0; k < NP; ++k) acc[i][k] = make_double2(0.0, 0.0);
+    constexpr int UB = 8 / NP;                     // columns per batch: 8 loads in flight
+    for (int t = t0; t < t1; t += UB) {
+      double2 g[UB][NP];
+#pragma unroll
+      for (int i = 0; i < UB; ++i) {
+        const int v = (t + i < t1) ? s.F[t + i] : -1;
+#pragma unroll
+        for (int k = 0; k < NP; ++k)
+          g[i][k] = v >= 0 ? *reinterpret_cast<const double2 *>(Gp + (size_t)ldg * v + 2 * k) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int i = 0; i < UB; ++i) {
+        const double ww = (t + i < t1) ? s.wF[t + i] : 0.0;
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+          acc[i & 1][k].x = fma(g[i][k].x, ww, acc[i & 1][k].x);
+          acc[i & 1][k].y = fma(g[i][k].y, ww, acc[i & 1][k].y);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NP; ++k)
+      *reinterpret_cast<double2 *>(part + sl * pstride + RPT * un + 2 * k) =
+          make_double2(acc[0][k].x + acc[1][k].x, acc[0][k].y + acc[1][k].y);
+  }
+  __syncthreads();
+  double mx = 0.0;
+  for (int m = tid; m < Mp; m += T) {
+    double sum = 0.0;
+    for (int q = 0; q < nsl; ++q) sum += part[q * pstride + m];
+    const double rv = s.cs[m] - sum;
+    s.r[m] = rv;
+    if (s.pos[m] >= 0) mx = fmax(mx, fabs(rv));
+  }
+  mx = warp_max(mx);
+  if (lane == 0) s.red[wid] = mx;
+  __syncthreads();
+  double x = s.red[0];
+#pragma unroll
+  for (int i = 1; i < NW; ++i) x = fmax(x, s.red[i]);
+  __syncthreads();
+  if (tid == 0) { s.stat[ST_GRAD] += 1; s.stat[ST_SUMP] += s.stat[ST_P]; }
+  return x;
+}
+
+// w_F += H r_F   (one DMMA product with a single live column)
+template <int T, int MODE>
+__device__ __noinline__ void refine3(const Cfg3 cf, int nt) {
+  const Sh3 s = make_sh3(cf);
+  const int nrows = nt * 8;
+  for (int idx = threadIdx.x; idx < nrows * 8; idx += T) {
+    const int q = idx / nrows, row = idx - q * nrows;
+    const int var = s.F[row];
+    s.Pa[pan(row, q)] = (q == 0 && var >= 0) ? s.r[var] : 0.0;
+  }
+  __syncthreads();
+  hmul3<T, MODE>(cf, s.Pa, s.Pb, nt);
+  __syncthreads();
+  for (int rw = threadIdx.x; rw < nrows; rw += T) {
+    const int var = s.F[rw];
+    if (var >= 0) s.w[var] += s.Pb[pan(rw, 0)];
+  }
+  __syncthreads();
+}
+
+// zero the tiles that may hold data (slots below the high-water mark) and reset the slot tables
+template <int T, int MODE>
+__device__ __noinline__ void clear_state3(const Cfg3 cf, int nt_used) {
+  const Sh3 s = make_sh3(cf);
+  const int ntiles = (nt_used * (nt_used + 1)) >> 1;
+  for (int i = threadIdx.x; i < (ntiles << 5); i += T) {
+    double2 *p = reinterpret_cast<double2 *>(tptr<MODE>(s, i >> 5)) + (i & 31);
+    *p = make_double2(0.0, 0.0);
+  }
+  for (int t = threadIdx.x; t < cf.cap; t += T) { s.F[t] = -1; s.smark[t] = 0; }
+  if (threadIdx.x == 0) s.stat[ST_P] = 0;
+}
+
+constexpr int SG_FREE = 2;   // sign class of an unconstrained variable (BnB nodes, src/PartitionedLSBnB.jl:74-79)
+
+// Solver state carried from one subproblem to the next (registers of every thread, uniform).
+struct Bpp3 {
+  int hwm;        // slots [0, hwm) may be in use
+  int nt_cur;     // tile rows covering them
+  int nt_dirty;   // tile rows that may hold non-zero data
+  bool r_valid;   // s.r is the gradient of the current s.w
+  bool grow_zero; // tile rows >= nt_dirty hold garbage (pooled BnB / Alt states): zero them before first use
+};
+
+#define PH_TICK3(which) do { if (threadIdx.x == 0) { const long long now_ = clock64(); s.prof[which] += now_ - s.stat[ST_TMARK]; s.stat[ST_TMARK] = now_; } } while (0)
+
+// Block principal pivoting from the current passive set to the KKT point of
+//     min w'Gw - 2c'w   s.t.  sg_m w_m >= 0  (sg_m = +-1),  w_m = 0 (sg_m = 0),  w_m free (SG_FREE)
+// (Judice-Pires / Kim-Park with Murty's single-pivot backup rule).  On return s.w / s.F / s.pos hold
+// the solution, s.r its gradient (st.r_valid), and s.red[0..NW) the partial sums of c_F'w_F.
+// Returns false if the iteration cap was hit or the inverse could not be rebuilt.
+template <int T, int MODE>
+__device__ __forceinline__ bool bpp_solve3(const Cfg3 cf, const Sh3 &s, const double *G, int ldg, int Mp,
+                                           double cmax, Bpp3 &st) {
+  constexpr int NW = T / 32;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int cap = cf.cap;
+  const double told = 1e-12 * cmax;
+  const int nvch = (Mp + 31) >> 5, nsch = (cap + 31) >> 5;   // <= 32 chunks each
+  int t_best = Mp + 1, pbar = 3, iters = 0;
+  bool ok = true;
+  for (;;) {
+    if (!st.r_valid) {
+      int rep = 0;
+      for (;;) {
+        PH_TICK3(PH_OUT);
+        const double rf = (Mp <= 2 * T) ? grad_eval3<T, 2>(cf, G, ldg, Mp, st.hwm)
+                                        : grad_eval3<T, 4>(cf, G, ldg, Mp, st.hwm);
+        PH_TICK3(PH_GRAD);
+        if (rf <= 1e-12 * cmax) break;          // carried solution already exact to working accuracy
+        refine3<T, MODE>(cf, st.nt_cur);
+        PH_TICK3(PH_REFINE);
+        if (rf <= 1e-9 * cmax) break;
+        if (++rep >= 4) {                       // inverse degraded: rebuild by re-adding the passive set
+          if (tid == 0) {
+            int n = 0;
+            for (int t = 0; t < st.hwm; ++t) if (s.F[t] >= 0) { s.lst[cap - 1 - n] = s.F[t]; s.asl[n] = n; ++n; }
+            s.ctl[5] = n;
+          }
+          __syncthreads();
+          const int pn = s.ctl[5];
+          clear_state3<T, MODE>(cf, max(st.nt_dirty, st.nt_cur));
+          for (int m = tid; m < Mp; m += T) { s.w[m] = 0.0; s.pos[m] = -1; }
+          __syncthreads();
+          const int ntr = (pn + 7) >> 3;
+          for (int q0 = 0; q0 < pn; q0 += 8)
+            block_add3<T, MODE>(cf, G, ldg, s.lst + (cap - 1 - q0), s.asl + q0, min(8, pn - q0), ntr);
+          st.hwm = pn; st.nt_cur = ntr;
+          st.nt_dirty = max(st.nt_dirty, ntr);
+          STAT_ADD3(ST_REBUILD, 1);
+          if (rep >= 6) { ok = false; break; }
+        }
+      }
+      if (!ok) break;
+    }
+    st.r_valid = false;
+    // ---- plan: infeasibility flags (passive variables with the wrong sign; active ones whose
+    //      sign-adjusted gradient is positive), ordered lists in index order, pivoting rule, slots
+    //      for the additions, new high-water mark.  Chunks of 32 variables / slots per warp pass,
+    //      one warp-wide prefix sum over the <= 32 chunk counts.
+    double cw = 0.0;
+    for (int ch = wid; ch < nvch; ch += NW) {
+      const int m = (ch << 5) + lane;
+      int f = 0;
+      if (m < Mp) {
+        const int sl = s.pos[m], sg = s.sg[m];    // sign class: -1, +1, 0 = fixed at zero, SG_FREE = unconstrained
+        if (sl >= 0) { cw = fma(s.cs[m], s.w[m], cw); if (sg != SG_FREE && (sg == 0 || (double)sg * s.w[m] < 0.0)) f = 1; }
+        else if (sg != 0 && s.vflag[m] != 3 && (sg == SG_FREE ? fabs(s.r[m]) > told : (double)sg * s.r[m] > told)) f = 2;
+        s.fl[m] = (signed char)f;
+      }
+      const unsigned br = __ballot_sync(0xffffffffu, f == 1);
+      const unsigned ba = __ballot_sync(0xffffffffu, f == 2);
+      const unsigned any = br | ba;
+      if (lane == 0) {
+        s.pl[ch] = __popc(br) | (__popc(ba) << 16);
+        s.pl[32 + ch] = any ? (ch << 5) + 31 - __clz(any) : -1;
+      }
+    }
+    cw = warp_sum(cw);
+    if (lane == 0) s.red[wid] = cw;
+    __syncthreads();
+    const int cnt_l = lane < nvch ? s.pl[lane] : 0;
+    const int incl_l = warp_incl_scan(cnt_l);
+    const int tot = __shfl_sync(0xffffffffu, incl_l, 31);
+    int nr = tot & 0xffff, na = tot >> 16;
+    const int mxi = warp_max_i(lane < nvch ? s.pl[32 + lane] : -1);
+    const int nv = nr + na;
+    if (nv == 0) { st.r_valid = true; PH_TICK3(PH_PLAN); break; }   // KKT point; r stays valid for the next orthant
+    const bool single = !(nv < t_best) && pbar < 1;              // Murty's rule: only the highest index moves
+    if (!single) {
+      for (int ch = wid; ch < nvch; ch += NW) {
+        const int m = (ch << 5) + lane;
+        const int f = m < Mp ? s.fl[m] : 0;
+        const unsigned br = __ballot_sync(0xffffffffu, f == 1);
+        const unsigned ba = __ballot_sync(0xffffffffu, f == 2);
+        const int pref = __shfl_sync(0xffffffffu, incl_l, ch) - __shfl_sync(0xffffffffu, cnt_l, ch);
+        const unsigned below = (1u << lane) - 1;
+        if (f == 1) { const int sl = s.pos[m]; s.lst[(pref & 0xffff) + __popc(br & below)] = sl; s.smark[sl] = 1; }
+        if (f == 2) s.lst[cap - 1 - ((pref >> 16) + __popc(ba & below))] = m;
+      }
+    } else {
+      if (s.pos[mxi] >= 0) { nr = 1; na = 0; if (tid == 0) { const int sl = s.pos[mxi]; s.lst[0] = sl; s.smark[sl] = 1; } }
+      else { nr = 0; na = 1; if (tid == 0) s.lst[cap - 1] = mxi; }
+    }
+    __syncthreads();
+    for (int ch = wid; ch < nsch; ch += NW) {
+      const int sl = (ch << 5) + lane;
+      const bool fr_my = sl < cap && !(s.F[sl] >= 0 && !s.smark[sl]);
+      const unsigned bal = __ballot_sync(0xffffffffu, fr_my);
+      if (lane == 0) s.pl[64 + ch] = __popc(bal);
+    }
+    __syncthreads();
+    const int cntf_l = lane < nsch ? s.pl[64 + lane] : 0;
+    const int inclf_l = warp_incl_scan(cntf_l);
+    for (int ch = wid; ch < nsch; ch += NW) {
+      const int sl = (ch << 5) + lane;
+      const bool used_my = sl < cap && s.F[sl] >= 0 && !s.smark[sl];
+      const bool fr_my = sl < cap && !used_my;
+      const unsigned bal = __ballot_sync(0xffffffffu, fr_my);
+      const int pref_f = __shfl_sync(0xffffffffu, inclf_l, ch) - __shfl_sync(0xffffffffu, cntf_l, ch);
+      const int rank_f = pref_f + __popc(bal & ((1u << lane) - 1));
+      const bool take = fr_my && rank_f < na;
+      if (take) s.asl[rank_f] = sl;
+      if (sl < cap && s.smark[sl]) s.smark[sl] = 0;
+      const unsigned after = __ballot_sync(0xffffffffu, used_my || take);
+      if (lane == 0) s.pl[96 + ch] = after ? (ch << 5) + 32 - __clz(after) : 0;
+    }
+    __syncthreads();
+    const int hw_after = warp_max_i(lane < nsch ? s.pl[96 + lane] : 0);
+    if (nv < t_best) { t_best = nv; pbar = 3; }
+    else if (pbar >= 1) { --pbar; }
+    const int nt_op = (max(st.hwm, hw_after) + 7) >> 3;
+    if (st.grow_zero && nt_op > st.nt_dirty) {
+      const int q0 = tile_q(st.nt_dirty, 0), q1 = tile_q(nt_op, 0);
+      for (int i = (q0 << 5) + tid; i < (q1 << 5); i += T)
+        reinterpret_cast<double2 *>(tptr<MODE>(s, i >> 5))[i & 31] = make_double2(0.0, 0.0);
+      __syncthreads();
+    }
+    st.nt_dirty = max(st.nt_dirty, nt_op);
+    PH_TICK3(PH_PLAN);
+    for (int q0 = 0; q0 < nr; q0 += 8) { block_remove3<T, MODE>(cf, s.lst + q0, min(8, nr - q0), nt_op); if (tid == 0) s.prof[PH_NREM]++; }
+    PH_TICK3(PH_REMOVE);
+    for (int q0 = 0; q0 < na; q0 += 8) {
+      if (tid == 0) s.prof[PH_NADD]++;
+      const int a = min(8, na - q0);
+      if (!block_add3<T, MODE>(cf, G, ldg, s.lst + (cap - 1 - q0), s.asl + q0, a, nt_op)) {
+        // numerically dependent column in the block: retry one variable at a time
+        for (int q = 0; q < a; ++q) {
+          if (!block_add3<T, MODE>(cf, G, ldg, s.lst + (cap - 1 - q0 - q), s.asl + q0 + q, 1, nt_op)) {
+            if (tid == 0) s.vflag[s.lst[cap - 1 - q0 - q]] = 3;
+            STAT_ADD3(ST_BLOCKED, 1);
+            __syncthreads();
+          }
+        }
+      }
+    }
+    PH_TICK3(PH_ADD);
+    st.hwm = hw_after; st.nt_cur = (hw_after + 7) >> 3;
+    STAT_ADD3(ST_ITER, 1);
+    if (++iters > 60 + 6 * Mp) { ok = false; break; }
+  }
+  if (!ok) STAT_ADD3(ST_NOCONV, 1);
+  return ok;
+}
+
+}  // namespace
+}  // namespace pls

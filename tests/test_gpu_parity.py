@@ -243,3 +243,55 @@ def test_full_size_config2_properties(ctx, oracle):
     ref = oc.opt_fit(X, y, P, eta, b_list=[r["b_best"]], nthreads=1)
     assert abs(ref["objs"][0] - r["opt"]) <= RTOL * r["opt"]
     assert np.all(np.abs(ref["alphas"][0] - r["alpha_raw"]) <= RTOL * np.abs(ref["alphas"][0]).max())
+
+
+# ---- fit(BnB, ...)  (src/PartitionedLSBnB.jl) ----------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_bnb_toy(pkg, oracle, dtype):
+    """test/runtests.jl:41-69 and :123-146 with Optimizer=BnB: opt ~ 0, yhat = y; the root relaxation is
+    already sign-consistent, so exactly one node is visited."""
+    o, _ = oracle
+    model, cache, rep = pkg.fit(pkg.BnB, o.TOY_X.astype(dtype), o.TOY_Y.astype(dtype), o.TOY_P, η=0.0)
+    assert cache is None and abs(rep.opt) < 1e-6 and rep.nopen == 1
+    assert abs(np.sum(pkg.predict(model, o.TOY_X) - o.TOY_Y) ** 2) < 1e-6
+    assert _close(model.α, [5 / 11, 6 / 11, 1.0]) and _close(model.β, [11 / 29, -16 / 29]) and abs(model.t - 60 / 29) < 1e-9
+
+
+@pytest.mark.parametrize("shape", [(400, 12, 3, 0.0, 11), (600, 20, 5, 1e-3, 12), (300, 16, 4, 0.05, 13),
+                                   (1000, 30, 6, 0.0, 14), (64, 10, 5, 1e-3, 15)])
+def test_bnb_against_oracle(ctx, pkg, oracle, shape):
+    """Mixed-sign ground truth so the tree branches.  Same optimum, signed weights and cleaned
+    alpha / beta / t as the depth-first restatement of BnB.jl:30-132; nopen is traversal dependent."""
+    o, _ = oracle
+    N, M, K, eta, seed = shape
+    X, y, P = o.make_synthetic(N, M, K, seed=seed, mixed_sign=True)
+    ref = o.fit_bnb(X, y, P, eta)
+    r = ctx.bnb_fit(X, y, P, eta=eta)
+    assert abs(r["opt"] - ref["opt"]) <= RTOL * ref["opt"]
+    assert np.all(np.abs(r["alpha_signed"] - ref["alpha_signed"]) <= RTOL * np.abs(ref["alpha_signed"]).max())
+    assert 1 <= r["nopen"] <= 2 ** (K + 2) and r["stats"]["waves"] >= 1
+    model, _, rep = pkg.fit(pkg.BnB, X, y, P, η=eta, ctx=ctx)
+    assert _close(model.α, ref["alpha"]) and _close(model.β, ref["beta"]) and abs(model.t - ref["t"]) <= RTOL * max(1.0, abs(ref["t"]))
+    assert ref["nopen"] >= 3      # the case really branches
+
+
+def test_bnb_equals_opt_and_small_pool(ctx, oracle):
+    """BnB and the exhaustive Opt enumeration reach the same optimum (README.md:54); a state pool of
+    only 12 slots forces the depth-first (bounded-memory) frontier order and still finds it."""
+    o, _ = oracle
+    X, y, P = o.make_synthetic(3000, 60, 8, seed=321, mixed_sign=True)
+    eta = 1e-3
+    ropt = ctx.opt_fit(X, y, P, eta=eta)
+    Xo, Po = o.homogeneous_coords(X, P)
+    w_opt = (Po @ o.index_to_beta(ropt["b_best"], P.shape[1] + 1)) * ropt["alpha_raw"]
+    r = ctx.bnb_fit(X, y, P, eta=eta)
+    assert abs(r["opt"] - ropt["opt"]) <= RTOL * ropt["opt"]
+    assert np.all(np.abs(r["alpha_signed"] - w_opt) <= RTOL * np.abs(w_opt).max())
+    assert r["nopen"] < 2 ** 9
+    os.environ["PLS_BNB_SLOTS"] = "12"
+    try:
+        r2 = ctx.bnb_fit(X, y, P, eta=eta)
+    finally:
+        os.environ.pop("PLS_BNB_SLOTS")
+    assert abs(r2["opt"] - r["opt"]) <= 1e-12 * r["opt"]
+    assert np.all(np.abs(r2["alpha_signed"] - r["alpha_signed"]) <= RTOL * np.abs(w_opt).max())
