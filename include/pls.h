@@ -107,6 +107,25 @@ int pls_bnb_fit(pls_ctx *ctx, const double *X, int64_t N, int64_t M, const doubl
 int pls_bnb_fit_resident(pls_ctx *ctx, uint32_t flags, double *alpha_signed, double *obj,
                          int64_t *nopen, pls_stats *stats);
 
+/* ---- fit(::Type{Alt}, ...)  (src/PartitionedLSAlt.jl:50-124) --------------------------------------
+ * Alternating optimisation, R random restarts as one batch (the reference runs one start: R = 1).
+ *   beta0[(K+1) x R]   column-major initial beta of every restart, drawn by the host exactly as
+ *                      Alt.jl:65-66 does ((rng(F, K') .- 0.5) .* 10) so RNG semantics stay on the host
+ *   eps, T             stopping rule of Alt.jl:77: while i <= T && abs(old - opt) > eps * old
+ *   alpha[M+1], beta[K+1]  the best restart's normalised alpha and beta (Alt.jl:119 takes
+ *                      alpha[1:M], beta[1:K], t = beta[K+1] * alpha[M+1])
+ *   obj                norm(Xo * (Po .* alpha) * beta - yo) of that restart, data-space recompute
+ *   best_restart, iters  which restart won (lowest loss, lowest index on ties) and its iterations
+ *   all_obj            nullable, R Gram-space losses (INFINITY for a restart whose K' x K' system
+ *                      was not positive definite) */
+int pls_alt_fit(pls_ctx *ctx, const double *X, int64_t N, int64_t M, const double *y,
+                const int64_t *P, int64_t K, double eta, const double *beta0, int64_t R, double eps,
+                int64_t T, uint32_t flags, double *alpha, double *beta, double *obj,
+                int64_t *best_restart, int64_t *iters, double *all_obj, pls_stats *stats);
+int pls_alt_fit_resident(pls_ctx *ctx, const double *beta0, int64_t R, double eps, int64_t T,
+                         uint32_t flags, double *alpha, double *beta, double *obj,
+                         int64_t *best_restart, int64_t *iters, double *all_obj, pls_stats *stats);
+
 /* ---- resident data set: upload once, fit many times -------------------------------------------
  * pls_load copies rows [0, N) of X (leading dimension ldx >= N), y and P to the device in the
  * library's augmented layout Z = [X | 1 | y] (zero padded).  In a multi-process run each rank loads

@@ -26,7 +26,7 @@ from . import _abi
 from ._abi import Context, PlsError  # noqa: F401
 
 __all__ = ["fit", "predict", "PartLSFitResult", "Opt", "Alt", "BnB", "homogeneousCoords",
-           "regularizeProblem", "Context", "PlsError", "default_context"]
+           "regularizeProblem", "Context", "PlsError", "default_context", "draw_alt_starts"]
 
 
 class Opt:   # src/PartitionedLSOpt.jl:1
@@ -109,6 +109,18 @@ def _cleanup_result(opt, alpha_raw, b, P):
     return opt, PartLSFitResult(aa, bb, t, P)
 
 
+def draw_alt_starts(rng, Mp, Kp, restarts=1):
+    """Initial values of Alt.jl:58-66 for `restarts` starts: per start alpha_0 = rng(M') is drawn first
+    (dead upstream, but it keeps the stream aligned) and then beta_0 = (rng(K') - 0.5) * 10.
+    rng: None (fresh entropy), an int seed, or a numpy Generator.  Returns (K', restarts)."""
+    g = rng if isinstance(rng, np.random.Generator) else np.random.default_rng(rng)
+    out = np.empty((Kp, restarts), order="F")
+    for r in range(restarts):
+        g.random(Mp)
+        out[:, r] = (g.random(Kp) - 0.5) * 10.0
+    return out
+
+
 def _bnb_postprocess(alpha_signed, P):
     """src/PartitionedLSBnB.jl:36-39 on the signed weights of the best leaf: beta_k = signed group
     sums, alpha = alpha ./ beta (no zero guard upstream: a group summing to 0 gives NaN),
@@ -127,8 +139,11 @@ def _bnb_postprocess(alpha_signed, P):
 def fit(alg, X, y, P, *, η=0.0, eta=None, nnlsalg="nnls", returnAllSolutions=False, ctx=None, **kw):
     """fit(Opt, X, y, P; η, nnlsalg, returnAllSolutions) -- src/PartitionedLSOpt.jl:73-104.
 
-    ``nnlsalg`` is accepted and ignored (the GPU path has a single Gram-space solver).  ``Alt`` and
-    ``BnB`` are not built yet in this round and raise."""
+    fit(BnB, X, y, P; η, nnlsalg)                 -- src/PartitionedLSBnB.jl:30-40 (report: opt, nopen)
+    fit(Alt, X, y, P; η, ϵ, T, nnlsalg, rng)      -- src/PartitionedLSAlt.jl:50-124 (report: opt); extra
+        keywords ``restarts`` (batched random restarts, best one returned) and ``beta0`` ((K+1) x R).
+
+    ``nnlsalg`` is accepted and ignored (the GPU path has a single Gram-space solver)."""
     if eta is not None:
         η = eta
     if alg is Opt or isinstance(alg, Opt):
@@ -145,7 +160,16 @@ def fit(alg, X, y, P, *, η=0.0, eta=None, nnlsalg="nnls", returnAllSolutions=Fa
         model = _bnb_postprocess(r["alpha_signed"], P)
         return model, None, SimpleNamespace(opt=r["opt"], nopen=r["nopen"], stats=r["stats"])
     if alg is Alt or isinstance(alg, Alt):
-        raise NotImplementedError("fit(Alt) is not part of this round's GPU hot path (SURVEY.md 8f)")
+        c = ctx or default_context()
+        Kp, Mp = np.asarray(P).shape[1] + 1, np.asarray(P).shape[0] + 1
+        beta0 = kw.get("beta0")
+        if beta0 is None:
+            beta0 = draw_alt_starts(kw.get("rng"), Mp, Kp, int(kw.get("restarts", 1)))
+        r = c.alt_fit(X, y, P, beta0, eta=float(η), eps=float(kw.get("ϵ", kw.get("eps", 1e-6))), T=int(kw.get("T", 100)))
+        a, b = r["alpha"], r["beta"]
+        model = PartLSFitResult(a[:-1].copy(), b[:-1].copy(), float(b[-1] * a[-1]), np.asarray(P, dtype=np.int64))   # Alt.jl:119
+        return model, None, SimpleNamespace(opt=r["opt"], best_restart=r["best_restart"], iters=r["iters"],
+                                            all_obj=r["all_obj"], stats=r["stats"])
     raise TypeError(f"unknown algorithm {alg!r}")
 
 

@@ -57,6 +57,10 @@ lib.pls_opt_fit.argtypes = [_vp, _dp, C.c_int64, C.c_int64, _dp, _ip, C.c_int64,
 lib.pls_bnb_fit.argtypes = [_vp, _dp, C.c_int64, C.c_int64, _dp, _ip, C.c_int64, C.c_double, C.c_uint32,
                             _dp, _dp, _ip, C.POINTER(PlsStats)]
 lib.pls_bnb_fit_resident.argtypes = [_vp, C.c_uint32, _dp, _dp, _ip, C.POINTER(PlsStats)]
+lib.pls_alt_fit.argtypes = [_vp, _dp, C.c_int64, C.c_int64, _dp, _ip, C.c_int64, C.c_double, _dp, C.c_int64,
+                            C.c_double, C.c_int64, C.c_uint32, _dp, _dp, _dp, _ip, _ip, _dp, C.POINTER(PlsStats)]
+lib.pls_alt_fit_resident.argtypes = [_vp, _dp, C.c_int64, C.c_double, C.c_int64, C.c_uint32, _dp, _dp, _dp, _ip, _ip,
+                                     _dp, C.POINTER(PlsStats)]
 lib.pls_load.argtypes = [_vp, _dp, C.c_int64, C.c_int64, C.c_int64, _dp, _ip, C.c_int64, C.c_double]
 lib.pls_opt_fit_resident.argtypes = [_vp, C.c_uint32, _dp, _ip, _dp, _dp, _dp, C.POINTER(PlsStats)]
 lib.pls_gram_build.argtypes = [_vp]
@@ -69,7 +73,7 @@ lib.pls_get_stats.argtypes = [_vp, C.POINTER(PlsStats)]
 lib.pls_gram.argtypes = [_vp, _dp, C.c_int64, C.c_int64, _dp, _ip, C.c_int64, C.c_double, _dp, _dp, _dp]
 lib.pls_nnls_batch.argtypes = [_vp, _dp, _dp, C.c_double, C.c_int64, C.POINTER(C.c_uint64), C.c_int64,
                                C.c_int64, C.c_int64, _dp, _dp]
-for _n in ("pls_create", "pls_opt_fit", "pls_bnb_fit", "pls_bnb_fit_resident", "pls_load", "pls_opt_fit_resident", "pls_gram_build", "pls_gram_raw",
+for _n in ("pls_create", "pls_opt_fit", "pls_bnb_fit", "pls_bnb_fit_resident", "pls_alt_fit", "pls_alt_fit_resident", "pls_load", "pls_opt_fit_resident", "pls_gram_build", "pls_gram_raw",
            "pls_gram_finalize", "pls_opt_solve_range", "pls_opt_residual_partial", "pls_opt_objective_finish",
            "pls_get_stats", "pls_gram", "pls_nnls_batch"):
     getattr(lib, _n).restype = C.c_int
@@ -153,6 +157,30 @@ class Context:
         a = np.zeros(M + 1); obj = C.c_double(); nopen = C.c_int64(); st = PlsStats()
         _check(lib.pls_bnb_fit_resident(self._h, flags, _d(a), C.byref(obj), C.byref(nopen), C.byref(st)))
         return dict(alpha_signed=a, opt=obj.value, nopen=nopen.value, stats=st.as_dict())
+
+    def alt_fit(self, X, y, P, beta0, eta=0.0, eps=1e-6, T=100, flags=0, prepared=False, resident=False):
+        """pls_alt_fit: beta0 is (K+1) x R (one column per restart).  Returns the best restart."""
+        if not resident:
+            if not prepared:
+                X, y, P = _as_inputs(X, y, P)
+            N, M = X.shape
+            K = P.shape[1]
+        else:
+            N, M, K = self._shape
+        b0 = np.asfortranarray(np.asarray(beta0, dtype=np.float64).reshape(K + 1, -1))
+        R = b0.shape[1]
+        a = np.zeros(M + 1); b = np.zeros(K + 1); obj = C.c_double(); rb = C.c_int64(); it = C.c_int64()
+        allo = np.zeros(R); st = PlsStats()
+        if resident:
+            _check(lib.pls_alt_fit_resident(self._h, _d(b0), R, float(eps), int(T), flags, _d(a), _d(b), C.byref(obj),
+                                            C.byref(rb), C.byref(it), _d(allo), C.byref(st)))
+        else:
+            _check(lib.pls_alt_fit(self._h, _d(X), N, M, _d(y), P.ctypes.data_as(_ip), K, float(eta), _d(b0), R,
+                                   float(eps), int(T), flags, _d(a), _d(b), C.byref(obj), C.byref(rb), C.byref(it),
+                                   _d(allo), C.byref(st)))
+            self._shape = (N, M, K)
+        return dict(alpha=a, beta=b, opt=obj.value, best_restart=rb.value, iters=it.value, all_obj=allo,
+                    stats=st.as_dict())
 
     # -- resident / stage-wise path ----------------------------------------------------------
     def load(self, X, y, P, eta=0.0, prepared=False):

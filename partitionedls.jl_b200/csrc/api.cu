@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <new>
@@ -77,7 +78,7 @@ void free_ws(pls_ctx *c) {
   SolveWs &ws = c->ws;
   cudaFree(ws.cta_obj); cudaFree(ws.cta_b); cudaFree(ws.cta_w); cudaFree(ws.hspill);
   cudaFree(ws.counters); cudaFree(ws.win); cudaFree(ws.all_obj); cudaFree(ws.all_alpha);
-  cudaFree(ws.resid_part);
+  cudaFree(ws.resid_part); cudaFree(ws.alt_win);
   ws = SolveWs();
 }
 
@@ -516,6 +517,84 @@ int pls_bnb_fit(pls_ctx *c, const double *X, int64_t N, int64_t M, const double 
   if (rc) return rc;
   c->stats.ms_upload = now_ms() - t0;
   rc = pls_bnb_fit_resident(c, flags, alpha_signed, obj, nopen, stats);
+  c->stats.ms_upload = 0.0;
+  return rc;
+}
+
+int pls_alt_fit_resident(pls_ctx *c, const double *beta0, int64_t R, double eps, int64_t T, uint32_t flags,
+                         double *alpha, double *beta, double *obj_out, int64_t *best_restart, int64_t *iters,
+                         double *all_obj, pls_stats *stats) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!c->pb.loaded) { set_error("no data set loaded"); return PLS_EINVAL; }
+  if (!beta0 || !alpha || !beta || !obj_out) { set_error("null pointer"); return PLS_EINVAL; }
+  if (R < 1 || T < 1 || !(eps > 0.0)) { set_error("alt: need R >= 1, T >= 1, eps > 0"); return PLS_EINVAL; }
+  const double t0 = now_ms();
+  const double keep_upload = c->stats.ms_upload;
+  memset(&c->stats, 0, sizeof(c->stats));
+  c->stats.ms_upload = keep_upload;
+  const int launches0 = c->launches;
+  Problem &pb = c->pb;
+  cudaStream_t st = c->stream;
+  const int Mp = pb.Mp, Kp = pb.Kp;
+  for (int64_t i = 0; i < R * Kp; ++i)
+    if (!std::isfinite(beta0[i])) { set_error("alt: non-finite initial beta"); return PLS_EINVAL; }
+  PLS_CUDA_TRY(cudaEventRecord(c->ev[0], st));
+  rc = k1_gram_build(pb, st, &c->launches); if (rc) return rc;
+  rc = k1_gram_finalize(pb, st, &c->launches); if (rc) return rc;
+  PLS_CUDA_TRY(cudaEventRecord(c->ev[1], st));
+  double *d_win = nullptr;
+  rc = k6_alt_run(pb, c->ws, c->h_gmask, beta0, R, eps, (int)std::min<int64_t>(T, 1 << 30), c->d_w, all_obj,
+                  c->sm_count, st, &c->launches, &d_win);
+  if (rc) return rc;
+  PLS_CUDA_TRY(cudaEventRecord(c->ev[2], st));
+  const bool recompute = !(flags & PLS_FLAG_NO_RECOMPUTE);
+  if (recompute) { rc = k4_residual(pb, c->ws, c->d_w, c->d_ssq, c->sm_count, st, &c->launches); if (rc) return rc; }
+  PLS_CUDA_TRY(cudaEventRecord(c->ev[3], st));
+  const int len = Mp + Kp + 1;
+  std::vector<double> h(len + 2 + Mp + 2);
+  std::vector<unsigned long long> cnt(CNT_NUM + 1 + 24);
+  PLS_CUDA_TRY(cudaMemcpyAsync(h.data(), d_win, sizeof(double) * (len + 2), cudaMemcpyDeviceToHost, st));
+  PLS_CUDA_TRY(cudaMemcpyAsync(h.data() + len + 2, c->d_w, sizeof(double) * Mp, cudaMemcpyDeviceToHost, st));
+  if (recompute) PLS_CUDA_TRY(cudaMemcpyAsync(h.data() + len + 2 + Mp, c->d_ssq, sizeof(double), cudaMemcpyDeviceToHost, st));
+  PLS_CUDA_TRY(cudaMemcpyAsync(h.data() + len + 3 + Mp, pb.scal + 3, sizeof(double), cudaMemcpyDeviceToHost, st));
+  PLS_CUDA_TRY(cudaMemcpyAsync(cnt.data(), c->ws.counters, sizeof(unsigned long long) * cnt.size(), cudaMemcpyDeviceToHost, st));
+  PLS_CUDA_TRY(cudaStreamSynchronize(st));
+  if (h[len + 3 + Mp] != 0.0) { set_error("non-finite values in X or y"); return PLS_ENUMERIC; }
+  long long rbest; memcpy(&rbest, &h[len + 1], sizeof(rbest));
+  if (rbest < 0) { set_error("alt: every restart failed (K' x K' system not positive definite or NNLS did not converge)"); return PLS_ENUMERIC; }
+  memcpy(alpha, h.data(), sizeof(double) * Mp);
+  memcpy(beta, h.data() + Mp, sizeof(double) * Kp);
+  double obj = h[len];
+  if (recompute) obj = std::sqrt(h[len + 2 + Mp] + eta_term_w(c, h.data() + len + 2));
+  *obj_out = obj;
+  if (best_restart) *best_restart = rbest;
+  if (iters) *iters = (int64_t)h[Mp + Kp];
+  float ms = 0.f;
+  pls_stats &s = c->stats;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); s.ms_gram = ms;
+  cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); s.ms_nnls = ms;
+  cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); s.ms_recompute = ms;
+  read_counters(c, cnt.data());
+  s.waves = s.spills; s.spills = 0;          // CNT_SPILLS carries the longest restart's iteration count
+  s.orthants = R;
+  const double Nd = (double)pb.N, Md = (double)Mp;
+  s.gram_flops = Nd * Md * (Md + 1.0) + 2.0 * Nd * Md + 2.0 * Nd;
+  s.kernel_launches = c->launches - launches0;
+  s.ms_total = now_ms() - t0 + s.ms_upload;
+  if (stats) *stats = s;
+  if (obj != obj) { set_error("NaN objective"); return PLS_ENUMERIC; }
+  return PLS_OK;
+}
+
+int pls_alt_fit(pls_ctx *c, const double *X, int64_t N, int64_t M, const double *y, const int64_t *P, int64_t K,
+                double eta, const double *beta0, int64_t R, double eps, int64_t T, uint32_t flags, double *alpha,
+                double *beta, double *obj, int64_t *best_restart, int64_t *iters, double *all_obj, pls_stats *stats) {
+  const double t0 = now_ms();
+  int rc = pls_load(c, X, N, N, M, y, P, K, eta);
+  if (rc) return rc;
+  c->stats.ms_upload = now_ms() - t0;
+  rc = pls_alt_fit_resident(c, beta0, R, eps, T, flags, alpha, beta, obj, best_restart, iters, all_obj, stats);
   c->stats.ms_upload = 0.0;
   return rc;
 }

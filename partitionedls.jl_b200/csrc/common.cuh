@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <vector>
 #include "../../include/pls.h"
 
 namespace pls {
@@ -59,6 +60,8 @@ struct SolveWs {
   size_t all_obj_n = 0, all_alpha_n = 0;
   int max_ctas = 0, Mp = 0;
   size_t hspill_bytes = 0;
+  double *alt_win = nullptr;      // K6 winner record [alpha | beta | iters | loss | restart]
+  int alt_win_len = 0;
   double *resid_part = nullptr;   // K4 block partials
   int resid_blocks = 0;
 };
@@ -103,6 +106,10 @@ int k2v3_launch(const K2Args &A, const K3Plan &pl, int grid, cudaStream_t st);
 // K5: branch and bound with batched frontier expansion (bnb.cu); winner left in ws.win
 struct BnbReport { long long visited, waves, max_open, pool_slots; double mu; };
 int k5_bnb_run(const Problem &pb, SolveWs &ws, int sm_count, cudaStream_t st, int *launches, BnbReport *rep);
+// K6: alternating optimisation, batched restarts (alt.cu)
+int k6_alt_run(const Problem &pb, SolveWs &ws, const std::vector<uint64_t> &h_gmask, const double *h_beta0, long long R,
+               double eps, int Tmax, double *d_w, double *h_all_obj, int sm_count, cudaStream_t st, int *launches,
+               double **d_win_out);
 int k4_residual(const Problem &pb, SolveWs &ws, const double *d_w, double *d_ssq, int sm_count,
                 cudaStream_t st, int *launches);
 

@@ -295,3 +295,54 @@ def test_bnb_equals_opt_and_small_pool(ctx, oracle):
         os.environ.pop("PLS_BNB_SLOTS")
     assert abs(r2["opt"] - r["opt"]) <= 1e-12 * r["opt"]
     assert np.all(np.abs(r2["alpha_signed"] - r["alpha_signed"]) <= RTOL * np.abs(w_opt).max())
+
+
+# ---- fit(Alt, ...)  (src/PartitionedLSAlt.jl) ----------------------------------------------------
+def test_alt_toy(pkg, oracle):
+    """test/runtests.jl:41-69 with Optimizer=Alt: converges to opt ~ 0 from any start."""
+    o, _ = oracle
+    for dtype in (np.float64, np.float32):
+        model, cache, rep = pkg.fit(pkg.Alt, o.TOY_X.astype(dtype), o.TOY_Y.astype(dtype), o.TOY_P, η=0.0, rng=123)
+        assert cache is None and abs(rep.opt) < 1e-6
+        assert abs(np.sum(pkg.predict(model, o.TOY_X) - o.TOY_Y) ** 2) < 1e-6
+    # determinism (test/runtests.jl:102-121): same seed, same result
+    a = pkg.fit(pkg.Alt, o.TOY_X, o.TOY_Y, o.TOY_P, rng=7, T=20)[2].opt
+    b = pkg.fit(pkg.Alt, o.TOY_X, o.TOY_Y, o.TOY_P, rng=7, T=20)[2].opt
+    assert a == b
+
+
+@pytest.mark.parametrize("shape", [(500, 12, 3, 0.0, 21), (800, 24, 5, 1e-3, 22), (400, 18, 6, 0.05, 23), (2000, 40, 8, 0.0, 24)])
+def test_alt_against_oracle(ctx, oracle, shape):
+    """Each restart follows the reference iteration (alpha-step NNLS, checkalpha, normalise, beta-step
+    least squares, relative stopping rule) from the same beta_0: same loss, alpha, beta, iteration
+    count; the batch returns the restart with the lowest loss."""
+    o, _ = oracle
+    N, M, K, eta, seed = shape
+    X, y, P = o.make_synthetic(N, M, K, seed=seed, mixed_sign=True)
+    rng = np.random.default_rng(seed)
+    R = 6
+    beta0 = (rng.random((K + 1, R)) - 0.5) * 10.0
+    refs = [o.fit_alt(X, y, P, beta0[:, r], eta=eta, eps=1e-6, T=100) for r in range(R)]
+    r = ctx.alt_fit(X, y, P, beta0, eta=eta, eps=1e-6, T=100)
+    ref_objs = np.array([q["opt"] for q in refs])
+    assert np.allclose(r["all_obj"], ref_objs, rtol=1e-8)
+    best = int(np.argmin(ref_objs))
+    assert r["best_restart"] == best
+    q = refs[best]
+    assert abs(r["opt"] - q["opt"]) <= 1e-8 * q["opt"]
+    assert r["iters"] == q["iters"]
+    assert np.all(np.abs(r["alpha"] - q["alpha_full"]) <= 1e-7 * np.abs(q["alpha_full"]).max())
+    assert np.all(np.abs(r["beta"] - q["beta_full"]) <= 1e-7 * np.abs(q["beta_full"]).max())
+
+
+def test_alt_single_start_is_the_reference_run(ctx, pkg, oracle):
+    """R = 1 is the reference's own behaviour (one start); T caps the iterations (Alt.jl:77)."""
+    o, _ = oracle
+    X, y, P = o.make_synthetic(700, 15, 4, seed=5, mixed_sign=False)
+    b0 = np.array([3.0, -1.0, 2.5, -4.0, 0.7])
+    for T in (1, 2, 100):
+        q = o.fit_alt(X, y, P, b0, eta=0.0, eps=1e-6, T=T)
+        model, _, rep = pkg.fit(pkg.Alt, X, y, P, η=0.0, T=T, beta0=b0, ctx=ctx)
+        assert rep.iters == q["iters"] and abs(rep.opt - q["opt"]) <= 1e-8 * q["opt"]
+        assert np.all(np.abs(model.α - q["alpha"]) <= 1e-7) and np.all(np.abs(model.β - q["beta"]) <= 1e-7 * np.abs(q["beta"]).max())
+        assert abs(model.t - q["t"]) <= 1e-7 * max(1.0, abs(q["t"]))
