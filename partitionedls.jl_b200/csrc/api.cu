@@ -135,6 +135,7 @@ void read_counters(pls_ctx *c, const unsigned long long *h) {
 int solve_range_dev(pls_ctx *c, int64_t b_begin, int64_t b_count, bool want_obj, bool want_alpha) {
   Problem &pb = c->pb;
   if (!pb.gram_ready) { set_error("Gram matrix not built (call pls_gram_build / pls_gram_finalize)"); return PLS_EINVAL; }
+  if (pb.Kp > 40) { set_error("K = %d: 2^(K+1) orthants cannot be enumerated (limit K <= 39); use fit(BnB) or fit(Alt)", pb.K); return PLS_EINVAL; }
   const int64_t total = (int64_t)1 << pb.Kp;
   if (b_begin < 0 || b_count <= 0 || b_begin + b_count > total) { set_error("orthant range out of bounds"); return PLS_EINVAL; }
   int rc = ensure_all_buffers(c, b_count, want_obj, want_alpha);
@@ -239,7 +240,7 @@ int pls_load(pls_ctx *c, const double *X, int64_t N, int64_t ldx, int64_t M, con
   if (rc) return rc;
   if (!X || !y || !P) { set_error("null input pointer"); return PLS_EINVAL; }
   if (N < 1 || M < 1 || K < 1 || ldx < N) { set_error("bad shape N=%lld M=%lld K=%lld ldx=%lld", (long long)N, (long long)M, (long long)K, (long long)ldx); return PLS_EINVAL; }
-  if (K + 1 > 40) { set_error("K = %lld: 2^(K+1) orthants cannot be enumerated (limit K <= 39)", (long long)K); return PLS_EINVAL; }
+  if (K + 1 > 64) { set_error("K = %lld: at most 63 groups (one bit per group and the intercept)", (long long)K); return PLS_EINVAL; }
   if (M + 2 > 4096) { set_error("M = %lld exceeds this build's limit (4094)", (long long)M); return PLS_EUNSUPPORTED; }
   if (!(eta >= 0.0) || !std::isfinite(eta)) { set_error("eta must be finite and >= 0"); return PLS_EINVAL; }
   std::vector<uint64_t> gm((size_t)M + 1, 0);
@@ -388,6 +389,7 @@ int pls_opt_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_raw, int64_t 
   Problem &pb = c->pb;
   cudaStream_t st = c->stream;
   const int Mp = pb.Mp;
+  if (pb.Kp > 40) { set_error("K = %d: 2^(K+1) orthants cannot be enumerated (limit K <= 39); use fit(BnB) or fit(Alt)", pb.K); return PLS_EINVAL; }
   const int64_t total = (int64_t)1 << pb.Kp;
   PLS_CUDA_TRY(cudaEventRecord(c->ev[0], st));
   rc = k1_gram_build(pb, st, &c->launches); if (rc) return rc;

@@ -309,6 +309,7 @@ int k5_bnb_run(const Problem &pb, SolveWs &ws, int sm_count, cudaStream_t st, in
   std::vector<BnbItem> items; std::vector<BnbChild> out;
   std::vector<OpenNode> open; std::vector<int> free_slots;
   long long visited = 0, waves = 0, max_open = 0;
+  const long long max_nodes = getenv("PLS_BNB_MAX_NODES") ? atoll(getenv("PLS_BNB_MAX_NODES")) : 0;
   double h_mu = INFINITY;
   const unsigned long long inf_bits = 0x7ff0000000000000ull;
 #define BNB_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); rc = e_ == cudaErrorMemoryAllocation ? PLS_ENOMEM : PLS_ECUDA; goto done; } } while (0)
@@ -386,6 +387,10 @@ int k5_bnb_run(const Problem &pb, SolveWs &ws, int sm_count, cudaStream_t st, in
     }
     max_open = std::max<long long>(max_open, (long long)open.size());
     if (open.empty()) break;
+    if (max_nodes > 0 && visited >= max_nodes) {
+      set_error("bnb: node budget PLS_BNB_MAX_NODES=%lld exhausted (%lld visited, %zu open, incumbent %.9g)", max_nodes, visited, open.size(), h_mu);
+      rc = PLS_EUNSUPPORTED; goto done;
+    }
     const bool low = free_slots.size() < (size_t)2 * wave_max;
     if (low) std::sort(open.begin(), open.end(), [](const OpenNode &a, const OpenNode &b) { return a.depth != b.depth ? a.depth < b.depth : a.lb > b.lb; });
     else std::sort(open.begin(), open.end(), [](const OpenNode &a, const OpenNode &b) { return a.lb > b.lb; });

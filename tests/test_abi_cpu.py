@@ -93,8 +93,24 @@ def test_host_rewrites_match_oracle(pkg, oracle):
     assert np.array_equal(Xa, Xa2) and np.array_equal(ya, ya2)
 
 
-def test_alt_bnb_fail_loudly_until_built(pkg):
-    with pytest.raises(NotImplementedError):
-        pkg.fit(pkg.Alt, np.ones((4, 3)), np.ones(4), np.array([[1, 0], [1, 0], [0, 1]]))
+def test_no_cpu_fallback_for_any_algorithm(pkg, oracle):
+    """Without a GPU every fit must fail loudly with PLS_ECUDA (no CPU fallback); unknown algorithm
+    types are a TypeError.  Host-side pieces of BnB / Alt are checked against the oracle."""
+    import ctypes
+    o, _ = oracle
+    X, y, P = np.ones((4, 3)), np.ones(4), np.array([[1, 0], [1, 0], [0, 1]])
     with pytest.raises(TypeError):
-        pkg.fit(object, np.ones((4, 3)), np.ones(4), np.array([[1, 0], [1, 0], [0, 1]]))
+        pkg.fit(object, X, y, P)
+    if pkg._abi.lib.pls_device_count() == 0:
+        for alg in (pkg.Opt, pkg.BnB, pkg.Alt):
+            with pytest.raises(pkg.PlsError) as e:
+                pkg.fit(alg, X, y, P)
+            assert e.value.code == pkg._abi.PLS_ECUDA
+    # BnB post-processing (BnB.jl:36-39) and the Alt start-value stream (Alt.jl:65-66)
+    a_s = np.array([0.5, 1.5, -2.0, 0.25])
+    m = pkg._bnb_postprocess(a_s, P)
+    assert np.allclose(m.β, [2.0, -2.0]) and np.allclose(m.α, [0.25, 0.75, 1.0]) and m.t == 0.25
+    b0 = pkg.draw_alt_starts(3, 4, 3, restarts=2)
+    g = np.random.default_rng(3); g.random(4); first = (g.random(3) - 0.5) * 10
+    assert b0.shape == (3, 2) and np.array_equal(b0[:, 0], first) and np.all(np.abs(b0) <= 5)
+    assert ctypes.sizeof(pkg._abi.PlsStats) == 8 * 21
