@@ -1,15 +1,19 @@
 # PartitionedLSCUDA.jl -- thin Julia host for libpls_cuda.so (the B200 solver core).
 #
-# Drop-in for the body of `fit(::Type{Opt}, X, y, P; η, nnlsalg, returnAllSolutions)`
-# (PartitionedLS.jl/src/PartitionedLSOpt.jl:73-104).  Everything between argument validation
-# and `cleanupResult` (Opt.jl:79-97) runs in the library; `cleanupResult` (Opt.jl:34-44),
+# Drop-in for the bodies of
+#   fit(::Type{Opt}, X, y, P; η, nnlsalg, returnAllSolutions)   PartitionedLS.jl/src/PartitionedLSOpt.jl:73-104
+#   fit(::Type{BnB}, X, y, P; η, nnlsalg)                        src/PartitionedLSBnB.jl:30-40
+#   fit(::Type{Alt}, X, y, P; η, ϵ, T, nnlsalg, rng)             src/PartitionedLSAlt.jl:50-124
+# Everything between argument validation and the result clean-up runs in the library; `cleanupResult`
+# (Opt.jl:34-44), the BnB post-processing (BnB.jl:36-39), the RNG draws of Alt (Alt.jl:58-66),
 # `PartLSFitResult` (PartitionedLS.jl:29-49) and `predict` (:132-155) are the reference's own.
 #
 # NOTE: Julia is not installed in the build image, so this file has been reviewed by eye only; the
 # same C ABI is exercised end to end by the Python twin (partitionedls.jl_b200/_abi.py + tests/).
 module PartitionedLSCUDA
 
-using PartitionedLS: PartLSFitResult, Opt, cleanupResult
+using PartitionedLS: PartLSFitResult, Opt, Alt, BnB, cleanupResult, homogeneousCoords
+using Random
 import PartitionedLS: fit
 
 const libpls = get(ENV, "LIBPLS_CUDA", "libpls_cuda.so")
@@ -20,6 +24,7 @@ struct PlsStats            # mirrors `pls_stats` in include/pls.h
     orthants::Int64; pivots::Int64; grad_evals::Int64; sum_p::Int64; sum_p2::Int64
     bpp_iters::Int64; spills::Int64; rebuilds::Int64; blocked::Int64; kernel_launches::Int64
     gram_flops::Cdouble; nnls_flops::Cdouble; nnls_l2_bytes::Cdouble
+    waves::Int64; max_open::Int64
 end
 
 const _ctx = Ref{Ptr{Cvoid}}(C_NULL)      # created lazily: never ccall at precompile time
@@ -75,6 +80,68 @@ function fit(::Type{Opt}, X::Array{<:AbstractFloat,2}, y::AbstractArray{<:Abstra
         return (model, nothing, (; solutions = sols))
     end
     return (model, nothing, (; opt = opt))
+end
+
+"""
+    fit(BnB, X, y, P; η=0.0, nnlsalg=:nnls)
+
+Same signature and return tuple as the reference (BnB.jl:30-40).  The library returns the signed
+weights α of the best feasible leaf (BnB.jl:84-89) and its objective; the post-processing of
+BnB.jl:36-39 runs here unchanged.  `nopen` counts the nodes visited by the batched traversal; it
+is traversal-order dependent and differs from the reference's depth-first count.
+"""
+function fit(::Type{BnB}, X::Array{<:AbstractFloat,2}, y::AbstractArray{<:AbstractFloat,1}, P::Array{Int,2};
+             η=0.0, nnlsalg=:nnls)
+    Xd = convert(Matrix{Float64}, X); yd = convert(Vector{Float64}, y); Pd = convert(Matrix{Int64}, P)
+    N, M = size(Xd); K = size(Pd, 2)
+    α = zeros(Float64, M + 1); obj = Ref{Cdouble}(0.0); nopen = Ref{Int64}(0); stats = Ref{PlsStats}()
+    GC.@preserve Xd yd Pd α begin
+        _check(ccall((:pls_bnb_fit, libpls), Cint,
+            (Ptr{Cvoid}, Ptr{Cdouble}, Int64, Int64, Ptr{Cdouble}, Ptr{Int64}, Int64, Cdouble, UInt32,
+             Ptr{Cdouble}, Ref{Cdouble}, Ref{Int64}, Ref{PlsStats}),
+            context(), Xd, N, M, yd, Pd, K, Float64(η), UInt32(0), α, obj, nopen, stats))
+    end
+    _, Po = homogeneousCoords(Xd[1:1, :], Pd)            # only Po is needed (PartitionedLS.jl:76-81)
+    β = sum(Po .* α, dims = 1)                           # BnB.jl:36
+    α = sum(Po .* α ./ β, dims = 2)                      # BnB.jl:37 (no zero guard upstream)
+    return (PartLSFitResult(α[1:end-1], β[1:end-1], β[end], P), nothing, (; opt = obj[], nopen = Int(nopen[])))
+end
+
+"""
+    fit(Alt, X, y, P; η=0.0, ϵ=1e-6, T=100, nnlsalg=:nnls, rng=nothing, restarts=1)
+
+Same signature and return tuple as the reference (Alt.jl:50-51, :119) plus `restarts`: the
+initial values of every restart are drawn HERE exactly as Alt.jl:58-66 does (α₀ first -- dead
+upstream but it keeps the stream aligned -- then β₀ = (rng(F, K') .- 0.5) .* 10), so a given
+`rng` seed means what it means upstream; the library iterates all restarts as one batch and
+returns the best one.  `restarts = 1` is the reference's behaviour.
+"""
+function fit(::Type{Alt}, X::Matrix{F}, y::Vector{F}, P::Array{Int,2};
+             η=0.0, ϵ=1e-6, T=100, nnlsalg=:nnls, rng=nothing, restarts::Int=1) where {F<:AbstractFloat}
+    Xd = convert(Matrix{Float64}, X); yd = convert(Vector{Float64}, y); Pd = convert(Matrix{Int64}, P)
+    N, M = size(Xd); K = size(Pd, 2)
+    if rng === nothing
+        rng = rand
+    elseif isa(rng, Int)
+        Random.seed!(rng)
+        rng = rand
+    end
+    β0 = zeros(Float64, K + 1, restarts)
+    for r in 1:restarts
+        rng(F, M + 1)                                    # α₀ (Alt.jl:65)
+        β0[:, r] = (rng(F, K + 1) .- F(0.5)) .* 10       # β₀ (Alt.jl:66)
+    end
+    α = zeros(Float64, M + 1); β = zeros(Float64, K + 1); obj = Ref{Cdouble}(0.0)
+    best = Ref{Int64}(0); iters = Ref{Int64}(0); stats = Ref{PlsStats}()
+    GC.@preserve Xd yd Pd β0 α β begin
+        _check(ccall((:pls_alt_fit, libpls), Cint,
+            (Ptr{Cvoid}, Ptr{Cdouble}, Int64, Int64, Ptr{Cdouble}, Ptr{Int64}, Int64, Cdouble,
+             Ptr{Cdouble}, Int64, Cdouble, Int64, UInt32,
+             Ptr{Cdouble}, Ptr{Cdouble}, Ref{Cdouble}, Ref{Int64}, Ref{Int64}, Ptr{Cdouble}, Ref{PlsStats}),
+            context(), Xd, N, M, yd, Pd, K, Float64(η), β0, restarts, Float64(ϵ), Int64(T), UInt32(0),
+            α, β, obj, best, iters, C_NULL, stats))
+    end
+    return (PartLSFitResult(α[1:end-1], β[1:end-1], β[end] * α[end], P), nothing, (; opt = obj[]))   # Alt.jl:119
 end
 
 end # module
