@@ -42,6 +42,7 @@ enum {
 /* flags for pls_opt_* */
 #define PLS_FLAG_DEFAULT 0u
 #define PLS_FLAG_NO_RECOMPUTE 1u /* skip the data-space recompute of the winner's objective (K4) */
+#define PLS_FLAG_GRAM_READY 256u /* resident Alt/BnB fits: reuse the Gram matrix already finalised on this context */
 
 typedef struct pls_ctx pls_ctx;
 
@@ -73,8 +74,11 @@ typedef struct pls_stats {
 /* ---- context ------------------------------------------------------------------------------ */
 int pls_version(void);
 const char *pls_last_error(void);
-/* device_ids == NULL or n_dev == 0: device 0.  n_dev > 1: PLS_EUNSUPPORTED in this build (multi-GPU
- * runs are one process per GPU, see pls_gram_raw / pls_opt_solve_range). */
+/* device_ids == NULL or n_dev == 0: device 0.  n_dev > 1: ONE process drives all listed GPUs (what a
+ * Julia host needs): pls_load shards the rows, pls_opt_fit / pls_alt_fit shard the orthant range /
+ * the restarts, the raw Gram sums are exchanged peer-to-peer over NVLink and summed in a fixed order,
+ * winners are compared with the (objective, b) rule -- results do not depend on the device count.
+ * The stage-wise entry points, the test hooks and fit(BnB) need a one-GPU context. */
 int pls_create(pls_ctx **out, const int *device_ids, int n_dev);
 void pls_destroy(pls_ctx *ctx);
 int pls_device_count(void);
@@ -152,6 +156,9 @@ int pls_opt_solve_range(pls_ctx *ctx, int64_t b_begin, int64_t b_count, double *
 int pls_opt_residual_partial(pls_ctx *ctx, const double *alpha_raw, int64_t b, double *ssq_out);
 int pls_opt_objective_finish(pls_ctx *ctx, const double *alpha_raw, int64_t b, double ssq_total,
                              double *obj_out);
+/* The same two steps for explicit signed weights w[M+1] (BnB leaves, Alt restarts: w = (Po .* alpha) * beta). */
+int pls_residual_partial_w(pls_ctx *ctx, const double *w, double *ssq_out);
+int pls_objective_finish_w(pls_ctx *ctx, const double *w, double ssq_total, double *obj_out);
 int pls_get_stats(pls_ctx *ctx, pls_stats *stats);
 
 /* ---- test / bench hooks ------------------------------------------------------------------------

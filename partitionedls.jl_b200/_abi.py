@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpls_cuda.so")
 
 PLS_OK, PLS_EINVAL, PLS_ECUDA, PLS_ENCCL, PLS_ENOMEM, PLS_ENUMERIC, PLS_EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
-PLS_FLAG_DEFAULT, PLS_FLAG_NO_RECOMPUTE = 0, 1
+PLS_FLAG_DEFAULT, PLS_FLAG_NO_RECOMPUTE, PLS_FLAG_GRAM_READY = 0, 1, 256
 _ERRNAMES = {-1: "PLS_EINVAL", -2: "PLS_ECUDA", -3: "PLS_ENCCL", -4: "PLS_ENOMEM",
              -5: "PLS_ENUMERIC", -6: "PLS_EUNSUPPORTED"}
 
@@ -69,11 +69,13 @@ lib.pls_gram_finalize.argtypes = [_vp]
 lib.pls_opt_solve_range.argtypes = [_vp, C.c_int64, C.c_int64, _dp, _ip, _dp, _dp, _dp]
 lib.pls_opt_residual_partial.argtypes = [_vp, _dp, C.c_int64, _dp]
 lib.pls_opt_objective_finish.argtypes = [_vp, _dp, C.c_int64, C.c_double, _dp]
+lib.pls_residual_partial_w.argtypes = [_vp, _dp, _dp]
+lib.pls_objective_finish_w.argtypes = [_vp, _dp, C.c_double, _dp]
 lib.pls_get_stats.argtypes = [_vp, C.POINTER(PlsStats)]
 lib.pls_gram.argtypes = [_vp, _dp, C.c_int64, C.c_int64, _dp, _ip, C.c_int64, C.c_double, _dp, _dp, _dp]
 lib.pls_nnls_batch.argtypes = [_vp, _dp, _dp, C.c_double, C.c_int64, C.POINTER(C.c_uint64), C.c_int64,
                                C.c_int64, C.c_int64, _dp, _dp]
-for _n in ("pls_create", "pls_opt_fit", "pls_bnb_fit", "pls_bnb_fit_resident", "pls_alt_fit", "pls_alt_fit_resident", "pls_load", "pls_opt_fit_resident", "pls_gram_build", "pls_gram_raw",
+for _n in ("pls_create", "pls_opt_fit", "pls_bnb_fit", "pls_bnb_fit_resident", "pls_alt_fit", "pls_alt_fit_resident", "pls_residual_partial_w", "pls_objective_finish_w", "pls_load", "pls_opt_fit_resident", "pls_gram_build", "pls_gram_raw",
            "pls_gram_finalize", "pls_opt_solve_range", "pls_opt_residual_partial", "pls_opt_objective_finish",
            "pls_get_stats", "pls_gram", "pls_nnls_batch"):
     getattr(lib, _n).restype = C.c_int
@@ -102,13 +104,16 @@ def _as_inputs(X, y, P):
 
 
 class Context:
-    """Owns one pls_ctx (one GPU)."""
+    """Owns one pls_ctx: one GPU (device = int) or, with a list of devices, one process driving several
+    GPUs (rows / orthants / restarts sharded inside the library, see multi.cu)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
         self._h = _vp()
-        dev = (C.c_int * 1)(device)
-        _check(lib.pls_create(C.byref(self._h), dev, 1))
-        self.device = device
+        devs = [int(d) for d in device] if isinstance(device, (list, tuple)) else [int(device)]
+        arr = (C.c_int * len(devs))(*devs)
+        _check(lib.pls_create(C.byref(self._h), arr, len(devs)))
+        self.device = devs[0]
+        self.devices = devs
         self._shape = None
 
     def close(self):
@@ -137,6 +142,7 @@ class Context:
         st = PlsStats()
         _check(lib.pls_opt_fit(self._h, _d(X), N, M, _d(y), P.ctypes.data_as(_ip), K, float(eta), flags,
                                _d(alpha), C.byref(b), C.byref(obj), _d(all_obj), _d(all_alpha), C.byref(st)))
+        self._shape = (N, M, K)
         return dict(alpha_raw=alpha, b_best=b.value, opt=obj.value, objs=all_obj, alphas=all_alpha,
                     stats=st.as_dict())
 
@@ -231,6 +237,22 @@ class Context:
         a = np.ascontiguousarray(alpha_raw, dtype=np.float64); o = C.c_double()
         _check(lib.pls_opt_objective_finish(self._h, _d(a), int(b), float(ssq_total), C.byref(o)))
         return o.value
+
+    def residual_partial_w(self, w):
+        a = np.ascontiguousarray(w, dtype=np.float64); s = C.c_double()
+        _check(lib.pls_residual_partial_w(self._h, _d(a), C.byref(s)))
+        return s.value
+
+    def objective_finish_w(self, w, ssq_total):
+        a = np.ascontiguousarray(w, dtype=np.float64); o = C.c_double()
+        _check(lib.pls_objective_finish_w(self._h, _d(a), float(ssq_total), C.byref(o)))
+        return o.value
+
+    def alt_fit_shard(self, beta0_cols, eps=1e-6, T=100):
+        """One rank's share of the restarts on the already finalised (all-reduced) Gram matrix; the
+        caller compares the ranks' bests and recomputes the winner's objective over all row shards."""
+        return self.alt_fit(None, None, None, beta0_cols, eps=eps, T=T, resident=True,
+                            flags=PLS_FLAG_NO_RECOMPUTE | PLS_FLAG_GRAM_READY)
 
     def stats(self):
         st = PlsStats()

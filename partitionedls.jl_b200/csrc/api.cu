@@ -10,7 +10,7 @@
 #include <new>
 #include <vector>
 
-#include "common.cuh"
+#include "ctx.cuh"
 
 namespace pls {
 
@@ -40,29 +40,15 @@ __global__ void winner_weights(const double *win, const uint64_t *gmask, int Mp,
   }
 }
 
+}  // namespace
+
 double now_ms() {
   using namespace std::chrono;
   return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
-
-}  // namespace
 }  // namespace pls
 
 using namespace pls;
-
-struct pls_ctx {
-  int dev = 0, sm_count = 0;
-  cudaStream_t stream = nullptr;
-  Problem pb;
-  SolveWs ws;
-  std::vector<uint64_t> h_gmask;
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  pls_stats stats;
-  double *d_w = nullptr, *d_ssq = nullptr;
-  double *h_pin = nullptr;   // pinned: winner record + ssq
-  size_t z_bytes = 0;
-  int launches = 0, launch_mark = 0;
-};
 
 namespace {
 
@@ -81,6 +67,10 @@ void free_ws(pls_ctx *c) {
   cudaFree(ws.resid_part); cudaFree(ws.alt_win);
   ws = SolveWs();
 }
+
+}  // namespace
+
+namespace pls {
 
 int check_ctx(pls_ctx *c) {
   if (!c) { set_error("null context"); return PLS_EINVAL; }
@@ -176,7 +166,23 @@ double eta_term_w(const pls_ctx *c, const double *w) {
   return pb.eta * tot;
 }
 
-}  // namespace
+// K4 on the loaded rows for explicit signed weights w
+int residual_partial_w(pls_ctx *c, const double *w, double *ssq_out) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  const int Mp = c->pb.Mp;
+  memcpy(c->h_pin, w, sizeof(double) * Mp);
+  cudaStream_t st = c->stream;
+  PLS_CUDA_TRY(cudaMemcpyAsync(c->d_w, c->h_pin, sizeof(double) * Mp, cudaMemcpyHostToDevice, st));
+  rc = k4_residual(c->pb, c->ws, c->d_w, c->d_ssq, c->sm_count, st, &c->launches);
+  if (rc) return rc;
+  PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin + Mp, c->d_ssq, sizeof(double), cudaMemcpyDeviceToHost, st));
+  PLS_CUDA_TRY(cudaStreamSynchronize(st));
+  *ssq_out = c->h_pin[Mp];
+  return PLS_OK;
+}
+
+}  // namespace pls
 
 extern "C" {
 
@@ -193,7 +199,16 @@ int pls_device_count(void) {
 int pls_create(pls_ctx **out, const int *device_ids, int n_dev) {
   if (!out) { set_error("out is null"); return PLS_EINVAL; }
   *out = nullptr;
-  if (n_dev > 1) { set_error("n_dev > 1: run one process per GPU and use the stage-wise entry points"); return PLS_EUNSUPPORTED; }
+  if (n_dev > 1) {
+    if (!device_ids) { set_error("device_ids is null"); return PLS_EINVAL; }
+    pls_ctx *m = new (std::nothrow) pls_ctx();
+    if (!m) { set_error("out of host memory"); return PLS_ENOMEM; }
+    memset(&m->stats, 0, sizeof(m->stats));
+    const int rc = multi_create(m, device_ids, n_dev);
+    if (rc) { multi_destroy(m); delete m; return rc; }
+    *out = m;
+    return PLS_OK;
+  }
   const int dev = (device_ids && n_dev == 1) ? device_ids[0] : 0;
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -224,6 +239,7 @@ int pls_create(pls_ctx **out, const int *device_ids, int n_dev) {
 
 void pls_destroy(pls_ctx *c) {
   if (!c) return;
+  if (!c->subs.empty()) { multi_destroy(c); delete c; return; }
   cudaSetDevice(c->dev);
   cudaStreamSynchronize(c->stream);
   free_problem(c); free_ws(c);
@@ -236,6 +252,7 @@ void pls_destroy(pls_ctx *c) {
 
 int pls_load(pls_ctx *c, const double *X, int64_t N, int64_t ldx, int64_t M, const double *y,
              const int64_t *P, int64_t K, double eta) {
+  if (c && !c->subs.empty()) return multi_load(c, X, N, ldx, M, y, P, K, eta);
   int rc = check_ctx(c);
   if (rc) return rc;
   if (!X || !y || !P) { set_error("null input pointer"); return PLS_EINVAL; }
@@ -293,6 +310,7 @@ int pls_load(pls_ctx *c, const double *X, int64_t N, int64_t ldx, int64_t M, con
 }
 
 int pls_gram_build(pls_ctx *c) {
+  if (c && !c->subs.empty()) { set_error("stage-wise entry points need a one-GPU context"); return PLS_EUNSUPPORTED; }
   int rc = check_ctx(c);
   if (rc) return rc;
   if (!c->pb.loaded) { set_error("no data set loaded"); return PLS_EINVAL; }
@@ -302,6 +320,7 @@ int pls_gram_build(pls_ctx *c) {
 }
 
 int pls_gram_raw(pls_ctx *c, void **dev_ptr, int64_t *count) {
+  if (c && !c->subs.empty()) { set_error("stage-wise entry points need a one-GPU context"); return PLS_EUNSUPPORTED; }
   int rc = check_ctx(c);
   if (rc) return rc;
   if (!c->pb.loaded || !dev_ptr || !count) { set_error("no data set loaded or null output"); return PLS_EINVAL; }
@@ -312,6 +331,7 @@ int pls_gram_raw(pls_ctx *c, void **dev_ptr, int64_t *count) {
 }
 
 int pls_gram_finalize(pls_ctx *c) {
+  if (c && !c->subs.empty()) { set_error("stage-wise entry points need a one-GPU context"); return PLS_EUNSUPPORTED; }
   int rc = check_ctx(c);
   if (rc) return rc;
   if (!c->pb.loaded) { set_error("no data set loaded"); return PLS_EINVAL; }
@@ -323,6 +343,7 @@ int pls_gram_finalize(pls_ctx *c) {
 
 int pls_opt_solve_range(pls_ctx *c, int64_t b_begin, int64_t b_count, double *alpha_raw,
                         int64_t *b_best, double *obj_best, double *all_obj, double *all_alpha) {
+  if (c && !c->subs.empty()) { set_error("stage-wise entry points need a one-GPU context"); return PLS_EUNSUPPORTED; }
   int rc = check_ctx(c);
   if (rc) return rc;
   if (!alpha_raw || !b_best || !obj_best) { set_error("null output pointer"); return PLS_EINVAL; }
@@ -354,6 +375,7 @@ int pls_opt_solve_range(pls_ctx *c, int64_t b_begin, int64_t b_count, double *al
 }
 
 int pls_opt_residual_partial(pls_ctx *c, const double *alpha_raw, int64_t b, double *ssq_out) {
+  if (c && !c->subs.empty()) { set_error("stage-wise entry points need a one-GPU context"); return PLS_EUNSUPPORTED; }
   int rc = check_ctx(c);
   if (rc) return rc;
   if (!c->pb.loaded || !alpha_raw || !ssq_out) { set_error("no data set loaded or null pointer"); return PLS_EINVAL; }
@@ -375,8 +397,21 @@ int pls_opt_objective_finish(pls_ctx *c, const double *alpha_raw, int64_t b, dou
   return PLS_OK;
 }
 
+int pls_residual_partial_w(pls_ctx *c, const double *w, double *ssq_out) {
+  if (c && !c->subs.empty()) { set_error("stage-wise entry points need a one-GPU context"); return PLS_EUNSUPPORTED; }
+  if (!c || !c->pb.loaded || !w || !ssq_out) { set_error("no data set loaded or null pointer"); return PLS_EINVAL; }
+  return residual_partial_w(c, w, ssq_out);
+}
+
+int pls_objective_finish_w(pls_ctx *c, const double *w, double ssq_total, double *obj_out) {
+  if (!c || !w || !obj_out) { set_error("null pointer"); return PLS_EINVAL; }
+  *obj_out = std::sqrt(ssq_total + eta_term_w(c, w));
+  return PLS_OK;
+}
+
 int pls_opt_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_raw, int64_t *b_best, double *obj_best,
                          double *all_obj, double *all_alpha, pls_stats *stats) {
+  if (c && !c->subs.empty()) return multi_opt_fit_resident(c, flags, alpha_raw, b_best, obj_best, all_obj, all_alpha, stats);
   int rc = check_ctx(c);
   if (rc) return rc;
   if (!c->pb.loaded) { set_error("no data set loaded"); return PLS_EINVAL; }
@@ -454,6 +489,7 @@ int pls_opt_fit(pls_ctx *c, const double *X, int64_t N, int64_t M, const double 
 
 int pls_bnb_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_signed, double *obj_out, int64_t *nopen,
                          pls_stats *stats) {
+  if (c && !c->subs.empty()) { set_error("fit(BnB) runs on one GPU in this build (create the context with one device)"); return PLS_EUNSUPPORTED; }
   int rc = check_ctx(c);
   if (rc) return rc;
   if (!c->pb.loaded) { set_error("no data set loaded"); return PLS_EINVAL; }
@@ -467,8 +503,10 @@ int pls_bnb_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_signed, doubl
   cudaStream_t st = c->stream;
   const int Mp = pb.Mp;
   PLS_CUDA_TRY(cudaEventRecord(c->ev[0], st));
-  rc = k1_gram_build(pb, st, &c->launches); if (rc) return rc;
-  rc = k1_gram_finalize(pb, st, &c->launches); if (rc) return rc;
+  if (!((flags & PLS_FLAG_GRAM_READY) && pb.gram_ready)) {
+    rc = k1_gram_build(pb, st, &c->launches); if (rc) return rc;
+    rc = k1_gram_finalize(pb, st, &c->launches); if (rc) return rc;
+  }
   PLS_CUDA_TRY(cudaEventRecord(c->ev[1], st));
   if (c->ws.Mp != pb.Mp && c->ws.win) { cudaFree(c->ws.win); c->ws.win = nullptr; }
   BnbReport rep;
@@ -526,6 +564,7 @@ int pls_bnb_fit(pls_ctx *c, const double *X, int64_t N, int64_t M, const double 
 int pls_alt_fit_resident(pls_ctx *c, const double *beta0, int64_t R, double eps, int64_t T, uint32_t flags,
                          double *alpha, double *beta, double *obj_out, int64_t *best_restart, int64_t *iters,
                          double *all_obj, pls_stats *stats) {
+  if (c && !c->subs.empty()) return multi_alt_fit_resident(c, beta0, R, eps, T, flags, alpha, beta, obj_out, best_restart, iters, all_obj, stats);
   int rc = check_ctx(c);
   if (rc) return rc;
   if (!c->pb.loaded) { set_error("no data set loaded"); return PLS_EINVAL; }
@@ -542,8 +581,10 @@ int pls_alt_fit_resident(pls_ctx *c, const double *beta0, int64_t R, double eps,
   for (int64_t i = 0; i < R * Kp; ++i)
     if (!std::isfinite(beta0[i])) { set_error("alt: non-finite initial beta"); return PLS_EINVAL; }
   PLS_CUDA_TRY(cudaEventRecord(c->ev[0], st));
-  rc = k1_gram_build(pb, st, &c->launches); if (rc) return rc;
-  rc = k1_gram_finalize(pb, st, &c->launches); if (rc) return rc;
+  if (!((flags & PLS_FLAG_GRAM_READY) && pb.gram_ready)) {
+    rc = k1_gram_build(pb, st, &c->launches); if (rc) return rc;
+    rc = k1_gram_finalize(pb, st, &c->launches); if (rc) return rc;
+  }
   PLS_CUDA_TRY(cudaEventRecord(c->ev[1], st));
   double *d_win = nullptr;
   rc = k6_alt_run(pb, c->ws, c->h_gmask, beta0, R, eps, (int)std::min<int64_t>(T, 1 << 30), c->d_w, all_obj,
@@ -610,6 +651,7 @@ int pls_get_stats(pls_ctx *c, pls_stats *stats) {
 int pls_gram(pls_ctx *c, const double *X, int64_t N, int64_t M, const double *y, const int64_t *P,
              int64_t K, double eta, double *G, double *cv, double *yy) {
   if (!G || !cv || !yy) { set_error("null output pointer"); return PLS_EINVAL; }
+  if (c && !c->subs.empty()) { set_error("test hooks need a one-GPU context"); return PLS_EUNSUPPORTED; }
   int rc = pls_load(c, X, N, N, M, y, P, K, eta);
   if (rc) return rc;
   rc = pls_gram_build(c); if (rc) return rc;
@@ -623,6 +665,7 @@ int pls_gram(pls_ctx *c, const double *X, int64_t N, int64_t M, const double *y,
 
 int pls_nnls_batch(pls_ctx *c, const double *G, const double *cv, double yy, int64_t Mp, const uint64_t *gmask,
                    int64_t Kp, int64_t b_begin, int64_t b_count, double *obj_out, double *alpha_out) {
+  if (c && !c->subs.empty()) { set_error("test hooks need a one-GPU context"); return PLS_EUNSUPPORTED; }
   int rc = check_ctx(c);
   if (rc) return rc;
   if (!G || !cv || !gmask) { set_error("null input pointer"); return PLS_EINVAL; }

@@ -1,0 +1,310 @@
+// Single-process multi-GPU orchestration behind pls_create(n_dev > 1): what a Julia host needs to use
+// a whole 8 x B200 box from one process.  One full one-GPU context per device, one
+// host worker thread per device for every stage (joined before returning), and three tiny exchanges:
+//
+//   K1  rows of X are sharded; the raw Gram sums S = Z'Z of devices 1..G-1 are copied peer-to-peer
+//       (NVLink) into a staging area on device 0, added there in a fixed order (deterministic), and
+//       the total is copied back to every device, which finalises its own G, c, yy -- bitwise equal
+//       on all devices;
+//   K2  the orthant range [0, 2^(K+1)) is split into contiguous chunk-aligned ranges, no exchange;
+//   K3  the per-device winners (objective, b, alpha) are compared on the host with the lexicographic
+//       (objective, b) rule of Opt.jl:96, so the result does not depend on the number of devices;
+//   K4  every device evaluates the winner on its own rows; the partial sums are added in device order.
+//
+// Alt: restarts are split across the devices (same Gram on each), the best (loss, restart) wins.
+#include <string.h>
+#include <cmath>
+#include <string>
+#include <thread>
+
+#include "ctx.cuh"
+
+namespace pls {
+namespace {
+
+__global__ void sum_parts(double *S, const double *stage, long long cnt, int nparts) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cnt) return;
+  double s = S[i];
+  for (int g = 0; g < nparts; ++g) s += stage[(size_t)g * cnt + i];
+  S[i] = s;
+}
+
+// f(g, sub) on one host thread per device; first failure wins, its message is re-raised here
+template <class F>
+int par_for(pls_ctx *c, F f) {
+  const int G = (int)c->subs.size();
+  std::vector<int> rcs(G, 0);
+  std::vector<std::string> msgs(G);
+  std::vector<std::thread> th;
+  th.reserve(G);
+  for (int g = 0; g < G; ++g)
+    th.emplace_back([&, g] {
+      rcs[g] = f(g, c->subs[g]);
+      if (rcs[g]) msgs[g] = pls_last_error();
+    });
+  for (auto &t : th) t.join();
+  for (int g = 0; g < G; ++g)
+    if (rcs[g]) { set_error("device %d: %s", c->subs[g]->dev, msgs[g].c_str()); return rcs[g]; }
+  return PLS_OK;
+}
+
+// K1 on every shard, then the peer-to-peer sum of the raw Gram sums and the per-device finalize
+int multi_gram(pls_ctx *c) {
+  const int G = (int)c->subs.size();
+  int rc = par_for(c, [](int, pls_ctx *s) -> int {
+    int r = check_ctx(s);
+    if (r) return r;
+    r = k1_gram_build(s->pb, s->stream, &s->launches);
+    if (r) return r;
+    PLS_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return PLS_OK;
+  });
+  if (rc) return rc;
+  pls_ctx *d0 = c->subs[0];
+  const long long cnt = (long long)d0->pb.zcols * d0->pb.zcols;
+  const size_t bytes = sizeof(double) * (size_t)cnt;
+  PLS_CUDA_TRY(cudaSetDevice(d0->dev));
+  if (c->stage_bytes < bytes * (G - 1)) {
+    cudaFree(c->stage); c->stage = nullptr; c->stage_bytes = 0;
+    PLS_CUDA_TRY(cudaMalloc(&c->stage, bytes * (G - 1)));
+    c->stage_bytes = bytes * (G - 1);
+  }
+  for (int g = 1; g < G; ++g)
+    PLS_CUDA_TRY(cudaMemcpyPeerAsync(c->stage + (size_t)(g - 1) * cnt, d0->dev, c->subs[g]->pb.S, c->subs[g]->dev, bytes, d0->stream));
+  sum_parts<<<(unsigned)((cnt + 255) / 256), 256, 0, d0->stream>>>(d0->pb.S, c->stage, cnt, G - 1);
+  PLS_CUDA_TRY(cudaGetLastError());
+  ++d0->launches;
+  for (int g = 1; g < G; ++g)
+    PLS_CUDA_TRY(cudaMemcpyPeerAsync(c->subs[g]->pb.S, c->subs[g]->dev, d0->pb.S, d0->dev, bytes, d0->stream));
+  PLS_CUDA_TRY(cudaStreamSynchronize(d0->stream));
+  return par_for(c, [](int, pls_ctx *s) -> int {
+    int r = check_ctx(s);
+    if (r) return r;
+    r = k1_gram_finalize(s->pb, s->stream, &s->launches);
+    if (r) return r;
+    PLS_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return PLS_OK;
+  });
+}
+
+bool lex_less(double oa, long long ba, double ob, long long bb) {   // Opt.jl:96: first minimum, NaN first
+  const bool na = oa != oa, nb = ob != ob;
+  if (na != nb) return na;
+  if (na) return ba < bb;
+  return oa < ob || (oa == ob && ba < bb);
+}
+
+void sum_stats(pls_ctx *c, pls_stats &s) {
+  for (pls_ctx *d : c->subs) {
+    const pls_stats &t = d->stats;
+    s.ms_gram = std::fmax(s.ms_gram, t.ms_gram); s.ms_nnls = std::fmax(s.ms_nnls, t.ms_nnls);
+    s.ms_recompute = std::fmax(s.ms_recompute, t.ms_recompute);
+    s.pivots += t.pivots; s.grad_evals += t.grad_evals; s.sum_p += t.sum_p; s.sum_p2 += t.sum_p2;
+    s.bpp_iters += t.bpp_iters; s.rebuilds += t.rebuilds; s.blocked += t.blocked;
+    s.nnls_flops += t.nnls_flops; s.nnls_l2_bytes += t.nnls_l2_bytes;
+    s.waves = std::max(s.waves, t.waves);
+  }
+}
+
+}  // namespace
+
+int multi_create(pls_ctx *c, const int *device_ids, int n_dev) {
+  for (int g = 0; g < n_dev; ++g)
+    for (int h = 0; h < g; ++h)
+      if (device_ids[g] == device_ids[h]) { set_error("device %d listed twice", device_ids[g]); return PLS_EINVAL; }
+  for (int g = 0; g < n_dev; ++g) {
+    pls_ctx *s = nullptr;
+    const int rc = pls_create(&s, device_ids + g, 1);
+    if (rc) return rc;
+    c->subs.push_back(s);
+  }
+  c->dev = device_ids[0];
+  c->sm_count = c->subs[0]->sm_count;
+  for (int g = 0; g < n_dev; ++g) {           // NVLink peer access where the topology allows it
+    cudaSetDevice(device_ids[g]);
+    for (int h = 0; h < n_dev; ++h) {
+      if (h == g) continue;
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, device_ids[g], device_ids[h]) == cudaSuccess && can) {
+        const cudaError_t e = cudaDeviceEnablePeerAccess(device_ids[h], 0);
+        if (e != cudaSuccess) cudaGetLastError();     // already enabled is fine
+      }
+    }
+  }
+  return PLS_OK;
+}
+
+void multi_destroy(pls_ctx *c) {
+  if (c->stage) { cudaSetDevice(c->subs.empty() ? c->dev : c->subs[0]->dev); cudaFree(c->stage); c->stage = nullptr; }
+  for (pls_ctx *s : c->subs) pls_destroy(s);
+  c->subs.clear();
+}
+
+int multi_load(pls_ctx *c, const double *X, int64_t N, int64_t ldx, int64_t M, const double *y, const int64_t *P,
+               int64_t K, double eta) {
+  const int G = (int)c->subs.size();
+  if (!X || !y || !P) { set_error("null input pointer"); return PLS_EINVAL; }
+  if (N < G) { set_error("N = %lld rows cannot be sharded over %d devices", (long long)N, G); return PLS_EINVAL; }
+  c->row0.assign(G + 1, 0);
+  for (int g = 0; g <= G; ++g) c->row0[g] = (N * g) / G;
+  const int rc = par_for(c, [&](int g, pls_ctx *s) -> int {
+    const int64_t r0 = c->row0[g], n = c->row0[g + 1] - r0;
+    return pls_load(s, X + r0, n, ldx, M, y + r0, P, K, eta);
+  });
+  if (rc) return rc;
+  c->pb.loaded = true;
+  c->pb.N = N; c->pb.M = (int)M; c->pb.K = (int)K; c->pb.Mp = (int)M + 1; c->pb.Kp = (int)K + 1; c->pb.eta = eta;
+  c->h_gmask = c->subs[0]->h_gmask;
+  return PLS_OK;
+}
+
+int multi_opt_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_raw, int64_t *b_best, double *obj_best,
+                           double *all_obj, double *all_alpha, pls_stats *stats) {
+  if (!c->pb.loaded) { set_error("no data set loaded"); return PLS_EINVAL; }
+  if (!alpha_raw || !b_best || !obj_best) { set_error("null output pointer"); return PLS_EINVAL; }
+  const int G = (int)c->subs.size();
+  const int Mp = c->pb.Mp, Kp = c->pb.Kp;
+  if (Kp > 40) { set_error("K = %d: 2^(K+1) orthants cannot be enumerated (limit K <= 39); use fit(BnB) or fit(Alt)", c->pb.K); return PLS_EINVAL; }
+  const double t0 = now_ms();
+  const double keep_upload = c->stats.ms_upload;
+  memset(&c->stats, 0, sizeof(c->stats));
+  c->stats.ms_upload = keep_upload;
+  int launches0 = 0;
+  for (pls_ctx *s : c->subs) { launches0 += s->launches; memset(&s->stats, 0, sizeof(s->stats)); }
+  const double tg0 = now_ms();
+  int rc = multi_gram(c);
+  if (rc) return rc;
+  const double tg1 = now_ms();
+  // contiguous, chunk-aligned orthant ranges (the Gray chains of K2 need power-of-two alignment)
+  const int64_t total = (int64_t)1 << Kp;
+  const int chunk_log2 = Kp < 12 ? (Kp > 3 ? Kp - 3 : 0) : 12;
+  const int64_t nchunks = total >> chunk_log2;
+  std::vector<std::vector<double>> rec(G, std::vector<double>(Mp + 2, 0.0));
+  std::vector<char> has(G, 0);
+  rc = par_for(c, [&](int g, pls_ctx *s) -> int {
+    const int64_t b0 = ((nchunks * g) / G) << chunk_log2, b1 = ((nchunks * (g + 1)) / G) << chunk_log2;
+    if (b1 <= b0) return PLS_OK;
+    int r = check_ctx(s);
+    if (r) return r;
+    cudaStream_t st = s->stream;
+    PLS_CUDA_TRY(cudaEventRecord(s->ev[2], st));
+    r = solve_range_dev(s, b0, b1 - b0, all_obj != nullptr, all_alpha != nullptr);
+    if (r) return r;
+    PLS_CUDA_TRY(cudaEventRecord(s->ev[3], st));
+    PLS_CUDA_TRY(cudaMemcpyAsync(s->h_pin, s->ws.win, sizeof(double) * (Mp + 2), cudaMemcpyDeviceToHost, st));
+    PLS_CUDA_TRY(cudaMemcpyAsync(s->h_pin + Mp + 4, s->ws.counters, sizeof(unsigned long long) * (CNT_NUM + 1 + 24), cudaMemcpyDeviceToHost, st));
+    if (all_obj) PLS_CUDA_TRY(cudaMemcpyAsync(all_obj + b0, s->ws.all_obj, sizeof(double) * (size_t)(b1 - b0), cudaMemcpyDeviceToHost, st));
+    if (all_alpha) PLS_CUDA_TRY(cudaMemcpyAsync(all_alpha + (size_t)b0 * Mp, s->ws.all_alpha, sizeof(double) * (size_t)(b1 - b0) * Mp, cudaMemcpyDeviceToHost, st));
+    PLS_CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]);
+    const unsigned long long *cnt = reinterpret_cast<const unsigned long long *>(s->h_pin + Mp + 4);
+    read_counters(s, cnt);
+    s->stats.ms_nnls = ms;
+    if (cnt[CNT_NOCONV]) { set_error("%llu orthant solves hit the iteration cap", cnt[CNT_NOCONV]); return PLS_ENUMERIC; }
+    memcpy(rec[g].data(), s->h_pin, sizeof(double) * (Mp + 2));
+    has[g] = 1;
+    return PLS_OK;
+  });
+  if (rc) return rc;
+  int win = -1; double wo = 0.0; long long wb = -1;
+  for (int g = 0; g < G; ++g) {
+    if (!has[g]) continue;
+    long long bb; memcpy(&bb, &rec[g][Mp + 1], sizeof(bb));
+    if (bb < 0) continue;
+    if (win < 0 || lex_less(rec[g][Mp], bb, wo, wb)) { win = g; wo = rec[g][Mp]; wb = bb; }
+  }
+  if (win < 0) { set_error("no orthant was solved"); return PLS_ENUMERIC; }
+  memcpy(alpha_raw, rec[win].data(), sizeof(double) * Mp);
+  *b_best = wb;
+  double obj = wo;
+  const double tr0 = now_ms();
+  if (!(flags & PLS_FLAG_NO_RECOMPUTE) && obj == obj) {
+    std::vector<double> w(Mp), ssq(G, 0.0);
+    for (int m = 0; m < Mp; ++m) w[m] = (double)host_d(c->h_gmask, m, wb) * alpha_raw[m];
+    rc = par_for(c, [&](int g, pls_ctx *s) -> int { return residual_partial_w(s, w.data(), &ssq[g]); });
+    if (rc) return rc;
+    double tot = 0.0;
+    for (int g = 0; g < G; ++g) tot += ssq[g];
+    obj = std::sqrt(tot + eta_term(c, alpha_raw, wb));
+  }
+  *obj_best = obj;
+  pls_stats &s = c->stats;
+  sum_stats(c, s);
+  s.ms_gram = tg1 - tg0;
+  s.ms_recompute = now_ms() - tr0;
+  s.orthants = total;
+  const double Nd = (double)c->pb.N, Md = (double)Mp;
+  s.gram_flops = Nd * Md * (Md + 1.0) + 2.0 * Nd * Md + 2.0 * Nd;
+  int launches1 = 0;
+  for (pls_ctx *d : c->subs) launches1 += d->launches;
+  s.kernel_launches = launches1 - launches0;
+  s.ms_total = now_ms() - t0 + s.ms_upload;
+  if (stats) *stats = s;
+  if (obj != obj) { set_error("NaN objective (non-finite input?)"); return PLS_ENUMERIC; }
+  return PLS_OK;
+}
+
+int multi_alt_fit_resident(pls_ctx *c, const double *beta0, int64_t R, double eps, int64_t T, uint32_t flags,
+                           double *alpha, double *beta, double *obj_out, int64_t *best_restart, int64_t *iters,
+                           double *all_obj, pls_stats *stats) {
+  if (!c->pb.loaded) { set_error("no data set loaded"); return PLS_EINVAL; }
+  if (!beta0 || !alpha || !beta || !obj_out) { set_error("null pointer"); return PLS_EINVAL; }
+  if (R < 1 || T < 1 || !(eps > 0.0)) { set_error("alt: need R >= 1, T >= 1, eps > 0"); return PLS_EINVAL; }
+  const int G = (int)c->subs.size();
+  const int Mp = c->pb.Mp, Kp = c->pb.Kp;
+  const double t0 = now_ms();
+  const double keep_upload = c->stats.ms_upload;
+  memset(&c->stats, 0, sizeof(c->stats));
+  c->stats.ms_upload = keep_upload;
+  const double tg0 = now_ms();
+  int rc = multi_gram(c);
+  if (rc) return rc;
+  const double tg1 = now_ms();
+  std::vector<std::vector<double>> a(G, std::vector<double>(Mp)), b(G, std::vector<double>(Kp));
+  std::vector<double> o(G, 0.0);
+  std::vector<int64_t> rb(G, -1), it(G, 0);
+  rc = par_for(c, [&](int g, pls_ctx *s) -> int {
+    const int64_t r0 = (R * g) / G, r1 = (R * (g + 1)) / G;
+    if (r1 <= r0) return PLS_OK;
+    const int r = pls_alt_fit_resident(s, beta0 + (size_t)r0 * Kp, r1 - r0, eps, T, PLS_FLAG_NO_RECOMPUTE | PLS_FLAG_GRAM_READY,
+                                       a[g].data(), b[g].data(), &o[g], &rb[g], &it[g], all_obj ? all_obj + r0 : nullptr, nullptr);
+    if (r == PLS_ENUMERIC) { rb[g] = -1; return PLS_OK; }     // every restart of this shard failed
+    if (r == PLS_OK) rb[g] += r0;
+    return r;
+  });
+  if (rc) return rc;
+  int win = -1;
+  for (int g = 0; g < G; ++g)
+    if (rb[g] >= 0 && (win < 0 || o[g] < o[win] || (o[g] == o[win] && rb[g] < rb[win]))) win = g;
+  if (win < 0) { set_error("alt: every restart failed"); return PLS_ENUMERIC; }
+  memcpy(alpha, a[win].data(), sizeof(double) * Mp);
+  memcpy(beta, b[win].data(), sizeof(double) * Kp);
+  if (best_restart) *best_restart = rb[win];
+  if (iters) *iters = it[win];
+  double obj = o[win];
+  if (!(flags & PLS_FLAG_NO_RECOMPUTE)) {
+    std::vector<double> w(Mp), ssq(G, 0.0);
+    for (int m = 0; m < Mp; ++m) {
+      double d = 0.0;
+      for (int k = 0; k < Kp; ++k) if (c->h_gmask[m] >> k & 1ull) d += beta[k];
+      w[m] = d * alpha[m];
+    }
+    rc = par_for(c, [&](int g, pls_ctx *s) -> int { return residual_partial_w(s, w.data(), &ssq[g]); });
+    if (rc) return rc;
+    double tot = 0.0;
+    for (int g = 0; g < G; ++g) tot += ssq[g];
+    obj = std::sqrt(tot + eta_term_w(c, w.data()));
+  }
+  *obj_out = obj;
+  pls_stats &s = c->stats;
+  sum_stats(c, s);
+  s.ms_gram = tg1 - tg0;
+  s.orthants = R;
+  s.ms_total = now_ms() - t0 + s.ms_upload;
+  if (stats) *stats = s;
+  return PLS_OK;
+}
+
+}  // namespace pls

@@ -23,7 +23,7 @@ namespace {
 template <int T, int MODE, int MINB>
 __global__ void __launch_bounds__(T, MINB) k2v3_orthant_chains(const K2Args A) {
   constexpr int NW = T / 32;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int tid = threadIdx.x;
   const int Mp = A.Mp, cap = A.cap;            // cap % 8 == 0, cap >= Mp
   const int ntc = cap >> 3;
   Cfg3 cf;

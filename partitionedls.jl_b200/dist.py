@@ -92,3 +92,43 @@ def opt_fit_sharded(backend, comm, Mp: int, Kp: int, *, reload=None):
     alpha, b, _, _ = pick_winner(comm.allgather(rec), Mp)
     ssq = comm.allreduce_sum(np.array([backend.residual_partial(alpha, b)]))[0]
     return b, backend.objective_finish(alpha, b, float(ssq)), alpha
+
+
+def shard_restarts(R: int, rank: int, world: int):
+    """Contiguous near-equal restart ranges (a rank may get none when R < world)."""
+    return (R * rank) // world, (R * (rank + 1)) // world
+
+
+def alt_fit_sharded(backend, comm, Po, beta0, eps=1e-6, T=100):
+    """fit(Alt) with batched restarts over `comm.world` ranks: rows sharded for the Gram build and the
+    final data-space loss, restarts sharded for the iteration (no exchange), the ranks' best
+    (loss, restart, alpha, beta) records all-gathered and the lexicographic minimum taken.
+    Po: (M+1) x (K+1) membership matrix incl. the intercept group; beta0: (K+1) x R.
+    Returns dict(alpha, beta, opt, best_restart, iters)."""
+    Po = np.asarray(Po, dtype=np.float64)
+    Mp, Kp = Po.shape
+    beta0 = np.asarray(beta0, dtype=np.float64).reshape(Kp, -1)
+    backend.gram_build()
+    ptr, count = backend.gram_raw()
+    if isinstance(ptr, np.ndarray):
+        ptr[...] = comm.allreduce_sum(ptr)
+    else:
+        comm.allreduce_sum_inplace_dev(ptr, count)
+    backend.gram_finalize()
+    r0, r1 = shard_restarts(beta0.shape[1], comm.rank, comm.world)
+    rec = np.zeros(Mp + Kp + 3)
+    rec[Mp + Kp], rec[Mp + Kp + 1] = np.inf, -1.0
+    if r1 > r0:
+        loc = backend.alt_fit_shard(beta0[:, r0:r1], eps=eps, T=T)
+        rec[:Mp], rec[Mp:Mp + Kp] = loc["alpha"], loc["beta"]
+        rec[Mp + Kp], rec[Mp + Kp + 1], rec[Mp + Kp + 2] = loc["opt"], r0 + loc["best_restart"], loc["iters"]
+    allrec = comm.allgather(rec)
+    cand = [q for q in allrec if q[Mp + Kp + 1] >= 0]
+    if not cand:
+        raise RuntimeError("alt: every restart failed")
+    best = min(cand, key=lambda q: (q[Mp + Kp], q[Mp + Kp + 1]))
+    alpha, beta = best[:Mp].copy(), best[Mp:Mp + Kp].copy()
+    w = alpha * (Po @ beta)
+    ssq = comm.allreduce_sum(np.array([backend.residual_partial_w(w)]))[0]
+    return dict(alpha=alpha, beta=beta, opt=backend.objective_finish_w(w, float(ssq)),
+                best_restart=int(best[Mp + Kp + 1]), iters=int(best[Mp + Kp + 2]))

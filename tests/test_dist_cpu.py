@@ -63,6 +63,22 @@ class OracleBackend:
         return float(np.sqrt(ssq + self.eta * np.sum((self.Po.T @ (d * alpha)) ** 2)))
 
 
+    # ---- Alt: restart shard on the full problem (test double; the plumbing is what is under test)
+    def alt_fit_shard(self, beta0_cols, eps=1e-6, T=100):
+        runs = [self.o.fit_alt(self.Xfull, self.yfull, self.P, beta0_cols[:, r], eta=self.eta, eps=eps, T=T)
+                for r in range(beta0_cols.shape[1])]
+        i = int(np.argmin([q["opt"] for q in runs]))
+        return dict(alpha=runs[i]["alpha_full"], beta=runs[i]["beta_full"], opt=runs[i]["opt"], best_restart=i,
+                    iters=runs[i]["iters"])
+
+    def residual_partial_w(self, w):
+        res = self.Z[:, :-1] @ w - self.Z[:, -1]
+        return float(res @ res)
+
+    def objective_finish_w(self, w, ssq):
+        return float(np.sqrt(ssq + self.eta * np.sum((self.Po.T @ w) ** 2)))
+
+
 def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -79,7 +95,9 @@ def _worker(rank, world, port, q):
         be = OracleBackend(o, oc, X, y, P, eta, distmod.shard_rows(400, rank, world))
         comm = distmod.TorchComm(device=None)
         b, obj, alpha = distmod.opt_fit_sharded(be, comm, Mp=11, Kp=4)
-        q.put((rank, b, obj, alpha))
+        beta0 = (np.random.default_rng(3).random((4, 5)) - 0.5) * 10.0      # 5 restarts over 2 ranks
+        ra = distmod.alt_fit_sharded(be, comm, be.Po, beta0, eps=1e-6, T=50)
+        q.put((rank, b, obj, alpha, ra))
     finally:
         dist.destroy_process_group()
 
@@ -99,10 +117,15 @@ def test_two_rank_sharded_fit_matches_single_process(oracle):
         assert p.exitcode == 0
     X, y, P = o.make_synthetic(400, 10, 3, seed=5, mixed_sign=True)
     ref = oc.opt_fit(X, y, P, 1e-2)
-    for rank, b, obj, alpha in res:
+    beta0 = (np.random.default_rng(3).random((4, 5)) - 0.5) * 10.0
+    runs = [o.fit_alt(X, y, P, beta0[:, r], eta=1e-2, eps=1e-6, T=50) for r in range(5)]
+    ibest = int(np.argmin([q_["opt"] for q_ in runs]))
+    for rank, b, obj, alpha, ra in res:
         assert b == ref["b_best"]
         assert abs(obj - ref["obj_best"]) <= 1e-9 * ref["obj_best"]
         assert np.all(np.abs(alpha - ref["alpha_best"]) <= 1e-8 * np.abs(ref["alpha_best"]).max())
+        assert ra["best_restart"] == ibest and abs(ra["opt"] - runs[ibest]["opt"]) <= 1e-9 * runs[ibest]["opt"]
+        assert np.allclose(ra["alpha"], runs[ibest]["alpha_full"]) and np.allclose(ra["beta"], runs[ibest]["beta_full"])
 
 
 def test_sharding_helpers(pkg):
@@ -111,6 +134,8 @@ def test_sharding_helpers(pkg):
     d = import_module(g.PKG_NAME + ".dist")
     assert [d.shard_rows(10, r, 3) for r in range(3)] == [(0, 3), (3, 6), (6, 10)]
     assert [d.shard_orthants(16, r, 4) for r in range(4)] == [(0, 4), (4, 4), (8, 4), (12, 4)]
+    assert [d.shard_restarts(5, r, 4) for r in range(4)] == [(0, 1), (1, 2), (2, 3), (3, 5)]
+    assert [d.shard_restarts(2, r, 4) for r in range(4)] == [(0, 0), (0, 1), (1, 1), (1, 2)]
     with pytest.raises(ValueError):
         d.shard_orthants(16, 0, 3)
     rec = np.array([[1.0, 2.0, 5.0, 7.0], [3.0, 4.0, 5.0, 3.0], [0.0, 0.0, 6.0, 0.0]])

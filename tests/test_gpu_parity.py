@@ -346,3 +346,39 @@ def test_alt_single_start_is_the_reference_run(ctx, pkg, oracle):
         assert rep.iters == q["iters"] and abs(rep.opt - q["opt"]) <= 1e-8 * q["opt"]
         assert np.all(np.abs(model.α - q["alpha"]) <= 1e-7) and np.all(np.abs(model.β - q["beta"]) <= 1e-7 * np.abs(q["beta"]).max())
         assert abs(model.t - q["t"]) <= 1e-7 * max(1.0, abs(q["t"]))
+
+
+# ---- one process, several GPUs (pls_create with n_dev > 1, multi.cu) ------------------------------
+def _n_gpus(pkg):
+    return pkg._abi.lib.pls_device_count()
+
+
+def test_multi_gpu_context_matches_single(ctx, pkg, oracle):
+    """Rows, orthant ranges and restarts sharded inside the library over 2 GPUs: same winner, objective
+    and alpha as the one-GPU context (Gram sums are added in a different order: 1e-9, not bitwise)."""
+    if _n_gpus(pkg) < 2:
+        pytest.skip("needs 2 GPUs")
+    o, _ = oracle
+    X, y, P = o.make_synthetic(5001, 40, 7, seed=88, mixed_sign=True)
+    eta = 1e-3
+    one = ctx.opt_fit(X, y, P, eta=eta, return_all=True)
+    mc = pkg.Context([0, 1])
+    try:
+        two = mc.opt_fit(X, y, P, eta=eta, return_all=True)
+        assert two["b_best"] == one["b_best"] and abs(two["opt"] - one["opt"]) <= RTOL * one["opt"]
+        assert np.all(np.abs(two["alpha_raw"] - one["alpha_raw"]) <= RTOL * np.abs(one["alpha_raw"]).max())
+        assert np.allclose(two["objs"], one["objs"], rtol=RTOL, atol=1e-6 * np.linalg.norm(y))
+        assert two["stats"]["orthants"] == 2 ** 8
+        again = mc.opt_fit_resident()
+        assert again["b_best"] == one["b_best"] and np.array_equal(again["alpha_raw"], two["alpha_raw"])
+        beta0 = pkg.draw_alt_starts(5, 41, 8, restarts=7)
+        a1 = ctx.alt_fit(X, y, P, beta0, eta=eta)
+        a2 = mc.alt_fit(X, y, P, beta0, eta=eta)
+        assert a2["best_restart"] == a1["best_restart"] and abs(a2["opt"] - a1["opt"]) <= 1e-8 * a1["opt"]
+        assert np.allclose(a2["alpha"], a1["alpha"], rtol=1e-7, atol=1e-10) and np.allclose(a2["beta"], a1["beta"], rtol=1e-7)
+        assert np.allclose(a2["all_obj"], a1["all_obj"], rtol=1e-8)
+        with pytest.raises(pkg.PlsError) as e:
+            mc.bnb_fit(X, y, P)
+        assert e.value.code == pkg._abi.PLS_EUNSUPPORTED
+    finally:
+        mc.close()
