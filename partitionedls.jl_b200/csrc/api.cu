@@ -280,8 +280,8 @@ int pls_load(pls_ctx *c, const double *X, int64_t N, int64_t ldx, int64_t M, con
     c->z_bytes = zb;
     PLS_CUDA_TRY(cudaMalloc(&pb.gmask, sizeof(uint64_t) * Mp));
     PLS_CUDA_TRY(cudaMalloc(&pb.S, sizeof(double) * (size_t)zc * zc));
-    pb.ldg = (int)round_up(Mp, 4);
-    PLS_CUDA_TRY(cudaMalloc(&pb.G, sizeof(double) * (size_t)pb.ldg * Mp));
+    pb.ldg = (int)round_up(Mp, 8);
+    PLS_CUDA_TRY(cudaMalloc(&pb.G, sizeof(double) * ((size_t)pb.ldg * Mp + 32)));   // + pad: gradient threads read whole 8/16-row units
     PLS_CUDA_TRY(cudaMalloc(&pb.c, sizeof(double) * Mp));
     PLS_CUDA_TRY(cudaMalloc(&pb.scal, sizeof(double) * 4));
     cudaFree(c->d_w); c->d_w = nullptr;
@@ -676,9 +676,9 @@ int pls_nnls_batch(pls_ctx *c, const double *G, const double *cv, double yy, int
   free_problem(c);
   Problem &pb = c->pb;
   pb.Mp = (int)Mp; pb.Kp = (int)Kp; pb.M = (int)Mp - 1; pb.K = (int)Kp - 1;
-  pb.ldg = (int)round_up(Mp, 4);
-  PLS_CUDA_TRY(cudaMalloc(&pb.G, sizeof(double) * (size_t)pb.ldg * Mp));
-  PLS_CUDA_TRY(cudaMemset(pb.G, 0, sizeof(double) * (size_t)pb.ldg * Mp));
+  pb.ldg = (int)round_up(Mp, 8);
+  PLS_CUDA_TRY(cudaMalloc(&pb.G, sizeof(double) * ((size_t)pb.ldg * Mp + 32)));   // + pad: gradient threads read whole 8/16-row units
+  PLS_CUDA_TRY(cudaMemset(pb.G, 0, sizeof(double) * ((size_t)pb.ldg * Mp + 32)));
   PLS_CUDA_TRY(cudaMalloc(&pb.c, sizeof(double) * Mp));
   PLS_CUDA_TRY(cudaMalloc(&pb.scal, sizeof(double) * 4));
   PLS_CUDA_TRY(cudaMalloc(&pb.gmask, sizeof(uint64_t) * Mp));

@@ -9,6 +9,9 @@ namespace pls {
 namespace {
 
 constexpr int CAP3MAX = 1024;
+#ifndef PLS_K3_IFL
+#define PLS_K3_IFL 4      // tiles of the packed inverse in flight per warp (rank update, H * panel); 8 measured slower (18.1 vs 16.0 ms at cfg2)
+#endif
 
 __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -142,70 +145,94 @@ __device__ __forceinline__ void h_set(const Sh3 &s, int i, int j, double v) {
   if ((a >> 3) == (b >> 3)) t[swz8(b & 7, a & 7)] = v;   // diagonal tiles hold both halves
 }
 
-// H(lower tiles) += Pa * Pb'   over the leading nt x nt tiles; four tiles in flight per warp
+// H(lower tiles) += Pa * Pb'   over the leading nt x nt tiles.  Every warp owns a contiguous run of the
+// packed tile sequence (tiles of one run are adjacent in memory) and keeps IFL tiles in flight; the
+// panel fragment offsets are lane constants (an 8-row block of a panel is 64 doubles), the tile
+// coordinates advance incrementally.
 template <int T, int MODE>
 __device__ __noinline__ void rank_update3(const Cfg3 cf, int nt) {
   const Sh3 s = make_sh3(cf);
   constexpr int NW = T / 32;
+  constexpr int IFL = PLS_K3_IFL;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int fr = lane >> 2, fk = lane & 3;
   const int ntiles = (nt * (nt + 1)) >> 1;
   const int coff = swz8(fr, fk * 2);
+  const int o0 = pan(fr, fk), o1 = pan(fr, 4 + fk);
   const double *Pa = s.Pa, *Pb = s.Pb;
-  for (int q = wid; q < ntiles; q += 4 * NW) {
-    int qq[4]; bool hv[4]; double2 *cp[4]; double2 c[4]; double a0[4], a1[4], b0[4], b1[4];
+  int q = (ntiles * wid) / NW;
+  const int q1 = (ntiles * (wid + 1)) / NW;
+  if (q >= q1) return;
+  int ti, tj;
+  { const int t = s.tmap[q]; ti = t >> 8; tj = t & 255; }
+  for (; q < q1; q += IFL) {
+    bool hv[IFL]; double2 *cp[IFL]; double2 c[IFL]; double a0[IFL], a1[IFL], b0[IFL], b1[IFL];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      hv[u] = q + u * NW < ntiles;
-      qq[u] = hv[u] ? q + u * NW : q;
-      cp[u] = reinterpret_cast<double2 *>(tptr<MODE>(s, qq[u]) + coff);
+    for (int u = 0; u < IFL; ++u) {
+      hv[u] = q + u < q1;
+      const int qi = hv[u] ? q + u : q, ra = hv[u] ? ti << 6 : 0, rb = hv[u] ? tj << 6 : 0;
+      cp[u] = reinterpret_cast<double2 *>(tptr<MODE>(s, qi) + coff);
       c[u] = *cp[u];
+      a0[u] = Pa[ra + o0]; a1[u] = Pa[ra + o1];
+      b0[u] = Pb[rb + o0]; b1[u] = Pb[rb + o1];
+      if (++tj > ti) { ++ti; tj = 0; }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int t = s.tmap[qq[u]];
-      const int ra = ((t >> 8) << 3) + fr, rb = ((t & 255) << 3) + fr;
-      a0[u] = Pa[pan(ra, fk)]; a1[u] = Pa[pan(ra, 4 + fk)];
-      b0[u] = Pb[pan(rb, fk)]; b1[u] = Pb[pan(rb, 4 + fk)];
-    }
+    for (int u = 0; u < IFL; ++u) dmma(c[u].x, c[u].y, a0[u], b0[u]);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) dmma(c[u].x, c[u].y, a0[u], b0[u]);
+    for (int u = 0; u < IFL; ++u) dmma(c[u].x, c[u].y, a1[u], b1[u]);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) dmma(c[u].x, c[u].y, a1[u], b1[u]);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) if (hv[u]) *cp[u] = c[u];
+    for (int u = 0; u < IFL; ++u) if (hv[u]) *cp[u] = c[u];
   }
 }
 
-// Pout = H * Pin  (H symmetric, nt x nt tiles; panels nt*8 x 8).  One warp per tile row.
+// Pout = H * Pin  (H symmetric, nt x nt tiles; panels nt*8 x 8).  One warp per tile row: first the
+// tiles stored in that row (contiguous), then the transposed tiles of the column below the diagonal
+// (tile_q(tk, ti) advances by tk + 1).  Fragment offsets are lane constants.
 template <int T, int MODE>
 __device__ __noinline__ void hmul3(const Cfg3 cf, const double *Pin, double *Pout, int nt) {
   const Sh3 s = make_sh3(cf);
   constexpr int NW = T / 32;
+  constexpr int IFL = PLS_K3_IFL;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int fr = lane >> 2, fk = lane & 3;
   const int off_d0 = swz8(fr, fk), off_d1 = swz8(fr, 4 + fk);      // direct tile (tj <= ti)
   const int off_t0 = swz8(fk, fr), off_t1 = swz8(4 + fk, fr);      // transposed tile (tj > ti)
+  const int op0 = pan(fk, fr), op1 = pan(4 + fk, fr);              // B fragments of the panel
   for (int ti = wid; ti < nt; ti += NW) {
     double acc[2][2][2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) acc[u][0][0] = acc[u][0][1] = acc[u][1][0] = acc[u][1][1] = 0.0;
     const int rowbase = (ti * (ti + 1)) >> 1;
-    for (int tj = 0; tj < nt; tj += 4) {
-      double h0[4], h1[4], p0[4], p1[4];
+    for (int tj = 0; tj <= ti; tj += IFL) {
+      double h0[IFL], h1[IFL], p0[IFL], p1[IFL];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int tk = tj + u;
-        const bool live = tk < nt;
-        const int tkk = live ? tk : ti;
-        const bool dj = tkk <= ti;
-        const double *tp = tptr<MODE>(s, dj ? rowbase + tkk : tile_q(tkk, ti));
-        h0[u] = tp[dj ? off_d0 : off_t0]; h1[u] = tp[dj ? off_d1 : off_t1];
-        p0[u] = live ? Pin[pan(tkk * 8 + fk, fr)] : 0.0;
-        p1[u] = live ? Pin[pan(tkk * 8 + 4 + fk, fr)] : 0.0;
+      for (int u = 0; u < IFL; ++u) {
+        const bool live = tj + u <= ti;
+        const int tk = live ? tj + u : 0;
+        const double *tp = tptr<MODE>(s, rowbase + tk);
+        h0[u] = tp[off_d0]; h1[u] = tp[off_d1];
+        p0[u] = live ? Pin[(tk << 6) + op0] : 0.0;
+        p1[u] = live ? Pin[(tk << 6) + op1] : 0.0;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { dmma(acc[u & 1][0][0], acc[u & 1][0][1], h0[u], p0[u]); dmma(acc[u & 1][1][0], acc[u & 1][1][1], h1[u], p1[u]); }
+      for (int u = 0; u < IFL; ++u) { dmma(acc[u & 1][0][0], acc[u & 1][0][1], h0[u], p0[u]); dmma(acc[u & 1][1][0], acc[u & 1][1][1], h1[u], p1[u]); }
+    }
+    int qt = tile_q(ti + 1, ti);
+    for (int tk0 = ti + 1; tk0 < nt; tk0 += IFL) {
+      double h0[IFL], h1[IFL], p0[IFL], p1[IFL];
+#pragma unroll
+      for (int u = 0; u < IFL; ++u) {
+        const int tk = tk0 + u;
+        const bool live = tk < nt;
+        const double *tp = tptr<MODE>(s, live ? qt : rowbase);
+        h0[u] = tp[off_t0]; h1[u] = tp[off_t1];
+        p0[u] = live ? Pin[(tk << 6) + op0] : 0.0;
+        p1[u] = live ? Pin[(tk << 6) + op1] : 0.0;
+        qt += tk + 1;
+      }
+#pragma unroll
+      for (int u = 0; u < IFL; ++u) { dmma(acc[u & 1][0][0], acc[u & 1][0][1], h0[u], p0[u]); dmma(acc[u & 1][1][0], acc[u & 1][1][1], h1[u], p1[u]); }
     }
     *reinterpret_cast<double2 *>(Pout + pan(ti * 8 + fr, fk * 2)) =
         make_double2((acc[0][0][0] + acc[0][1][0]) + (acc[1][0][0] + acc[1][1][0]),
@@ -420,16 +447,21 @@ __device__ __noinline__ bool block_add3(const Cfg3 cf, const double *G, int ldg,
   return true;
 }
 
-// r = c - G[:,F] w_F for all variables; the passive columns of G stream from L2 as double2 row
-// pairs (M' <= T*2 rows) or two row pairs per thread (larger M'), the slot range is split over nsl
-// thread slices.  Returns max |r_F| (normal-equation residual), same on all threads.  Pb = scratch.
+// r = c - G[:,F] w_F for all variables.  A thread owns RPT consecutive rows (RPT / 2 double2 loads per
+// passive column, the column index / weight / address computed once for all of them); the slot range
+// is cut into batches of UB columns (8 loads in flight) that are dealt to nsl thread slices, so the
+// inner loop has no bounds checks: slots >= hw are free (F = -1) and their weights are zeroed here.
+// Returns max |r_F| (normal-equation residual), same on all threads.  Pb = scratch.  G must be
+// readable up to row round_up(M', RPT) of every column (the allocation is padded).
 template <int T, int RPT>
 __device__ __noinline__ double grad_eval3(const Cfg3 cf, const double *G, int ldg, int Mp, int hw) {
   const Sh3 s = make_sh3(cf);
   constexpr int NW = T / 32;
   constexpr int NP = RPT / 2;                      // double2 loads per thread and column
+  constexpr int UB = NP >= 8 ? 1 : 8 / NP;         // columns per batch
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  for (int t = tid; t < hw; t += T) { const int var = s.F[t]; s.wF[t] = var >= 0 ? s.w[var] : 0.0; }
+  const int hw8 = (hw + 7) & ~7;
+  for (int t = tid; t < hw8; t += T) { const int var = s.F[t]; s.wF[t] = var >= 0 ? s.w[var] : 0.0; }
   __syncthreads();
   const int nunits = (Mp + RPT - 1) / RPT;         // <= T by construction
   int nsl = T / nunits;
@@ -438,26 +470,26 @@ __device__ __noinline__ double grad_eval3(const Cfg3 cf, const double *G, int ld
   double *part = s.Pb;                             // [nsl][nunits * RPT]
   const int pstride = nunits * RPT;
   if (sl < nsl) {
-    const int t0 = (hw * sl) / nsl, t1 = (hw * (sl + 1)) / nsl;
+    const int nb = hw8 / UB;
+    const int t0 = ((nb * sl) / nsl) * UB, t1 = ((nb * (sl + 1)) / nsl) * UB;
     const double *Gp = G + RPT * un;
     double2 acc[2][NP];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
       for (int k = 0; k < NP; ++k) acc[i][k] = make_double2(0.0, 0.0);
-    constexpr int UB = 8 / NP;                     // columns per batch: 8 loads in flight
     for (int t = t0; t < t1; t += UB) {
       double2 g[UB][NP];
 #pragma unroll
       for (int i = 0; i < UB; ++i) {
-        const int v = (t + i < t1) ? s.F[t + i] : -1;
+        const int v = s.F[t + i];
+        const double2 *gp = reinterpret_cast<const double2 *>(Gp + (size_t)ldg * (v >= 0 ? v : 0));
 #pragma unroll
-        for (int k = 0; k < NP; ++k)
-          g[i][k] = v >= 0 ? *reinterpret_cast<const double2 *>(Gp + (size_t)ldg * v + 2 * k) : make_double2(0.0, 0.0);
+        for (int k = 0; k < NP; ++k) g[i][k] = gp[k];          // free slot: column 0 times weight 0
       }
 #pragma unroll
       for (int i = 0; i < UB; ++i) {
-        const double ww = (t + i < t1) ? s.wF[t + i] : 0.0;
+        const double ww = s.wF[t + i];
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
           acc[i & 1][k].x = fma(g[i][k].x, ww, acc[i & 1][k].x);
@@ -556,8 +588,8 @@ __device__ __forceinline__ bool bpp_solve3(const Cfg3 cf, const Sh3 &s, const do
       int rep = 0;
       for (;;) {
         PH_TICK3(PH_OUT);
-        const double rf = (Mp <= 2 * T) ? grad_eval3<T, 2>(cf, G, ldg, Mp, st.hwm)
-                                        : grad_eval3<T, 4>(cf, G, ldg, Mp, st.hwm);
+        const double rf = (Mp <= 4 * T) ? grad_eval3<T, 8>(cf, G, ldg, Mp, st.hwm)
+                                        : grad_eval3<T, 16>(cf, G, ldg, Mp, st.hwm);
         PH_TICK3(PH_GRAD);
         if (rf <= 1e-12 * cmax) break;          // carried solution already exact to working accuracy
         refine3<T, MODE>(cf, st.nt_cur);
