@@ -145,7 +145,7 @@ int k2v3_plan(int Mp, K3Plan *pl) {
   PLS_CUDA_TRY(cudaGetDevice(&dev));
   PLS_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   const char *eT = getenv("PLS_K3_T"), *eQ = getenv("PLS_K3_QS"), *eB = getenv("PLS_K3_MINB");
-  int T = eT ? atoi(eT) : (Mp <= 256 ? 128 : 256);   // measured: cfg2 16.1 ms at 5 x 128, M'=513 166 ms at 2 x 256
+  int T = eT ? atoi(eT) : (Mp <= 256 ? 128 : 256);   // measured: cfg2 15.3 ms at 4 x 128 threads per SM, M'=513 163 ms at 2 x 256
   if (T != 128 && T != 256 && T != 512) T = 256;
   while (Mp > 4 * T) T *= 2;
   int qs = eQ ? atoi(eQ) : 0;
@@ -153,7 +153,7 @@ int k2v3_plan(int Mp, K3Plan *pl) {
   while (qs > 0 && v3_smem_bytes(cap, qs) > (size_t)max_smem) --qs;
   if (v3_smem_bytes(cap, qs) > (size_t)max_smem) { set_error("k2v3: M' = %d needs more shared memory than one SM has", Mp); return PLS_EUNSUPPORTED; }
   const int mode = qs == 0 ? 1 : (qs == ntiles ? 0 : 2);
-  int minb = eB ? atoi(eB) : (T == 128 ? 5 : (T == 256 ? (Mp <= 256 ? 3 : 2) : 1));
+  int minb = eB ? atoi(eB) : (T == 128 ? 4 : (T == 256 ? (Mp <= 256 ? 3 : 2) : 1));
   const Variant *best = nullptr;
   for (const Variant &v : kVariants)
     if (v.T == T && v.mode == mode && (!best || abs(v.minb - minb) < abs(best->minb - minb))) best = &v;

@@ -447,32 +447,34 @@ __device__ __noinline__ bool block_add3(const Cfg3 cf, const double *G, int ldg,
   return true;
 }
 
-// r = c - G[:,F] w_F for all variables.  A thread owns RPT consecutive rows (RPT / 2 double2 loads per
-// passive column, the column index / weight / address computed once for all of them); the slot range
-// is cut into batches of UB columns (8 loads in flight) that are dealt to nsl thread slices, so the
-// inner loop has no bounds checks: slots >= hw are free (F = -1) and their weights are zeroed here.
-// Returns max |r_F| (normal-equation residual), same on all threads.  Pb = scratch.  G must be
-// readable up to row round_up(M', RPT) of every column (the allocation is padded).
-template <int T, int RPT>
+// r = c - G[:,F] w_F for all variables.  A thread owns NP row PAIRS that are W pairs apart (W = threads
+// per slice), so the k-th double2 load of a warp covers consecutive 16-byte pieces of the column
+// (fully coalesced) while the column index / weight / address are computed once for all NP loads.
+// The slot range is cut into batches of UB columns (8 loads in flight) that are dealt to nsl thread
+// slices; slots >= hw are free (F = -1), free slots are skipped.  Returns max |r_F| (normal-equation
+// residual), same on all threads.  Pb = scratch.  G must be readable up to row 2 * NP * W of every
+// column (ldg is a multiple of 8 and the allocation is padded).
+template <int T, int NP>
 __device__ __noinline__ double grad_eval3(const Cfg3 cf, const double *G, int ldg, int Mp, int hw) {
   const Sh3 s = make_sh3(cf);
   constexpr int NW = T / 32;
-  constexpr int NP = RPT / 2;                      // double2 loads per thread and column
   constexpr int UB = NP >= 8 ? 1 : 8 / NP;         // columns per batch
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int hw8 = (hw + 7) & ~7;
   for (int t = tid; t < hw8; t += T) { const int var = s.F[t]; s.wF[t] = var >= 0 ? s.w[var] : 0.0; }
   __syncthreads();
-  const int nunits = (Mp + RPT - 1) / RPT;         // <= T by construction
-  int nsl = T / nunits;
+  const int npairs = (Mp + 1) >> 1;
+  const int W = (npairs + NP - 1) / NP;            // threads per slice, <= T by construction
+  int nsl = T / W;
   if (nsl > 8) nsl = 8;
-  const int sl = tid / nunits, un = tid - sl * nunits;
-  double *part = s.Pb;                             // [nsl][nunits * RPT]
-  const int pstride = nunits * RPT;
+  const int sl = tid / W, un = tid - sl * W;
+  double *part = s.Pb;                             // [nsl][2 * NP * W]
+  const int pstride = 2 * NP * W;
   if (sl < nsl) {
     const int nb = hw8 / UB;
     const int t0 = ((nb * sl) / nsl) * UB, t1 = ((nb * (sl + 1)) / nsl) * UB;
-    const double *Gp = G + RPT * un;
+    const double2 *Gp = reinterpret_cast<const double2 *>(G) + un;
+    const int ldg2 = ldg >> 1;
     double2 acc[2][NP];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
@@ -483,9 +485,9 @@ __device__ __noinline__ double grad_eval3(const Cfg3 cf, const double *G, int ld
 #pragma unroll
       for (int i = 0; i < UB; ++i) {
         const int v = s.F[t + i];
-        const double2 *gp = reinterpret_cast<const double2 *>(Gp + (size_t)ldg * (v >= 0 ? v : 0));
+        const double2 *gp = Gp + (size_t)ldg2 * (v >= 0 ? v : 0);
 #pragma unroll
-        for (int k = 0; k < NP; ++k) g[i][k] = gp[k];          // free slot: column 0 times weight 0
+        for (int k = 0; k < NP; ++k) g[i][k] = v >= 0 ? gp[k * W] : make_double2(0.0, 0.0);
       }
 #pragma unroll
       for (int i = 0; i < UB; ++i) {
@@ -499,7 +501,7 @@ __device__ __noinline__ double grad_eval3(const Cfg3 cf, const double *G, int ld
     }
 #pragma unroll
     for (int k = 0; k < NP; ++k)
-      *reinterpret_cast<double2 *>(part + sl * pstride + RPT * un + 2 * k) =
+      *reinterpret_cast<double2 *>(part + sl * pstride + 2 * (un + k * W)) =
           make_double2(acc[0][k].x + acc[1][k].x, acc[0][k].y + acc[1][k].y);
   }
   __syncthreads();
@@ -588,8 +590,7 @@ __device__ __forceinline__ bool bpp_solve3(const Cfg3 cf, const Sh3 &s, const do
       int rep = 0;
       for (;;) {
         PH_TICK3(PH_OUT);
-        const double rf = (Mp <= 4 * T) ? grad_eval3<T, 8>(cf, G, ldg, Mp, st.hwm)
-                                        : grad_eval3<T, 16>(cf, G, ldg, Mp, st.hwm);
+        const double rf = grad_eval3<T, 4>(cf, G, ldg, Mp, st.hwm);      // 4 row pairs per thread: M' <= 8 T
         PH_TICK3(PH_GRAD);
         if (rf <= 1e-12 * cmax) break;          // carried solution already exact to working accuracy
         refine3<T, MODE>(cf, st.nt_cur);

@@ -14,6 +14,8 @@ CONFIGS = {
     "cfg2_k19": (100_000, 200, 19, 1e-3, 20240416, False),
     "k20_m200": (100_000, 200, 20, 1e-3, 20240420, False),
     "cfg3": (1_000_000, 512, 24, 0.0, 20240417, False),
+    "m512_k16": (200_000, 512, 16, 0.0, 20240417, False),      # configs[2]'s width at a one-GPU orthant count
+    "m512_k20": (200_000, 512, 20, 0.0, 20240417, False),
     "small": (20_000, 64, 10, 1e-3, 20240415, False),
 }
 
