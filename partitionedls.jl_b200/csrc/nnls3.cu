@@ -163,6 +163,7 @@ int k2v3_plan(int Mp, K3Plan *pl) {
   int oc = 1;
   PLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, best->fn, T, sm));
   if (oc < 1) oc = 1;
+  if (const char *eO = getenv("PLS_K3_OCC")) { const int o = atoi(eO); if (o >= 1 && o < oc) oc = o; }   // experiments: fewer CTAs per SM
   pl->cap = cap; pl->qs = qs; pl->T = T; pl->mode = mode; pl->occ = oc; pl->smem = sm;
   pl->variant = (int)(best - kVariants);
   pl->hstride = mode == 0 ? 0 : ((size_t)(ntiles - qs) << 6);

@@ -18,7 +18,7 @@ ctx = pkg.Context(0)
 ctx.load(X, y, P, eta=eta)
 ctx.gram_build(); ctx.gram_finalize()
 total = 1 << (K + 1)
-KEYS = ("PLS_K2_IMPL", "PLS_K3_QS", "PLS_K3_T", "PLS_K3_MINB", "PLS_K3_CHAIN", "PLS_K2_PHASES")
+KEYS = ("PLS_K2_IMPL", "PLS_K3_QS", "PLS_K3_T", "PLS_K3_MINB", "PLS_K3_CHAIN", "PLS_K2_PHASES", "PLS_K3_OCC")
 ref = None
 for setting in sys.argv[2:]:
     for k in KEYS:
