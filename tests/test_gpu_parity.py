@@ -382,3 +382,66 @@ def test_multi_gpu_context_matches_single(ctx, pkg, oracle):
         assert e.value.code == pkg._abi.PLS_EUNSUPPORTED
     finally:
         mc.close()
+
+
+# ---- edge cases of the group structure -----------------------------------------------------------
+def test_empty_group_and_groupless_feature(ctx, pkg, oracle):
+    """A column of P that is all zero (empty group: its sign bit does not matter, the pair of orthants ties
+    exactly and the first minimum -- lower b -- must win, Opt.jl:96) and a feature that belongs to no group
+    (d = 0: its column of Xb is zero, alpha stays 0)."""
+    o, oc = oracle
+    X, y, P = o.make_synthetic(500, 14, 4, seed=31, mixed_sign=True)
+    P = P.copy()
+    P[:, 2] = 0                      # group 2 is empty; its former members are now group-less
+    ref = oc.opt_fit(X, y, P, 1e-3)
+    r = ctx.opt_fit(X, y, P, eta=1e-3, return_all=True)
+    assert r["b_best"] == ref["b_best"] and (r["b_best"] >> 2) & 1 == 0
+    assert abs(r["opt"] - ref["obj_best"]) <= RTOL * ref["obj_best"]
+    assert np.allclose(r["objs"], ref["objs"], rtol=RTOL, atol=1e-6 * np.linalg.norm(y))
+    scale = np.abs(ref["alphas"]).max(axis=1, keepdims=True)
+    assert np.all(np.abs(r["alphas"] - ref["alphas"]) <= RTOL * scale + 1e-300)
+    groupless = np.flatnonzero(P.sum(axis=1) == 0)
+    assert len(groupless) > 0 and np.all(r["alphas"][:, groupless] == 0.0)
+    # BnB on the same structure.  The reference's BnB never constrains a group-less feature (it is in no
+    # p_k, BnB.jl:117-121) and its relaxation keeps both signs of it (BnB.jl:74-79), so BnB's optimum is
+    # BELOW Opt's here; the library follows the reference (oracle: fit_bnb), not Opt.
+    refb = o.fit_bnb(X, y, P, 1e-3)
+    rb = ctx.bnb_fit(X, y, P, eta=1e-3)
+    assert abs(rb["opt"] - refb["opt"]) <= RTOL * refb["opt"] and refb["opt"] < ref["obj_best"]
+    assert np.all(np.abs(rb["alpha_signed"] - refb["alpha_signed"]) <= RTOL * np.abs(refb["alpha_signed"]).max())
+
+
+def test_zero_response_and_constant_column(ctx, oracle):
+    """y = 0 (every orthant's solution is alpha = 0, objective 0, b* = 0) and a column equal to the
+    intercept column (exactly dependent: the solver must refuse one of the pair and still reach the
+    reference objective)."""
+    o, oc = oracle
+    X, y, P = o.make_synthetic(300, 8, 2, seed=41)
+    r = ctx.opt_fit(X, np.zeros_like(y), P, eta=0.0, return_all=True)
+    assert r["b_best"] == 0 and r["opt"] == 0.0 and np.all(r["alphas"] == 0.0)
+    Xc = X.copy(); Xc[:, 3] = 1.0
+    ref = oc.opt_fit(Xc, y, P, 0.0)
+    r = ctx.opt_fit(Xc, y, P, eta=0.0, return_all=True)
+    assert abs(r["opt"] - ref["obj_best"]) <= 1e-9 * ref["obj_best"]
+    assert np.allclose(r["objs"], ref["objs"], rtol=1e-9, atol=1e-6 * np.linalg.norm(y))
+
+
+def test_wide_long_chains_kkt(ctx, oracle):
+    """M' = 513 with 2^13 orthants (Gray chains of 16-32 orthants on the L2-resident inverse): KKT conditions
+    of the winner on a numpy Gram matrix, and the winner against the C oracle's data-space solve."""
+    o, oc = oracle
+    N, M, K = 6000, 512, 12
+    X, y, P = o.make_synthetic(N, M, K, seed=777)
+    r = ctx.opt_fit(X, y, P, eta=1e-3)
+    assert r["stats"]["orthants"] == 2 ** 13 and r["stats"]["rebuilds"] == 0
+    Xo, Po = o.homogeneous_coords(X, P)
+    G = Xo.T @ Xo + 1e-3 * (Po @ Po.T); c = Xo.T @ y
+    d = Po @ o.index_to_beta(r["b_best"], K + 1)
+    w = d * r["alpha_raw"]
+    grad = c - G @ w
+    passive = r["alpha_raw"] > 0
+    assert np.abs(grad[passive]).max() <= 1e-9 * np.abs(c).max()
+    assert np.all((d * grad)[~passive] <= 1e-9 * np.abs(c).max())
+    ref = oc.opt_fit(X, y, P, 1e-3, b_list=[r["b_best"]], nthreads=1)
+    assert abs(ref["objs"][0] - r["opt"]) <= RTOL * r["opt"]
+    assert np.all(np.abs(ref["alphas"][0] - r["alpha_raw"]) <= RTOL * np.abs(ref["alphas"][0]).max())
