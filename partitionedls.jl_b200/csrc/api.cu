@@ -62,7 +62,7 @@ void free_problem(pls_ctx *c) {
 
 void free_ws(pls_ctx *c) {
   SolveWs &ws = c->ws;
-  cudaFree(ws.cta_obj); cudaFree(ws.cta_b); cudaFree(ws.cta_w); cudaFree(ws.hspill);
+  cudaFree(ws.cta_obj); cudaFree(ws.cta_b); cudaFree(ws.cta_w); cudaFree(ws.hspill); cudaFree(ws.tab);
   cudaFree(ws.counters); cudaFree(ws.win); cudaFree(ws.all_obj); cudaFree(ws.all_alpha);
   cudaFree(ws.resid_part); cudaFree(ws.alt_win);
   ws = SolveWs();
@@ -109,7 +109,7 @@ void read_counters(pls_ctx *c, const unsigned long long *h) {
   pls_stats &s = c->stats;
   if (getenv("PLS_K2_PHASES")) {
     static const char *nm[] = {"start", "plan", "remove", "add", "grad", "refine", "out", "n_remove_blocks", "n_add_blocks",
-                               "r_gather", "r_panel", "r_rank", "r_zero", "a_gather", "a_hmul", "a_spart", "a_inv", "a_panel", "a_rank", "a_rows", "a_inv1_load", "a_inv2_gj", "a_inv3_theta"};
+                               "r_gather", "r_panel", "r_rank", "r_zero", "a_gather", "a_hmul", "a_spart", "a_inv", "a_panel", "a_rank", "a_rows", "n_tab_sweep_in", "n_tab_unsweep", "tab_ops"};
     for (int i = 0; i < 23; ++i) fprintf(stderr, "k2 phase %-16s %llu\n", nm[i], h[CNT_NUM + 1 + i]);
   }
   s.pivots = (int64_t)h[CNT_PIVOTS]; s.grad_evals = (int64_t)h[CNT_GRAD];

@@ -60,6 +60,8 @@ struct SolveWs {
   size_t all_obj_n = 0, all_alpha_n = 0;
   int max_ctas = 0, Mp = 0;
   size_t hspill_bytes = 0;
+  double *tab = nullptr;          // K2 two-level path: per-CTA tableaus
+  size_t tab_bytes = 0;
   double *alt_win = nullptr;      // K6 winner record [alpha | beta | iters | loss | restart]
   int alt_win_len = 0;
   double *resid_part = nullptr;   // K4 block partials
@@ -82,6 +84,10 @@ struct K2Args {
   int qs;                        // v3: tiles of the packed inverse kept in shared memory
   double *hglob;                 // v3: [grid][hstride] global tiles (L2-resident), or null
   size_t hstride;
+  double *tab = nullptr;         // v4: [grid][tabstride] per-CTA tableaus (cap x cap, symmetric)
+  size_t tabstride = 0;
+  unsigned long long lowmask = 0;  // v4: groups whose variables are never committed (the fastest Gray bits)
+  int verify_every = 64;         // v4: orthants between KKT checks against the original G
   double *cta_obj; long long *cta_b; double *cta_w;
   double *all_obj; double *all_alpha;   // nullable, indexed by (b - b_begin)
   unsigned long long *counters;
@@ -103,6 +109,10 @@ int k2v2_config(int Mp, int *cap, size_t *smem, int *occ);
 struct K3Plan { int cap, qs, T, mode, occ, variant; size_t smem, hstride; };
 int k2v3_plan(int Mp, K3Plan *pl);
 int k2v3_launch(const K2Args &A, const K3Plan &pl, int grid, cudaStream_t st);
+// v4 = two-level path: v3's core on the reduced problem of a per-CTA swept tableau (nnls4.cu)
+struct K4Plan { int cap, qs, T, mode, occ, variant, low_groups, verify_every; size_t smem, hstride, tabstride; };
+int k2v4_plan(int Mp, int Kp, K4Plan *pl);
+int k2v4_launch(const K2Args &A, const K4Plan &pl, int grid, cudaStream_t st);
 // K5: branch and bound with batched frontier expansion (bnb.cu); winner left in ws.win
 struct BnbReport { long long visited, waves, max_open, pool_slots; double mu; };
 int k5_bnb_run(const Problem &pb, SolveWs &ws, int sm_count, cudaStream_t st, int *launches, BnbReport *rep);

@@ -469,9 +469,20 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   if (impl && strcmp(impl, "v1") == 0) variant = 1;
   if (impl && strcmp(impl, "v2") == 0 && Mp <= 208) variant = 2;
   if (impl && strcmp(impl, "v3") == 0 && Mp <= 1024) variant = 3;
+  // v4 (two-level, default): needs an aligned power-of-two range long enough to amortise one cold
+  // start per CTA
+  const bool pow2 = (b_count & (b_count - 1)) == 0 && (b_begin % b_count) == 0;
+  if (variant == 3 && Mp + 1 <= 1024 && pow2 && b_count >= 64ll * sm_count && !(impl && strcmp(impl, "v3") == 0)) variant = 4;
+  if (impl && strcmp(impl, "v4") == 0 && Mp + 1 <= 1024 && pow2) variant = 4;
   int cap = Mp, occ = 1;
   size_t smem = 0;
   K3Plan plan3;
+  K4Plan plan4;
+  if (variant == 4) {
+    const int rc = k2v4_plan(Mp, Kp, &plan4);
+    if (rc == PLS_EUNSUPPORTED) variant = 3; else if (rc) return rc;
+    else { cap = plan4.cap; occ = plan4.occ; smem = plan4.smem; }
+  }
   if (variant == 2 && k2v2_config(Mp, &cap, &smem, &occ) != PLS_OK) variant = 3;
   if (variant == 3) {
     const int rc = k2v3_plan(Mp, &plan3);
@@ -509,7 +520,11 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   if (const char *ec = getenv("PLS_K3_CHAIN")) chain_log2 = atoi(ec);
   if (chain_log2 > align_log2) chain_log2 = align_log2;
   if (chain_log2 > Kp) chain_log2 = Kp;
-  const long long n_chains = b_count >> chain_log2;
+  long long n_chains = b_count >> chain_log2;
+  if (variant == 4) {                                            // static partition of the Gray sequence
+    n_chains = b_count; chain_log2 = 0;
+    if (const char *eg = getenv("PLS_K4_GRID")) { const long long g = atoll(eg); if (g >= 1 && g < grid) grid = g; }   // tests: long walks on small problems
+  }
   if (grid > n_chains) grid = n_chains;
 
   // per-CTA workspaces
@@ -526,6 +541,16 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   size_t hneed = 0;
   if (variant == 1 && cap < Mp) hneed = (size_t)max_grid * Mp * Mp * sizeof(double);
   if (variant == 3) hneed = (size_t)max_grid * plan3.hstride * sizeof(double);
+  if (variant == 4) {
+    hneed = (size_t)max_grid * plan4.hstride * sizeof(double);
+    const size_t tneed = (size_t)max_grid * plan4.tabstride * sizeof(double);
+    if (tneed > ws.tab_bytes) {
+      if (ws.tab) cudaFree(ws.tab);
+      ws.tab = nullptr; ws.tab_bytes = 0;
+      PLS_CUDA_TRY(cudaMalloc(&ws.tab, tneed));
+      ws.tab_bytes = tneed;
+    }
+  }
   if (hneed > ws.hspill_bytes) {
     if (ws.hspill) cudaFree(ws.hspill);
     ws.hspill = nullptr; ws.hspill_bytes = 0;
@@ -550,6 +575,12 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   A.all_obj = d_all_obj; A.all_alpha = d_all_alpha; A.counters = ws.counters;
   if (variant == 2) {
     const int rc = k2v2_launch(A, (int)grid, st);
+    if (rc) return rc;
+  } else if (variant == 4) {
+    A.qs = plan4.qs; A.hglob = ws.hspill; A.hstride = plan4.hstride;
+    A.tab = ws.tab; A.tabstride = plan4.tabstride;
+    A.lowmask = (1ull << plan4.low_groups) - 1ull; A.verify_every = plan4.verify_every;
+    const int rc = k2v4_launch(A, plan4, (int)grid, st);
     if (rc) return rc;
   } else if (variant == 3) {
     A.qs = plan3.qs; A.hglob = plan3.hstride ? ws.hspill : nullptr; A.hstride = plan3.hstride;

@@ -56,24 +56,44 @@ struct Cfg3 {
   int cap;        // slots (multiple of 8)
   int qs;         // tiles [0, qs) live in shared memory
   double *hg;     // this CTA's global tiles: tile q >= qs at hg + (q - qs) * 64
+  // two-level mode (nnls4.cu): this CTA's tableau, a full symmetric cap x cap matrix (row stride ldt)
+  // = the Gram system [G c; c' yy] swept on the "committed" passive variables.  Null otherwise.
+  double *tab = nullptr;
+  int ldt = 0;
+  unsigned long long lowmask = 0;    // groups that flip often: their variables are never committed
+  unsigned long long flipmask = 0;   // group(s) whose sign changed at the current orthant
+  const unsigned long long *gmask_g = nullptr;   // group masks, read from global memory in this mode
+  const double *gorig = nullptr;     // the original G (pivot references G_jj)
+  int ldgo = 0;
 };
 
 struct Sh3 {
   double *Hs, *Hg;
   int qs;
   double *Pa, *Pb, *w, *r, *wF, *cs, *Sinv, *Gaa, *Spart, *rho, *theta, *cA, *red;
+  double *yyr;                       // two-level mode: reduced y'y (one double)
   unsigned long long *gms;
   long long *stat, *prof;
   int *F, *pos, *lst, *asl, *ctl, *pl;
   unsigned short *tmap;
   signed char *sg, *dd, *vflag, *smark, *fl;
+  signed char *swp, *ncm;            // two-level mode: variable is swept into the tableau / must not be committed
 };
 
 enum Phase3 { PH_START = 0, PH_PLAN, PH_REMOVE, PH_ADD, PH_GRAD, PH_REFINE, PH_OUT, PH_NREM, PH_NADD,
               PH_R_GATHER, PH_R_PANEL, PH_R_RANK, PH_R_ZERO, PH_A_GATHER, PH_A_HMUL, PH_A_SPART, PH_A_INV, PH_A_PANEL,
               PH_A_RANK, PH_A_ROWS, PH_A_INV1, PH_A_INV2, PH_A_INV3, PH_NUM };
 enum Stat3 { ST_P = 0, ST_PIV, ST_GRAD, ST_SUMP, ST_SUMP2, ST_ITER, ST_REBUILD, ST_BLOCKED, ST_NOCONV, ST_TMARK, ST_TSUB, ST_NUM };
+#ifndef PLS_K3_PROF
+#define PLS_K3_PROF 1     // per-phase cycle counters (clock64 by thread 0); nnls4.cu builds without them unless -DPLS_K4_PROF=1
+#endif
+#if PLS_K3_PROF
+#define PROF_ONLY3(x) x
 #define SUBTICK3(which) do { if (threadIdx.x == 0) { const long long now_ = clock64(); s.prof[which] += now_ - s.stat[ST_TSUB]; s.stat[ST_TSUB] = now_; } } while (0)
+#else
+#define PROF_ONLY3(x)
+#define SUBTICK3(which) do { } while (0)
+#endif
 #define STAT_ADD3(which, v) do { if (threadIdx.x == 0) s.stat[which] += (long long)(v); } while (0)
 
 __host__ __device__ inline size_t sh3_doubles(int cap) {
@@ -106,7 +126,8 @@ __device__ __forceinline__ Sh3 make_sh3(const Cfg3 &cf) {
   s.theta = dp; dp += 8;
   s.cA = dp; dp += 8;
   s.red = dp; dp += 32;
-  s.gms = reinterpret_cast<unsigned long long *>(dp); dp += cap;
+  if (cf.tab) s.gms = const_cast<unsigned long long *>(cf.gmask_g);       // read-only in every kernel after set-up
+  else { s.gms = reinterpret_cast<unsigned long long *>(dp); dp += cap; }
   s.stat = reinterpret_cast<long long *>(dp); dp += ST_NUM;
   s.prof = reinterpret_cast<long long *>(dp); dp += PH_NUM;
   int *ip = reinterpret_cast<int *>(dp);
@@ -123,6 +144,9 @@ __device__ __forceinline__ Sh3 make_sh3(const Cfg3 &cf) {
   s.vflag = cp; cp += cap;
   s.smark = cp; cp += cap;
   s.fl = cp; cp += cap;
+  s.yyr = s.red + 24;
+  if (cf.tab) { s.swp = cp; cp += cap; s.ncm = cp; cp += cap; }   // two-level extras live past the layout every other kernel sizes
+  else { s.swp = nullptr; s.ncm = nullptr; }
   return s;
 }
 
@@ -300,10 +324,10 @@ __device__ __noinline__ void block_remove3(const Cfg3 cf, const int *Rs, int r, 
   constexpr int NW = T / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nrows = nt * 8;
-  if (tid == 0) s.stat[ST_TSUB] = clock64();
+  PROF_ONLY3(if (tid == 0) s.stat[ST_TSUB] = clock64());
   if (wid < NW - 1) {                           // B = H[:, R]
     for (int idx = tid; idx < nrows * 8; idx += T - 32) {
-      const int q = idx / nrows, row = idx - q * nrows;
+      const int row = idx >> 3, q = idx & 7;
       s.Pb[pan(row, q)] = (q < r) ? h_get<MODE>(s, row, Rs[q]) : 0.0;
     }
   } else {                                      // S = H[R,R] straight from the tiles, then invert
@@ -330,9 +354,9 @@ __device__ __noinline__ void block_remove3(const Cfg3 cf, const int *Rs, int r, 
   rank_update3<T, MODE>(cf, nt);                          // H -= B inv(S) B'
   __syncthreads();
   SUBTICK3(PH_R_RANK);
-  for (int idx = tid; idx < nrows * r; idx += T) {        // rows / columns R become exact zeros
-    const int q = idx / nrows, row = idx - q * nrows;
-    h_set<MODE>(s, Rs[q], row, 0.0);
+  for (int idx = tid; idx < nrows * 8; idx += T) {        // rows / columns R become exact zeros
+    const int row = idx >> 3, q = idx & 7;
+    if (q < r) h_set<MODE>(s, Rs[q], row, 0.0);
   }
   if (tid < r) {
     const int sl = Rs[tid], var = s.F[sl];
@@ -351,10 +375,10 @@ __device__ __noinline__ bool block_add3(const Cfg3 cf, const double *G, int ldg,
   constexpr int NW = T / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nrows = nt * 8;
-  if (tid == 0) s.stat[ST_TSUB] = clock64();
+  PROF_ONLY3(if (tid == 0) s.stat[ST_TSUB] = clock64());
   if (wid < NW - 1) {                           // V = G[F, A]  (free slots: zero rows)
     for (int idx = tid; idx < nrows * 8; idx += T - 32) {
-      const int q = idx / nrows, row = idx - q * nrows;
+      const int row = idx >> 3, q = idx & 7;
       const int var = s.F[row];
       s.Pa[pan(row, q)] = (q < a && var >= 0) ? G[(size_t)ldg * Av[-q] + var] : 0.0;
       if (q == 0) s.wF[row] = var >= 0 ? s.w[var] : 0.0;
@@ -403,7 +427,7 @@ __device__ __noinline__ bool block_add3(const Cfg3 cf, const double *G, int ldg,
       if (j0 >= a) e0 = 0.0;
       if (j0 + 1 >= a) e1 = 0.0;
     }
-    if (lane < 8) s.theta[lane] = s.Gaa[lane * 8 + lane];     // pivot reference: G_jj
+    if (lane < 8) s.theta[lane] = (cf.gorig && lane < a) ? cf.gorig[(size_t)cf.ldgo * Av[-lane] + Av[-lane]] : s.Gaa[lane * 8 + lane];   // pivot reference: G_jj
     __syncwarp();
     const bool ok = warp_inv8(e0, e1, a, s.theta, 1e-13, s.Sinv);
     const bool all_ok = __all_sync(0xffffffffu, ok);
@@ -427,9 +451,9 @@ __device__ __noinline__ bool block_add3(const Cfg3 cf, const double *G, int ldg,
   rank_update3<T, MODE>(cf, nt);                          // H += T U'
   __syncthreads();
   SUBTICK3(PH_A_RANK);
-  for (int idx = tid; idx < nrows * a; idx += T) {        // new rows / columns: -T
-    const int q = idx / nrows, row = idx - q * nrows;
-    if (s.F[row] >= 0) h_set<MODE>(s, As[q], row, -s.Pa[pan(row, q)]);
+  for (int idx = tid; idx < nrows * 8; idx += T) {        // new rows / columns: -T
+    const int row = idx >> 3, q = idx & 7;
+    if (q < a && s.F[row] >= 0) h_set<MODE>(s, As[q], row, -s.Pa[pan(row, q)]);
   }
   __syncthreads();
   if (tid < 64) {
@@ -530,7 +554,7 @@ __device__ __noinline__ void refine3(const Cfg3 cf, int nt) {
   const Sh3 s = make_sh3(cf);
   const int nrows = nt * 8;
   for (int idx = threadIdx.x; idx < nrows * 8; idx += T) {
-    const int q = idx / nrows, row = idx - q * nrows;
+    const int row = idx >> 3, q = idx & 7;
     const int var = s.F[row];
     s.Pa[pan(row, q)] = (q == 0 && var >= 0) ? s.r[var] : 0.0;
   }
@@ -568,14 +592,243 @@ struct Bpp3 {
   bool grow_zero; // tile rows >= nt_dirty hold garbage (pooled BnB / Alt states): zero them before first use
 };
 
+// ---- two-level mode: tableau operations ----------------------------------------------------------
+// The tableau is the symmetric matrix  sweep([G c; c' yy], O)  over the committed ("swept") passive
+// variables O:  tab[O,O] = -inv(G_OO),  tab[O,r] = inv(G_OO) G_Or,  tab[r,r] = G_rr - G_rO inv(G_OO) G_Or
+// (the Schur complement = the Gram system of the REDUCED problem over the un-swept variables r, the
+// right-hand side / y'y living in row / column Mp).  The pivoting core runs on the reduced problem
+// with the tableau in the role of G; for a swept variable m the "gradient" entry
+// tab[m,rhs] - tab[m,F] w_F  is its implied weight.  Moving up to 8 variables in or out of O is one
+// rank-8 DMMA update of the whole tableau -- rare: only for groups that flip seldom in Gray order
+// and for the few swept variables whose sign constraint becomes active.
+
+template <int T>
+__device__ __forceinline__ void tab_gather3(const Cfg3 &cf, const int *Bv, int nb, double *P) {
+  const int cap = cf.cap;
+  for (int q = 0; q < 8; ++q) {
+    const double *src = cf.tab + (size_t)cf.ldt * (q < nb ? Bv[q] : 0);     // symmetric: column = row, contiguous
+#pragma unroll 2
+    for (int row = threadIdx.x; row < cap; row += T) P[pan(row, q)] = q < nb ? src[row] : 0.0;
+  }
+}
+
+// Pa = sign * Pb * Sinv over all cap rows
+template <int T>
+__device__ __forceinline__ void tab_panel3(const Cfg3 &cf, const Sh3 &s, double sign) {
+  constexpr int NW = T / 32;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  const double b0 = sign * s.Sinv[fk * 8 + fr], b1 = sign * s.Sinv[(4 + fk) * 8 + fr];
+  for (int ti = wid; ti < (cf.cap >> 3); ti += NW) {
+    double c0 = 0.0, c1 = 0.0;
+    dmma(c0, c1, s.Pb[pan(ti * 8 + fr, fk)], b0);
+    dmma(c0, c1, s.Pb[pan(ti * 8 + fr, 4 + fk)], b1);
+    *reinterpret_cast<double2 *>(s.Pa + pan(ti * 8 + fr, fk * 2)) = make_double2(c0, c1);
+  }
+}
+
+// tab += Pa * Pb'   (all cap/8 x cap/8 tiles; one warp per tile row, IFL tiles in flight)
+template <int T>
+__device__ __noinline__ void tab_rank_update3(const Cfg3 cf) {
+  const Sh3 s = make_sh3(cf);
+  constexpr int NW = T / 32;
+  constexpr int IFL = 4;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int nt = cf.cap >> 3;
+  const int o0 = pan(fr, fk), o1 = pan(fr, 4 + fk);
+  for (int ti = wid; ti < nt; ti += NW) {
+    const double a0 = s.Pa[(ti << 6) + o0], a1 = s.Pa[(ti << 6) + o1];
+    double *rowp = cf.tab + (size_t)(ti * 8 + fr) * cf.ldt + 2 * fk;
+    for (int tj = 0; tj < nt; tj += IFL) {
+      double2 c[IFL]; double b0[IFL], b1[IFL];
+#pragma unroll
+      for (int u = 0; u < IFL; ++u) {
+        const int tq = tj + u < nt ? tj + u : tj;
+        c[u] = *reinterpret_cast<const double2 *>(rowp + tq * 8);
+        b0[u] = s.Pb[(tq << 6) + o0]; b1[u] = s.Pb[(tq << 6) + o1];
+      }
+#pragma unroll
+      for (int u = 0; u < IFL; ++u) { dmma(c[u].x, c[u].y, a0, b0[u]); dmma(c[u].x, c[u].y, a1, b1[u]); }
+#pragma unroll
+      for (int u = 0; u < IFL; ++u) if (tj + u < nt) *reinterpret_cast<double2 *>(rowp + (tj + u) * 8) = c[u];
+    }
+  }
+}
+
+// refresh the shared copies of the reduced right-hand side and y'y from the tableau
+template <int T>
+__device__ __forceinline__ void tab_refresh3(const Cfg3 &cf, const Sh3 &s, int Mp) {
+  for (int m = threadIdx.x; m < cf.cap; m += T) s.cs[m] = m < Mp ? cf.tab[(size_t)cf.ldt * Mp + m] : 0.0;
+  if (threadIdx.x == 0) *s.yyr = cf.tab[(size_t)cf.ldt * Mp + Mp];
+}
+
+// Commit the nb <= 8 passive variables in the slots Bs[0..nb) of the small inverse into the tableau
+// (forward sweep).  Returns false (nothing changed) if their Schur block is not safely positive definite.
+template <int T, int MODE>
+__device__ __noinline__ bool tab_sweep_in3(const Cfg3 cf, const int *Bs, int nb, int Mp, int nt_sig) {
+  const Sh3 s = make_sh3(cf);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int cap = cf.cap;
+  if (tid < 8) { s.pl[tid] = tid < nb ? s.F[Bs[tid]] : 0; s.pl[8 + tid] = tid < nb ? Bs[tid] : 0; }
+  __syncthreads();
+  const int *Bv = s.pl, *Bsl = s.pl + 8;
+  tab_gather3<T>(cf, Bv, nb, s.Pb);
+  __syncthreads();
+  if (wid == 0) {
+    const int i = lane >> 2, j0 = (lane & 3) << 1;
+    double e0 = (i < nb && j0 < nb) ? s.Pb[pan(Bv[i], j0)] : (i == j0 ? 1.0 : 0.0);
+    double e1 = (i < nb && j0 + 1 < nb) ? s.Pb[pan(Bv[i], j0 + 1)] : (i == j0 + 1 ? 1.0 : 0.0);
+    if (lane < 8) s.theta[lane] = lane < nb ? cf.gorig[(size_t)cf.ldgo * Bv[lane] + Bv[lane]] : 1.0;
+    __syncwarp();
+    const bool ok = warp_inv8(e0, e1, nb, s.theta, 1e-13, s.Sinv);
+    const bool all_ok = __all_sync(0xffffffffu, ok);
+    s.Sinv[i * 8 + j0] = e0; s.Sinv[i * 8 + j0 + 1] = e1;
+    if (lane == 0) s.ctl[4] = all_ok ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s.ctl[4]) { __syncthreads(); return false; }
+  tab_panel3<T>(cf, s, -1.0);                       // Pa = -P inv(D)
+  __syncthreads();
+  tab_rank_update3<T>(cf);                          // tab -= P inv(D) P'
+  __syncthreads();
+  for (int q = 0; q < nb; ++q) {                    // rows / columns B: + P inv(D)
+#pragma unroll 2
+    for (int row = tid; row < cap; row += T) {
+      const double v = -s.Pa[pan(row, q)];
+      cf.tab[(size_t)cf.ldt * Bv[q] + row] = v;
+      cf.tab[(size_t)cf.ldt * row + Bv[q]] = v;
+    }
+  }
+  const int nrows = nt_sig * 8;
+  for (int idx = tid; idx < nrows * 8; idx += T) {   // their rows / columns of the small inverse: exact zeros
+    const int row = idx >> 3, q = idx & 7;
+    if (q < nb) h_set<MODE>(s, Bsl[q], row, 0.0);
+  }
+  __syncthreads();
+  if (tid < 64) {
+    const int i = tid >> 3, j = tid & 7;
+    if (i < nb && j < nb) cf.tab[(size_t)cf.ldt * Bv[i] + Bv[j]] = -s.Sinv[i * 8 + j];
+  }
+  if (tid >= 64 && tid < 64 + nb) {
+    const int q = tid - 64, var = Bv[q], sl = Bsl[q];
+    s.r[var] = s.w[var]; s.w[var] = 0.0; s.pos[var] = -1; s.F[sl] = -1; s.swp[var] = 1;
+  }
+  __syncthreads();
+  tab_refresh3<T>(cf, s, Mp);
+  if (tid == 0) {
+    s.stat[ST_P] -= nb; s.stat[ST_PIV] += nb; s.stat[ST_SUMP2] += (long long)nb * cap * cap / 2;
+    s.prof[PH_A_INV1]++;
+  }
+  __syncthreads();
+  return true;
+}
+
+// Move the nb <= 8 swept variables Bvar[0..nb) back into the small inverse (reverse sweep of the
+// tableau + bordering of the small inverse with their rows of inv(G_FF)); the solution is unchanged.
+template <int T, int MODE>
+__device__ __noinline__ void tab_unsweep3(const Cfg3 cf, const int *Bvar, int nb, int Mp, Bpp3 &st) {
+  const Sh3 s = make_sh3(cf);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int cap = cf.cap;
+  const int nt_old = st.nt_cur, nrows = nt_old * 8;
+  if (tid < 8) s.pl[tid] = tid < nb ? Bvar[tid] : 0;
+  if (tid == 32) {                                  // nb free slots, lowest first
+    int q = 0, top = st.hwm;
+    for (int sl = 0; sl < cap && q < nb; ++sl) if (s.F[sl] < 0) { s.pl[8 + q] = sl; ++q; if (sl + 1 > top) top = sl + 1; }
+    s.pl[16] = top;
+  }
+  __syncthreads();
+  const int *Bv = s.pl, *Bsl = s.pl + 8;
+  const int hw_new = s.pl[16];
+  tab_gather3<T>(cf, Bv, nb, s.Pb);                 // P = tab[:, B]
+  __syncthreads();
+  for (int idx = tid; idx < nrows * 8; idx += T) {  // V = P restricted to the small inverse's slots
+    const int row = idx >> 3, q = idx & 7;
+    const int var = s.F[row];
+    s.Pa[pan(row, q)] = (q < nb && var >= 0) ? s.Pb[pan(var, q)] : 0.0;
+  }
+  if (tid < 64) {
+    const int i = tid >> 3, j = tid & 7;
+    s.Gaa[tid] = (i < nb && j < nb) ? s.Pb[pan(Bv[i], j)] : (i == j ? -1.0 : 0.0);   // D = tab[B,B] = -inv(G_OO)[B,B]
+  }
+  __syncthreads();
+  if (nt_old > 0) {
+    hmul3<T, MODE>(cf, s.Pa, s.Pb, nt_old);         // U = Sig V
+    __syncthreads();
+  }
+  if (tid < 64) {                                   // Xi = -D + V' U   (the B x B block of inv(G_FF))
+    const int i = tid >> 3, j = tid & 7;
+    double acc = 0.0;
+    if (nt_old > 0) for (int row = 0; row < nrows; ++row) acc = fma(s.Pa[pan(row, i)], s.Pb[pan(row, j)], acc);
+    s.Spart[tid] = acc - s.Gaa[tid];
+  }
+  for (int idx = tid; idx < nrows * 8; idx += T) {  // new rows / columns of the small inverse: -U
+    const int row = idx >> 3, q = idx & 7;
+    if (q < nb && s.F[row] >= 0) h_set<MODE>(s, Bsl[q], row, -s.Pb[pan(row, q)]);
+  }
+  __syncthreads();
+  if (tid < 64) {
+    const int i = tid >> 3, j = tid & 7;
+    if (i < nb && j <= i) h_set<MODE>(s, Bsl[i], Bsl[j], 0.5 * (s.Spart[i * 8 + j] + s.Spart[j * 8 + i]));
+  }
+  tab_gather3<T>(cf, Bv, nb, s.Pb);                 // P again (the panel was reused)
+  __syncthreads();
+  if (wid == 0) {                                   // inv(-D): -D is a principal block of inv(G_OO), SPD
+    const int i = lane >> 2, j0 = (lane & 3) << 1;
+    double e0 = -s.Gaa[i * 8 + j0], e1 = -s.Gaa[i * 8 + j0 + 1];
+    if (lane < 8) s.cA[lane] = 0.0;
+    __syncwarp();
+    warp_inv8(e0, e1, nb, s.cA, -1.0, s.Sinv);
+    s.Sinv[i * 8 + j0] = e0; s.Sinv[i * 8 + j0 + 1] = e1;
+  }
+  __syncthreads();
+  tab_panel3<T>(cf, s, 1.0);                        // Pa = P inv(-D) = -P inv(D)
+  __syncthreads();
+  tab_rank_update3<T>(cf);                          // tab -= P inv(D) P'
+  __syncthreads();
+  for (int q = 0; q < nb; ++q) {                    // rows / columns B: -P inv(D)
+#pragma unroll 2
+    for (int row = tid; row < cap; row += T) {
+      const double v = s.Pa[pan(row, q)];
+      cf.tab[(size_t)cf.ldt * Bv[q] + row] = v;
+      cf.tab[(size_t)cf.ldt * row + Bv[q]] = v;
+    }
+  }
+  __syncthreads();
+  if (tid < 64) {
+    const int i = tid >> 3, j = tid & 7;
+    if (i < nb && j < nb) cf.tab[(size_t)cf.ldt * Bv[i] + Bv[j]] = s.Sinv[i * 8 + j];   // -inv(D)
+  }
+  if (tid >= 64 && tid < 64 + nb) {
+    const int q = tid - 64, var = Bv[q], sl = Bsl[q];
+    s.w[var] = s.r[var]; s.r[var] = 0.0; s.pos[var] = sl; s.F[sl] = var; s.swp[var] = 0;
+    if ((s.gms[var] & cf.flipmask) == 0) s.ncm[var] = 1;     // left although its own groups kept their sign: fickle
+  }
+  __syncthreads();
+  tab_refresh3<T>(cf, s, Mp);
+  if (tid == 0) {
+    s.stat[ST_P] += nb; s.stat[ST_PIV] += nb; s.stat[ST_SUMP2] += (long long)nb * cap * cap / 2;
+    s.prof[PH_A_INV2]++;
+  }
+  st.hwm = hw_new; st.nt_cur = (hw_new + 7) >> 3;
+  if (st.nt_cur > st.nt_dirty) st.nt_dirty = st.nt_cur;
+  __syncthreads();
+}
+
+
+#if PLS_K3_PROF
 #define PH_TICK3(which) do { if (threadIdx.x == 0) { const long long now_ = clock64(); s.prof[which] += now_ - s.stat[ST_TMARK]; s.stat[ST_TMARK] = now_; } } while (0)
+#else
+#define PH_TICK3(which) do { } while (0)
+#endif
 
 // Block principal pivoting from the current passive set to the KKT point of
 //     min w'Gw - 2c'w   s.t.  sg_m w_m >= 0  (sg_m = +-1),  w_m = 0 (sg_m = 0),  w_m free (SG_FREE)
 // (Judice-Pires / Kim-Park with Murty's single-pivot backup rule).  On return s.w / s.F / s.pos hold
 // the solution, s.r its gradient (st.r_valid), and s.red[0..NW) the partial sums of c_F'w_F.
 // Returns false if the iteration cap was hit or the inverse could not be rebuilt.
-template <int T, int MODE>
+template <int T, int MODE, bool TL = false>
 __device__ __forceinline__ bool bpp_solve3(const Cfg3 cf, const Sh3 &s, const double *G, int ldg, int Mp,
                                            double cmax, Bpp3 &st) {
   constexpr int NW = T / 32;
@@ -624,12 +877,17 @@ __device__ __forceinline__ bool bpp_solve3(const Cfg3 cf, const Sh3 &s, const do
     //      for the additions, new high-water mark.  Chunks of 32 variables / slots per warp pass,
     //      one warp-wide prefix sum over the <= 32 chunk counts.
     double cw = 0.0;
+    int any3 = 0;
     for (int ch = wid; ch < nvch; ch += NW) {
       const int m = (ch << 5) + lane;
       int f = 0;
       if (m < Mp) {
         const int sl = s.pos[m], sg = s.sg[m];    // sign class: -1, +1, 0 = fixed at zero, SG_FREE = unconstrained
         if (sl >= 0) { cw = fma(s.cs[m], s.w[m], cw); if (sg != SG_FREE && (sg == 0 || (double)sg * s.w[m] < 0.0)) f = 1; }
+        else if (TL && s.swp[m]) {                // swept variable: r holds its implied weight
+          const double wv = s.r[m];
+          if (sg == 0 ? wv != 0.0 : (double)sg * wv < 0.0) { f = 3; any3 = 1; }
+        }
         else if (sg != 0 && s.vflag[m] != 3 && (sg == SG_FREE ? fabs(s.r[m]) > told : (double)sg * s.r[m] > told)) f = 2;
         s.fl[m] = (signed char)f;
       }
@@ -643,7 +901,24 @@ __device__ __forceinline__ bool bpp_solve3(const Cfg3 cf, const Sh3 &s, const do
     }
     cw = warp_sum(cw);
     if (lane == 0) s.red[wid] = cw;
-    __syncthreads();
+    if (TL) {
+      any3 = __syncthreads_or(any3);
+      if (any3) {                                 // swept variables that must leave: back into the small inverse first
+        if (tid == 0) {
+          int n = 0;
+          for (int m = 0; m < Mp; ++m) if (s.fl[m] == 3) s.lst[n++] = m;
+          s.ctl[5] = n;
+        }
+        __syncthreads();
+        const int n3 = s.ctl[5];
+        for (int q0 = 0; q0 < n3; q0 += 8) tab_unsweep3<T, MODE>(cf, s.lst + q0, min(8, n3 - q0), Mp, st);
+        st.r_valid = true;                        // same point, same gradient: plan again
+        PH_TICK3(PH_A_INV3);
+        continue;
+      }
+    } else {
+      __syncthreads();
+    }
     const int cnt_l = lane < nvch ? s.pl[lane] : 0;
     const int incl_l = warp_incl_scan(cnt_l);
     const int tot = __shfl_sync(0xffffffffu, incl_l, 31);
@@ -703,10 +978,10 @@ __device__ __forceinline__ bool bpp_solve3(const Cfg3 cf, const Sh3 &s, const do
     }
     st.nt_dirty = max(st.nt_dirty, nt_op);
     PH_TICK3(PH_PLAN);
-    for (int q0 = 0; q0 < nr; q0 += 8) { block_remove3<T, MODE>(cf, s.lst + q0, min(8, nr - q0), nt_op); if (tid == 0) s.prof[PH_NREM]++; }
+    for (int q0 = 0; q0 < nr; q0 += 8) { block_remove3<T, MODE>(cf, s.lst + q0, min(8, nr - q0), nt_op); PROF_ONLY3(if (tid == 0) s.prof[PH_NREM]++); }
     PH_TICK3(PH_REMOVE);
     for (int q0 = 0; q0 < na; q0 += 8) {
-      if (tid == 0) s.prof[PH_NADD]++;
+      PROF_ONLY3(if (tid == 0) s.prof[PH_NADD]++);
       const int a = min(8, na - q0);
       if (!block_add3<T, MODE>(cf, G, ldg, s.lst + (cap - 1 - q0), s.asl + q0, a, nt_op)) {
         // numerically dependent column in the block: retry one variable at a time

@@ -22,8 +22,12 @@ K2_VARIANTS = {
     "v3g": {"PLS_K2_IMPL": "v3", "PLS_K3_QS": "0"},                     # inverse in L2 (global), T = 256
     "v3h": {"PLS_K2_IMPL": "v3", "PLS_K3_QS": "10"},                    # first 10 tiles shared, rest global
     "v3s512": {"PLS_K2_IMPL": "v3", "PLS_K3_QS": "-1", "PLS_K3_T": "512"},  # as much as fits shared, T = 512
+    # two-level path (nnls4.cu), forced onto small problems: few CTAs so that each walks a long piece of the Gray
+    # sequence (commits, reverse sweeps, compaction), frequent KKT checks against the original Gram system
+    "v4": {"PLS_K2_IMPL": "v4", "PLS_K4_GRID": "3", "PLS_K4_L": "2", "PLS_K4_VERIFY": "5"},
+    "v4q": {"PLS_K2_IMPL": "v4", "PLS_K4_GRID": "2", "PLS_K4_L": "1", "PLS_K4_QS": "6", "PLS_K4_T": "256"},
 }
-_K2_KEYS = ("PLS_K2_IMPL", "PLS_K3_QS", "PLS_K3_T", "PLS_K3_MINB")
+_K2_KEYS = ("PLS_K2_IMPL", "PLS_K3_QS", "PLS_K3_T", "PLS_K3_MINB", "PLS_K4_GRID", "PLS_K4_L", "PLS_K4_VERIFY", "PLS_K4_QS", "PLS_K4_T")
 
 
 @pytest.fixture(params=list(K2_VARIANTS))

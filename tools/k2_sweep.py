@@ -18,7 +18,7 @@ ctx = pkg.Context(0)
 ctx.load(X, y, P, eta=eta)
 ctx.gram_build(); ctx.gram_finalize()
 total = 1 << (K + 1)
-KEYS = ("PLS_K2_IMPL", "PLS_K3_QS", "PLS_K3_T", "PLS_K3_MINB", "PLS_K3_CHAIN", "PLS_K2_PHASES", "PLS_K3_OCC")
+KEYS = ("PLS_K4_L", "PLS_K4_T", "PLS_K4_QS", "PLS_K4_MINB", "PLS_K4_VERIFY", "PLS_K4_GRID", "PLS_K4_OCC", "PLS_K2_IMPL", "PLS_K3_QS", "PLS_K3_T", "PLS_K3_MINB", "PLS_K3_CHAIN", "PLS_K2_PHASES", "PLS_K3_OCC")
 ref = None
 for setting in sys.argv[2:]:
     for k in KEYS:
