@@ -113,6 +113,8 @@ int k2v3_launch(const K2Args &A, const K3Plan &pl, int grid, cudaStream_t st);
 struct K4Plan { int cap, qs, T, mode, occ, variant, low_groups, verify_every; size_t smem, hstride, tabstride; };
 int k2v4_plan(int Mp, int Kp, K4Plan *pl);
 int k2v4_launch(const K2Args &A, const K4Plan &pl, int grid, cudaStream_t st);
+int k2v4_plan_prof(int Mp, int Kp, K4Plan *pl);      // nnls4p.cu: same kernels with phase counters
+int k2v4_launch_prof(const K2Args &A, const K4Plan &pl, int grid, cudaStream_t st);
 // K5: branch and bound with batched frontier expansion (bnb.cu); winner left in ws.win
 struct BnbReport { long long visited, waves, max_open, pool_slots; double mu; };
 int k5_bnb_run(const Problem &pb, SolveWs &ws, int sm_count, cudaStream_t st, int *launches, BnbReport *rep);

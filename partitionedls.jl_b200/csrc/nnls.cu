@@ -479,7 +479,7 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   K3Plan plan3;
   K4Plan plan4;
   if (variant == 4) {
-    const int rc = k2v4_plan(Mp, Kp, &plan4);
+    const int rc = getenv("PLS_K2_PHASES") ? k2v4_plan_prof(Mp, Kp, &plan4) : k2v4_plan(Mp, Kp, &plan4);
     if (rc == PLS_EUNSUPPORTED) variant = 3; else if (rc) return rc;
     else { cap = plan4.cap; occ = plan4.occ; smem = plan4.smem; }
   }
@@ -580,7 +580,7 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
     A.qs = plan4.qs; A.hglob = ws.hspill; A.hstride = plan4.hstride;
     A.tab = ws.tab; A.tabstride = plan4.tabstride;
     A.lowmask = (1ull << plan4.low_groups) - 1ull; A.verify_every = plan4.verify_every;
-    const int rc = k2v4_launch(A, plan4, (int)grid, st);
+    const int rc = getenv("PLS_K2_PHASES") ? k2v4_launch_prof(A, plan4, (int)grid, st) : k2v4_launch(A, plan4, (int)grid, st);
     if (rc) return rc;
   } else if (variant == 3) {
     A.qs = plan3.qs; A.hglob = plan3.hstride ? ws.hspill : nullptr; A.hstride = plan3.hstride;

@@ -627,7 +627,9 @@ __device__ __forceinline__ void tab_panel3(const Cfg3 &cf, const Sh3 &s, double 
   }
 }
 
-// tab += Pa * Pb'   (all cap/8 x cap/8 tiles; one warp per tile row, IFL tiles in flight)
+// tab += Pa * Pb'  where Pa * Pb' is symmetric (Pa = -+P inv(D), Pb = P): only the tiles on or below the
+// diagonal are computed (contiguous runs of the packed tile sequence per warp, IFL tiles in flight);
+// off-diagonal tiles are stored twice, the second time transposed (8 consecutive doubles per row).
 template <int T>
 __device__ __noinline__ void tab_rank_update3(const Cfg3 cf) {
   const Sh3 s = make_sh3(cf);
@@ -635,23 +637,32 @@ __device__ __noinline__ void tab_rank_update3(const Cfg3 cf) {
   constexpr int IFL = 4;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int fr = lane >> 2, fk = lane & 3;
-  const int nt = cf.cap >> 3;
+  const int nt = cf.cap >> 3, ntl = (nt * (nt + 1)) >> 1;
   const int o0 = pan(fr, fk), o1 = pan(fr, 4 + fk);
-  for (int ti = wid; ti < nt; ti += NW) {
-    const double a0 = s.Pa[(ti << 6) + o0], a1 = s.Pa[(ti << 6) + o1];
-    double *rowp = cf.tab + (size_t)(ti * 8 + fr) * cf.ldt + 2 * fk;
-    for (int tj = 0; tj < nt; tj += IFL) {
-      double2 c[IFL]; double b0[IFL], b1[IFL];
+  const size_t ldt = (size_t)cf.ldt;
+  int q = (ntl * wid) / NW;
+  const int q1 = (ntl * (wid + 1)) / NW;
+  for (; q < q1; q += IFL) {
+    double2 c[IFL]; double a0[IFL], a1[IFL], b0[IFL], b1[IFL]; int ti[IFL], tj[IFL];
 #pragma unroll
-      for (int u = 0; u < IFL; ++u) {
-        const int tq = tj + u < nt ? tj + u : tj;
-        c[u] = *reinterpret_cast<const double2 *>(rowp + tq * 8);
-        b0[u] = s.Pb[(tq << 6) + o0]; b1[u] = s.Pb[(tq << 6) + o1];
+    for (int u = 0; u < IFL; ++u) {
+      const int t = s.tmap[q + u < q1 ? q + u : q1 - 1];
+      ti[u] = t >> 8; tj[u] = t & 255;
+      c[u] = *reinterpret_cast<const double2 *>(cf.tab + (size_t)(ti[u] * 8 + fr) * ldt + tj[u] * 8 + 2 * fk);
+      a0[u] = s.Pa[(ti[u] << 6) + o0]; a1[u] = s.Pa[(ti[u] << 6) + o1];
+      b0[u] = s.Pb[(tj[u] << 6) + o0]; b1[u] = s.Pb[(tj[u] << 6) + o1];
+    }
+#pragma unroll
+    for (int u = 0; u < IFL; ++u) { dmma(c[u].x, c[u].y, a0[u], b0[u]); dmma(c[u].x, c[u].y, a1[u], b1[u]); }
+#pragma unroll
+    for (int u = 0; u < IFL; ++u) {
+      if (q + u < q1) {
+        *reinterpret_cast<double2 *>(cf.tab + (size_t)(ti[u] * 8 + fr) * ldt + tj[u] * 8 + 2 * fk) = c[u];
+        if (ti[u] != tj[u]) {
+          double *mp = cf.tab + (size_t)(tj[u] * 8 + 2 * fk) * ldt + ti[u] * 8 + fr;
+          mp[0] = c[u].x; mp[ldt] = c[u].y;
+        }
       }
-#pragma unroll
-      for (int u = 0; u < IFL; ++u) { dmma(c[u].x, c[u].y, a0, b0[u]); dmma(c[u].x, c[u].y, a1, b1[u]); }
-#pragma unroll
-      for (int u = 0; u < IFL; ++u) if (tj + u < nt) *reinterpret_cast<double2 *>(rowp + (tj + u) * 8) = c[u];
     }
   }
 }

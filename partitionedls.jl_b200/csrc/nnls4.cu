@@ -20,7 +20,8 @@
 // Each CTA walks one contiguous piece of the Gray sequence of the whole range (static partition), so
 // the cold start (full solve + commit of ~3/4 of the passive set) is paid once per CTA.
 #ifndef PLS_K4_PROF
-#define PLS_K4_PROF 0
+#define PLS_K4_PROF 0          // nnls4p.cu compiles this file a second time with the per-phase cycle counters on
+#define K4_NAME(x) x
 #endif
 #define PLS_K3_PROF PLS_K4_PROF
 #include "nnls3_core.cuh"
@@ -276,7 +277,7 @@ const Variant4 kVariants4[] = {
 
 // Environment overrides for tuning: PLS_K4_T, PLS_K4_QS (tiles of the small inverse in shared memory),
 // PLS_K4_MINB, PLS_K4_L (number of fast groups that are never committed), PLS_K4_VERIFY.
-int k2v4_plan(int Mp, int Kp, K4Plan *pl) {
+int K4_NAME(k2v4_plan)(int Mp, int Kp, K4Plan *pl) {
   if (Mp + 1 > CAP3MAX) return PLS_EUNSUPPORTED;
   const int cap = (Mp + 1 + 7) & ~7;
   const int ntc = cap >> 3, ntiles = ntc * (ntc + 1) / 2;
@@ -304,10 +305,10 @@ int k2v4_plan(int Mp, int Kp, K4Plan *pl) {
   PLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, best->fn, T, sm));
   if (oc < 1) oc = 1;
   if (const char *eO = getenv("PLS_K4_OCC")) { const int o = atoi(eO); if (o >= 1 && o < oc) oc = o; }
-  // fast groups: the small inverse should hold ~32 variables -- about half of the variables of the l
-  // fastest groups are passive at any time
-  const double gsize = (double)Mp / (double)(Kp > 0 ? Kp : 1);
-  int l = (int)(64.0 / gsize + 0.5);
+  // fast groups (never committed).  Measured optimum: l = 5 at M' = 201 (groups of 12), l = 6 at M' = 513
+  // (groups of 30): a larger l makes the full-tableau updates rarer (every 2^l orthants) and the small
+  // inverse / gradient columns larger; both terms grow with M', so l moves little.
+  int l = Mp <= 256 ? 5 : 6;
   if (eL) l = atoi(eL);
   if (l < 1) l = 1;
   if (l > 10) l = 10;
@@ -322,7 +323,7 @@ int k2v4_plan(int Mp, int Kp, K4Plan *pl) {
   return PLS_OK;
 }
 
-int k2v4_launch(const K2Args &A, const K4Plan &pl, int grid, cudaStream_t st) {
+int K4_NAME(k2v4_launch)(const K2Args &A, const K4Plan &pl, int grid, cudaStream_t st) {
   kVariants4[pl.variant].fn<<<grid, pl.T, pl.smem, st>>>(A);
   PLS_CUDA_TRY(cudaGetLastError());
   return PLS_OK;
