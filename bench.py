@@ -58,10 +58,15 @@ def load_peaks():
     return peaks
 
 
+def st_kernel_name(st):
+    return ("k2v4_orthant_ranges (batched orthant NNLS, two-level: per-CTA swept tableau + block pivoting on the fast Gray groups; "
+            "FP64 DMMA rank-8 updates + DFMA gradient; tcgen05 has no f64 kind)")
+
+
 def ncu_dram_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the K2 launch from the committed ncu --set full
-    capture (profiles/r01_v3_k2_raw_summary.txt); None if the summary is missing."""
-    p = os.path.join(ROOT, "profiles", "r01_v3_k2_raw_summary.txt")
+    capture (profiles/r01_v4_k2_raw_summary.txt); None if the summary is missing."""
+    p = os.path.join(ROOT, "profiles", "r01_v4_k2_raw_summary.txt")
     if not os.path.exists(p):
         return None
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -221,26 +226,36 @@ def run_native(args, rank, world, local_rank):
         return bb, obj, alpha, ctx.stats()
 
     def timed(fn, steps, warmup, sample_clocks):
+        """Times `steps` calls of fn on the device: CUDA events recorded on torch's current stream right
+        before and right after each call.  The library call is blocking (it synchronises its own stream
+        before it returns), so the closing event is reached only after all of the step's kernels and
+        copies have finished; barrier + synchronize bracket every step.  Returns the max over ranks."""
         for _ in range(warmup):
             fn()
         sampler = ClockSampler(local_rank) if sample_clocks else None
-        per_step, last = [], None
+        per_step, host_step, last = [], [], None
         barrier()
         if sampler:
             sampler.start()
         for _ in range(steps):
             flush.zero_()                  # L2 flush, outside the timed step
             barrier()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             t0 = time.perf_counter()
+            e0.record()
             last = fn()
+            e1.record()
             torch.cuda.synchronize()
-            per_step.append(time.perf_counter() - t0)
+            host_step.append(time.perf_counter() - t0)
+            per_step.append(e0.elapsed_time(e1) * 1e-3)
         barrier()
         clocks = sampler.stop() if sampler else None
-        tt = torch.tensor([sum(per_step)], dtype=torch.float64, device=dev)
+        tt = torch.tensor([sum(per_step), sum(host_step)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt.item()), last, clocks
+        if clocks is not None:
+            clocks["host_clock_s"] = float(tt[1].item())
+        return float(tt[0].item()), last, clocks
 
     ctx.load(Xs, ys, Pc, eta=eta, prepared=True)
     t_res, last, clocks = timed(step_resident, args.steps, args.warmup, True)
@@ -266,12 +281,16 @@ def run_native(args, rank, world, local_rank):
                 "d2h_bytes_per_step": int((Mp + 4 + 10) * 8 * world)},
         "gpu_launches": int(st["kernel_launches"] * args.steps * world),
         "roofline": {
-            "kernel": "k2v3_orthant_chains (batched orthant NNLS, block pivoting: FP64 DMMA rank-8 updates + DFMA gradient; tcgen05 has no f64 kind)",
+            "kernel": st_kernel_name(st),
             "bound": "tensor", "achieved": k2_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": k2_tflops / fp64_peak if fp64_peak else None, "traffic": ncu_dram_traffic(),
             "peak_source": "FP64 DFMA peak measured by tools/fp64_peak.cu on this pool (profiles/fp64_peaks_r01.json); MEASURED_PEAKS.json holds no FP64 figure",
             "algorithmic_flops_per_launch": st["nnls_flops"], "launch_ms": k2_ms,
+            "flops_per_orthant": st["nnls_flops"] / max(1, st["orthants"]),
             "l2_model_gbs": st["nnls_l2_bytes"] / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else None,
+            "note": "K2 is latency-bound, not FLOP- or HBM-bound (DESIGN.md 3): the two-level solver cuts the work per orthant "
+                    "~4x against the one-level v3 kernel (0.65 MFLOP/orthant), so the FLOP rate falls while solves/s rise; "
+                    "frac is reported on the work actually done",
         },
         "stages_ms": {"gram_k1": st["ms_gram"], "nnls_k2_k3": st["ms_nnls"], "recompute_k4": st["ms_recompute"]},
         "k1_gram": {"tflops": st["gram_flops"] / (st["ms_gram"] * 1e-3) / 1e12 if st["ms_gram"] > 0 else None,

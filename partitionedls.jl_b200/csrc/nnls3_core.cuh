@@ -47,6 +47,25 @@ __device__ __forceinline__ bool lex_better(double oa, long long ba, double ob, l
   return oa < ob || (oa == ob && ba < bb);
 }
 
+// L2 eviction hints for the full-tableau passes of the two-level mode: they stream through memory that
+// is not touched again for many orthants and must not push the hot tableau rows (the gradient's
+// columns) out of L2.
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ double2 ld_stream2(const double *p, unsigned long long pol) {
+  double2 v;
+  asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_stream2(double *p, double2 v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" :: "l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_stream1(double *p, double v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" :: "l"(p), "d"(v), "l"(pol) : "memory");
+}
 // ---- tile-packed symmetric storage --------------------------------------------------------------
 __device__ __forceinline__ int tile_q(int ti, int tj) { return ((ti * (ti + 1)) >> 1) + tj; }
 __device__ __forceinline__ int swz8(int r, int c) { return (r << 3) + (c ^ ((r & 2) << 1)); }
@@ -389,6 +408,9 @@ __device__ __noinline__ bool block_add3(const Cfg3 cf, const double *G, int ldg,
       s.Gaa[e] = (i < a && j < a) ? G[(size_t)ldg * Av[-j] + Av[-i]] : (i == j ? 1.0 : 0.0);
     }
     if (lane < 8) s.cA[lane] = (lane < a) ? s.cs[Av[-lane]] : 0.0;
+    // pivot references G_jj of the ORIGINAL matrix (two-level mode: the tableau's diagonal is a Schur
+    // complement), fetched here so that the global-memory latency overlaps the gather
+    if (cf.gorig && lane >= 8 && lane < 16) { const int q = lane - 8; s.red[16 + q] = q < a ? cf.gorig[(size_t)cf.ldgo * Av[-q] + Av[-q]] : 1.0; }
   }
   __syncthreads();
   SUBTICK3(PH_A_GATHER);
@@ -427,7 +449,7 @@ __device__ __noinline__ bool block_add3(const Cfg3 cf, const double *G, int ldg,
       if (j0 >= a) e0 = 0.0;
       if (j0 + 1 >= a) e1 = 0.0;
     }
-    if (lane < 8) s.theta[lane] = (cf.gorig && lane < a) ? cf.gorig[(size_t)cf.ldgo * Av[-lane] + Av[-lane]] : s.Gaa[lane * 8 + lane];   // pivot reference: G_jj
+    if (lane < 8) s.theta[lane] = cf.gorig ? s.red[16 + lane] : s.Gaa[lane * 8 + lane];   // pivot reference: G_jj
     __syncwarp();
     const bool ok = warp_inv8(e0, e1, a, s.theta, 1e-13, s.Sinv);
     const bool all_ok = __all_sync(0xffffffffu, ok);
@@ -640,6 +662,7 @@ __device__ __noinline__ void tab_rank_update3(const Cfg3 cf) {
   const int nt = cf.cap >> 3, ntl = (nt * (nt + 1)) >> 1;
   const int o0 = pan(fr, fk), o1 = pan(fr, 4 + fk);
   const size_t ldt = (size_t)cf.ldt;
+  const unsigned long long pol = l2_evict_first_policy();
   int q = (ntl * wid) / NW;
   const int q1 = (ntl * (wid + 1)) / NW;
   for (; q < q1; q += IFL) {
@@ -648,7 +671,7 @@ __device__ __noinline__ void tab_rank_update3(const Cfg3 cf) {
     for (int u = 0; u < IFL; ++u) {
       const int t = s.tmap[q + u < q1 ? q + u : q1 - 1];
       ti[u] = t >> 8; tj[u] = t & 255;
-      c[u] = *reinterpret_cast<const double2 *>(cf.tab + (size_t)(ti[u] * 8 + fr) * ldt + tj[u] * 8 + 2 * fk);
+      c[u] = ld_stream2(cf.tab + (size_t)(ti[u] * 8 + fr) * ldt + tj[u] * 8 + 2 * fk, pol);
       a0[u] = s.Pa[(ti[u] << 6) + o0]; a1[u] = s.Pa[(ti[u] << 6) + o1];
       b0[u] = s.Pb[(tj[u] << 6) + o0]; b1[u] = s.Pb[(tj[u] << 6) + o1];
     }
@@ -657,10 +680,10 @@ __device__ __noinline__ void tab_rank_update3(const Cfg3 cf) {
 #pragma unroll
     for (int u = 0; u < IFL; ++u) {
       if (q + u < q1) {
-        *reinterpret_cast<double2 *>(cf.tab + (size_t)(ti[u] * 8 + fr) * ldt + tj[u] * 8 + 2 * fk) = c[u];
+        st_stream2(cf.tab + (size_t)(ti[u] * 8 + fr) * ldt + tj[u] * 8 + 2 * fk, c[u], pol);
         if (ti[u] != tj[u]) {
           double *mp = cf.tab + (size_t)(tj[u] * 8 + 2 * fk) * ldt + ti[u] * 8 + fr;
-          mp[0] = c[u].x; mp[ldt] = c[u].y;
+          st_stream1(mp, c[u].x, pol); st_stream1(mp + ldt, c[u].y, pol);
         }
       }
     }

@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(T, MINB) k2v4_orthant_ranges(const K2Args A) {
     if (cold) {
       clear_state3<T, MODE>(cf, nt_dirty);
       nt_dirty = 0; hwm = 0; nt_cur = 0;
+      const unsigned long long pol0 = l2_evict_first_policy();
       for (int idx = tid; idx < cap * (cap >> 1); idx += T) {       // tableau <- [G c; c' yy], zero padding
         const int row = idx / (cap >> 1), col = (idx - row * (cap >> 1)) << 1;
         double2 v = make_double2(0.0, 0.0);
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(T, MINB) k2v4_orthant_ranges(const K2Args A) {
           v.x = col < Mp ? A.c[col] : (col == Mp ? yy : 0.0);
           v.y = col + 1 < Mp ? A.c[col + 1] : (col + 1 == Mp ? yy : 0.0);
         }
-        *reinterpret_cast<double2 *>(cf.tab + (size_t)cf.ldt * row + col) = v;
+        st_stream2(cf.tab + (size_t)cf.ldt * row + col, v, pol0);
       }
       for (int m = tid; m < cap; m += T) {
         const double cm = m < Mp ? A.c[m] : 0.0;

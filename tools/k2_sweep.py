@@ -10,7 +10,8 @@ from importlib import import_module
 synth = import_module(g.PKG_NAME + ".synth")
 SHAPES = {"cfg2": (100_000, 200, 16, 1e-3, 20240416), "m512": (200_000, 512, 13, 0.0, 20240417),
           "m512k16": (200_000, 512, 16, 0.0, 20240417), "m800": (100_000, 800, 11, 0.0, 20240419),
-          "small": (20_000, 64, 10, 1e-3, 20240415)}
+          "small": (20_000, 64, 10, 1e-3, 20240415), "m512k24": (100_000, 512, 24, 0.0, 20240417),
+          "k20": (100_000, 200, 20, 1e-3, 20240420), "m1000k50": (60_000, 1000, 50, 0.0, 20240418)}
 shape = sys.argv[1]
 N, M, K, eta, seed = SHAPES[shape]
 X, y, P = synth.make_synthetic(N, M, K, seed)
@@ -18,6 +19,8 @@ ctx = pkg.Context(0)
 ctx.load(X, y, P, eta=eta)
 ctx.gram_build(); ctx.gram_finalize()
 total = 1 << (K + 1)
+if os.environ.get("SWEEP_COUNT_LOG2"):
+    total = min(total, 1 << int(os.environ["SWEEP_COUNT_LOG2"]))   # an aligned sub-range of the enumeration
 KEYS = ("PLS_K4_L", "PLS_K4_T", "PLS_K4_QS", "PLS_K4_MINB", "PLS_K4_VERIFY", "PLS_K4_GRID", "PLS_K4_OCC", "PLS_K2_IMPL", "PLS_K3_QS", "PLS_K3_T", "PLS_K3_MINB", "PLS_K3_CHAIN", "PLS_K2_PHASES", "PLS_K3_OCC")
 ref = None
 for setting in sys.argv[2:]:
