@@ -78,7 +78,9 @@ const char *pls_last_error(void);
  * Julia host needs): pls_load shards the rows, pls_opt_fit / pls_alt_fit shard the orthant range /
  * the restarts, the raw Gram sums are exchanged peer-to-peer over NVLink and summed in a fixed order,
  * winners are compared with the (objective, b) rule -- results do not depend on the device count.
- * The stage-wise entry points, the test hooks and fit(BnB) need a one-GPU context. */
+ * pls_bnb_fit grows the frontier on the first device, deals the open nodes to all devices (one state
+ * pool per device) and shares the incumbent after every wave.  The stage-wise entry points and the test hooks
+ * need a one-GPU context. */
 int pls_create(pls_ctx **out, const int *device_ids, int n_dev);
 void pls_destroy(pls_ctx *ctx);
 int pls_device_count(void);

@@ -489,7 +489,7 @@ int pls_opt_fit(pls_ctx *c, const double *X, int64_t N, int64_t M, const double 
 
 int pls_bnb_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_signed, double *obj_out, int64_t *nopen,
                          pls_stats *stats) {
-  if (c && !c->subs.empty()) { set_error("fit(BnB) runs on one GPU in this build (create the context with one device)"); return PLS_EUNSUPPORTED; }
+  if (c && !c->subs.empty()) return multi_bnb_fit_resident(c, flags, alpha_signed, obj_out, nopen, stats);
   int rc = check_ctx(c);
   if (rc) return rc;
   if (!c->pb.loaded) { set_error("no data set loaded"); return PLS_EINVAL; }

@@ -18,6 +18,7 @@
 // wave.  The incumbent mu is a device double updated with atomicMin by every leaf, so a positive
 // child's leaf already prunes its sibling.  The optimum does not depend on the traversal order;
 // the number of visited nodes (`nopen`) does, and is reported for this traversal.
+#include <string.h>
 #include <algorithm>
 #include <cmath>
 #include <vector>
@@ -271,7 +272,9 @@ struct OpenNode {
 }  // namespace
 
 // Host driver.  Leaves the winner (signed weights, objective, leaf sequence) in ws.win.
-int k5_bnb_run(const Problem &pb, SolveWs &ws, int sm_count, cudaStream_t st, int *launches, BnbReport *rep) {
+int k5_bnb_run(const Problem &pb, SolveWs &ws, int sm_count, cudaStream_t st, int *launches, BnbReport *rep,
+               BnbShard *shard) {
+  std::atomic<unsigned long long> *shared_mu = shard ? shard->shared_mu : nullptr;
   const int Mp = pb.Mp, Kp = pb.Kp;
   if (Mp > CAP3MAX) { set_error("bnb: M' = %d exceeds this build's limit (%d)", Mp, CAP3MAX); return PLS_EUNSUPPORTED; }
   if (Kp > 64) { set_error("bnb: more than 63 groups"); return PLS_EUNSUPPORTED; }
@@ -298,6 +301,7 @@ int k5_bnb_run(const Problem &pb, SolveWs &ws, int sm_count, cudaStream_t st, in
   const size_t slot_bytes = slot_doubles * sizeof(double);
   size_t n_slots = (size_t)(0.5 * (double)free_b) / slot_bytes;
   if (n_slots > 65536) n_slots = 65536;
+  if (shard && shard->stop_open > 0) n_slots = std::min<size_t>(n_slots, std::max<size_t>(2048, 16 * (size_t)shard->stop_open));   // frontier seeding pass: small pool
   if (const char *e = getenv("PLS_BNB_SLOTS")) n_slots = (size_t)atoll(e);
   if (n_slots < 4) { set_error("bnb: not enough device memory for the state pool"); return PLS_ENOMEM; }
   const int wave_max = (int)std::min<size_t>((size_t)max_grid * 2, n_slots / 2);
@@ -308,7 +312,9 @@ int k5_bnb_run(const Problem &pb, SolveWs &ws, int sm_count, cudaStream_t st, in
   int rc = PLS_OK;
   std::vector<BnbItem> items; std::vector<BnbChild> out;
   std::vector<OpenNode> open; std::vector<int> free_slots;
+  std::vector<BnbItem> pending;
   long long visited = 0, waves = 0, max_open = 0;
+  bool complete = true;
   const long long max_nodes = getenv("PLS_BNB_MAX_NODES") ? atoll(getenv("PLS_BNB_MAX_NODES")) : 0;
   double h_mu = INFINITY;
   const unsigned long long inf_bits = 0x7ff0000000000000ull;
@@ -318,7 +324,13 @@ int k5_bnb_run(const Problem &pb, SolveWs &ws, int sm_count, cudaStream_t st, in
   BNB_TRY(cudaMalloc(&d_items, sizeof(BnbItem) * wave_max));
   BNB_TRY(cudaMalloc(&d_out, sizeof(BnbChild) * 2 * wave_max));
   BNB_TRY(cudaMalloc(&d_ctr, sizeof(unsigned long long) * 2));
-  BNB_TRY(cudaMemcpyAsync(mu, &inf_bits, sizeof(double), cudaMemcpyHostToDevice, st));
+  {
+    // start from the incumbent other devices / an earlier pass already hold
+    const unsigned long long start_bits = shared_mu ? std::min(shared_mu->load(), inf_bits) : inf_bits;
+    memcpy(&h_mu, &start_bits, sizeof(double));
+    BNB_TRY(cudaMemcpyAsync(mu, &h_mu, sizeof(double), cudaMemcpyHostToDevice, st));
+    BNB_TRY(cudaStreamSynchronize(st));
+  }
   if (max_grid > ws.max_ctas || Mp != ws.Mp) {
     cudaFree(ws.cta_obj); cudaFree(ws.cta_b); cudaFree(ws.cta_w);
     ws.cta_obj = nullptr; ws.cta_b = nullptr; ws.cta_w = nullptr; ws.max_ctas = 0;
@@ -338,8 +350,20 @@ int k5_bnb_run(const Problem &pb, SolveWs &ws, int sm_count, cudaStream_t st, in
   free_slots.reserve(n_slots);
   for (size_t i = n_slots; i-- > 1;) free_slots.push_back((int)i);
   {
-    BnbItem r; r.parent_slot = -1; r.spare_slot = 0; r.k = -1; r.pad = 0; r.pos_mask = 0; r.neg_mask = 0;
-    items.push_back(r);
+    // first wave: the root(s), solved cold.  More roots than one wave holds wait in `pending`.
+    const size_t n_roots = shard && !shard->root_pos.empty() ? shard->root_pos.size() : 1;
+    for (size_t i = 0; i < n_roots; ++i) {
+      BnbItem r; r.parent_slot = -1; r.spare_slot = -1; r.k = -1; r.pad = 0;
+      r.pos_mask = shard && !shard->root_pos.empty() ? shard->root_pos[i] : 0ull;
+      r.neg_mask = shard && !shard->root_pos.empty() ? shard->root_neg[i] : 0ull;
+      pending.push_back(r);
+    }
+    free_slots.push_back(0);
+    while (!pending.empty() && (int)items.size() < wave_max && free_slots.size() > (size_t)(Kp + 2)) {
+      BnbItem r = pending.back(); pending.pop_back();
+      r.spare_slot = free_slots.back(); free_slots.pop_back();
+      items.push_back(r);
+    }
   }
   for (;;) {
     const int n = (int)items.size();
@@ -357,6 +381,17 @@ int k5_bnb_run(const Problem &pb, SolveWs &ws, int sm_count, cudaStream_t st, in
     BNB_TRY(cudaMemcpyAsync(out.data(), d_out, sizeof(BnbChild) * 2 * n, cudaMemcpyDeviceToHost, st));
     BNB_TRY(cudaMemcpyAsync(&h_mu, mu, sizeof(double), cudaMemcpyDeviceToHost, st));
     BNB_TRY(cudaStreamSynchronize(st));
+    if (shared_mu) {                 // exchange the incumbent with the other devices (bit patterns of doubles >= 0 order like integers)
+      unsigned long long mine, cur = shared_mu->load();
+      memcpy(&mine, &h_mu, sizeof(mine));
+      while (mine < cur && !shared_mu->compare_exchange_weak(cur, mine)) {}
+      cur = shared_mu->load();
+      if (cur < mine) {
+        memcpy(&h_mu, &cur, sizeof(double));
+        BNB_TRY(cudaMemcpyAsync(mu, &h_mu, sizeof(double), cudaMemcpyHostToDevice, st));   // leaves only ever lower it further
+        BNB_TRY(cudaStreamSynchronize(st));
+      }
+    }
     for (int i = 0; i < n; ++i) {
       const BnbItem &itx = items[i];
       const bool root = itx.k < 0;
@@ -386,7 +421,14 @@ int k5_bnb_run(const Problem &pb, SolveWs &ws, int sm_count, cudaStream_t st, in
       open.resize(keep);
     }
     max_open = std::max<long long>(max_open, (long long)open.size());
-    if (open.empty()) break;
+    if (open.empty() && pending.empty()) break;
+    if (shard && pending.empty() && ((shard->stop_waves > 0 && waves >= shard->stop_waves) ||
+                                     (shard->stop_open > 0 && (long long)open.size() >= shard->stop_open))) {
+      complete = false;                        // hand the frontier back (best lower bound first)
+      std::sort(open.begin(), open.end(), [](const OpenNode &a, const OpenNode &b) { return a.lb < b.lb; });
+      for (const OpenNode &nd : open) { shard->open_pos.push_back(nd.pos); shard->open_neg.push_back(nd.neg); }
+      break;
+    }
     if (max_nodes > 0 && visited >= max_nodes) {
       set_error("bnb: node budget PLS_BNB_MAX_NODES=%lld exhausted (%lld visited, %zu open, incumbent %.9g)", max_nodes, visited, open.size(), h_mu);
       rc = PLS_EUNSUPPORTED; goto done;
@@ -397,6 +439,11 @@ int k5_bnb_run(const Problem &pb, SolveWs &ws, int sm_count, cudaStream_t st, in
     items.clear();
     // depth-first needs at most Kp + 1 slots per node in flight before a leaf frees one
     const int limit = low ? (int)std::max<size_t>(1, free_slots.size() / (size_t)(Kp + 1)) : wave_max;
+    while (!pending.empty() && (int)items.size() < std::min(limit, wave_max) && !free_slots.empty()) {   // roots not started yet
+      BnbItem r = pending.back(); pending.pop_back();
+      r.spare_slot = free_slots.back(); free_slots.pop_back();
+      items.push_back(r);
+    }
     while (!open.empty() && (int)items.size() < std::min(limit, wave_max) && !free_slots.empty()) {
       const OpenNode nd = open.back(); open.pop_back();
       BnbItem it; it.parent_slot = nd.slot; it.spare_slot = free_slots.back(); free_slots.pop_back();
@@ -409,7 +456,10 @@ int k5_bnb_run(const Problem &pb, SolveWs &ws, int sm_count, cudaStream_t st, in
   BNB_TRY(cudaGetLastError());
   ++*launches;
   BNB_TRY(cudaStreamSynchronize(st));
-  if (rep) { rep->visited = visited; rep->waves = waves; rep->max_open = max_open; rep->pool_slots = (long long)n_slots; rep->mu = h_mu; }
+  if (rep) {
+    rep->visited = visited; rep->waves = waves; rep->max_open = max_open; rep->pool_slots = (long long)n_slots; rep->mu = h_mu;
+    rep->complete = complete; rep->has_leaf = false;
+  }
 done:
   cudaFree(pool); cudaFree(mu); cudaFree(d_items); cudaFree(d_out); cudaFree(d_ctr);
   return rc;

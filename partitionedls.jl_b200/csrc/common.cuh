@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <vector>
 #include "../../include/pls.h"
 
@@ -116,8 +117,19 @@ int k2v4_launch(const K2Args &A, const K4Plan &pl, int grid, cudaStream_t st);
 int k2v4_plan_prof(int Mp, int Kp, K4Plan *pl);      // nnls4p.cu: same kernels with phase counters
 int k2v4_launch_prof(const K2Args &A, const K4Plan &pl, int grid, cudaStream_t st);
 // K5: branch and bound with batched frontier expansion (bnb.cu); winner left in ws.win
-struct BnbReport { long long visited, waves, max_open, pool_slots; double mu; };
-int k5_bnb_run(const Problem &pb, SolveWs &ws, int sm_count, cudaStream_t st, int *launches, BnbReport *rep);
+struct BnbReport { long long visited, waves, max_open, pool_slots; double mu; bool complete, has_leaf; };
+// Multi-GPU sharding of the search (multi.cu).  roots: the subtrees this call searches, each given by the
+// groups fixed to + / - at its root (empty = the whole tree); shared_mu: bit pattern of an incumbent shared
+// with the other devices, read and lowered after every wave; stop_waves / stop_open: hand the frontier
+// back (open_pos / open_neg, rep->complete = false) once that many waves ran or that many nodes are open.
+struct BnbShard {
+  std::vector<unsigned long long> root_pos, root_neg;
+  std::atomic<unsigned long long> *shared_mu = nullptr;
+  long long stop_waves = 0, stop_open = 0;
+  std::vector<unsigned long long> open_pos, open_neg;
+};
+int k5_bnb_run(const Problem &pb, SolveWs &ws, int sm_count, cudaStream_t st, int *launches, BnbReport *rep,
+               BnbShard *shard = nullptr);
 // K6: alternating optimisation, batched restarts (alt.cu)
 int k6_alt_run(const Problem &pb, SolveWs &ws, const std::vector<uint64_t> &h_gmask, const double *h_beta0, long long R,
                double eps, int Tmax, double *d_w, double *h_all_obj, int sm_count, cudaStream_t st, int *launches,

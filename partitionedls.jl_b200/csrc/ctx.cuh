@@ -41,6 +41,7 @@ int multi_load(pls_ctx *c, const double *X, int64_t N, int64_t ldx, int64_t M, c
                int64_t K, double eta);
 int multi_opt_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_raw, int64_t *b_best, double *obj_best,
                            double *all_obj, double *all_alpha, pls_stats *stats);
+int multi_bnb_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_signed, double *obj_out, int64_t *nopen, pls_stats *stats);
 int multi_alt_fit_resident(pls_ctx *c, const double *beta0, int64_t R, double eps, int64_t T, uint32_t flags,
                            double *alpha, double *beta, double *obj_out, int64_t *best_restart, int64_t *iters,
                            double *all_obj, pls_stats *stats);

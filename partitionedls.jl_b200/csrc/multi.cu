@@ -12,7 +12,14 @@
 //   K4  every device evaluates the winner on its own rows; the partial sums are added in device order.
 //
 // Alt: restarts are split across the devices (same Gram on each), the best (loss, restart) wins.
+// BnB: device 0 runs the ordinary search until the frontier holds 16 nodes per device (or 6 waves; an
+//      easy problem ends there, as in the reference: nopen = 1 when the unconstrained root is already
+//      sign-consistent); then the open nodes are dealt to the devices, every device re-solves its
+//      nodes from their sign masks and searches below them with its own state pool, and the incumbent
+//      is shared through a host atomic after every wave so that one device's leaf prunes the others.
 #include <string.h>
+#include <atomic>
+#include <algorithm>
 #include <cmath>
 #include <string>
 #include <thread>
@@ -239,6 +246,109 @@ int multi_opt_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_raw, int64_
   s.gram_flops = Nd * Md * (Md + 1.0) + 2.0 * Nd * Md + 2.0 * Nd;
   int launches1 = 0;
   for (pls_ctx *d : c->subs) launches1 += d->launches;
+  s.kernel_launches = launches1 - launches0;
+  s.ms_total = now_ms() - t0 + s.ms_upload;
+  if (stats) *stats = s;
+  if (obj != obj) { set_error("NaN objective (non-finite input?)"); return PLS_ENUMERIC; }
+  return PLS_OK;
+}
+
+int multi_bnb_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_signed, double *obj_out, int64_t *nopen, pls_stats *stats) {
+  if (!c->pb.loaded) { set_error("no data set loaded"); return PLS_EINVAL; }
+  if (!alpha_signed || !obj_out || !nopen) { set_error("null output pointer"); return PLS_EINVAL; }
+  const int G = (int)c->subs.size();
+  const int Mp = c->pb.Mp, Kp = c->pb.Kp;
+  const double t0 = now_ms();
+  const double keep_upload = c->stats.ms_upload;
+  memset(&c->stats, 0, sizeof(c->stats));
+  c->stats.ms_upload = keep_upload;
+  int launches0 = 0;
+  for (pls_ctx *s : c->subs) { launches0 += s->launches; memset(&s->stats, 0, sizeof(s->stats)); }
+  const double tg0 = now_ms();
+  int rc = multi_gram(c);
+  if (rc) return rc;
+  const double tg1 = now_ms();
+  std::atomic<unsigned long long> shared_mu(0x7ff0000000000000ull);
+  std::vector<std::vector<double>> rec(G, std::vector<double>(Mp + 2, 0.0));
+  std::vector<char> has(G, 0);
+  std::vector<long long> visited(G, 0), waves(G, 0), max_open(G, 0);
+  // one search (whole tree or a set of subtrees) on one device; keeps the device's best leaf in rec[g]
+  auto run_one = [&](int g, pls_ctx *s, BnbShard *sh, bool *complete) -> int {
+    int r = check_ctx(s);
+    if (r) return r;
+    if (s->ws.Mp != s->pb.Mp && s->ws.win) { cudaFree(s->ws.win); s->ws.win = nullptr; }
+    BnbReport rep;
+    r = k5_bnb_run(s->pb, s->ws, s->sm_count, s->stream, &s->launches, &rep, sh);
+    if (r) return r;
+    visited[g] += rep.visited; waves[g] += rep.waves; max_open[g] = std::max(max_open[g], rep.max_open);
+    if (complete) *complete = rep.complete;
+    PLS_CUDA_TRY(cudaMemcpyAsync(s->h_pin, s->ws.win, sizeof(double) * (Mp + 2), cudaMemcpyDeviceToHost, s->stream));
+    PLS_CUDA_TRY(cudaMemcpyAsync(s->h_pin + Mp + 4, s->ws.counters, sizeof(unsigned long long) * (CNT_NUM + 1 + 24), cudaMemcpyDeviceToHost, s->stream));
+    PLS_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    const unsigned long long *cnt = reinterpret_cast<const unsigned long long *>(s->h_pin + Mp + 4);
+    pls_stats keep = s->stats;
+    read_counters(s, cnt);
+    s->stats.pivots += keep.pivots; s->stats.grad_evals += keep.grad_evals; s->stats.sum_p += keep.sum_p; s->stats.sum_p2 += keep.sum_p2;
+    s->stats.bpp_iters += keep.bpp_iters; s->stats.rebuilds += keep.rebuilds; s->stats.blocked += keep.blocked;
+    s->stats.nnls_flops += keep.nnls_flops; s->stats.nnls_l2_bytes += keep.nnls_l2_bytes;
+    long long seq; memcpy(&seq, &s->h_pin[Mp + 1], sizeof(seq));
+    if (seq >= 0 && (!has[g] || s->h_pin[Mp] < rec[g][Mp])) { memcpy(rec[g].data(), s->h_pin, sizeof(double) * (Mp + 2)); has[g] = 1; }
+    return PLS_OK;
+  };
+  const double ts0 = now_ms();
+  bool complete = false;
+  BnbShard first;
+  first.shared_mu = &shared_mu; first.stop_waves = 6; first.stop_open = 16ll * G;
+  {
+    pls_ctx *d0 = c->subs[0];
+    PLS_CUDA_TRY(cudaSetDevice(d0->dev));
+    rc = run_one(0, d0, &first, &complete);
+    if (rc) return rc;
+  }
+  if (!complete) {
+    // deal the frontier (sorted by lower bound) to the devices like cards; every device re-solves its
+    // nodes cold from their sign masks and searches below them
+    std::vector<BnbShard> sh(G);
+    for (size_t i = 0; i < first.open_pos.size(); ++i) {
+      sh[i % G].root_pos.push_back(first.open_pos[i]); sh[i % G].root_neg.push_back(first.open_neg[i]);
+    }
+    rc = par_for(c, [&](int g, pls_ctx *s) -> int {
+      if (sh[g].root_pos.empty()) return PLS_OK;
+      sh[g].shared_mu = &shared_mu;
+      return run_one(g, s, &sh[g], nullptr);
+    });
+    if (rc) return rc;
+  }
+  const double ts1 = now_ms();
+  int win = -1;
+  for (int g = 0; g < G; ++g)
+    if (has[g] && (win < 0 || rec[g][Mp] < rec[win][Mp])) win = g;
+  if (win < 0) { set_error("bnb: no feasible leaf found"); return PLS_ENUMERIC; }
+  memcpy(alpha_signed, rec[win].data(), sizeof(double) * Mp);
+  double obj = rec[win][Mp];
+  const double tr0 = now_ms();
+  if (!(flags & PLS_FLAG_NO_RECOMPUTE) && obj == obj) {
+    std::vector<double> ssq(G, 0.0);
+    rc = par_for(c, [&](int g, pls_ctx *s) -> int { return residual_partial_w(s, alpha_signed, &ssq[g]); });
+    if (rc) return rc;
+    double tot = 0.0;
+    for (int g = 0; g < G; ++g) tot += ssq[g];
+    obj = std::sqrt(tot + eta_term_w(c, alpha_signed));
+  }
+  *obj_out = obj;
+  long long vis = 0;
+  for (int g = 0; g < G; ++g) vis += visited[g];
+  *nopen = vis;
+  pls_stats &s = c->stats;
+  sum_stats(c, s);
+  s.ms_gram = tg1 - tg0; s.ms_nnls = ts1 - ts0; s.ms_recompute = now_ms() - tr0;
+  s.orthants = vis;
+  s.waves = 0; s.max_open = 0;
+  for (int g = 0; g < G; ++g) { s.waves = std::max<int64_t>(s.waves, waves[g]); s.max_open = std::max<int64_t>(s.max_open, max_open[g]); }
+  const double Nd = (double)c->pb.N, Md = (double)Mp;
+  s.gram_flops = Nd * Md * (Md + 1.0) + 2.0 * Nd * Md + 2.0 * Nd;
+  int launches1 = 0;
+  for (pls_ctx *dd : c->subs) launches1 += dd->launches;
   s.kernel_launches = launches1 - launches0;
   s.ms_total = now_ms() - t0 + s.ms_upload;
   if (stats) *stats = s;

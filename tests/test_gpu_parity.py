@@ -358,8 +358,8 @@ def _n_gpus(pkg):
 
 
 def test_multi_gpu_context_matches_single(ctx, pkg, oracle):
-    """Rows, orthant ranges and restarts sharded inside the library over 2 GPUs: same winner, objective
-    and alpha as the one-GPU context (Gram sums are added in a different order: 1e-9, not bitwise)."""
+    """Rows, orthant ranges, restarts and BnB subtrees sharded inside the library over 2 GPUs: same winner,
+    objective and alpha as the one-GPU context (Gram sums are added in a different order: 1e-9, not bitwise)."""
     if _n_gpus(pkg) < 2:
         pytest.skip("needs 2 GPUs")
     o, _ = oracle
@@ -381,9 +381,17 @@ def test_multi_gpu_context_matches_single(ctx, pkg, oracle):
         assert a2["best_restart"] == a1["best_restart"] and abs(a2["opt"] - a1["opt"]) <= 1e-8 * a1["opt"]
         assert np.allclose(a2["alpha"], a1["alpha"], rtol=1e-7, atol=1e-10) and np.allclose(a2["beta"], a1["beta"], rtol=1e-7)
         assert np.allclose(a2["all_obj"], a1["all_obj"], rtol=1e-8)
-        with pytest.raises(pkg.PlsError) as e:
-            mc.bnb_fit(X, y, P)
-        assert e.value.code == pkg._abi.PLS_EUNSUPPORTED
+        # BnB over 2 GPUs: subtrees with a shared incumbent -- same optimum and weights as one GPU
+        b1 = ctx.bnb_fit(X, y, P, eta=eta)
+        b2 = mc.bnb_fit(X, y, P, eta=eta)
+        assert abs(b2["opt"] - b1["opt"]) <= RTOL * b1["opt"]
+        assert np.all(np.abs(b2["alpha_signed"] - b1["alpha_signed"]) <= RTOL * np.abs(b1["alpha_signed"]).max())
+        assert b2["nopen"] >= 1
+        # a problem whose unconstrained root is already sign-consistent ends in the first pass on device 0
+        Xc, yc, Pc = o.make_synthetic(3000, 24, 4, seed=5, mixed_sign=False)
+        t1 = ctx.bnb_fit(Xc, yc, Pc, eta=0.0)
+        t2 = mc.bnb_fit(Xc, yc, Pc, eta=0.0)
+        assert abs(t2["opt"] - t1["opt"]) <= RTOL * t1["opt"] and t2["nopen"] == t1["nopen"]
     finally:
         mc.close()
 

@@ -10,7 +10,8 @@ synth = import_module(g.PKG_NAME + ".synth")
 N, M, K, R = (int(a) for a in sys.argv[1:5])
 eta = float(sys.argv[5]) if len(sys.argv) > 5 else 0.0
 X, y, P = synth.make_synthetic(N, M, K, 20240418, mixed_sign=False)
-ctx = pkg.Context(0)
+_ng = int(os.environ.get('NGPU', '1'))
+ctx = pkg.Context(list(range(_ng)) if _ng > 1 else 0)
 ctx.load(X, y, P, eta=eta)
 beta0 = pkg.draw_alt_starts(20240418, M + 1, K + 1, R)
 for rep in range(2):

@@ -23,7 +23,8 @@ else:
     y = X @ w + 0.5 + rng.standard_normal(N)
     P = np.zeros((M, K), dtype=np.int64); P[np.arange(M), gidx] = 1
     P = np.asfortranarray(P)
-ctx = pkg.Context(0)
+_ng = int(os.environ.get('NGPU', '1'))
+ctx = pkg.Context(list(range(_ng)) if _ng > 1 else 0)
 ctx.load(X, y, P, eta=eta)
 for rep in range(int(os.environ.get("BNB_REPS", "2"))):
     t0 = time.perf_counter(); r = ctx.bnb_fit_resident(); dt = time.perf_counter() - t0
