@@ -457,3 +457,78 @@ def test_wide_long_chains_kkt(ctx, oracle):
     ref = oc.opt_fit(X, y, P, 1e-3, b_list=[r["b_best"]], nthreads=1)
     assert abs(ref["objs"][0] - r["opt"]) <= RTOL * r["opt"]
     assert np.all(np.abs(ref["alphas"][0] - r["alpha_raw"]) <= RTOL * np.abs(ref["alphas"][0]).max())
+
+
+# ---- the two-level K2 path (nnls4.cu) on the edge cases ---------------------------------------------
+@pytest.fixture(params=["v4_few_ctas", "v4_one_cta", "v4_default_dispatch"])
+def twolevel(request):
+    """Forces the two-level kernel onto small problems: 3 CTAs / 1 CTA walking long pieces of the Gray
+    sequence with l = 2 / 1 fast groups and KKT checks every 4 orthants; the third setting leaves the
+    dispatcher alone (v4 only for ranges >= 64 orthants per SM)."""
+    env = {"v4_few_ctas": {"PLS_K2_IMPL": "v4", "PLS_K4_GRID": "3", "PLS_K4_L": "2", "PLS_K4_VERIFY": "4"},
+           "v4_one_cta": {"PLS_K2_IMPL": "v4", "PLS_K4_GRID": "1", "PLS_K4_L": "1", "PLS_K4_VERIFY": "4"},
+           "v4_default_dispatch": {}}[request.param]
+    old = {k: os.environ.get(k) for k in _K2_KEYS}
+    for k in _K2_KEYS:
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    yield request.param
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+
+
+@pytest.mark.parametrize("M", [39, 47, 56])
+def test_twolevel_tableau_sizes(ctx, oracle, twolevel, M):
+    """M' = 40, 48 (multiples of 8: the tableau needs one more tile row for the right-hand side) and 57."""
+    o, oc = oracle
+    X, y, P = o.make_synthetic(900, M, 6, seed=500 + M, mixed_sign=True, rho=0.3)
+    ref = oc.opt_fit(X, y, P, 1e-3)
+    r = ctx.opt_fit(X, y, P, eta=1e-3, return_all=True)
+    assert r["b_best"] == ref["b_best"] and abs(r["opt"] - ref["obj_best"]) <= RTOL * ref["obj_best"]
+    assert np.allclose(r["objs"], ref["objs"], rtol=RTOL, atol=1e-6 * np.linalg.norm(y))
+    scale = np.abs(ref["alphas"]).max(axis=1, keepdims=True)
+    assert np.all(np.abs(r["alphas"] - ref["alphas"]) <= RTOL * scale + 1e-300)
+    assert r["stats"]["rebuilds"] == 0
+
+
+def test_twolevel_edge_structures(ctx, oracle, twolevel):
+    """Empty group + group-less features, overlapping groups (d = 0, +-2), y = 0, an exactly dependent column."""
+    o, oc = oracle
+    X, y, P = o.make_synthetic(500, 14, 4, seed=31, mixed_sign=True)
+    P = P.copy(); P[:, 2] = 0
+    P[0, 1] = 1; P[0, 0] = 1; P[5, 3] = 1; P[5, 0] = 1          # two features in two groups each
+    ref = oc.opt_fit(X, y, P, 1e-3)
+    r = ctx.opt_fit(X, y, P, eta=1e-3, return_all=True)
+    assert r["b_best"] == ref["b_best"] and abs(r["opt"] - ref["obj_best"]) <= RTOL * ref["obj_best"]
+    assert np.allclose(r["objs"], ref["objs"], rtol=RTOL, atol=1e-6 * np.linalg.norm(y))
+    scale = np.abs(ref["alphas"]).max(axis=1, keepdims=True)
+    assert np.all(np.abs(r["alphas"] - ref["alphas"]) <= RTOL * scale + 1e-300)
+    X2, y2, P2 = o.make_synthetic(300, 8, 3, seed=41)
+    r = ctx.opt_fit(X2, np.zeros_like(y2), P2, eta=0.0, return_all=True)
+    assert r["b_best"] == 0 and r["opt"] == 0.0 and np.all(r["alphas"] == 0.0)
+    Xc = X2.copy(); Xc[:, 3] = 1.0
+    ref = oc.opt_fit(Xc, y2, P2, 0.0)
+    r = ctx.opt_fit(Xc, y2, P2, eta=0.0, return_all=True)
+    assert abs(r["opt"] - ref["obj_best"]) <= 1e-9 * ref["obj_best"]
+    assert np.allclose(r["objs"], ref["objs"], rtol=1e-9, atol=1e-6 * np.linalg.norm(y2))
+
+
+def test_twolevel_long_walk_kkt_every_orthant(ctx, oracle):
+    """2^15 orthants at M' = 97 through the default dispatcher (v4, ~55 orthants per CTA), every orthant's
+    objective against a numpy active-set solve of a random sample, the winner against the C oracle."""
+    o, oc = oracle
+    N, M, K = 4000, 96, 14
+    X, y, P = o.make_synthetic(N, M, K, seed=2024, mixed_sign=True, rho=0.2)
+    r = ctx.opt_fit(X, y, P, eta=1e-3, return_all=True)
+    assert r["stats"]["orthants"] == 2 ** 15 and r["stats"]["rebuilds"] == 0
+    rng = np.random.default_rng(3)
+    bl = np.unique(np.concatenate([rng.integers(0, 2 ** 15, size=40), [r["b_best"]]])).astype(np.int64)
+    ref = oc.opt_fit(X, y, P, 1e-3, b_list=bl, nthreads=4)
+    for j, b in enumerate(bl):
+        assert abs(ref["objs"][j] - r["objs"][b]) <= RTOL * ref["objs"][j] + 1e-6 * np.linalg.norm(y)
+        sc = max(np.abs(ref["alphas"][j]).max(), 1e-300)
+        assert np.all(np.abs(ref["alphas"][j] - r["alphas"][b]) <= RTOL * sc)
+    assert int(np.argmin(r["objs"])) == r["b_best"]
