@@ -38,6 +38,22 @@ __device__ __forceinline__ int warp_incl_scan(int v) {
   for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
   return v;
 }
+// Warp 0 writes the indices m in [0, n) with pred(m) != 0, in increasing order, to out[] and returns
+// their number in *count (shared).  Other warps do nothing; the caller synchronises afterwards.
+template <class Pred>
+__device__ __forceinline__ void warp0_compact(int n, Pred pred, int *out, int *count) {
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  int base = 0;
+  for (int m0 = 0; m0 < n; m0 += 32) {
+    const int m = m0 + lane;
+    const int v = m < n ? pred(m) : -1;           // pred returns the value to store (>= 0) or -1
+    const unsigned bal = __ballot_sync(0xffffffffu, v >= 0);
+    if (v >= 0) out[base + __popc(bal & ((1u << lane) - 1))] = v;
+    base += __popc(bal);
+  }
+  if (lane == 0) *count = base;
+}
 __device__ __forceinline__ bool lex_better(double oa, long long ba, double ob, long long bb) {
   if (bb < 0) return ba >= 0;
   if (ba < 0) return false;
@@ -482,8 +498,8 @@ __device__ __noinline__ bool block_add3(const Cfg3 cf, const double *G, int ldg,
     const int i = tid >> 3, j = tid & 7;
     if (i < a && j <= i) h_set<MODE>(s, As[i], As[j], s.Sinv[i * 8 + j]);
   }
-  if (tid >= 64 && tid < 64 + a) {
-    const int q = tid - 64;
+  if (tid >= T - 32 && tid < T - 32 + a) {        // last warp (T >= 64)
+    const int q = tid - (T - 32);
     const int var = Av[-q], sl = As[q];
     s.w[var] = s.theta[q]; s.F[sl] = var; s.pos[var] = sl;
   }
@@ -744,8 +760,8 @@ __device__ __noinline__ bool tab_sweep_in3(const Cfg3 cf, const int *Bs, int nb,
     const int i = tid >> 3, j = tid & 7;
     if (i < nb && j < nb) cf.tab[(size_t)cf.ldt * Bv[i] + Bv[j]] = -s.Sinv[i * 8 + j];
   }
-  if (tid >= 64 && tid < 64 + nb) {
-    const int q = tid - 64, var = Bv[q], sl = Bsl[q];
+  if (tid >= T - 32 && tid < T - 32 + nb) {
+    const int q = tid - (T - 32), var = Bv[q], sl = Bsl[q];
     s.r[var] = s.w[var]; s.w[var] = 0.0; s.pos[var] = -1; s.F[sl] = -1; s.swp[var] = 1;
   }
   __syncthreads();
@@ -834,8 +850,8 @@ __device__ __noinline__ void tab_unsweep3(const Cfg3 cf, const int *Bvar, int nb
     const int i = tid >> 3, j = tid & 7;
     if (i < nb && j < nb) cf.tab[(size_t)cf.ldt * Bv[i] + Bv[j]] = s.Sinv[i * 8 + j];   // -inv(D)
   }
-  if (tid >= 64 && tid < 64 + nb) {
-    const int q = tid - 64, var = Bv[q], sl = Bsl[q];
+  if (tid >= T - 32 && tid < T - 32 + nb) {
+    const int q = tid - (T - 32), var = Bv[q], sl = Bsl[q];
     s.w[var] = s.r[var]; s.r[var] = 0.0; s.pos[var] = sl; s.F[sl] = var; s.swp[var] = 0;
     if ((s.gms[var] & cf.flipmask) == 0) s.ncm[var] = 1;     // left although its own groups kept their sign: fickle
   }
@@ -938,11 +954,7 @@ __device__ __forceinline__ bool bpp_solve3(const Cfg3 cf, const Sh3 &s, const do
     if (TL) {
       any3 = __syncthreads_or(any3);
       if (any3) {                                 // swept variables that must leave: back into the small inverse first
-        if (tid == 0) {
-          int n = 0;
-          for (int m = 0; m < Mp; ++m) if (s.fl[m] == 3) s.lst[n++] = m;
-          s.ctl[5] = n;
-        }
+        warp0_compact(Mp, [&](int m) { return s.fl[m] == 3 ? m : -1; }, s.lst, &s.ctl[5]);
         __syncthreads();
         const int n3 = s.ctl[5];
         for (int q0 = 0; q0 < n3; q0 += 8) tab_unsweep3<T, MODE>(cf, s.lst + q0, min(8, n3 - q0), Mp, st);

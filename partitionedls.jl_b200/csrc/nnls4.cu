@@ -36,16 +36,11 @@ __device__ __noinline__ double verify_true3(const Cfg3 cf, const double *G, int 
   const Sh3 s = make_sh3(cf);
   constexpr int NW = T / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) {
-    int n = 0;
-    for (int m = 0; m < Mp; ++m) {
-      if (s.pos[m] >= 0) { s.lst[n] = m; s.wF[n] = s.w[m]; ++n; }
-      else if (s.swp[m]) { s.lst[n] = m; s.wF[n] = s.r[m]; ++n; }
-    }
-    s.ctl[5] = n;
-  }
+  warp0_compact(Mp, [&](int m) { return (s.pos[m] >= 0 || s.swp[m]) ? m : -1; }, s.lst, &s.ctl[5]);
   __syncthreads();
   const int n = s.ctl[5];
+  for (int t = tid; t < n; t += T) { const int m = s.lst[t]; s.wF[t] = s.pos[m] >= 0 ? s.w[m] : s.r[m]; }
+  __syncthreads();
   double mx = 0.0;
 #pragma unroll 1
   for (int m = tid; m < Mp; m += T) {
@@ -169,6 +164,7 @@ __global__ void __launch_bounds__(T, MINB) k2v4_orthant_ranges(const K2Args A) {
         continue;
       }
     }
+    const bool was_cold = just_cold;
     just_cold = false;
 
     // ---- objective  sqrt(yy - c_F' w_F)  (= norm(Xa w - ya) at the KKT point, Opt.jl:90)
@@ -194,17 +190,16 @@ __global__ void __launch_bounds__(T, MINB) k2v4_orthant_ranges(const K2Args A) {
     }
 
     // ---- commit: passive variables of slow groups go into the tableau
-    int el = 0;
-    if (ok && r_valid)
-      for (int m = tid; m < Mp; m += T) if (s.pos[m] >= 0 && (s.gms[m] & A.lowmask) == 0 && !s.ncm[m]) el = 1;
-    if (__syncthreads_or(el)) {
-      if (tid == 0) {
-        int n = 0;
-        for (int m = 0; m < Mp; ++m) if (s.pos[m] >= 0 && (s.gms[m] & A.lowmask) == 0 && !s.ncm[m]) s.lst[n++] = s.pos[m];
-        s.ctl[5] = n;
-      }
+    // (looked for after a slow group moved, after a cold start, and every 8th orthant for the odd
+    // slow-group variable that entered on the side)
+    const bool look = ok && r_valid && (fb >= low_bits || was_cold || (i & 7) == 7);
+    int n = 0;
+    if (look) {
+      warp0_compact(Mp, [&](int m) { return (s.pos[m] >= 0 && (s.gms[m] & A.lowmask) == 0 && !s.ncm[m]) ? s.pos[m] : -1; }, s.lst, &s.ctl[5]);
       __syncthreads();
-      const int n = s.ctl[5];
+      n = s.ctl[5];
+    }
+    if (n > 0) {
       for (int q0 = 0; q0 < n; q0 += 8) {
         const int nb = min(8, n - q0);
         if (!tab_sweep_in3<T, MODE>(cf, s.lst + q0, nb, Mp, nt_cur)) {
@@ -268,6 +263,7 @@ size_t v4_smem_bytes(int cap, int qs) {
 typedef void (*K4Fn)(const K2Args);
 struct Variant4 { int T, mode, minb; K4Fn fn; };
 const Variant4 kVariants4[] = {
+    {64, 1, 5, k2v4_orthant_ranges<64, 1, 5>}, {64, 1, 4, k2v4_orthant_ranges<64, 1, 4>}, {64, 1, 3, k2v4_orthant_ranges<64, 1, 3>},
     {128, 1, 4, k2v4_orthant_ranges<128, 1, 4>}, {128, 1, 5, k2v4_orthant_ranges<128, 1, 5>},
     {128, 2, 4, k2v4_orthant_ranges<128, 2, 4>}, {128, 1, 3, k2v4_orthant_ranges<128, 1, 3>},
     {256, 1, 2, k2v4_orthant_ranges<256, 1, 2>}, {256, 1, 3, k2v4_orthant_ranges<256, 1, 3>},
@@ -288,14 +284,14 @@ int K4_NAME(k2v4_plan)(int Mp, int Kp, K4Plan *pl) {
   const char *eT = getenv("PLS_K4_T"), *eQ = getenv("PLS_K4_QS"), *eB = getenv("PLS_K4_MINB"), *eL = getenv("PLS_K4_L"),
              *eV = getenv("PLS_K4_VERIFY");
   int T = eT ? atoi(eT) : (Mp <= 256 ? 128 : 256);
-  if (T != 128 && T != 256 && T != 512) T = 256;
+  if (T != 64 && T != 128 && T != 256 && T != 512) T = 256;
   while (Mp > 4 * T) T *= 2;
   int qs = eQ ? atoi(eQ) : 0;
   if (qs < 0 || qs > ntiles) qs = ntiles;
   while (qs > 0 && v4_smem_bytes(cap, qs) > (size_t)max_smem) --qs;
   if (v4_smem_bytes(cap, qs) > (size_t)max_smem) { set_error("k2v4: M' = %d needs more shared memory than one SM has", Mp); return PLS_EUNSUPPORTED; }
   const int mode = qs == 0 ? 1 : 2;
-  const int minb = eB ? atoi(eB) : (T == 128 ? 4 : (T == 256 ? 2 : 1));
+  const int minb = eB ? atoi(eB) : (T == 64 ? 5 : (T == 128 ? 4 : (T == 256 ? 2 : 1)));
   const Variant4 *best = nullptr;
   for (const Variant4 &v : kVariants4)
     if (v.T == T && v.mode == mode && (!best || abs(v.minb - minb) < abs(best->minb - minb))) best = &v;
@@ -319,7 +315,7 @@ int K4_NAME(k2v4_plan)(int Mp, int Kp, K4Plan *pl) {
   pl->hstride = (size_t)(ntiles - qs) << 6;
   pl->tabstride = (size_t)cap * cap + 64;
   pl->low_groups = l;
-  pl->verify_every = eV ? atoi(eV) : 64;
+  pl->verify_every = eV ? atoi(eV) : 128;
   if (pl->verify_every < 1) pl->verify_every = 1;
   return PLS_OK;
 }
