@@ -287,6 +287,9 @@ def run_native(args, rank, world, local_rank):
             "peak_source": "FP64 DFMA peak measured by tools/fp64_peak.cu on this pool (profiles/fp64_peaks_r01.json); MEASURED_PEAKS.json holds no FP64 figure",
             "algorithmic_flops_per_launch": st["nnls_flops"], "launch_ms": k2_ms,
             "flops_per_orthant": st["nnls_flops"] / max(1, st["orthants"]),
+            # a cold Gram-space active-set solve of this shape costs 3.18 MFLOP (M=200, K=16 probe);
+            # the rate at which the kernel retires that reference work -- NOT the arithmetic it executes
+            "effective_tflops_on_cold_solve_model": (3.18e6 * st["orthants"] / (k2_ms * 1e-3) / 1e12) if (k2_ms > 0 and M == 200) else None,
             "l2_model_gbs": st["nnls_l2_bytes"] / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else None,
             "note": "K2 is latency-bound, not FLOP- or HBM-bound (DESIGN.md 3): the two-level solver cuts the work per orthant "
                     "~4x against the one-level v3 kernel (0.65 MFLOP/orthant), so the FLOP rate falls while solves/s rise; "
