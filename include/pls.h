@@ -161,6 +161,11 @@ int pls_opt_objective_finish(pls_ctx *ctx, const double *alpha_raw, int64_t b, d
 /* The same two steps for explicit signed weights w[M+1] (BnB leaves, Alt restarts: w = (Po .* alpha) * beta). */
 int pls_residual_partial_w(pls_ctx *ctx, const double *w, double *ssq_out);
 int pls_objective_finish_w(pls_ctx *ctx, const double *w, double ssq_total, double *obj_out);
+/* Predictions on the resident data set (after pls_load / any fit):  yhat[n] = X[n,:] . w[0..M) + w[M],  w = the
+ * signed feature weights (P .* alpha) * beta with the intercept t last -- predict(model, X),
+ * src/PartitionedLS.jl:132-134, for the X already in HBM (one streaming pass, HBM-bound).  yhat: N doubles
+ * (host).  Works on one-GPU and multi-GPU contexts (every device predicts its row shard). */
+int pls_predict_resident(pls_ctx *ctx, const double *w, double *yhat);
 int pls_get_stats(pls_ctx *ctx, pls_stats *stats);
 
 /* ---- test / bench hooks ------------------------------------------------------------------------

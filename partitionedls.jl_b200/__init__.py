@@ -25,7 +25,7 @@ import numpy as np
 from . import _abi
 from ._abi import Context, PlsError  # noqa: F401
 
-__all__ = ["fit", "predict", "PartLSFitResult", "Opt", "Alt", "BnB", "homogeneousCoords",
+__all__ = ["fit", "predict", "predict_resident", "PartLSFitResult", "Opt", "Alt", "BnB", "homogeneousCoords",
            "regularizeProblem", "Context", "PlsError", "default_context", "draw_alt_starts"]
 
 
@@ -171,6 +171,14 @@ def fit(alg, X, y, P, *, η=0.0, eta=None, nnlsalg="nnls", returnAllSolutions=Fa
         return model, None, SimpleNamespace(opt=r["opt"], best_restart=r["best_restart"], iters=r["iters"],
                                             all_obj=r["all_obj"], stats=r["stats"])
     raise TypeError(f"unknown algorithm {alg!r}")
+
+
+def predict_resident(model, ctx, N):
+    """predict(model, X) for the X already loaded on `ctx` (device-resident pass, pls_predict_resident):
+    w = (P .* alpha) * beta with t appended -- src/PartitionedLS.jl:132-134."""
+    P = np.asarray(model.P, dtype=np.float64)
+    w = np.concatenate([(P * np.asarray(model.α)[:, None]) @ np.asarray(model.β), [model.t]])
+    return ctx.predict_resident(w, N)
 
 
 def predict(model_or_alpha, *args):

@@ -70,12 +70,13 @@ lib.pls_opt_solve_range.argtypes = [_vp, C.c_int64, C.c_int64, _dp, _ip, _dp, _d
 lib.pls_opt_residual_partial.argtypes = [_vp, _dp, C.c_int64, _dp]
 lib.pls_opt_objective_finish.argtypes = [_vp, _dp, C.c_int64, C.c_double, _dp]
 lib.pls_residual_partial_w.argtypes = [_vp, _dp, _dp]
+lib.pls_predict_resident.argtypes = [_vp, _dp, _dp]
 lib.pls_objective_finish_w.argtypes = [_vp, _dp, C.c_double, _dp]
 lib.pls_get_stats.argtypes = [_vp, C.POINTER(PlsStats)]
 lib.pls_gram.argtypes = [_vp, _dp, C.c_int64, C.c_int64, _dp, _ip, C.c_int64, C.c_double, _dp, _dp, _dp]
 lib.pls_nnls_batch.argtypes = [_vp, _dp, _dp, C.c_double, C.c_int64, C.POINTER(C.c_uint64), C.c_int64,
                                C.c_int64, C.c_int64, _dp, _dp]
-for _n in ("pls_create", "pls_opt_fit", "pls_bnb_fit", "pls_bnb_fit_resident", "pls_alt_fit", "pls_alt_fit_resident", "pls_residual_partial_w", "pls_objective_finish_w", "pls_load", "pls_opt_fit_resident", "pls_gram_build", "pls_gram_raw",
+for _n in ("pls_create", "pls_opt_fit", "pls_bnb_fit", "pls_bnb_fit_resident", "pls_alt_fit", "pls_alt_fit_resident", "pls_residual_partial_w", "pls_predict_resident", "pls_objective_finish_w", "pls_load", "pls_opt_fit_resident", "pls_gram_build", "pls_gram_raw",
            "pls_gram_finalize", "pls_opt_solve_range", "pls_opt_residual_partial", "pls_opt_objective_finish",
            "pls_get_stats", "pls_gram", "pls_nnls_batch"):
     getattr(lib, _n).restype = C.c_int
@@ -242,6 +243,12 @@ class Context:
         a = np.ascontiguousarray(w, dtype=np.float64); s = C.c_double()
         _check(lib.pls_residual_partial_w(self._h, _d(a), C.byref(s)))
         return s.value
+
+    def predict_resident(self, w, N):
+        """pls_predict_resident: X_resident @ w[:M] + w[M] for the N rows loaded on this context."""
+        a = np.ascontiguousarray(w, dtype=np.float64); out = np.empty(int(N), dtype=np.float64)
+        _check(lib.pls_predict_resident(self._h, _d(a), _d(out)))
+        return out
 
     def objective_finish_w(self, w, ssq_total):
         a = np.ascontiguousarray(w, dtype=np.float64); o = C.c_double()

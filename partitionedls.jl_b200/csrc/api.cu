@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <thread>
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -64,7 +65,7 @@ void free_ws(pls_ctx *c) {
   SolveWs &ws = c->ws;
   cudaFree(ws.cta_obj); cudaFree(ws.cta_b); cudaFree(ws.cta_w); cudaFree(ws.hspill); cudaFree(ws.tab);
   cudaFree(ws.counters); cudaFree(ws.win); cudaFree(ws.all_obj); cudaFree(ws.all_alpha);
-  cudaFree(ws.resid_part); cudaFree(ws.alt_win);
+  cudaFree(ws.resid_part); cudaFree(ws.alt_win); cudaFree(ws.yhat);
   ws = SolveWs();
 }
 
@@ -401,6 +402,51 @@ int pls_residual_partial_w(pls_ctx *c, const double *w, double *ssq_out) {
   if (c && !c->subs.empty()) { set_error("stage-wise entry points need a one-GPU context"); return PLS_EUNSUPPORTED; }
   if (!c || !c->pb.loaded || !w || !ssq_out) { set_error("no data set loaded or null pointer"); return PLS_EINVAL; }
   return residual_partial_w(c, w, ssq_out);
+}
+
+// K7 on one device: yhat[0..N) of this context's resident rows (host pointer)
+static int predict_dev(pls_ctx *c, const double *w, double *yhat) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  const int Mp = c->pb.Mp;
+  const size_t n2 = (size_t)((c->pb.N + 1) / 2) * 2;
+  if (c->ws.yhat_n < n2) {
+    cudaFree(c->ws.yhat); c->ws.yhat = nullptr; c->ws.yhat_n = 0;
+    PLS_CUDA_TRY(cudaMalloc(&c->ws.yhat, sizeof(double) * n2));
+    c->ws.yhat_n = n2;
+  }
+  memcpy(c->h_pin, w, sizeof(double) * Mp);
+  cudaStream_t st = c->stream;
+  PLS_CUDA_TRY(cudaMemcpyAsync(c->d_w, c->h_pin, sizeof(double) * Mp, cudaMemcpyHostToDevice, st));
+  PLS_CUDA_TRY(cudaEventRecord(c->ev[4], st));
+  rc = k7_predict(c->pb, c->d_w, c->ws.yhat, c->sm_count, st, &c->launches);
+  if (rc) return rc;
+  PLS_CUDA_TRY(cudaEventRecord(c->ev[5], st));
+  PLS_CUDA_TRY(cudaMemcpyAsync(yhat, c->ws.yhat, sizeof(double) * (size_t)c->pb.N, cudaMemcpyDeviceToHost, st));
+  PLS_CUDA_TRY(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
+  c->stats.ms_recompute = ms;                    // kernel time of the prediction pass (reported through pls_get_stats)
+  return PLS_OK;
+}
+
+int pls_predict_resident(pls_ctx *c, const double *w, double *yhat) {
+  if (!c || !c->pb.loaded || !w || !yhat) { set_error("no data set loaded or null pointer"); return PLS_EINVAL; }
+  if (c->subs.empty()) return predict_dev(c, w, yhat);
+  const int G = (int)c->subs.size();
+  std::vector<int> rcs(G, 0);
+  std::vector<std::string> msgs(G);
+  std::vector<std::thread> th;
+  for (int g = 0; g < G; ++g)
+    th.emplace_back([&, g] { rcs[g] = predict_dev(c->subs[g], w, yhat + c->row0[g]); if (rcs[g]) msgs[g] = pls_last_error(); });
+  for (auto &t : th) t.join();
+  double mx = 0.0;
+  for (int g = 0; g < G; ++g) {
+    if (rcs[g]) { set_error("device %d: %s", c->subs[g]->dev, msgs[g].c_str()); return rcs[g]; }
+    mx = std::fmax(mx, c->subs[g]->stats.ms_recompute);
+  }
+  c->stats.ms_recompute = mx;
+  return PLS_OK;
 }
 
 int pls_objective_finish_w(pls_ctx *c, const double *w, double ssq_total, double *obj_out) {

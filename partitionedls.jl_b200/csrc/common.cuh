@@ -65,6 +65,8 @@ struct SolveWs {
   size_t tab_bytes = 0;
   double *alt_win = nullptr;      // K6 winner record [alpha | beta | iters | loss | restart]
   int alt_win_len = 0;
+  double *yhat = nullptr;         // K7 predictions of the resident rows
+  size_t yhat_n = 0;
   double *resid_part = nullptr;   // K4 block partials
   int resid_blocks = 0;
 };
@@ -136,5 +138,6 @@ int k6_alt_run(const Problem &pb, SolveWs &ws, const std::vector<uint64_t> &h_gm
                double **d_win_out);
 int k4_residual(const Problem &pb, SolveWs &ws, const double *d_w, double *d_ssq, int sm_count,
                 cudaStream_t st, int *launches);
+int k7_predict(const Problem &pb, const double *d_w, double *d_yhat, int sm_count, cudaStream_t st, int *launches);
 
 }  // namespace pls

@@ -144,4 +144,17 @@ function fit(::Type{Alt}, X::Matrix{F}, y::Vector{F}, P::Array{Int,2};
     return (PartLSFitResult(α[1:end-1], β[1:end-1], β[end] * α[end], P), nothing, (; opt = obj[]))   # Alt.jl:119
 end
 
+"""
+    predict_resident(model, N)
+
+`predict(model, X)` (src/PartitionedLS.jl:132-134) for the `X` of the last `fit`, which is still resident
+in HBM: one streaming pass on the GPU instead of `X * (P .* α) * β .+ t` on the host.
+"""
+function predict_resident(model::PartLSFitResult, N::Integer)
+    w = vcat(Float64.((model.P .* model.α) * model.β), Float64(model.t))
+    yhat = Vector{Float64}(undef, N)
+    _check(ccall((:pls_predict_resident, libpls), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), context(), w, yhat))
+    return yhat
+end
+
 end # module

@@ -532,3 +532,25 @@ def test_twolevel_long_walk_kkt_every_orthant(ctx, oracle):
         sc = max(np.abs(ref["alphas"][j]).max(), 1e-300)
         assert np.all(np.abs(ref["alphas"][j] - r["alphas"][b]) <= RTOL * sc)
     assert int(np.argmin(r["objs"])) == r["b_best"]
+
+
+def test_predict_resident(ctx, pkg, oracle):
+    """K7: predict(model, X) for the resident X (src/PartitionedLS.jl:132-134) against the host formula,
+    odd N (pad row), zero weights skipped; on the toy problem the fit is exact (runtests.jl:36)."""
+    o, _ = oracle
+    model, _, rep = pkg.fit(pkg.Opt, o.TOY_X, o.TOY_Y, o.TOY_P, η=0.0, ctx=ctx)
+    yh = pkg.predict_resident(model, ctx, len(o.TOY_Y))
+    assert np.allclose(yh, o.TOY_Y, atol=1e-9) and np.allclose(yh, pkg.predict(model, o.TOY_X), rtol=1e-12, atol=1e-12)
+    X, y, P = o.make_synthetic(10001, 37, 5, seed=3, mixed_sign=True)
+    model, _, rep = pkg.fit(pkg.Opt, X, y, P, η=1e-3, ctx=ctx)
+    yh = pkg.predict_resident(model, ctx, len(y))
+    ref = pkg.predict(model, X)
+    assert yh.shape == ref.shape and np.all(np.abs(yh - ref) <= 1e-12 * np.abs(ref).max())
+    if _n_gpus(pkg) >= 2:
+        mc = pkg.Context([0, 1])
+        try:
+            model2, _, _ = pkg.fit(pkg.Opt, X, y, P, η=1e-3, ctx=mc)
+            yh2 = pkg.predict_resident(model2, mc, len(y))
+            assert np.all(np.abs(yh2 - ref) <= 1e-9 * np.abs(ref).max())
+        finally:
+            mc.close()
