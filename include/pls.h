@@ -60,7 +60,8 @@ typedef struct pls_stats {
   int64_t sum_p;         /* sum of passive-set sizes over gradient evaluations */
   int64_t sum_p2;        /* sum of squared passive-set sizes over pivots */
   int64_t bpp_iters;     /* block-pivoting iterations */
-  int64_t spills;        /* chains whose inverse outgrew shared memory (global-memory slow path) */
+  int64_t spills;        /* v1 kernel: chains whose inverse outgrew shared memory; two-level kernel: cold restarts forced by
+                            the periodic KKT check against the original Gram system (tableau drift) */
   int64_t rebuilds;      /* inverses rebuilt from scratch after a failed refinement */
   int64_t blocked;       /* variables refused as numerically dependent */
   int64_t kernel_launches; /* kernels launched by the call */

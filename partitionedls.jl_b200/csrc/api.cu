@@ -113,6 +113,7 @@ void read_counters(pls_ctx *c, const unsigned long long *h) {
                                "r_gather", "r_panel", "r_rank", "r_zero", "a_gather", "a_hmul", "a_spart", "a_inv", "a_panel", "a_rank", "a_rows", "n_tab_sweep_in", "n_tab_unsweep", "tab_ops"};
     for (int i = 0; i < 23; ++i) fprintf(stderr, "k2 phase %-16s %llu\n", nm[i], h[CNT_NUM + 1 + i]);
   }
+  if (getenv("PLS_K4_DRIFT")) { double d; memcpy(&d, &h[CNT_NUM + 24], sizeof(d)); fprintf(stderr, "k2v4 max KKT violation vs the original system / max|c| = %.3e, cold restarts %llu\n", d, h[CNT_SPILLS]); }
   s.pivots = (int64_t)h[CNT_PIVOTS]; s.grad_evals = (int64_t)h[CNT_GRAD];
   s.sum_p = (int64_t)h[CNT_SUMP]; s.sum_p2 = (int64_t)h[CNT_SUMP2];
   s.bpp_iters = (int64_t)h[CNT_ITERS]; s.spills = (int64_t)h[CNT_SPILLS];

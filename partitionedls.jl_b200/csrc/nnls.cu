@@ -469,11 +469,11 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   if (impl && strcmp(impl, "v1") == 0) variant = 1;
   if (impl && strcmp(impl, "v2") == 0 && Mp <= 208) variant = 2;
   if (impl && strcmp(impl, "v3") == 0 && Mp <= 1024) variant = 3;
-  // v4 (two-level, default): needs an aligned power-of-two range long enough to amortise one cold
-  // start per CTA
+  // v4 (two-level, default): needs an aligned power-of-two range long enough to amortise one cold start per
+  // CTA -- measured crossover against v3: ~20 orthants per CTA at M' = 201, ~80 at M' = 513
   const bool pow2 = (b_count & (b_count - 1)) == 0 && (b_begin % b_count) == 0;
-  if (variant == 3 && Mp + 1 <= 1024 && pow2 && b_count >= 64ll * sm_count && !(impl && strcmp(impl, "v3") == 0)) variant = 4;
-  if (impl && strcmp(impl, "v4") == 0 && Mp + 1 <= 1024 && pow2) variant = 4;
+  const bool force4 = impl && strcmp(impl, "v4") == 0;
+  if (variant == 3 && Mp + 1 <= 1024 && pow2 && (force4 || !impl)) variant = 4;
   int cap = Mp, occ = 1;
   size_t smem = 0;
   K3Plan plan3;
@@ -481,6 +481,7 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   if (variant == 4) {
     const int rc = getenv("PLS_K2_PHASES") ? k2v4_plan_prof(Mp, Kp, &plan4) : k2v4_plan(Mp, Kp, &plan4);
     if (rc == PLS_EUNSUPPORTED) variant = 3; else if (rc) return rc;
+    else if (!force4 && b_count < (long long)sm_count * plan4.occ * (Mp <= 256 ? 24 : 96)) variant = 3;   // too short a walk per CTA
     else { cap = plan4.cap; occ = plan4.occ; smem = plan4.smem; }
   }
   if (variant == 2 && k2v2_config(Mp, &cap, &smem, &occ) != PLS_OK) variant = 3;

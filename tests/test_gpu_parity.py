@@ -554,3 +554,14 @@ def test_predict_resident(ctx, pkg, oracle):
             assert np.all(np.abs(yh2 - ref) <= 1e-9 * np.abs(ref).max())
         finally:
             mc.close()
+
+
+def test_twolevel_differential_fuzz():
+    """tools/v4_fuzz.py: random shapes / correlations (rho up to 0.9) / group layouts / CTA counts / fast-group
+    counts -- every orthant's objective and alpha of the two-level kernel against the one-level kernel."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "v4_fuzz.py"), "12", "3"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert '"result": "all equal"' in r.stdout
