@@ -257,7 +257,7 @@ int multi_bnb_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_signed, dou
   if (!c->pb.loaded) { set_error("no data set loaded"); return PLS_EINVAL; }
   if (!alpha_signed || !obj_out || !nopen) { set_error("null output pointer"); return PLS_EINVAL; }
   const int G = (int)c->subs.size();
-  const int Mp = c->pb.Mp, Kp = c->pb.Kp;
+  const int Mp = c->pb.Mp;
   const double t0 = now_ms();
   const double keep_upload = c->stats.ms_upload;
   memset(&c->stats, 0, sizeof(c->stats));
