@@ -174,9 +174,11 @@ def make_workload(args, world):
         name = {1: "cfg2", 2: "cfg2_k17", 4: "cfg2_k18", 8: "cfg2_k19"}.get(world, "cfg2")
     N, M, K, eta, seed, mixed = synth.CONFIGS[name]
     X, y, P = synth.make_synthetic(N, M, K, seed, mixed_sign=mixed)
-    wl = {"workload": f"{name}: synthetic N={N} M={M} K={K} eta={eta} fit(Opt); 2^(K+1)={1 << (K + 1)} orthant NNLS "
-                      f"(reference count, intercept sign enumerated)",
-          "N": N, "M": M, "K": K, "eta": eta, "orthants": 1 << (K + 1), "seed": seed,
+    wl = {"workload": f"{name}: synthetic N={N} M={M} K={K} eta={eta} fit(Opt); the reference enumerates 2^(K+1)={1 << (K + 1)} "
+                      f"orthants (intercept sign included); `value` counts those orthants resolved per second.  The library solves "
+                      f"2^K={1 << K} NNLS problems with the intercept sign left free -- each resolves the two orthants that differ only "
+                      f"in the intercept sign (same b*, alpha, objective; tests/test_gpu_parity.py) -- and reports both counts",
+          "N": N, "M": M, "K": K, "eta": eta, "orthants": 1 << (K + 1), "nnls_problems_per_fit": 1 << K, "seed": seed,
           "l2": "inputs larger than L2 (Z = %.0f MB) and an L2 flush (256 MB memset) before every timed step" % (N * (M + 2) * 8 / 1e6)}
     return X, y, P, eta, wl
 
@@ -286,19 +288,21 @@ def run_native(args, rank, world, local_rank):
             "frac": k2_tflops / fp64_peak if fp64_peak else None, "traffic": ncu_dram_traffic(),
             "peak_source": "FP64 DFMA peak measured by tools/fp64_peak.cu on this pool (profiles/fp64_peaks_r01.json); MEASURED_PEAKS.json holds no FP64 figure",
             "algorithmic_flops_per_launch": st["nnls_flops"], "launch_ms": k2_ms,
-            "flops_per_orthant": st["nnls_flops"] / max(1, st["orthants"]),
+            "flops_per_nnls_problem": st["nnls_flops"] / max(1, st["nnls_problems"]),
             # a cold Gram-space active-set solve of this shape costs 3.18 MFLOP (M=200, K=16 probe);
             # the rate at which the kernel retires that reference work -- NOT the arithmetic it executes
-            "effective_tflops_on_cold_solve_model": (3.18e6 * st["orthants"] / (k2_ms * 1e-3) / 1e12) if (k2_ms > 0 and M == 200) else None,
+            "effective_tflops_on_cold_solve_model": (3.18e6 * st["orthants"] / (k2_ms * 1e-3) / 1e12) if (k2_ms > 0 and M == 200) else None,   # reference orthants resolved x 3.18 MFLOP
             "l2_model_gbs": st["nnls_l2_bytes"] / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else None,
             "note": "K2 is latency-bound, not FLOP- or HBM-bound (DESIGN.md 3): the two-level solver cuts the work per orthant "
-                    "~4x against the one-level v3 kernel (0.65 MFLOP/orthant), so the FLOP rate falls while solves/s rise; "
+                    "~4x against the one-level v3 kernel (0.65 MFLOP/orthant) and the free intercept halves the number of problems, "
+                    "so the FLOP rate falls while orthants/s rise; "
                     "frac is reported on the work actually done",
         },
         "stages_ms": {"gram_k1": st["ms_gram"], "nnls_k2_k3": st["ms_nnls"], "recompute_k4": st["ms_recompute"]},
         "k1_gram": {"tflops": st["gram_flops"] / (st["ms_gram"] * 1e-3) / 1e12 if st["ms_gram"] > 0 else None,
                     "peak_tflops": float(peaks["fp64"].get("dmma_m8n8k4_tflops", 37.1))},
-        "solver_counters": {k: st[k] for k in ("pivots", "grad_evals", "sum_p", "sum_p2", "bpp_iters", "spills", "rebuilds", "blocked")},
+        "solver_counters": {k: st[k] for k in ("pivots", "grad_evals", "sum_p", "sum_p2", "bpp_iters", "spills", "rebuilds", "blocked", "nnls_problems")},
+        "nnls_problems_per_sec": (total // 2) * args.steps / t_res,
         "result": {"b_best": int(bb), "opt": float(obj)},
         "time_to_solution_ms": {"resident": 1e3 * t_res / args.steps, "from_host": 1e3 * t_e2e / args.steps},
     }

@@ -42,6 +42,10 @@ enum {
 /* flags for pls_opt_* */
 #define PLS_FLAG_DEFAULT 0u
 #define PLS_FLAG_NO_RECOMPUTE 1u /* skip the data-space recompute of the winner's objective (K4) */
+#define PLS_FLAG_ENUMERATE_INTERCEPT 2u /* Opt: enumerate the intercept sign like the reference does (2^(K+1) NNLS
+                                          problems).  Default when only the winner is returned: 2^K problems with
+                                          the intercept left free, each resolving the two reference orthants that
+                                          differ in the intercept sign -- same b*, alpha, objective. */
 #define PLS_FLAG_GRAM_READY 256u /* resident Alt/BnB fits: reuse the Gram matrix already finalised on this context */
 
 typedef struct pls_ctx pls_ctx;
@@ -54,7 +58,7 @@ typedef struct pls_stats {
   double ms_select;      /* K3: argmin over orthants */
   double ms_recompute;   /* K4: data-space objective of the winner */
   double ms_total;       /* wall time of the call (host clock) */
-  int64_t orthants;      /* NNLS problems solved */
+  int64_t orthants;      /* reference orthants resolved (Opt: 2^(K+1) per fit; BnB: nodes visited; Alt: restarts) */
   int64_t pivots;        /* variables moved in/out of passive sets (rank-1 inverse updates) */
   int64_t grad_evals;    /* gradient evaluations r = c - G[:,F] w_F */
   int64_t sum_p;         /* sum of passive-set sizes over gradient evaluations */
@@ -70,6 +74,7 @@ typedef struct pls_stats {
   double nnls_l2_bytes;  /* model: 8*M'*sum_p  (columns of G streamed by gradient evaluations) */
   int64_t waves;         /* BnB: frontier batches launched; Alt: alternating iterations of the longest restart */
   int64_t max_open;      /* BnB: largest number of open nodes (= live pooled states) */
+  int64_t nnls_problems; /* Opt: NNLS problems actually solved (= orthants / 2 with paired orthants, else = orthants) */
 } pls_stats;
 
 /* ---- context ------------------------------------------------------------------------------ */
@@ -154,6 +159,11 @@ int pls_gram_finalize(pls_ctx *ctx);
  * multiple of it (or the full range).  Outputs the local winner. */
 int pls_opt_solve_range(pls_ctx *ctx, int64_t b_begin, int64_t b_count, double *alpha_raw,
                         int64_t *b_best, double *obj_best, double *all_obj, double *all_alpha);
+/* Paired orthants: sign patterns p in [p_begin, p_begin + p_count) of the K user groups, intercept sign free;
+ * each solve resolves the reference orthants p and p + 2^K.  b_best is the full orthant index of the winner
+ * (top bit = sign of the intercept weight; 0 if that weight is zero -- the first of the pair, Opt.jl:96). */
+int pls_opt_solve_pairs(pls_ctx *ctx, int64_t p_begin, int64_t p_count, double *alpha_raw, int64_t *b_best,
+                        double *obj_best);
 /* K4 on the loaded rows: sum over local rows of (Xo*(d.*alpha) - y)^2 for orthant b.  The caller
  * sums over ranks and calls pls_opt_objective_finish to add the eta rows and take the root. */
 int pls_opt_residual_partial(pls_ctx *ctx, const double *alpha_raw, int64_t b, double *ssq_out);

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpls_cuda.so")
 
 PLS_OK, PLS_EINVAL, PLS_ECUDA, PLS_ENCCL, PLS_ENOMEM, PLS_ENUMERIC, PLS_EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
-PLS_FLAG_DEFAULT, PLS_FLAG_NO_RECOMPUTE, PLS_FLAG_GRAM_READY = 0, 1, 256
+PLS_FLAG_DEFAULT, PLS_FLAG_NO_RECOMPUTE, PLS_FLAG_ENUMERATE_INTERCEPT, PLS_FLAG_GRAM_READY = 0, 1, 2, 256
 _ERRNAMES = {-1: "PLS_EINVAL", -2: "PLS_ECUDA", -3: "PLS_ENCCL", -4: "PLS_ENOMEM",
              -5: "PLS_ENUMERIC", -6: "PLS_EUNSUPPORTED"}
 
@@ -32,7 +32,7 @@ class PlsStats(C.Structure):
                 ("orthants", "pivots", "grad_evals", "sum_p", "sum_p2", "bpp_iters", "spills",
                  "rebuilds", "blocked", "kernel_launches")] + \
                [(n, C.c_double) for n in ("gram_flops", "nnls_flops", "nnls_l2_bytes")] + \
-               [(n, C.c_int64) for n in ("waves", "max_open")]
+               [(n, C.c_int64) for n in ("waves", "max_open", "nnls_problems")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -67,6 +67,7 @@ lib.pls_gram_build.argtypes = [_vp]
 lib.pls_gram_raw.argtypes = [_vp, C.POINTER(_vp), _ip]
 lib.pls_gram_finalize.argtypes = [_vp]
 lib.pls_opt_solve_range.argtypes = [_vp, C.c_int64, C.c_int64, _dp, _ip, _dp, _dp, _dp]
+lib.pls_opt_solve_pairs.argtypes = [_vp, C.c_int64, C.c_int64, _dp, _ip, _dp]
 lib.pls_opt_residual_partial.argtypes = [_vp, _dp, C.c_int64, _dp]
 lib.pls_opt_objective_finish.argtypes = [_vp, _dp, C.c_int64, C.c_double, _dp]
 lib.pls_residual_partial_w.argtypes = [_vp, _dp, _dp]
@@ -77,7 +78,7 @@ lib.pls_gram.argtypes = [_vp, _dp, C.c_int64, C.c_int64, _dp, _ip, C.c_int64, C.
 lib.pls_nnls_batch.argtypes = [_vp, _dp, _dp, C.c_double, C.c_int64, C.POINTER(C.c_uint64), C.c_int64,
                                C.c_int64, C.c_int64, _dp, _dp]
 for _n in ("pls_create", "pls_opt_fit", "pls_bnb_fit", "pls_bnb_fit_resident", "pls_alt_fit", "pls_alt_fit_resident", "pls_residual_partial_w", "pls_predict_resident", "pls_objective_finish_w", "pls_load", "pls_opt_fit_resident", "pls_gram_build", "pls_gram_raw",
-           "pls_gram_finalize", "pls_opt_solve_range", "pls_opt_residual_partial", "pls_opt_objective_finish",
+           "pls_gram_finalize", "pls_opt_solve_range", "pls_opt_solve_pairs", "pls_opt_residual_partial", "pls_opt_objective_finish",
            "pls_get_stats", "pls_gram", "pls_nnls_batch"):
     getattr(lib, _n).restype = C.c_int
 
@@ -228,6 +229,14 @@ class Context:
         _check(lib.pls_opt_solve_range(self._h, b_begin, b_count, _d(alpha), C.byref(b), C.byref(obj),
                                        _d(all_obj), _d(all_alpha)))
         return dict(alpha_raw=alpha, b_best=b.value, obj_gram=obj.value, objs=all_obj, alphas=all_alpha)
+
+    def opt_solve_pairs(self, p_begin, p_count):
+        """pls_opt_solve_pairs: sign patterns of the K user groups with the intercept sign free; each resolves the
+        reference orthants p and p + 2^K.  b_best is the winner's full orthant index."""
+        N, M, K = self._shape
+        alpha = np.zeros(M + 1); b = C.c_int64(); obj = C.c_double()
+        _check(lib.pls_opt_solve_pairs(self._h, p_begin, p_count, _d(alpha), C.byref(b), C.byref(obj)))
+        return dict(alpha_raw=alpha, b_best=b.value, obj_gram=obj.value, objs=None, alphas=None)
 
     def residual_partial(self, alpha_raw, b):
         a = np.ascontiguousarray(alpha_raw, dtype=np.float64); s = C.c_double()

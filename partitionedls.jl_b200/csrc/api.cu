@@ -124,11 +124,14 @@ void read_counters(pls_ctx *c, const unsigned long long *h) {
 }
 
 // K2 + K3 over a range, winner record left in ws.win.  Caller holds the device.
-int solve_range_dev(pls_ctx *c, int64_t b_begin, int64_t b_count, bool want_obj, bool want_alpha) {
+// pairs: [b_begin, b_begin + b_count) are sign patterns of the K user groups; the intercept sign is left free, so
+// every solve resolves the two reference orthants b and b + 2^K (the winner record carries the full b).
+int solve_range_dev(pls_ctx *c, int64_t b_begin, int64_t b_count, bool want_obj, bool want_alpha, bool pairs) {
   Problem &pb = c->pb;
   if (!pb.gram_ready) { set_error("Gram matrix not built (call pls_gram_build / pls_gram_finalize)"); return PLS_EINVAL; }
   if (pb.Kp > 40) { set_error("K = %d: 2^(K+1) orthants cannot be enumerated (limit K <= 39); use fit(BnB) or fit(Alt)", pb.K); return PLS_EINVAL; }
-  const int64_t total = (int64_t)1 << pb.Kp;
+  if (pairs && (want_obj || want_alpha)) { set_error("per-orthant outputs need the full enumeration"); return PLS_EINVAL; }
+  const int64_t total = (int64_t)1 << (pairs ? pb.Kp - 1 : pb.Kp);
   if (b_begin < 0 || b_count <= 0 || b_begin + b_count > total) { set_error("orthant range out of bounds"); return PLS_EINVAL; }
   int rc = ensure_all_buffers(c, b_count, want_obj, want_alpha);
   if (rc) return rc;
@@ -137,7 +140,13 @@ int solve_range_dev(pls_ctx *c, int64_t b_begin, int64_t b_count, bool want_obj,
     PLS_CUDA_TRY(cudaMemsetAsync(c->ws.counters, 0, sizeof(unsigned long long) * (CNT_NUM + 1 + 24), c->stream));
   return k2_solve_range(pb, pb.G, pb.ldg, pb.c, pb.scal, pb.gmask, pb.Mp, pb.Kp, c->ws, b_begin, b_count,
                         want_obj ? c->ws.all_obj : nullptr, want_alpha ? c->ws.all_alpha : nullptr,
-                        c->sm_count, c->stream, &c->launches);
+                        c->sm_count, c->stream, &c->launches, pairs);
+}
+
+// Paired orthants are used whenever only the winner is asked for, the problem fits the block-pivoting
+// kernels, and the caller did not ask for the reference's literal enumeration.
+bool use_pairs(const pls_ctx *c, uint32_t flags, bool per_orthant_outputs) {
+  return !per_orthant_outputs && !(flags & PLS_FLAG_ENUMERATE_INTERCEPT) && c->pb.Mp <= 1024 && c->pb.Kp >= 2;
 }
 
 double eta_term(const pls_ctx *c, const double *alpha_raw, int64_t b) {
@@ -351,7 +360,7 @@ int pls_opt_solve_range(pls_ctx *c, int64_t b_begin, int64_t b_count, double *al
   if (!alpha_raw || !b_best || !obj_best) { set_error("null output pointer"); return PLS_EINVAL; }
   cudaStream_t st = c->stream;
   PLS_CUDA_TRY(cudaEventRecord(c->ev[2], st));
-  rc = solve_range_dev(c, b_begin, b_count, all_obj != nullptr, all_alpha != nullptr);
+  rc = solve_range_dev(c, b_begin, b_count, all_obj != nullptr, all_alpha != nullptr, false);
   if (rc) return rc;
   PLS_CUDA_TRY(cudaEventRecord(c->ev[3], st));
   const int Mp = c->pb.Mp;
@@ -363,7 +372,7 @@ int pls_opt_solve_range(pls_ctx *c, int64_t b_begin, int64_t b_count, double *al
   float ms = 0.f;
   cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
   c->stats.ms_nnls = ms;
-  c->stats.orthants = b_count;
+  c->stats.orthants = b_count; c->stats.nnls_problems = b_count;
   const unsigned long long *cnt = reinterpret_cast<const unsigned long long *>(c->h_pin + Mp + 4);
   read_counters(c, cnt);
   memcpy(alpha_raw, c->h_pin, sizeof(double) * Mp);
@@ -371,6 +380,37 @@ int pls_opt_solve_range(pls_ctx *c, int64_t b_begin, int64_t b_count, double *al
   long long bb; memcpy(&bb, &c->h_pin[Mp + 1], sizeof(bb));
   *b_best = bb;
   c->stats.kernel_launches = c->launches - c->launch_mark + 3;   // + winner-weights / K4 launches that follow
+  if (cnt[CNT_NOCONV]) { set_error("%llu orthant solves hit the iteration cap", cnt[CNT_NOCONV]); return PLS_ENUMERIC; }
+  if (*obj_best != *obj_best) { set_error("NaN objective (non-finite input?)"); return PLS_ENUMERIC; }
+  return PLS_OK;
+}
+
+int pls_opt_solve_pairs(pls_ctx *c, int64_t p_begin, int64_t p_count, double *alpha_raw, int64_t *b_best, double *obj_best) {
+  if (c && !c->subs.empty()) { set_error("stage-wise entry points need a one-GPU context"); return PLS_EUNSUPPORTED; }
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!alpha_raw || !b_best || !obj_best) { set_error("null output pointer"); return PLS_EINVAL; }
+  if (c->pb.Mp > 1024 || c->pb.Kp < 2) { set_error("paired orthants need M + 1 <= 1024 and K >= 1"); return PLS_EUNSUPPORTED; }
+  cudaStream_t st = c->stream;
+  PLS_CUDA_TRY(cudaEventRecord(c->ev[2], st));
+  rc = solve_range_dev(c, p_begin, p_count, false, false, true);
+  if (rc) return rc;
+  PLS_CUDA_TRY(cudaEventRecord(c->ev[3], st));
+  const int Mp = c->pb.Mp;
+  PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin, c->ws.win, sizeof(double) * (Mp + 2), cudaMemcpyDeviceToHost, st));
+  PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin + Mp + 4, c->ws.counters, sizeof(unsigned long long) * (CNT_NUM + 1 + 24), cudaMemcpyDeviceToHost, st));
+  PLS_CUDA_TRY(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
+  c->stats.ms_nnls = ms;
+  c->stats.orthants = 2 * p_count; c->stats.nnls_problems = p_count;
+  const unsigned long long *cnt = reinterpret_cast<const unsigned long long *>(c->h_pin + Mp + 4);
+  read_counters(c, cnt);
+  memcpy(alpha_raw, c->h_pin, sizeof(double) * Mp);
+  *obj_best = c->h_pin[Mp];
+  long long bb; memcpy(&bb, &c->h_pin[Mp + 1], sizeof(bb));
+  *b_best = bb;
+  c->stats.kernel_launches = c->launches - c->launch_mark + 3;
   if (cnt[CNT_NOCONV]) { set_error("%llu orthant solves hit the iteration cap", cnt[CNT_NOCONV]); return PLS_ENUMERIC; }
   if (*obj_best != *obj_best) { set_error("NaN objective (non-finite input?)"); return PLS_ENUMERIC; }
   return PLS_OK;
@@ -477,7 +517,8 @@ int pls_opt_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_raw, int64_t 
   rc = k1_gram_build(pb, st, &c->launches); if (rc) return rc;
   rc = k1_gram_finalize(pb, st, &c->launches); if (rc) return rc;
   PLS_CUDA_TRY(cudaEventRecord(c->ev[1], st));
-  rc = solve_range_dev(c, 0, total, all_obj != nullptr, all_alpha != nullptr); if (rc) return rc;
+  const bool pairs = use_pairs(c, flags, all_obj != nullptr || all_alpha != nullptr);
+  rc = solve_range_dev(c, 0, pairs ? total / 2 : total, all_obj != nullptr, all_alpha != nullptr, pairs); if (rc) return rc;
   PLS_CUDA_TRY(cudaEventRecord(c->ev[2], st));
   const bool recompute = !(flags & PLS_FLAG_NO_RECOMPUTE);
   if (recompute) {
@@ -509,7 +550,7 @@ int pls_opt_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_raw, int64_t 
   cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); s.ms_nnls = ms;
   cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); s.ms_recompute = ms;
   s.ms_select = 0.0;   // K3 is timed with K2 (same stream, ~microseconds)
-  s.orthants = total;
+  s.orthants = total; s.nnls_problems = pairs ? total / 2 : total;
   const unsigned long long *cnt = reinterpret_cast<const unsigned long long *>(c->h_pin + Mp + 4);
   read_counters(c, cnt);
   const double Nd = (double)pb.N, Md = (double)Mp;

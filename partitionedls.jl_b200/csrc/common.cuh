@@ -91,6 +91,11 @@ struct K2Args {
   size_t tabstride = 0;
   unsigned long long lowmask = 0;  // v4: groups whose variables are never committed (the fastest Gray bits)
   int verify_every = 64;         // v4: orthants between KKT checks against the original G
+  // Paired orthants: the top group (bit Kp - 1) is the singleton intercept group of homogeneousCoords; its
+  // variable (index Mp - 1) is left FREE and only the Kp - 1 lower bits are enumerated -- each solve resolves
+  // the two reference orthants that differ in the intercept sign, and reports the full b (top bit = sign of
+  // the intercept weight, 0 when it is zero: the first of the two in the reference's order, Opt.jl:96).
+  int free_top = 0;
   double *cta_obj; long long *cta_b; double *cta_w;
   double *all_obj; double *all_alpha;   // nullable, indexed by (b - b_begin)
   unsigned long long *counters;
@@ -102,7 +107,7 @@ int k1_gram_finalize(Problem &pb, cudaStream_t st, int *launches);
 int k2_solve_range(const Problem &pb, const double *G, int ldg, const double *c, const double *scal,
                    const uint64_t *gmask, int Mp, int Kp, SolveWs &ws, int64_t b_begin,
                    int64_t b_count, double *d_all_obj, double *d_all_alpha, int sm_count,
-                   cudaStream_t st, int *launches);
+                   cudaStream_t st, int *launches, bool free_top = false);
 // K2 variants: v2 = block pivoting with DMMA rank-8 updates on a tile-packed symmetric inverse
 // (M' <= 208); v1 = rank-1 updates on a dense inverse with a global-memory spill path (any M').
 int k2v2_launch(const K2Args &A, int grid, cudaStream_t st);
@@ -110,7 +115,7 @@ int k2v2_config(int Mp, int *cap, size_t *smem, int *occ);
 // v3 = v2's algorithm with the inverse split between shared memory and an L2-resident global slice,
 // any thread count, M' <= 1024 (nnls3.cu)
 struct K3Plan { int cap, qs, T, mode, occ, variant; size_t smem, hstride; };
-int k2v3_plan(int Mp, K3Plan *pl);
+int k2v3_plan(int Mp, K3Plan *pl, bool ignore_env = false);   // ignore_env: no PLS_K3_* tuning overrides
 int k2v3_launch(const K2Args &A, const K3Plan &pl, int grid, cudaStream_t st);
 // v4 = two-level path: v3's core on the reduced problem of a per-CTA swept tableau (nnls4.cu)
 struct K4Plan { int cap, qs, T, mode, occ, variant, low_groups, verify_every; size_t smem, hstride, tabstride; };

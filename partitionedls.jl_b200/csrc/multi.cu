@@ -184,8 +184,11 @@ int multi_opt_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_raw, int64_
   if (rc) return rc;
   const double tg1 = now_ms();
   // contiguous, chunk-aligned orthant ranges (the Gray chains of K2 need power-of-two alignment)
-  const int64_t total = (int64_t)1 << Kp;
-  const int chunk_log2 = Kp < 12 ? (Kp > 3 ? Kp - 3 : 0) : 12;
+  // paired orthants (intercept sign free, 2^K problems) unless per-orthant outputs or the literal enumeration are asked for
+  const bool pairs = use_pairs(c, flags, all_obj != nullptr || all_alpha != nullptr) && c->subs[0]->pb.Mp <= 1024;
+  const int Ke = pairs ? Kp - 1 : Kp;
+  const int64_t total = (int64_t)1 << Ke;
+  const int chunk_log2 = Ke < 12 ? (Ke > 3 ? Ke - 3 : 0) : 12;
   const int64_t nchunks = total >> chunk_log2;
   std::vector<std::vector<double>> rec(G, std::vector<double>(Mp + 2, 0.0));
   std::vector<char> has(G, 0);
@@ -196,7 +199,7 @@ int multi_opt_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_raw, int64_
     if (r) return r;
     cudaStream_t st = s->stream;
     PLS_CUDA_TRY(cudaEventRecord(s->ev[2], st));
-    r = solve_range_dev(s, b0, b1 - b0, all_obj != nullptr, all_alpha != nullptr);
+    r = solve_range_dev(s, b0, b1 - b0, all_obj != nullptr, all_alpha != nullptr, pairs);
     if (r) return r;
     PLS_CUDA_TRY(cudaEventRecord(s->ev[3], st));
     PLS_CUDA_TRY(cudaMemcpyAsync(s->h_pin, s->ws.win, sizeof(double) * (Mp + 2), cudaMemcpyDeviceToHost, st));
@@ -241,7 +244,7 @@ int multi_opt_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_raw, int64_
   sum_stats(c, s);
   s.ms_gram = tg1 - tg0;
   s.ms_recompute = now_ms() - tr0;
-  s.orthants = total;
+  s.orthants = (int64_t)1 << Kp; s.nnls_problems = total;
   const double Nd = (double)c->pb.N, Md = (double)Mp;
   s.gram_flops = Nd * Md * (Md + 1.0) + 2.0 * Nd * Md + 2.0 * Nd;
   int launches1 = 0;

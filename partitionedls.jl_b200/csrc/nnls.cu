@@ -458,16 +458,17 @@ size_t k2_smem_bytes(int Mp, int cap) {
 int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, const double *scal,
                    const uint64_t *gmask, int Mp, int Kp, SolveWs &ws, int64_t b_begin,
                    int64_t b_count, double *d_all_obj, double *d_all_alpha, int sm_count,
-                   cudaStream_t st, int *launches) {
+                   cudaStream_t st, int *launches, bool free_top) {
   if (b_count <= 0) { set_error("k2: empty orthant range"); return PLS_EINVAL; }
+  if (free_top && (Mp > 1024 || d_all_obj || d_all_alpha)) { set_error("k2: paired orthants need M' <= 1024 and no per-orthant outputs"); return PLS_EUNSUPPORTED; }
   // variant (PLS_K2_IMPL = v1 | v2 | v3 overrides):
   //   v2  block pivoting, DMMA, tile-packed inverse entirely in shared memory   (M' <= 208)
   //   v3  same algorithm, inverse split between shared memory and L2           (M' <= 1024)
   //   v1  rank-1 updates on a dense inverse with a global spill path           (any M')
   const char *impl = getenv("PLS_K2_IMPL");
   int variant = Mp <= 1024 ? 3 : 1;
-  if (impl && strcmp(impl, "v1") == 0) variant = 1;
-  if (impl && strcmp(impl, "v2") == 0 && Mp <= 208) variant = 2;
+  if (impl && strcmp(impl, "v1") == 0 && !free_top) variant = 1;
+  if (impl && strcmp(impl, "v2") == 0 && Mp <= 208 && !free_top) variant = 2;
   if (impl && strcmp(impl, "v3") == 0 && Mp <= 1024) variant = 3;
   // v4 (two-level, default): needs an aligned power-of-two range long enough to amortise one cold start per
   // CTA -- measured crossover against v3: ~20 orthants per CTA at M' = 201, ~80 at M' = 513
@@ -486,10 +487,12 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   }
   if (variant == 2 && k2v2_config(Mp, &cap, &smem, &occ) != PLS_OK) variant = 3;
   if (variant == 3) {
-    const int rc = k2v3_plan(Mp, &plan3);
+    int rc = k2v3_plan(Mp, &plan3);
+    if (rc == PLS_EUNSUPPORTED && free_top) rc = k2v3_plan(Mp, &plan3, true);   // a tuning override asked for a variant that does not exist
     if (rc == PLS_EUNSUPPORTED) variant = 1; else if (rc) return rc;
     else { cap = plan3.cap; occ = plan3.occ; smem = plan3.smem; }
   }
+  if (variant == 1 && free_top) { set_error("k2: paired orthants are not available on the rank-1 kernel"); return PLS_EUNSUPPORTED; }
   if (variant == 1) {
     int dev = 0, max_smem = 0;
     PLS_CUDA_TRY(cudaGetDevice(&dev));
@@ -572,6 +575,7 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   A.cap = cap;
   A.hspill = (variant == 1 && cap < Mp) ? ws.hspill : nullptr;
   A.qs = 0; A.hglob = nullptr; A.hstride = 0;
+  A.free_top = free_top ? 1 : 0;
   A.cta_obj = ws.cta_obj; A.cta_b = ws.cta_b; A.cta_w = ws.cta_w;
   A.all_obj = d_all_obj; A.all_alpha = d_all_alpha; A.counters = ws.counters;
   if (variant == 2) {

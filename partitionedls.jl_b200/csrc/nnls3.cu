@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(T, MINB) k2v3_orthant_chains(const K2Args A) {
       for (int m = tid; m < Mp; m += T) {   // d_m = sum_k Po[m,k] (2 bit_k(b) - 1)   (Opt.jl:28-29)
         const uint64_t gm = s.gms[m];
         const int d = 2 * __popcll(gm & (uint64_t)b) - __popcll(gm);
-        s.dd[m] = (signed char)d; s.sg[m] = (signed char)((d > 0) - (d < 0));
+        const bool fr = A.free_top && ((gm >> (A.Kp - 1)) & 1ull);        // paired orthants: the intercept is free
+        s.dd[m] = (signed char)d; s.sg[m] = (signed char)(fr ? SG_FREE : (d > 0) - (d < 0));
         s.vflag[m] = 0;
       }
       __syncthreads();
@@ -83,6 +84,9 @@ __global__ void __launch_bounds__(T, MINB) k2v3_orthant_chains(const K2Args A) {
       for (int q = 0; q < NW; ++q) tot += s.red[q];
       const double obj = ok ? sqrt(fmax(yy - tot, 0.0)) : __longlong_as_double(0x7ff8000000000000ll);
       const long long rel = b - A.b_begin;
+      // paired orthants: the full orthant index carries the sign of the intercept weight in its top bit
+      const double w_top = (A.free_top && s.pos[Mp - 1] >= 0) ? s.w[Mp - 1] : 0.0;
+      const long long b_full = A.free_top ? (b | ((w_top > 0.0 ? 1ll : 0ll) << (A.Kp - 1))) : b;
       if (A.all_obj && tid == 0) A.all_obj[rel] = obj;
       if (A.all_alpha) {
         for (int m = tid; m < Mp; m += T) {
@@ -90,11 +94,13 @@ __global__ void __launch_bounds__(T, MINB) k2v3_orthant_chains(const K2Args A) {
           A.all_alpha[(size_t)rel * Mp + m] = (s.pos[m] >= 0 && d != 0) ? fmax(s.w[m] / (double)d, 0.0) : 0.0;
         }
       }
-      if (lex_better(obj, b, best_obj, best_b)) {
-        best_obj = obj; best_b = b;
+      if (lex_better(obj, b_full, best_obj, best_b)) {
+        best_obj = obj; best_b = b_full;
         for (int m = tid; m < Mp; m += T) {
           const int d = s.dd[m];
-          A.cta_w[(size_t)blockIdx.x * Mp + m] = (s.pos[m] >= 0 && d != 0) ? fmax(s.w[m] / (double)d, 0.0) : 0.0;
+          double a = (s.pos[m] >= 0 && d != 0) ? fmax(s.w[m] / (double)d, 0.0) : 0.0;
+          if (s.sg[m] == SG_FREE) a = s.pos[m] >= 0 ? fabs(s.w[m]) : 0.0;
+          A.cta_w[(size_t)blockIdx.x * Mp + m] = a;
         }
       }
       __syncthreads();
@@ -137,14 +143,15 @@ const Variant kVariants[] = {
 
 // Chooses thread count, storage mode and the number of shared-memory tiles.  Environment overrides
 // for tuning: PLS_K3_T (256|512), PLS_K3_QS (tiles in shared memory, -1 = all), PLS_K3_MINB.
-int k2v3_plan(int Mp, K3Plan *pl) {
+int k2v3_plan(int Mp, K3Plan *pl, bool ignore_env) {
   if (Mp > CAP3MAX) return PLS_EUNSUPPORTED;
   const int cap = (Mp + 7) & ~7;
   const int ntc = cap >> 3, ntiles = ntc * (ntc + 1) / 2;
   int dev = 0, max_smem = 0;
   PLS_CUDA_TRY(cudaGetDevice(&dev));
   PLS_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  const char *eT = getenv("PLS_K3_T"), *eQ = getenv("PLS_K3_QS"), *eB = getenv("PLS_K3_MINB");
+  const char *eT = ignore_env ? nullptr : getenv("PLS_K3_T"), *eQ = ignore_env ? nullptr : getenv("PLS_K3_QS"),
+             *eB = ignore_env ? nullptr : getenv("PLS_K3_MINB");
   int T = eT ? atoi(eT) : (Mp <= 256 ? 128 : 256);   // measured: cfg2 15.3 ms at 4 x 128 threads per SM, M'=513 163 ms at 2 x 256
   if (T != 128 && T != 256 && T != 512) T = 256;
   while (Mp > 4 * T) T *= 2;

@@ -936,7 +936,7 @@ __device__ __forceinline__ bool bpp_solve3(const Cfg3 cf, const Sh3 &s, const do
         if (sl >= 0) { cw = fma(s.cs[m], s.w[m], cw); if (sg != SG_FREE && (sg == 0 || (double)sg * s.w[m] < 0.0)) f = 1; }
         else if (TL && s.swp[m]) {                // swept variable: r holds its implied weight
           const double wv = s.r[m];
-          if (sg == 0 ? wv != 0.0 : (double)sg * wv < 0.0) { f = 3; any3 = 1; }
+          if (sg != SG_FREE && (sg == 0 ? wv != 0.0 : (double)sg * wv < 0.0)) { f = 3; any3 = 1; }
         }
         else if (sg != 0 && s.vflag[m] != 3 && (sg == SG_FREE ? fabs(s.r[m]) > told : (double)sg * s.r[m] > told)) f = 2;
         s.fl[m] = (signed char)f;

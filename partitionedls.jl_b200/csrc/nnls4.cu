@@ -54,6 +54,7 @@ __device__ __noinline__ double verify_true3(const Cfg3 cf, const double *G, int 
     const double rv = a0 + a1;
     const int sg = s.sg[m];
     if (s.pos[m] >= 0 || s.swp[m]) mx = fmax(mx, fabs(rv));
+    else if (sg == SG_FREE) mx = fmax(mx, fabs(rv));
     else if (sg != 0 && s.vflag[m] != 3) mx = fmax(mx, (double)sg * rv);
   }
   mx = warp_max(mx);
@@ -136,7 +137,8 @@ __global__ void __launch_bounds__(T, MINB) k2v4_orthant_ranges(const K2Args A) {
     for (int m = tid; m < Mp; m += T) {   // d_m = sum_k Po[m,k] (2 bit_k(b) - 1)   (Opt.jl:28-29)
       const uint64_t gm = s.gms[m];
       const int d = 2 * __popcll(gm & (uint64_t)b) - __popcll(gm);
-      s.dd[m] = (signed char)d; s.sg[m] = (signed char)((d > 0) - (d < 0));
+      const bool fr = A.free_top && ((gm >> (A.Kp - 1)) & 1ull);          // paired orthants: the intercept is free
+      s.dd[m] = (signed char)d; s.sg[m] = (signed char)(fr ? SG_FREE : (d > 0) - (d < 0));
       s.vflag[m] = 0;
       if (forget) s.ncm[m] = 0;
     }
@@ -178,6 +180,9 @@ __global__ void __launch_bounds__(T, MINB) k2v4_orthant_ranges(const K2Args A) {
     // ---- objective  sqrt(yy - c_F' w_F)  (= norm(Xa w - ya) at the KKT point, Opt.jl:90)
     const double obj = ok ? sqrt(fmax(yyr - tot, 0.0)) : __longlong_as_double(0x7ff8000000000000ll);
     const long long rel = b - A.b_begin;
+    // paired orthants: the full orthant index carries the sign of the intercept weight in its top bit
+    const double w_top = !A.free_top ? 0.0 : (s.pos[Mp - 1] >= 0 ? s.w[Mp - 1] : (s.swp[Mp - 1] ? s.r[Mp - 1] : 0.0));
+    const long long b_full = A.free_top ? (b | ((w_top > 0.0 ? 1ll : 0ll) << (A.Kp - 1))) : b;
     if (A.all_obj && tid == 0) A.all_obj[rel] = obj;
     if (A.all_alpha) {
 #pragma unroll 1
@@ -187,13 +192,13 @@ __global__ void __launch_bounds__(T, MINB) k2v4_orthant_ranges(const K2Args A) {
         A.all_alpha[(size_t)rel * Mp + m] = d != 0 ? fmax(wv / (double)d, 0.0) : 0.0;
       }
     }
-    if (lex_better(obj, b, best_obj, best_b)) {
-      best_obj = obj; best_b = b;
+    if (lex_better(obj, b_full, best_obj, best_b)) {
+      best_obj = obj; best_b = b_full;
 #pragma unroll 1
       for (int m = tid; m < Mp; m += T) {
         const int d = s.dd[m];
         const double wv = s.pos[m] >= 0 ? s.w[m] : (s.swp[m] ? s.r[m] : 0.0);
-        A.cta_w[(size_t)blockIdx.x * Mp + m] = d != 0 ? fmax(wv / (double)d, 0.0) : 0.0;
+        A.cta_w[(size_t)blockIdx.x * Mp + m] = s.sg[m] == SG_FREE ? fabs(wv) : (d != 0 ? fmax(wv / (double)d, 0.0) : 0.0);
       }
     }
 

@@ -74,9 +74,11 @@ class TorchComm:
         return self.torch.stack(out).cpu().numpy()
 
 
-def opt_fit_sharded(backend, comm, Mp: int, Kp: int, *, reload=None):
+def opt_fit_sharded(backend, comm, Mp: int, Kp: int, *, reload=None, pairs=None):
     """One Opt fit over `comm.world` ranks on data already loaded in `backend` (or loaded by the
-    `reload()` callback first -- the end-to-end variant).  Returns (b*, objective, alpha_raw)."""
+    `reload()` callback first -- the end-to-end variant).  Returns (b*, objective, alpha_raw).
+    pairs (default: whenever the backend offers it and the problem fits): shard the 2^K sign patterns of
+    the user groups and leave the intercept sign free -- each solve resolves two reference orthants."""
     if reload is not None:
         reload()
     backend.gram_build()
@@ -86,8 +88,14 @@ def opt_fit_sharded(backend, comm, Mp: int, Kp: int, *, reload=None):
     else:
         comm.allreduce_sum_inplace_dev(ptr, count)
     backend.gram_finalize()
-    b0, bn = shard_orthants(1 << Kp, comm.rank, comm.world)
-    loc = backend.opt_solve_range(b0, bn)
+    if pairs is None:
+        pairs = hasattr(backend, "opt_solve_pairs") and Mp <= 1024 and Kp >= 2 and (1 << (Kp - 1)) >= comm.world
+    if pairs:
+        b0, bn = shard_orthants(1 << (Kp - 1), comm.rank, comm.world)
+        loc = backend.opt_solve_pairs(b0, bn)
+    else:
+        b0, bn = shard_orthants(1 << Kp, comm.rank, comm.world)
+        loc = backend.opt_solve_range(b0, bn)
     rec = np.concatenate([loc["alpha_raw"], [loc["obj_gram"], float(loc["b_best"])]])
     alpha, b, _, _ = pick_winner(comm.allgather(rec), Mp)
     ssq = comm.allreduce_sum(np.array([backend.residual_partial(alpha, b)]))[0]

@@ -24,7 +24,7 @@ struct PlsStats            # mirrors `pls_stats` in include/pls.h
     orthants::Int64; pivots::Int64; grad_evals::Int64; sum_p::Int64; sum_p2::Int64
     bpp_iters::Int64; spills::Int64; rebuilds::Int64; blocked::Int64; kernel_launches::Int64
     gram_flops::Cdouble; nnls_flops::Cdouble; nnls_l2_bytes::Cdouble
-    waves::Int64; max_open::Int64
+    waves::Int64; max_open::Int64; nnls_problems::Int64
 end
 
 const _ctx = Ref{Ptr{Cvoid}}(C_NULL)      # created lazily: never ccall at precompile time

@@ -53,6 +53,18 @@ class OracleBackend:
                 best = dict(alpha_raw=alpha, b_best=b, obj_gram=obj)
         return best
 
+    def opt_solve_pairs(self, p0, pn):
+        # the two reference orthants p and p + 2^K of every sign pattern p of the user groups (what the
+        # GPU solves as ONE problem with a free intercept): the better of the two, first one on a tie
+        K = self.Po.shape[1] - 1
+        best = None
+        for p in range(p0, p0 + pn):
+            for b in (p, p + (1 << K)):
+                r = self.opt_solve_range(b, 1)
+                if best is None or (r["obj_gram"], r["b_best"]) < (best["obj_gram"], best["b_best"]):
+                    best = r
+        return best
+
     def residual_partial(self, alpha, b):
         d = self.Po @ self.o.index_to_beta(b, self.Po.shape[1])
         res = self.Z[:, :-1] @ (d * alpha) - self.Z[:, -1]
@@ -94,7 +106,9 @@ def _worker(rank, world, port, q):
         eta = 1e-2
         be = OracleBackend(o, oc, X, y, P, eta, distmod.shard_rows(400, rank, world))
         comm = distmod.TorchComm(device=None)
-        b, obj, alpha = distmod.opt_fit_sharded(be, comm, Mp=11, Kp=4)
+        b, obj, alpha = distmod.opt_fit_sharded(be, comm, Mp=11, Kp=4)                 # paired orthants (default)
+        b_f, obj_f, alpha_f = distmod.opt_fit_sharded(be, comm, Mp=11, Kp=4, pairs=False)   # literal enumeration
+        assert b_f == b and abs(obj_f - obj) <= 1e-12 * obj and np.allclose(alpha_f, alpha, rtol=1e-10, atol=1e-14)
         beta0 = (np.random.default_rng(3).random((4, 5)) - 0.5) * 10.0      # 5 restarts over 2 ranks
         ra = distmod.alt_fit_sharded(be, comm, be.Po, beta0, eps=1e-6, T=50)
         q.put((rank, b, obj, alpha, ra))

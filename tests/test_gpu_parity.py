@@ -565,3 +565,41 @@ def test_twolevel_differential_fuzz():
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "v4_fuzz.py"), "12", "3"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert '"result": "all equal"' in r.stdout
+
+
+# ---- paired orthants: 2^K problems with the intercept sign free instead of 2^(K+1) ----------
+@pytest.mark.parametrize("shape", [(1500, 40, 6, 0.0, False, 0.0, 0.5), (900, 33, 9, 1e-3, True, 0.5, -3.0),
+                                   (700, 64, 13, 1e-3, True, 0.2, 0.0), (300, 12, 3, 0.0, True, 0.0, -0.5)])
+def test_paired_orthants_equal_the_literal_enumeration(ctx, pkg, oracle, shape):
+    """Winner-only fits leave the intercept sign free (one NNLS problem per sign pattern of the K user groups);
+    PLS_FLAG_ENUMERATE_INTERCEPT enumerates it like the reference.  Same b*, alpha, objective -- against each
+    other and against the oracle's literal loop (Opt.jl:85-96), for positive and negative intercepts."""
+    o, oc = oracle
+    N, M, K, eta, mixed, rho, shift = shape
+    X, y, P = o.make_synthetic(N, M, K, seed=900 + M, mixed_sign=mixed, rho=rho)
+    y = y - 0.5 + shift                                  # make_synthetic adds an intercept of 0.5
+    ref = oc.opt_fit(X, y, P, eta, want_alpha=True)
+    a = ctx.opt_fit(X, y, P, eta=eta)                                                   # paired (default)
+    b = ctx.opt_fit(X, y, P, eta=eta, flags=pkg._abi.PLS_FLAG_ENUMERATE_INTERCEPT)      # literal
+    assert a["stats"]["nnls_problems"] == 2 ** K and b["stats"]["nnls_problems"] == 2 ** (K + 1)
+    assert a["stats"]["orthants"] == b["stats"]["orthants"] == 2 ** (K + 1)
+    for r in (a, b):
+        assert r["b_best"] == ref["b_best"]
+        assert abs(r["opt"] - ref["obj_best"]) <= RTOL * ref["obj_best"]
+        assert np.all(np.abs(r["alpha_raw"] - ref["alpha_best"]) <= RTOL * np.abs(ref["alpha_best"]).max())
+    if shift != 0.0:
+        assert ((a["b_best"] >> K) & 1) == (1 if shift > 0 else 0)                     # top bit = sign of the intercept
+    # stage-wise entry point on half of the patterns
+    ctx.load(X, y, P, eta=eta); ctx.gram_build(); ctx.gram_finalize()
+    h = ctx.opt_solve_pairs(0, 2 ** (K - 1))
+    objs = np.minimum(ref["objs"][:2 ** (K - 1)], ref["objs"][2 ** K:2 ** K + 2 ** (K - 1)])
+    assert abs(h["obj_gram"] - objs.min()) <= RTOL * objs.min() + 1e-6 * np.linalg.norm(y)
+
+
+def test_paired_orthants_zero_intercept_ties(ctx, oracle):
+    """y = 0: every weight is zero, both orthants of every pair tie, and the first one in the reference's order
+    (top bit 0) must be reported -- b* = 0 as in the literal enumeration (Opt.jl:96: first minimum)."""
+    o, _ = oracle
+    X, y, P = o.make_synthetic(300, 8, 3, seed=41)
+    r = ctx.opt_fit(X, np.zeros_like(y), P, eta=0.0)
+    assert r["b_best"] == 0 and r["opt"] == 0.0 and np.all(r["alpha_raw"] == 0.0)
