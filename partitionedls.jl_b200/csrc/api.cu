@@ -126,7 +126,7 @@ void read_counters(pls_ctx *c, const unsigned long long *h) {
 // K2 + K3 over a range, winner record left in ws.win.  Caller holds the device.
 // pairs: [b_begin, b_begin + b_count) are sign patterns of the K user groups; the intercept sign is left free, so
 // every solve resolves the two reference orthants b and b + 2^K (the winner record carries the full b).
-int solve_range_dev(pls_ctx *c, int64_t b_begin, int64_t b_count, bool want_obj, bool want_alpha, bool pairs) {
+int solve_range_dev(pls_ctx *c, int64_t b_begin, int64_t b_count, bool want_obj, bool want_alpha, bool pairs, int force_variant) {
   Problem &pb = c->pb;
   if (!pb.gram_ready) { set_error("Gram matrix not built (call pls_gram_build / pls_gram_finalize)"); return PLS_EINVAL; }
   if (pb.Kp > 40) { set_error("K = %d: 2^(K+1) orthants cannot be enumerated (limit K <= 39); use fit(BnB) or fit(Alt)", pb.K); return PLS_EINVAL; }
@@ -140,7 +140,34 @@ int solve_range_dev(pls_ctx *c, int64_t b_begin, int64_t b_count, bool want_obj,
     PLS_CUDA_TRY(cudaMemsetAsync(c->ws.counters, 0, sizeof(unsigned long long) * (CNT_NUM + 1 + 24), c->stream));
   return k2_solve_range(pb, pb.G, pb.ldg, pb.c, pb.scal, pb.gmask, pb.Mp, pb.Kp, c->ws, b_begin, b_count,
                         want_obj ? c->ws.all_obj : nullptr, want_alpha ? c->ws.all_alpha : nullptr,
-                        c->sm_count, c->stream, &c->launches, pairs);
+                        c->sm_count, c->stream, &c->launches, pairs, force_variant);
+}
+
+// Precondition: c->h_pin holds the winner record [alpha | obj | b] and, from h_pin + Mp + 4, the K2 counters of the
+// range just solved (stream synchronised).  The two-level kernel reports the largest KKT violation against the
+// ORIGINAL Gram system that any of its periodic checks saw; above 1e-13 max|c| its tableau was losing digits on
+// this (ill-conditioned) problem, and the winner is solved once more -- one orthant / pair, cold, by the one-level
+// kernel, whose every iterate is checked against the original system.  The new record replaces the old one in
+// ws.win and h_pin; the counters of the main run are kept.
+int polish_if_drifted(pls_ctx *c, bool pairs, bool *did) {
+  *did = false;
+  const int Mp = c->pb.Mp;
+  unsigned long long *cnt = reinterpret_cast<unsigned long long *>(c->h_pin + Mp + 4);
+  double drift; memcpy(&drift, &cnt[CNT_NUM + 24], sizeof(drift));
+  if (!(drift > 1e-13)) return PLS_OK;
+  long long bb; memcpy(&bb, &c->h_pin[Mp + 1], sizeof(bb));
+  if (bb < 0 || c->h_pin[Mp] != c->h_pin[Mp]) return PLS_OK;
+  std::vector<unsigned long long> keep(cnt, cnt + CNT_NUM + 1 + 24);
+  const int64_t idx = pairs ? (int64_t)(bb & (((long long)1 << (c->pb.Kp - 1)) - 1)) : (int64_t)bb;
+  int rc = solve_range_dev(c, idx, 1, false, false, pairs, 3);
+  if (rc) return rc;
+  cudaStream_t st = c->stream;
+  PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin, c->ws.win, sizeof(double) * (Mp + 2), cudaMemcpyDeviceToHost, st));
+  PLS_CUDA_TRY(cudaStreamSynchronize(st));
+  keep[CNT_REBUILDS] += 1;                      // reported as a rebuild
+  memcpy(cnt, keep.data(), sizeof(unsigned long long) * keep.size());
+  *did = true;
+  return PLS_OK;
 }
 
 // Paired orthants are used whenever only the winner is asked for, the problem fits the block-pivoting
@@ -373,6 +400,7 @@ int pls_opt_solve_range(pls_ctx *c, int64_t b_begin, int64_t b_count, double *al
   cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
   c->stats.ms_nnls = ms;
   c->stats.orthants = b_count; c->stats.nnls_problems = b_count;
+  { bool did = false; rc = polish_if_drifted(c, false, &did); if (rc) return rc; }
   const unsigned long long *cnt = reinterpret_cast<const unsigned long long *>(c->h_pin + Mp + 4);
   read_counters(c, cnt);
   memcpy(alpha_raw, c->h_pin, sizeof(double) * Mp);
@@ -404,6 +432,7 @@ int pls_opt_solve_pairs(pls_ctx *c, int64_t p_begin, int64_t p_count, double *al
   cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
   c->stats.ms_nnls = ms;
   c->stats.orthants = 2 * p_count; c->stats.nnls_problems = p_count;
+  { bool did = false; rc = polish_if_drifted(c, true, &did); if (rc) return rc; }
   const unsigned long long *cnt = reinterpret_cast<const unsigned long long *>(c->h_pin + Mp + 4);
   read_counters(c, cnt);
   memcpy(alpha_raw, c->h_pin, sizeof(double) * Mp);
@@ -537,6 +566,19 @@ int pls_opt_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_raw, int64_t 
   PLS_CUDA_TRY(cudaStreamSynchronize(st));
 
   if (c->h_pin[Mp + 3] != 0.0) { set_error("non-finite values in X or y"); return PLS_ENUMERIC; }
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]);
+  const float ms_nnls_main = ms;
+  bool polished = false;
+  rc = polish_if_drifted(c, pairs, &polished); if (rc) return rc;
+  if (polished && recompute) {                 // data-space objective of the polished winner
+    winner_weights<<<1, 256, 0, st>>>(c->ws.win, pb.gmask, Mp, c->d_w);
+    PLS_CUDA_TRY(cudaGetLastError());
+    ++c->launches;
+    rc = k4_residual(pb, c->ws, c->d_w, c->d_ssq, c->sm_count, st, &c->launches); if (rc) return rc;
+    PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin + Mp + 2, c->d_ssq, sizeof(double), cudaMemcpyDeviceToHost, st));
+    PLS_CUDA_TRY(cudaStreamSynchronize(st));
+  }
   memcpy(alpha_raw, c->h_pin, sizeof(double) * Mp);
   long long bb; memcpy(&bb, &c->h_pin[Mp + 1], sizeof(bb));
   *b_best = bb;
@@ -544,10 +586,9 @@ int pls_opt_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_raw, int64_t 
   if (recompute && obj == obj) obj = std::sqrt(c->h_pin[Mp + 2] + eta_term(c, alpha_raw, bb));
   *obj_best = obj;
 
-  float ms = 0.f;
   pls_stats &s = c->stats;
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); s.ms_gram = ms;
-  cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); s.ms_nnls = ms;
+  s.ms_nnls = ms_nnls_main;
   cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); s.ms_recompute = ms;
   s.ms_select = 0.0;   // K3 is timed with K2 (same stream, ~microseconds)
   s.orthants = total; s.nnls_problems = pairs ? total / 2 : total;

@@ -107,7 +107,7 @@ int k1_gram_finalize(Problem &pb, cudaStream_t st, int *launches);
 int k2_solve_range(const Problem &pb, const double *G, int ldg, const double *c, const double *scal,
                    const uint64_t *gmask, int Mp, int Kp, SolveWs &ws, int64_t b_begin,
                    int64_t b_count, double *d_all_obj, double *d_all_alpha, int sm_count,
-                   cudaStream_t st, int *launches, bool free_top = false);
+                   cudaStream_t st, int *launches, bool free_top = false, int force_variant = 0);
 // K2 variants: v2 = block pivoting with DMMA rank-8 updates on a tile-packed symmetric inverse
 // (M' <= 208); v1 = rank-1 updates on a dense inverse with a global-memory spill path (any M').
 int k2v2_launch(const K2Args &A, int grid, cudaStream_t st);

@@ -209,6 +209,7 @@ int multi_opt_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_raw, int64_
     PLS_CUDA_TRY(cudaStreamSynchronize(st));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]);
+    { bool did = false; r = polish_if_drifted(s, pairs, &did); if (r) return r; }
     const unsigned long long *cnt = reinterpret_cast<const unsigned long long *>(s->h_pin + Mp + 4);
     read_counters(s, cnt);
     s->stats.ms_nnls = ms;

@@ -458,7 +458,7 @@ size_t k2_smem_bytes(int Mp, int cap) {
 int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, const double *scal,
                    const uint64_t *gmask, int Mp, int Kp, SolveWs &ws, int64_t b_begin,
                    int64_t b_count, double *d_all_obj, double *d_all_alpha, int sm_count,
-                   cudaStream_t st, int *launches, bool free_top) {
+                   cudaStream_t st, int *launches, bool free_top, int force_variant) {
   if (b_count <= 0) { set_error("k2: empty orthant range"); return PLS_EINVAL; }
   if (free_top && (Mp > 1024 || d_all_obj || d_all_alpha)) { set_error("k2: paired orthants need M' <= 1024 and no per-orthant outputs"); return PLS_EUNSUPPORTED; }
   // variant (PLS_K2_IMPL = v1 | v2 | v3 overrides):
@@ -474,7 +474,10 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   // CTA -- measured crossover against v3: ~20 orthants per CTA at M' = 201, ~80 at M' = 513
   const bool pow2 = (b_count & (b_count - 1)) == 0 && (b_begin % b_count) == 0;
   const bool force4 = impl && strcmp(impl, "v4") == 0;
-  if (variant == 3 && Mp + 1 <= 1024 && pow2 && (force4 || !impl)) variant = 4;
+  // per-orthant outputs (returnAllSolutions) stay on the one-level kernel: every orthant is then checked against
+  // the original G (accuracy on ill-conditioned data matters more than speed on that path)
+  if (variant == 3 && Mp + 1 <= 1024 && pow2 && (force4 || (!impl && !d_all_obj && !d_all_alpha))) variant = 4;
+  if (force_variant == 3 && Mp <= 1024) variant = 3;
   int cap = Mp, occ = 1;
   size_t smem = 0;
   K3Plan plan3;
@@ -487,7 +490,7 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   }
   if (variant == 2 && k2v2_config(Mp, &cap, &smem, &occ) != PLS_OK) variant = 3;
   if (variant == 3) {
-    int rc = k2v3_plan(Mp, &plan3);
+    int rc = k2v3_plan(Mp, &plan3, force_variant == 3);
     if (rc == PLS_EUNSUPPORTED && free_top) rc = k2v3_plan(Mp, &plan3, true);   // a tuning override asked for a variant that does not exist
     if (rc == PLS_EUNSUPPORTED) variant = 1; else if (rc) return rc;
     else { cap = plan3.cap; occ = plan3.occ; smem = plan3.smem; }
