@@ -65,7 +65,7 @@ def st_kernel_name(st):
 
 def ncu_dram_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the K2 launch from the committed ncu --set full
-    capture (profiles/r01_v4_k2_raw_summary.txt); None if the summary is missing."""
+    capture (profiles/r01_final3_k2_raw_summary.txt); None if the summary is missing."""
     p = os.path.join(ROOT, "profiles", "r01_v4_k2_raw_summary.txt")
     if not os.path.exists(p):
         return None

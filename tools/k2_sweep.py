@@ -32,7 +32,9 @@ for setting in sys.argv[2:]:
     try:
         ts = []
         for rep in range(3):
-            t0 = time.perf_counter(); r = ctx.opt_solve_range(0, total); ts.append(time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            r = ctx.opt_solve_pairs(0, total // 2) if os.environ.get("SWEEP_PAIRS") else ctx.opt_solve_range(0, total)
+            ts.append(time.perf_counter() - t0)
         st = ctx.stats()
         rec = dict(shape=shape, setting=setting, ms=min(ts) * 1e3, ms_kernel=st["ms_nnls"], solves_per_s=total / min(ts),
                    b_best=r["b_best"], obj=r["obj_gram"], pivots=st["pivots"], grad_evals=st["grad_evals"],
