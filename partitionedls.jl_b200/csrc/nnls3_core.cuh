@@ -9,6 +9,9 @@ namespace pls {
 namespace {
 
 constexpr int CAP3MAX = 1024;
+#ifndef PLS_K4_KEEP
+#define PLS_K4_KEEP 0      // 1: gradient loads of the two-level kernel carry an L2 evict-last hint (measured: no gain at M'=201 or 513)
+#endif
 #ifndef PLS_K3_IFL
 #define PLS_K3_IFL 4      // tiles of the packed inverse in flight per warp (rank update, H * panel); 8 measured slower (18.1 vs 16.0 ms at cfg2)
 #endif
@@ -516,7 +519,7 @@ __device__ __noinline__ bool block_add3(const Cfg3 cf, const double *G, int ldg,
 // slices; slots >= hw are free (F = -1), free slots are skipped.  Returns max |r_F| (normal-equation
 // residual), same on all threads.  Pb = scratch.  G must be readable up to row 2 * NP * W of every
 // column (ldg is a multiple of 8 and the allocation is padded).
-template <int T, int NP>
+template <int T, int NP, bool KEEP = false>
 __device__ __noinline__ double grad_eval3(const Cfg3 cf, const double *G, int ldg, int Mp, int hw) {
   const Sh3 s = make_sh3(cf);
   constexpr int NW = T / 32;
@@ -536,6 +539,8 @@ __device__ __noinline__ double grad_eval3(const Cfg3 cf, const double *G, int ld
     const int nb = hw8 / UB;
     const int t0 = ((nb * sl) / nsl) * UB, t1 = ((nb * (sl + 1)) / nsl) * UB;
     const double2 *Gp = reinterpret_cast<const double2 *>(G) + un;
+    unsigned long long keep_pol = 0;
+    if (KEEP) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep_pol));   // hot tableau rows: stay in L2
     const int ldg2 = ldg >> 1;
     double2 acc[2][NP];
 #pragma unroll
@@ -549,7 +554,10 @@ __device__ __noinline__ double grad_eval3(const Cfg3 cf, const double *G, int ld
         const int v = s.F[t + i];
         const double2 *gp = Gp + (size_t)ldg2 * (v >= 0 ? v : 0);
 #pragma unroll
-        for (int k = 0; k < NP; ++k) g[i][k] = v >= 0 ? gp[k * W] : make_double2(0.0, 0.0);
+        for (int k = 0; k < NP; ++k) {
+          if (KEEP) g[i][k] = v >= 0 ? ld_stream2(reinterpret_cast<const double *>(gp + k * W), keep_pol) : make_double2(0.0, 0.0);
+          else g[i][k] = v >= 0 ? gp[k * W] : make_double2(0.0, 0.0);
+        }
       }
 #pragma unroll
       for (int i = 0; i < UB; ++i) {
@@ -893,7 +901,7 @@ __device__ __forceinline__ bool bpp_solve3(const Cfg3 cf, const Sh3 &s, const do
       int rep = 0;
       for (;;) {
         PH_TICK3(PH_OUT);
-        const double rf = grad_eval3<T, 4>(cf, G, ldg, Mp, st.hwm);      // 4 row pairs per thread: M' <= 8 T
+        const double rf = grad_eval3<T, 4, TL && PLS_K4_KEEP>(cf, G, ldg, Mp, st.hwm);      // 4 row pairs per thread: M' <= 8 T
         PH_TICK3(PH_GRAD);
         if (rf <= 1e-12 * cmax) break;          // carried solution already exact to working accuracy
         refine3<T, MODE>(cf, st.nt_cur);
