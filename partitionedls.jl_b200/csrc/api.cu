@@ -170,6 +170,48 @@ int polish_if_drifted(pls_ctx *c, bool pairs, bool *did) {
   return PLS_OK;
 }
 
+// Precondition as for polish_if_drifted.  Block pivoting moves every violating variable at once, and on data with
+// N barely above M' and strongly correlated columns an INTERMEDIATE passive set can be nearly singular: the
+// explicit inverse then cannot meet its residual test and the solve is given up (counted in CNT_NOCONV) although
+// the orthant's optimum is well conditioned.  The range is then solved again by the single-pivot kernel (v1: one
+// variable per step behind a pivot test, as Lawson-Hanson, which never forms such sets) -- literally enumerated, so
+// a paired range becomes its two halves b and b + 2^K.  Leaves the winner in ws.win / h_pin, per-orthant outputs
+// (literal ranges only) in the device staging buffers, and the first run's counters (+1 rebuild) in h_pin.
+int fallback_if_stalled(pls_ctx *c, int64_t b_begin, int64_t b_count, bool want_obj, bool want_alpha, bool pairs, bool *did) {
+  *did = false;
+  const int Mp = c->pb.Mp;
+  unsigned long long *cnt = reinterpret_cast<unsigned long long *>(c->h_pin + Mp + 4);
+  if (!cnt[CNT_NOCONV]) return PLS_OK;
+  std::vector<unsigned long long> keep(cnt, cnt + CNT_NUM + 1 + 24);
+  cudaStream_t st = c->stream;
+  std::vector<double> best;
+  const int n_half = pairs ? 2 : 1;
+  for (int h = 0; h < n_half; ++h) {
+    const int64_t b0 = b_begin + (h ? ((int64_t)1 << (c->pb.Kp - 1)) : 0);
+    int rc = solve_range_dev(c, b0, b_count, want_obj, want_alpha, false, 1);
+    if (rc) return rc;
+    PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin, c->ws.win, sizeof(double) * (Mp + 2), cudaMemcpyDeviceToHost, st));
+    PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin + Mp + 4, c->ws.counters, sizeof(unsigned long long) * (CNT_NUM + 1 + 24), cudaMemcpyDeviceToHost, st));
+    PLS_CUDA_TRY(cudaStreamSynchronize(st));
+    if (cnt[CNT_NOCONV]) { set_error("%llu orthant solves did not converge (block pivoting and the single-pivot fallback)", cnt[CNT_NOCONV]); return PLS_ENUMERIC; }
+    long long bb; memcpy(&bb, &c->h_pin[Mp + 1], sizeof(bb));
+    bool better = best.empty();
+    if (!better) {
+      long long b1; memcpy(&b1, &best[Mp + 1], sizeof(b1));
+      const double o0 = c->h_pin[Mp], o1 = best[Mp];
+      better = (o0 != o0 && o1 == o1) || (o0 < o1) || (o0 == o1 && bb < b1);
+    }
+    if (better) best.assign(c->h_pin, c->h_pin + Mp + 2);
+  }
+  memcpy(c->h_pin, best.data(), sizeof(double) * (Mp + 2));
+  PLS_CUDA_TRY(cudaMemcpyAsync(c->ws.win, c->h_pin, sizeof(double) * (Mp + 2), cudaMemcpyHostToDevice, st));
+  PLS_CUDA_TRY(cudaStreamSynchronize(st));
+  keep[CNT_NOCONV] = 0; keep[CNT_REBUILDS] += 1; keep[CNT_NUM + 24] = 0;     // resolved; no polish needed after v1
+  memcpy(cnt, keep.data(), sizeof(unsigned long long) * keep.size());
+  *did = true;
+  return PLS_OK;
+}
+
 // Paired orthants are used whenever only the winner is asked for, the problem fits the block-pivoting
 // kernels, and the caller did not ask for the reference's literal enumeration.
 bool use_pairs(const pls_ctx *c, uint32_t flags, bool per_orthant_outputs) {
@@ -400,7 +442,16 @@ int pls_opt_solve_range(pls_ctx *c, int64_t b_begin, int64_t b_count, double *al
   cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
   c->stats.ms_nnls = ms;
   c->stats.orthants = b_count; c->stats.nnls_problems = b_count;
-  { bool did = false; rc = polish_if_drifted(c, false, &did); if (rc) return rc; }
+  {
+    bool fell = false, did = false;
+    rc = fallback_if_stalled(c, b_begin, b_count, all_obj != nullptr, all_alpha != nullptr, false, &fell); if (rc) return rc;
+    if (fell) {
+      if (all_obj) PLS_CUDA_TRY(cudaMemcpyAsync(all_obj, c->ws.all_obj, sizeof(double) * (size_t)b_count, cudaMemcpyDeviceToHost, st));
+      if (all_alpha) PLS_CUDA_TRY(cudaMemcpyAsync(all_alpha, c->ws.all_alpha, sizeof(double) * (size_t)b_count * Mp, cudaMemcpyDeviceToHost, st));
+      PLS_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    rc = polish_if_drifted(c, false, &did); if (rc) return rc;
+  }
   const unsigned long long *cnt = reinterpret_cast<const unsigned long long *>(c->h_pin + Mp + 4);
   read_counters(c, cnt);
   memcpy(alpha_raw, c->h_pin, sizeof(double) * Mp);
@@ -432,7 +483,12 @@ int pls_opt_solve_pairs(pls_ctx *c, int64_t p_begin, int64_t p_count, double *al
   cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
   c->stats.ms_nnls = ms;
   c->stats.orthants = 2 * p_count; c->stats.nnls_problems = p_count;
-  { bool did = false; rc = polish_if_drifted(c, true, &did); if (rc) return rc; }
+  {
+    bool fell = false, did = false;
+    rc = fallback_if_stalled(c, p_begin, p_count, false, false, true, &fell); if (rc) return rc;
+    if (fell) c->stats.nnls_problems = 3 * p_count;
+    rc = polish_if_drifted(c, true, &did); if (rc) return rc;
+  }
   const unsigned long long *cnt = reinterpret_cast<const unsigned long long *>(c->h_pin + Mp + 4);
   read_counters(c, cnt);
   memcpy(alpha_raw, c->h_pin, sizeof(double) * Mp);
@@ -569,9 +625,16 @@ int pls_opt_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_raw, int64_t 
   float ms = 0.f;
   cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]);
   const float ms_nnls_main = ms;
-  bool polished = false;
+  bool polished = false, fell = false;
+  rc = fallback_if_stalled(c, 0, pairs ? total / 2 : total, all_obj != nullptr, all_alpha != nullptr, pairs, &fell); if (rc) return rc;
+  if (fell) {
+    if (all_obj) PLS_CUDA_TRY(cudaMemcpyAsync(all_obj, c->ws.all_obj, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost, st));
+    if (all_alpha) PLS_CUDA_TRY(cudaMemcpyAsync(all_alpha, c->ws.all_alpha, sizeof(double) * (size_t)total * Mp, cudaMemcpyDeviceToHost, st));
+    PLS_CUDA_TRY(cudaStreamSynchronize(st));
+  }
   rc = polish_if_drifted(c, pairs, &polished); if (rc) return rc;
-  if (polished && recompute) {                 // data-space objective of the polished winner
+  polished = polished || fell;
+  if (polished && recompute) {                 // data-space objective of the new winner record
     winner_weights<<<1, 256, 0, st>>>(c->ws.win, pb.gmask, Mp, c->d_w);
     PLS_CUDA_TRY(cudaGetLastError());
     ++c->launches;
@@ -831,7 +894,7 @@ int pls_nnls_batch(pls_ctx *c, const double *G, const double *cv, double yy, int
   const unsigned long long *cnt = reinterpret_cast<const unsigned long long *>(c->h_pin + Mp + 4);
   c->stats.orthants = b_count;
   read_counters(c, cnt);
-  if (cnt[CNT_NOCONV]) { set_error("%llu orthant solves hit the iteration cap", cnt[CNT_NOCONV]); return PLS_ENUMERIC; }
+  if (cnt[CNT_NOCONV]) { set_error("%llu orthant solves did not converge", cnt[CNT_NOCONV]); return PLS_ENUMERIC; }
   return PLS_OK;
 }
 

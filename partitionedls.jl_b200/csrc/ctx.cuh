@@ -31,6 +31,7 @@ int host_d(const std::vector<uint64_t> &gm, int m, int64_t b);
 void read_counters(pls_ctx *c, const unsigned long long *h);
 int solve_range_dev(pls_ctx *c, int64_t b_begin, int64_t b_count, bool want_obj, bool want_alpha, bool pairs = false, int force_variant = 0);
 int polish_if_drifted(pls_ctx *c, bool pairs, bool *did);
+int fallback_if_stalled(pls_ctx *c, int64_t b_begin, int64_t b_count, bool want_obj, bool want_alpha, bool pairs, bool *did);
 bool use_pairs(const pls_ctx *c, uint32_t flags, bool per_orthant_outputs);
 double eta_term(const pls_ctx *c, const double *alpha_raw, int64_t b);
 double eta_term_w(const pls_ctx *c, const double *w);

@@ -209,7 +209,16 @@ int multi_opt_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_raw, int64_
     PLS_CUDA_TRY(cudaStreamSynchronize(st));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]);
-    { bool did = false; r = polish_if_drifted(s, pairs, &did); if (r) return r; }
+    {
+      bool fell = false, did = false;
+      r = fallback_if_stalled(s, b0, b1 - b0, all_obj != nullptr, all_alpha != nullptr, pairs, &fell); if (r) return r;
+      if (fell) {
+        if (all_obj) PLS_CUDA_TRY(cudaMemcpyAsync(all_obj + b0, s->ws.all_obj, sizeof(double) * (size_t)(b1 - b0), cudaMemcpyDeviceToHost, st));
+        if (all_alpha) PLS_CUDA_TRY(cudaMemcpyAsync(all_alpha + (size_t)b0 * Mp, s->ws.all_alpha, sizeof(double) * (size_t)(b1 - b0) * Mp, cudaMemcpyDeviceToHost, st));
+        PLS_CUDA_TRY(cudaStreamSynchronize(st));
+      }
+      r = polish_if_drifted(s, pairs, &did); if (r) return r;
+    }
     const unsigned long long *cnt = reinterpret_cast<const unsigned long long *>(s->h_pin + Mp + 4);
     read_counters(s, cnt);
     s->stats.ms_nnls = ms;

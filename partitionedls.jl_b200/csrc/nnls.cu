@@ -478,6 +478,7 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   // the original G (accuracy on ill-conditioned data matters more than speed on that path)
   if (variant == 3 && Mp + 1 <= 1024 && pow2 && (force4 || (!impl && !d_all_obj && !d_all_alpha))) variant = 4;
   if (force_variant == 3 && Mp <= 1024) variant = 3;
+  if (force_variant == 1 && !free_top) variant = 1;
   int cap = Mp, occ = 1;
   size_t smem = 0;
   K3Plan plan3;

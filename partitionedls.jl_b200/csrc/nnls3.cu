@@ -76,6 +76,14 @@ __global__ void __launch_bounds__(T, MINB) k2v3_orthant_chains(const K2Args A) {
       Bpp3 st; st.grow_zero = false; st.hwm = hwm; st.nt_cur = nt_cur; st.nt_dirty = nt_dirty; st.r_valid = r_valid;
       const bool ok = bpp_solve3<T, MODE>(cf, s, A.G, A.ldg, Mp, cmax, st);
       hwm = st.hwm; nt_cur = st.nt_cur; nt_dirty = st.nt_dirty; r_valid = st.r_valid;
+      if (!ok) {                               // failed solve (counted; the caller re-solves the range): restart the chain state
+        __syncthreads();
+        clear_state3<T, MODE>(cf, max(nt_dirty, nt_cur));
+        nt_dirty = 0; hwm = 0; nt_cur = 0;
+        for (int m = tid; m < Mp; m += T) { s.w[m] = 0.0; s.r[m] = s.cs[m]; s.pos[m] = -1; }
+        r_valid = true;
+        __syncthreads();
+      }
 
       // ---- objective  sqrt(yy - c_F' w_F)   (= norm(Xa w - ya) at the KKT point, Opt.jl:90); the
       //      partial sums were left in s.red by the plan step that found no violation

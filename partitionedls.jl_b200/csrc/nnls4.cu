@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(T, MINB) k2v4_orthant_ranges(const K2Args A) {
     Bpp3 st; st.grow_zero = false; st.hwm = hwm; st.nt_cur = nt_cur; st.nt_dirty = nt_dirty; st.r_valid = r_valid;
     const bool ok = bpp_solve3<T, MODE, true>(cf, s, cf.tab, cf.ldt, Mp, cmax, st);
     hwm = st.hwm; nt_cur = st.nt_cur; nt_dirty = st.nt_dirty; r_valid = st.r_valid;
+    if (!ok) cold = true;                      // failed solve (counted; the caller re-solves the range): next orthant starts cold
 
     // c~_F' w_F of the reduced problem: partial sums left in s.red by the plan step that found no violation
     double tot = 0.0;

@@ -603,3 +603,22 @@ def test_paired_orthants_zero_intercept_ties(ctx, oracle):
     X, y, P = o.make_synthetic(300, 8, 3, seed=41)
     r = ctx.opt_fit(X, np.zeros_like(y), P, eta=0.0)
     assert r["b_best"] == 0 and r["opt"] == 0.0 and np.all(r["alpha_raw"] == 0.0)
+
+
+def test_stalled_block_pivoting_falls_back_to_single_pivots(ctx, oracle):
+    """N = 144, M' = 118, AR(1) columns with rho = 0.9 (found by tools/v4_fuzz.py): in two orthants block pivoting passes
+    through a nearly singular intermediate passive set (106 of 118 variables from 144 rows) and gives the solve up; the
+    library re-solves the range with the single-pivot kernel.  Every orthant against the C oracle, both fit modes."""
+    o, oc = oracle
+    g = np.load(os.path.join(GOLD, "stall_n144_m117_rho09.npz"))
+    X, y, P, eta = np.asfortranarray(g["X"]), g["y"], np.asfortranarray(g["P"]), float(g["eta"])
+    ref = oc.opt_fit(X, y, P, eta)
+    r = ctx.opt_fit(X, y, P, eta=eta, return_all=True)
+    assert r["b_best"] == ref["b_best"] and abs(r["opt"] - ref["obj_best"]) <= RTOL * ref["obj_best"]
+    assert np.allclose(r["objs"], ref["objs"], rtol=RTOL, atol=1e-6 * np.linalg.norm(y))
+    scale = np.abs(ref["alphas"]).max(axis=1, keepdims=True)
+    assert np.all(np.abs(r["alphas"] - ref["alphas"]) <= RTOL * scale + 1e-300)
+    assert r["stats"]["rebuilds"] >= 1                       # the fallback (or a rebuild) was needed on this problem
+    w = ctx.opt_fit(X, y, P, eta=eta)                        # winner only: paired orthants
+    assert w["b_best"] == ref["b_best"] and abs(w["opt"] - ref["obj_best"]) <= RTOL * ref["obj_best"]
+    assert np.all(np.abs(w["alpha_raw"] - ref["alpha_best"]) <= RTOL * np.abs(ref["alpha_best"]).max())
