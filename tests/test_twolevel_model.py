@@ -47,3 +47,33 @@ def test_tableau_walk_matches_oracle(oracle, shape):
         assert abs(np.sqrt(max(obj2, 0.0)) - ref["objs"][b]) <= 1e-9 * ref["objs"][b] + 1e-6 * np.sqrt(yy)
         tl.commit()
     assert tl.n_sweep_blocks > 0 and tl.n_unsweep_blocks > 0   # both tableau operations were exercised
+
+
+@pytest.mark.parametrize("shape", [(300, 14, 4, 1e-3, 0.4, 0.8), (200, 9, 3, 0.0, 0.0, -1.5), (250, 12, 5, 1e-2, 0.6, 0.0)])
+def test_free_intercept_resolves_both_orthants_of_a_pair(oracle, shape):
+    """The claim behind the paired-orthant mode: for every sign pattern p of the K user groups, the
+    NNLS problem with the intercept sign left FREE has the optimum of the better of the two reference orthants p and
+    p + 2^K (Opt.jl:85-96 enumerates both), and the sign of its intercept weight tells which one.  Checked with the
+    oracle's Lawson-Hanson: free intercept = the intercept column entered twice, as +1 and -1 (both >= 0)."""
+    o, oc = oracle
+    N, M, K, eta, rho, shift = shape
+    X, y, P = o.make_synthetic(N, M, K, seed=11 * M, mixed_sign=True, rho=rho)
+    y = y - 0.5 + shift
+    ref = oc.opt_fit(X, y, P, eta)
+    Xo, Po = o.homogeneous_coords(X, P)
+    Xa, ya = o.regularize_problem(Xo, y, Po, eta)
+    for p in range(1 << K):
+        beta = o.index_to_beta(p, K + 1).astype(float)          # top bit 0: intercept sign -1 (ignored below)
+        d = Po @ beta
+        A = np.hstack([Xa[:, :M] * d[None, :M], Xa[:, M:M + 1], -Xa[:, M:M + 1]])
+        a = o.nonneg_lsq(A, ya)
+        t = a[M] - a[M + 1]
+        obj = float(np.linalg.norm(A @ a - ya))
+        lo, hi = ref["objs"][p], ref["objs"][p + (1 << K)]
+        assert abs(obj - min(lo, hi)) <= 1e-9 * max(min(lo, hi), 1e-12) + 1e-12 * np.linalg.norm(y)
+        if abs(lo - hi) > 1e-9 * max(lo, hi):
+            assert (t > 0) == (hi < lo)                         # the intercept's sign names the better orthant
+        b_full = p | ((1 << K) if t > 0 else 0)
+        alpha = np.concatenate([a[:M], [abs(t)]])
+        sc = max(np.abs(ref["alphas"][b_full]).max(), 1e-300)
+        assert np.abs(alpha - ref["alphas"][b_full]).max() <= 1e-8 * sc
