@@ -37,7 +37,7 @@ import __graft_entry__ as entry  # noqa: E402
 
 _JSON_OUT = sys.stdout
 METRIC = "opt_fit_orthant_nnls_solves_per_sec"
-UNIT = "solves/s"
+UNIT = "orthants/s"      # orthants of the reference enumeration (2^(K+1) per fit) resolved per second, both arms
 
 
 def load_peaks():
