@@ -119,9 +119,9 @@ int k2v3_plan(int Mp, K3Plan *pl, bool ignore_env = false);   // ignore_env: no 
 int k2v3_launch(const K2Args &A, const K3Plan &pl, int grid, cudaStream_t st);
 // v4 = two-level path: v3's core on the reduced problem of a per-CTA swept tableau (nnls4.cu)
 struct K4Plan { int cap, qs, T, mode, occ, variant, low_groups, verify_every; size_t smem, hstride, tabstride; };
-int k2v4_plan(int Mp, int Kp, K4Plan *pl);
+int k2v4_plan(int Mp, int Kp, K4Plan *pl, long long per_sm = 0);   // per_sm: problems per SM of this launch (0 = unknown)
 int k2v4_launch(const K2Args &A, const K4Plan &pl, int grid, cudaStream_t st);
-int k2v4_plan_prof(int Mp, int Kp, K4Plan *pl);      // nnls4p.cu: same kernels with phase counters
+int k2v4_plan_prof(int Mp, int Kp, K4Plan *pl, long long per_sm = 0);      // nnls4p.cu: same kernels with phase counters
 int k2v4_launch_prof(const K2Args &A, const K4Plan &pl, int grid, cudaStream_t st);
 // K5: branch and bound with batched frontier expansion (bnb.cu); winner left in ws.win
 struct BnbReport { long long visited, waves, max_open, pool_slots; double mu; bool complete, has_leaf; };

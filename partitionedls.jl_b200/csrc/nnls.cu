@@ -484,7 +484,8 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   K3Plan plan3;
   K4Plan plan4;
   if (variant == 4) {
-    const int rc = getenv("PLS_K2_PHASES") ? k2v4_plan_prof(Mp, Kp, &plan4) : k2v4_plan(Mp, Kp, &plan4);
+    const long long per_sm = b_count / (sm_count > 0 ? sm_count : 1);
+    const int rc = getenv("PLS_K2_PHASES") ? k2v4_plan_prof(Mp, Kp, &plan4, per_sm) : k2v4_plan(Mp, Kp, &plan4, per_sm);
     if (rc == PLS_EUNSUPPORTED) variant = 3; else if (rc) return rc;
     else if (!force4 && b_count < (long long)sm_count * plan4.occ * (Mp <= 256 ? 24 : 96)) variant = 3;   // too short a walk per CTA
     else { cap = plan4.cap; occ = plan4.occ; smem = plan4.smem; }
