@@ -525,9 +525,23 @@ __device__ __noinline__ double grad_eval3(const Cfg3 cf, const double *G, int ld
   constexpr int NW = T / 32;
   constexpr int UB = NP >= 8 ? 1 : 8 / NP;         // columns per batch
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int hw8 = (hw + 7) & ~7;
-  for (int t = tid; t < hw8; t += T) { const int var = s.F[t]; s.wF[t] = var >= 0 ? s.w[var] : 0.0; }
+  // compact list of the passive slots (warp ballots): column -> s.lst, weight -> s.wF, padded with weight-0 entries to
+  // a whole batch -- the streaming loop below then has neither holes nor predicates
+  if (wid == 0) {
+    int base = 0;
+    for (int t0 = 0; t0 < hw; t0 += 32) {
+      const int t = t0 + lane;
+      const int var = t < hw ? s.F[t] : -1;
+      const unsigned bal = __ballot_sync(0xffffffffu, var >= 0);
+      if (var >= 0) { const int p = base + __popc(bal & ((1u << lane) - 1)); s.lst[p] = var; s.wF[p] = s.w[var]; }
+      base += __popc(bal);
+    }
+    const int padded = (base + 7) & ~7;
+    for (int p = base + lane; p < padded; p += 32) { s.lst[p] = 0; s.wF[p] = 0.0; }
+    if (lane == 0) s.ctl[6] = padded;
+  }
   __syncthreads();
+  const int np8 = s.ctl[6];
   const int npairs = (Mp + 1) >> 1;
   const int W = (npairs + NP - 1) / NP;            // threads per slice, <= T by construction
   int nsl = T / W;
@@ -536,11 +550,9 @@ __device__ __noinline__ double grad_eval3(const Cfg3 cf, const double *G, int ld
   double *part = s.Pb;                             // [nsl][2 * NP * W]
   const int pstride = 2 * NP * W;
   if (sl < nsl) {
-    const int nb = hw8 / UB;
+    const int nb = np8 / UB;
     const int t0 = ((nb * sl) / nsl) * UB, t1 = ((nb * (sl + 1)) / nsl) * UB;
     const double2 *Gp = reinterpret_cast<const double2 *>(G) + un;
-    unsigned long long keep_pol = 0;
-    if (KEEP) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep_pol));   // hot tableau rows: stay in L2
     const int ldg2 = ldg >> 1;
     double2 acc[2][NP];
 #pragma unroll
@@ -551,13 +563,9 @@ __device__ __noinline__ double grad_eval3(const Cfg3 cf, const double *G, int ld
       double2 g[UB][NP];
 #pragma unroll
       for (int i = 0; i < UB; ++i) {
-        const int v = s.F[t + i];
-        const double2 *gp = Gp + (size_t)ldg2 * (v >= 0 ? v : 0);
+        const double2 *gp = Gp + (size_t)ldg2 * s.lst[t + i];
 #pragma unroll
-        for (int k = 0; k < NP; ++k) {
-          if (KEEP) g[i][k] = v >= 0 ? ld_stream2(reinterpret_cast<const double *>(gp + k * W), keep_pol) : make_double2(0.0, 0.0);
-          else g[i][k] = v >= 0 ? gp[k * W] : make_double2(0.0, 0.0);
-        }
+        for (int k = 0; k < NP; ++k) g[i][k] = gp[k * W];
       }
 #pragma unroll
       for (int i = 0; i < UB; ++i) {
