@@ -75,6 +75,14 @@ typedef struct pls_stats {
   int64_t waves;         /* BnB: frontier batches launched; Alt: alternating iterations of the longest restart */
   int64_t max_open;      /* BnB: largest number of open nodes (= live pooled states) */
   int64_t nnls_problems; /* Opt: NNLS problems actually solved (= orthants / 2 with paired orthants, else = orthants) */
+  int64_t k2_variant;    /* which K2 kernel solved the main range of the last Opt fit: 1 = single-pivot (nnls.cu), 3 = one-level
+                            block pivoting (nnls3.cu), 4 = two-level CTA-per-chain (nnls4.cu), 5 = two-level warp-per-chain
+                            (nnls5.cu); BnB / Alt leave 0 */
+  int64_t k2_threads;    /* threads per CTA of that launch */
+  int64_t k2_ctas_per_sm; /* resident CTAs per SM the launch was sized for */
+  int64_t k2_grid;       /* CTAs launched */
+  double k2_max_drift;   /* two-level kernels: largest KKT violation against the ORIGINAL Gram system seen by the periodic
+                            checks, relative to max|c| */
 } pls_stats;
 
 /* ---- context ------------------------------------------------------------------------------ */

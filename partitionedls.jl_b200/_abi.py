@@ -32,7 +32,9 @@ class PlsStats(C.Structure):
                 ("orthants", "pivots", "grad_evals", "sum_p", "sum_p2", "bpp_iters", "spills",
                  "rebuilds", "blocked", "kernel_launches")] + \
                [(n, C.c_double) for n in ("gram_flops", "nnls_flops", "nnls_l2_bytes")] + \
-               [(n, C.c_int64) for n in ("waves", "max_open", "nnls_problems")]
+               [(n, C.c_int64) for n in ("waves", "max_open", "nnls_problems", "k2_variant", "k2_threads",
+                                         "k2_ctas_per_sm", "k2_grid")] + \
+               [("k2_max_drift", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -118,6 +118,7 @@ void read_counters(pls_ctx *c, const unsigned long long *h) {
   s.sum_p = (int64_t)h[CNT_SUMP]; s.sum_p2 = (int64_t)h[CNT_SUMP2];
   s.bpp_iters = (int64_t)h[CNT_ITERS]; s.spills = (int64_t)h[CNT_SPILLS];
   s.rebuilds = (int64_t)h[CNT_REBUILDS]; s.blocked = (int64_t)h[CNT_BLOCKED];
+  { double d; memcpy(&d, &h[CNT_NUM + 24], sizeof(d)); s.k2_max_drift = d; }
   const double Mp = c->pb.Mp;
   s.nnls_flops = 2.0 * Mp * (double)s.sum_p + 4.0 * (double)s.sum_p2;
   s.nnls_l2_bytes = 8.0 * Mp * (double)s.sum_p;
@@ -135,12 +136,17 @@ int solve_range_dev(pls_ctx *c, int64_t b_begin, int64_t b_count, bool want_obj,
   if (b_begin < 0 || b_count <= 0 || b_begin + b_count > total) { set_error("orthant range out of bounds"); return PLS_EINVAL; }
   int rc = ensure_all_buffers(c, b_count, want_obj, want_alpha);
   if (rc) return rc;
-  if (c->ws.Mp != pb.Mp && c->ws.win) { cudaFree(c->ws.win); c->ws.win = nullptr; }
+  PLS_CUDA_TRY(ensure_win(c->ws, pb.Mp + 2));
   if (c->ws.counters)
     PLS_CUDA_TRY(cudaMemsetAsync(c->ws.counters, 0, sizeof(unsigned long long) * (CNT_NUM + 1 + 24), c->stream));
-  return k2_solve_range(pb, pb.G, pb.ldg, pb.c, pb.scal, pb.gmask, pb.Mp, pb.Kp, c->ws, b_begin, b_count,
-                        want_obj ? c->ws.all_obj : nullptr, want_alpha ? c->ws.all_alpha : nullptr,
-                        c->sm_count, c->stream, &c->launches, pairs, force_variant);
+  rc = k2_solve_range(pb, pb.G, pb.ldg, pb.c, pb.scal, pb.gmask, pb.Mp, pb.Kp, c->ws, b_begin, b_count,
+                      want_obj ? c->ws.all_obj : nullptr, want_alpha ? c->ws.all_alpha : nullptr,
+                      c->sm_count, c->stream, &c->launches, pairs, force_variant);
+  if (rc == PLS_OK && force_variant == 0) {      // the main range of a fit (not a polish / fallback re-solve)
+    c->stats.k2_variant = c->ws.last_variant; c->stats.k2_threads = c->ws.last_threads;
+    c->stats.k2_ctas_per_sm = c->ws.last_occ; c->stats.k2_grid = c->ws.last_grid;
+  }
+  return rc;
 }
 
 // Precondition: c->h_pin holds the winner record [alpha | obj | b] and, from h_pin + Mp + 4, the K2 counters of the
@@ -700,7 +706,7 @@ int pls_bnb_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_signed, doubl
     rc = k1_gram_finalize(pb, st, &c->launches); if (rc) return rc;
   }
   PLS_CUDA_TRY(cudaEventRecord(c->ev[1], st));
-  if (c->ws.Mp != pb.Mp && c->ws.win) { cudaFree(c->ws.win); c->ws.win = nullptr; }
+  PLS_CUDA_TRY(ensure_win(c->ws, pb.Mp + 2));
   BnbReport rep;
   rc = k5_bnb_run(pb, c->ws, c->sm_count, st, &c->launches, &rep); if (rc) return rc;
   PLS_CUDA_TRY(cudaEventRecord(c->ev[2], st));

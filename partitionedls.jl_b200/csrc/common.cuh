@@ -69,7 +69,22 @@ struct SolveWs {
   size_t yhat_n = 0;
   double *resid_part = nullptr;   // K4 block partials
   int resid_blocks = 0;
+  int win_len = 0;                // doubles allocated at win
+  // what the last k2_solve_range launched (reported through pls_stats.k2_*)
+  int last_variant = 0, last_threads = 0, last_occ = 0, last_grid = 0;
 };
+
+// (Re)allocates the winner record ws.win so that it holds at least `len` doubles.  The record is shared by Opt
+// (M'+2), BnB (M'+2) and -- through ws.Mp, which every solver resets -- follows the widest problem this context
+// has seen; sizing it by its own length (not by ws.Mp) keeps a context that is reused with a larger M safe.
+static inline cudaError_t ensure_win(SolveWs &ws, int len) {
+  if (ws.win && ws.win_len >= len) return cudaSuccess;
+  if (ws.win) cudaFree(ws.win);
+  ws.win = nullptr; ws.win_len = 0;
+  const cudaError_t e = cudaMalloc(&ws.win, sizeof(double) * (size_t)len);
+  if (e == cudaSuccess) ws.win_len = len;
+  return e;
+}
 
 // Arguments of the K2 kernels (both variants).
 struct K2Args {

@@ -111,6 +111,8 @@ void sum_stats(pls_ctx *c, pls_stats &s) {
     s.bpp_iters += t.bpp_iters; s.rebuilds += t.rebuilds; s.blocked += t.blocked;
     s.nnls_flops += t.nnls_flops; s.nnls_l2_bytes += t.nnls_l2_bytes;
     s.waves = std::max(s.waves, t.waves);
+    s.k2_grid += t.k2_grid; s.k2_max_drift = std::fmax(s.k2_max_drift, t.k2_max_drift);
+    if (t.k2_variant) { s.k2_variant = t.k2_variant; s.k2_threads = t.k2_threads; s.k2_ctas_per_sm = t.k2_ctas_per_sm; }
   }
 }
 
@@ -289,7 +291,7 @@ int multi_bnb_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_signed, dou
   auto run_one = [&](int g, pls_ctx *s, BnbShard *sh, bool *complete) -> int {
     int r = check_ctx(s);
     if (r) return r;
-    if (s->ws.Mp != s->pb.Mp && s->ws.win) { cudaFree(s->ws.win); s->ws.win = nullptr; }
+    PLS_CUDA_TRY(ensure_win(s->ws, s->pb.Mp + 2));
     BnbReport rep;
     r = k5_bnb_run(s->pb, s->ws, s->sm_count, s->stream, &s->launches, &rep, sh);
     if (r) return r;

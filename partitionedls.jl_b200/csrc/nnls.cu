@@ -570,8 +570,10 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
     PLS_CUDA_TRY(cudaMalloc(&ws.counters, sizeof(unsigned long long) * (CNT_NUM + 1 + 24)));
     PLS_CUDA_TRY(cudaMemsetAsync(ws.counters, 0, sizeof(unsigned long long) * (CNT_NUM + 1 + 24), st));
   }
-  if (!ws.win) PLS_CUDA_TRY(cudaMalloc(&ws.win, sizeof(double) * (Mp + 2)));
+  PLS_CUDA_TRY(ensure_win(ws, Mp + 2));
   PLS_CUDA_TRY(cudaMemsetAsync(ws.counters + CNT_NUM, 0, sizeof(unsigned long long), st));
+  ws.last_variant = variant; ws.last_occ = occ; ws.last_grid = (int)grid;
+  ws.last_threads = variant == 4 ? plan4.T : (variant == 3 ? plan3.T : T2);
 
   K2Args A;
   A.G = G; A.ldg = ldg; A.c = c; A.scal = scal; A.gmask = gmask; A.Mp = Mp; A.Kp = Kp;

@@ -40,3 +40,33 @@ def make_config(name):
     N, M, K, eta, seed, mixed = CONFIGS[name]
     X, y, P = make_synthetic(N, M, K, seed, mixed_sign=mixed)
     return X, y, P, eta
+
+
+def make_synthetic_parallel(N, M, K, seed, nthreads=None):
+    """Same model as make_synthetic for the multi-GB shapes (configs[2]: 4.1 GB): the columns of X are drawn in
+    blocks by worker threads from independent child streams of `seed` (numpy's generators release the GIL), so
+    the values differ from make_synthetic's single stream but are fixed for a given (seed, M) -- block
+    boundaries do not depend on the thread count."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    nthreads = nthreads or min(16, os.cpu_count() or 1)
+    X = np.empty((N, M), order="F")
+    blk = 16
+    starts = list(range(0, M, blk))
+    children = np.random.SeedSequence(seed).spawn(len(starts) + 1)
+
+    def fill(i):
+        g = np.random.default_rng(children[i])
+        for m in range(starts[i], min(M, starts[i] + blk)):
+            g.standard_normal(N, out=X[:, m])
+
+    with ThreadPoolExecutor(nthreads) as ex:
+        list(ex.map(fill, range(len(starts))))
+    rng = np.random.default_rng(children[-1])
+    g = (np.arange(M) * K) // M
+    s = rng.choice([-1.0, 1.0], size=K)
+    w = np.abs(rng.standard_normal(M)) * s[g]
+    y = X @ w + 0.5 + rng.standard_normal(N)
+    P = np.zeros((M, K), dtype=np.int64)
+    P[np.arange(M), g] = 1
+    return X, y, np.asfortranarray(P)

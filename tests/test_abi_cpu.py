@@ -113,4 +113,4 @@ def test_no_cpu_fallback_for_any_algorithm(pkg, oracle):
     b0 = pkg.draw_alt_starts(3, 4, 3, restarts=2)
     g = np.random.default_rng(3); g.random(4); first = (g.random(3) - 0.5) * 10
     assert b0.shape == (3, 2) and np.array_equal(b0[:, 0], first) and np.all(np.abs(b0) <= 5)
-    assert ctypes.sizeof(pkg._abi.PlsStats) == 8 * 22
+    assert ctypes.sizeof(pkg._abi.PlsStats) == 8 * 27
