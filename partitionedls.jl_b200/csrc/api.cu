@@ -141,7 +141,8 @@ int solve_range_dev(pls_ctx *c, int64_t b_begin, int64_t b_count, bool want_obj,
     PLS_CUDA_TRY(cudaMemsetAsync(c->ws.counters, 0, sizeof(unsigned long long) * (CNT_NUM + 1 + 24), c->stream));
   rc = k2_solve_range(pb, pb.G, pb.ldg, pb.c, pb.scal, pb.gmask, pb.Mp, pb.Kp, c->ws, b_begin, b_count,
                       want_obj ? c->ws.all_obj : nullptr, want_alpha ? c->ws.all_alpha : nullptr,
-                      c->sm_count, c->stream, &c->launches, pairs, force_variant);
+                      c->sm_count, c->stream, &c->launches, pairs, force_variant,
+                      c->h_gmask.size() == (size_t)pb.Mp ? c->h_gmask.data() : nullptr);
   if (rc == PLS_OK && force_variant == 0) {      // the main range of a fit (not a polish / fallback re-solve)
     c->stats.k2_variant = c->ws.last_variant; c->stats.k2_threads = c->ws.last_threads;
     c->stats.k2_ctas_per_sm = c->ws.last_occ; c->stats.k2_grid = c->ws.last_grid;

@@ -122,11 +122,9 @@ int k1_gram_finalize(Problem &pb, cudaStream_t st, int *launches);
 int k2_solve_range(const Problem &pb, const double *G, int ldg, const double *c, const double *scal,
                    const uint64_t *gmask, int Mp, int Kp, SolveWs &ws, int64_t b_begin,
                    int64_t b_count, double *d_all_obj, double *d_all_alpha, int sm_count,
-                   cudaStream_t st, int *launches, bool free_top = false, int force_variant = 0);
-// K2 variants: v2 = block pivoting with DMMA rank-8 updates on a tile-packed symmetric inverse
-// (M' <= 208); v1 = rank-1 updates on a dense inverse with a global-memory spill path (any M').
-int k2v2_launch(const K2Args &A, int grid, cudaStream_t st);
-int k2v2_config(int Mp, int *cap, size_t *smem, int *occ);
+                   cudaStream_t st, int *launches, bool free_top = false, int force_variant = 0,
+                   const uint64_t *h_gmask = nullptr);
+// K2 variants: v1 = rank-1 updates on a dense inverse with a global-memory spill path (any M').
 // v3 = v2's algorithm with the inverse split between shared memory and an L2-resident global slice,
 // any thread count, M' <= 1024 (nnls3.cu)
 struct K3Plan { int cap, qs, T, mode, occ, variant; size_t smem, hstride; };
@@ -138,6 +136,10 @@ int k2v4_plan(int Mp, int Kp, K4Plan *pl, long long per_sm = 0);   // per_sm: pr
 int k2v4_launch(const K2Args &A, const K4Plan &pl, int grid, cudaStream_t st);
 int k2v4_plan_prof(int Mp, int Kp, K4Plan *pl, long long per_sm = 0);      // nnls4p.cu: same kernels with phase counters
 int k2v4_launch_prof(const K2Args &A, const K4Plan &pl, int grid, cudaStream_t st);
+// v5 = two swept tableaus per Gray walk, one warp per walk (nnls5.cu)
+struct K5Plan { int variant, T, NR, ld1, occ, low_groups, verify_every; size_t smem, tabstride; };
+int k2v5_plan(int Mp, int n_bits, const uint64_t *h_gmask, K5Plan *pl);
+int k2v5_launch(const K2Args &A, const K5Plan &pl, int grid, cudaStream_t st);
 // K5: branch and bound with batched frontier expansion (bnb.cu); winner left in ws.win
 struct BnbReport { long long visited, waves, max_open, pool_slots; double mu; bool complete, has_leaf; };
 // Multi-GPU sharding of the search (multi.cu).  roots: the subtrees this call searches, each given by the

@@ -458,7 +458,7 @@ size_t k2_smem_bytes(int Mp, int cap) {
 int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, const double *scal,
                    const uint64_t *gmask, int Mp, int Kp, SolveWs &ws, int64_t b_begin,
                    int64_t b_count, double *d_all_obj, double *d_all_alpha, int sm_count,
-                   cudaStream_t st, int *launches, bool free_top, int force_variant) {
+                   cudaStream_t st, int *launches, bool free_top, int force_variant, const uint64_t *h_gmask) {
   if (b_count <= 0) { set_error("k2: empty orthant range"); return PLS_EINVAL; }
   if (free_top && (Mp > 1024 || d_all_obj || d_all_alpha)) { set_error("k2: paired orthants need M' <= 1024 and no per-orthant outputs"); return PLS_EUNSUPPORTED; }
   // variant (PLS_K2_IMPL = v1 | v2 | v3 overrides):
@@ -468,7 +468,6 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   const char *impl = getenv("PLS_K2_IMPL");
   int variant = Mp <= 1024 ? 3 : 1;
   if (impl && strcmp(impl, "v1") == 0 && !free_top) variant = 1;
-  if (impl && strcmp(impl, "v2") == 0 && Mp <= 208 && !free_top) variant = 2;
   if (impl && strcmp(impl, "v3") == 0 && Mp <= 1024) variant = 3;
   // v4 (two-level, default): needs an aligned power-of-two range long enough to amortise one cold start per
   // CTA -- measured crossover against v3: ~20 orthants per CTA at M' = 201, ~80 at M' = 513
@@ -476,13 +475,25 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   const bool force4 = impl && strcmp(impl, "v4") == 0;
   // per-orthant outputs (returnAllSolutions) stay on the one-level kernel: every orthant is then checked against
   // the original G (accuracy on ill-conditioned data matters more than speed on that path)
-  if (variant == 3 && Mp + 1 <= 1024 && pow2 && (force4 || (!impl && !d_all_obj && !d_all_alpha))) variant = 4;
+  if (variant == 3 && Mp + 1 <= 1024 && pow2 && (force4 || (impl && strcmp(impl, "v5") == 0) || (!impl && !d_all_obj && !d_all_alpha))) variant = 4;
+  // v5 (two swept tableaus, one warp per walk): preferred over v4 wherever its window fits (M' + 1 <= 584 and at
+  // least one fast group) and the walks are long enough to amortise a cold start
+  const bool force5 = impl && strcmp(impl, "v5") == 0;
+  const bool no5 = getenv("PLS_K2_NO_V5") != nullptr;
   if (force_variant == 3 && Mp <= 1024) variant = 3;
   if (force_variant == 1 && !free_top) variant = 1;
   int cap = Mp, occ = 1;
   size_t smem = 0;
   K3Plan plan3;
   K4Plan plan4;
+  K5Plan plan5;
+  if (variant == 4 && !force4 && !no5 && h_gmask) {
+    int n_bits = 0;
+    while ((b_count >> (n_bits + 1)) > 0) ++n_bits;
+    const int rc = k2v5_plan(Mp, n_bits, h_gmask, &plan5);
+    if (rc == PLS_OK && (force5 || b_count >= (long long)sm_count * plan5.occ * 16)) { variant = 5; cap = plan5.ld1; occ = plan5.occ; smem = plan5.smem; }
+    else if (rc != PLS_OK && rc != PLS_EUNSUPPORTED) return rc;
+  }
   if (variant == 4) {
     const long long per_sm = b_count / (sm_count > 0 ? sm_count : 1);
     const int rc = getenv("PLS_K2_PHASES") ? k2v4_plan_prof(Mp, Kp, &plan4, per_sm) : k2v4_plan(Mp, Kp, &plan4, per_sm);
@@ -490,7 +501,6 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
     else if (!force4 && b_count < (long long)sm_count * plan4.occ * (Mp <= 256 ? 24 : 96)) variant = 3;   // too short a walk per CTA
     else { cap = plan4.cap; occ = plan4.occ; smem = plan4.smem; }
   }
-  if (variant == 2 && k2v2_config(Mp, &cap, &smem, &occ) != PLS_OK) variant = 3;
   if (variant == 3) {
     int rc = k2v3_plan(Mp, &plan3, force_variant == 3);
     if (rc == PLS_EUNSUPPORTED && free_top) rc = k2v3_plan(Mp, &plan3, true);   // a tuning override asked for a variant that does not exist
@@ -530,9 +540,9 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   if (chain_log2 > align_log2) chain_log2 = align_log2;
   if (chain_log2 > Kp) chain_log2 = Kp;
   long long n_chains = b_count >> chain_log2;
-  if (variant == 4) {                                            // static partition of the Gray sequence
+  if (variant == 4 || variant == 5) {                            // static partition of the Gray sequence
     n_chains = b_count; chain_log2 = 0;
-    if (const char *eg = getenv("PLS_K4_GRID")) { const long long g = atoll(eg); if (g >= 1 && g < grid) grid = g; }   // tests: long walks on small problems
+    if (const char *eg = getenv(variant == 4 ? "PLS_K4_GRID" : "PLS_K5_GRID")) { const long long g = atoll(eg); if (g >= 1 && g < grid) grid = g; }   // tests: long walks on small problems
   }
   if (grid > n_chains) grid = n_chains;
 
@@ -550,9 +560,9 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   size_t hneed = 0;
   if (variant == 1 && cap < Mp) hneed = (size_t)max_grid * Mp * Mp * sizeof(double);
   if (variant == 3) hneed = (size_t)max_grid * plan3.hstride * sizeof(double);
-  if (variant == 4) {
-    hneed = (size_t)max_grid * plan4.hstride * sizeof(double);
-    const size_t tneed = (size_t)max_grid * plan4.tabstride * sizeof(double);
+  if (variant == 4 || variant == 5) {
+    if (variant == 4) hneed = (size_t)max_grid * plan4.hstride * sizeof(double);
+    const size_t tneed = (size_t)max_grid * (variant == 4 ? plan4.tabstride : plan5.tabstride) * sizeof(double);
     if (tneed > ws.tab_bytes) {
       if (ws.tab) cudaFree(ws.tab);
       ws.tab = nullptr; ws.tab_bytes = 0;
@@ -573,7 +583,7 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   PLS_CUDA_TRY(ensure_win(ws, Mp + 2));
   PLS_CUDA_TRY(cudaMemsetAsync(ws.counters + CNT_NUM, 0, sizeof(unsigned long long), st));
   ws.last_variant = variant; ws.last_occ = occ; ws.last_grid = (int)grid;
-  ws.last_threads = variant == 4 ? plan4.T : (variant == 3 ? plan3.T : T2);
+  ws.last_threads = variant == 5 ? plan5.T : (variant == 4 ? plan4.T : (variant == 3 ? plan3.T : T2));
 
   K2Args A;
   A.G = G; A.ldg = ldg; A.c = c; A.scal = scal; A.gmask = gmask; A.Mp = Mp; A.Kp = Kp;
@@ -585,8 +595,10 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   A.free_top = free_top ? 1 : 0;
   A.cta_obj = ws.cta_obj; A.cta_b = ws.cta_b; A.cta_w = ws.cta_w;
   A.all_obj = d_all_obj; A.all_alpha = d_all_alpha; A.counters = ws.counters;
-  if (variant == 2) {
-    const int rc = k2v2_launch(A, (int)grid, st);
+  if (variant == 5) {
+    A.tab = ws.tab; A.tabstride = plan5.tabstride;
+    A.lowmask = (1ull << plan5.low_groups) - 1ull; A.verify_every = plan5.verify_every;
+    const int rc = k2v5_launch(A, plan5, (int)grid, st);
     if (rc) return rc;
   } else if (variant == 4) {
     A.qs = plan4.qs; A.hglob = ws.hspill; A.hstride = plan4.hstride;

@@ -1,0 +1,863 @@
+// K2, v5: two swept tableaus per Gray walk, one SMALL CTA (64 / 128 threads) per walk, 8 walks per SM
+// (default for winner-only Opt fits, M' <= 575).
+//
+// Same subproblems, same KKT points and the same reference lines as the other K2 kernels
+// (src/PartitionedLSOpt.jl:85-96: one non-negative least-squares problem per sign pattern b, the residual
+// norm of each, first minimum).  What changes against nnls4.cu is where the per-orthant work lives:
+//
+//   T1 = sweep([G c; c' yy], O)      this walk's private (M'+1)^2 tableau in global memory (L2 where it is hot),
+//                                    changed only by FOLDS (rank-8 DMMA passes, ~2 per 2^l orthants);
+//   T2 = sweep(T1[Rb, Rb], S)        a SMALL packed-symmetric tableau in shared memory over a window R of
+//                                    variables (the variables of the l fastest Gray groups plus whatever
+//                                    joined), S = the window variables toggled since T1 was last folded.
+//
+// The passive set is P = O xor S.  For a window variable the first column of its T2 row IS its weight (passive)
+// or its gradient (active): block principal pivoting reads it and TOGGLES violators by sweeping T2 -- a
+// warp-wide rank-1 update of ~60 x 60 / 2 doubles in shared memory, no barrier, no gradient evaluation, no 8 x 8
+// inverse.  Everything outside the window is checked once per converged orthant by ONE streaming pass
+//       v = T1[rhs, :] - sum_{s in S} y_s T1[s, :],     y_s = e_s T2[s, rhs],  e_s = +1 (entered) / -1 (left)
+// which yields the implied weight of every committed variable, the gradient of every active one, the
+// objective (v[rhs] = y'y - c_P' w_P) and -- on the rows of S themselves -- the residual of the S-system, an
+// independent accuracy check of T2.  A variable outside the window that violates its condition JOINS the window
+// (one |S| x |R| product; T1 is not touched) and is toggled like any other.  After a slow Gray group has moved,
+// or when the window fills up, the toggled SLOW variables are folded into T1 (mixed forward / reverse block
+// sweep: T1 -= P inv(D) P', one DMMA pass per <= 8 variables) and the untoggled slow ones leave the window.
+//
+// A small CTA owns a walk; 8 CTAs per SM share the 227 KB of shared memory (T2 is 21 KB) and all of them execute the
+// same few KB of code.  A T2 sweep is 3 barriers apart and ~70 instructions per thread; there is no 8 x 8 inverse,
+// no gradient evaluation and no global-memory access inside the pivoting loop.
+//
+// Drift control as in nnls4.cu: every `verify_every` orthants (and at the end of the walk) the KKT conditions are
+// evaluated against the ORIGINAL G and c; above 1e-12 max|c| the walk restarts cold at that orthant.  T2 is
+// rebuilt from T1 at every fold (so its rounding errors live for at most ~2^l orthants) and whenever the
+// residual of the S-system exceeds 1e-12 max|c|.
+#include "common.cuh"
+
+namespace pls {
+namespace {
+
+constexpr int SG_FREE5 = 2;
+constexpr unsigned char ST_INO = 1;   // variable is swept in T1 (committed)
+constexpr unsigned char ST_PAS = 2;   // variable is passive now
+constexpr unsigned char ST_BLK = 4;   // refused by the pivot test at this orthant
+#define SYNC5() __syncthreads()
+
+__device__ __forceinline__ void dmma5(double &d0, double &d1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double wsum5(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double wmax5(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int wmaxi5(int v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ bool lex_better5(double oa, long long ba, double ob, long long bb) {
+  if (bb < 0) return ba >= 0;
+  if (ba < 0) return false;
+  const bool na = oa != oa, nb = ob != ob;
+  if (na != nb) return na;
+  if (na) return ba < bb;
+  return oa < ob || (oa == ob && ba < bb);
+}
+// packed lower triangle with rows padded to an even length: row i holds columns 0..i at off5(i);
+// rows 2p and 2p + 1 both take 2p + 2 doubles
+__device__ __forceinline__ int off5(int i) {
+  const int h = (i + 1) >> 1;
+  return (i & 1) ? 2 * h * h : 2 * h * (h + 1);
+}
+__host__ __device__ constexpr int t2_doubles(int nr) { return 2 * (nr / 2) * (nr / 2 + 1); }
+
+struct Sh5 {
+  double *T2;      // [t2_doubles(NR)]  (aliased by the fold's W panel: ld1 x 8)
+  double *v;       // [ld1]   streaming result
+  double *tv, *uv; // [NR]    pivot column, pivot column / pivot
+  double *yv;      // [NR]    y_s of the S list (stream), coefficients (join)
+  double *D;       // [64]    fold: D, then inv(D)
+  double *red;     // [32]    block reductions
+  int *ctl;        // [16]    broadcast slots
+  short *slot;     // [ld1]   window slot of variable m, -1 outside
+  short *rvar;     // [NR]    variable of window slot k (slot 0 = the right-hand side, variable index Mp)
+  short *lst;      // [ld1]   list scratch (S list / join list / fold list)
+  short *lstE;     // [NR]    entering list
+  signed char *sg; // [ld1]
+  unsigned char *st; // [ld1]
+};
+enum { C_NL = 0, C_NE, C_MX, C_NS, C_OK, C_CNT, C_N, C_NJ, C_NSLOW, C_NP };
+
+__host__ __device__ inline size_t sh5_bytes(int NR, int ld1) {
+  return sizeof(double) * ((size_t)t2_doubles(NR) + ld1 + 3 * (size_t)NR + 64 + 32) + sizeof(int) * 16 +
+         sizeof(short) * (2 * (size_t)ld1 + 2 * (size_t)NR) + 2 * (size_t)ld1 + 16;
+}
+
+__device__ __forceinline__ Sh5 make_sh5(int NR, int ld1) {
+  extern __shared__ __align__(16) unsigned char smem_raw5[];
+  Sh5 s;
+  double *dp = reinterpret_cast<double *>(smem_raw5);
+  s.T2 = dp; dp += t2_doubles(NR);
+  s.v = dp; dp += ld1;
+  s.tv = dp; dp += NR;
+  s.uv = dp; dp += NR;
+  s.yv = dp; dp += NR;
+  s.D = dp; dp += 64;
+  s.red = dp; dp += 32;
+  int *ip = reinterpret_cast<int *>(dp);
+  s.ctl = ip; ip += 16;
+  short *sp = reinterpret_cast<short *>(ip);
+  s.slot = sp; sp += ld1;
+  s.rvar = sp; sp += NR;
+  s.lst = sp; sp += ld1;
+  s.lstE = sp; sp += NR;
+  signed char *cp = reinterpret_cast<signed char *>(sp);
+  s.sg = cp; cp += ld1;
+  s.st = reinterpret_cast<unsigned char *>(cp);
+  return s;
+}
+
+// walk state (CTA-uniform registers)
+struct W5 {
+  double *T1; int ld1;      // this walk's tableau, row stride
+  double *Pg;               // [8][ld1] global scratch: the fold's P rows / the verify pass's weights
+  int Mp;
+  int n;                    // window size incl. slot 0 (rhs)
+  unsigned long long lowmask;
+  const unsigned long long *gmask;
+  const double *G; int ldg;
+  // counters (thread 0's copy is reported)
+  unsigned long long n_sweep, n_stream, sum_s, sum_p2, n_iter, n_blk, n_rebuild, n_fold;
+};
+
+template <int T>
+__device__ __forceinline__ double bmax5(const Sh5 &s, double v) {
+  constexpr int NW = T / 32;
+  v = wmax5(v);
+  if ((threadIdx.x & 31) == 0) s.red[threadIdx.x >> 5] = v;
+  SYNC5();
+  double r = s.red[0];
+#pragma unroll
+  for (int i = 1; i < NW; ++i) r = fmax(r, s.red[i]);
+  SYNC5();
+  return r;
+}
+
+// ---- T2: symmetric sweep on window slot k (fwd: the variable enters, else it leaves) ------------------------
+// T2[i,j] -= t_i t_j / d everywhere, then row / column k = +-t / d and T2[k,k] = -1/d.  Row pairs (2p, 2p+1) have the
+// same stored length 2p + 2: a warp takes a row pair, a lane a column pair (the pad element (2p, 2p+1) is updated
+// along -- it is never read).
+template <int T>
+__device__ __noinline__ void t2_sweep(const Sh5 s, int n, int k, bool fwd) {
+  constexpr int NW = T / 32;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int offk = off5(k);
+  const double dinv = 1.0 / s.T2[offk + k];
+  for (int i = tid; i < n; i += T) { const double t = i <= k ? s.T2[offk + i] : s.T2[off5(i) + k]; s.tv[i] = t; s.uv[i] = t * dinv; }
+  if (tid == 0 && (n & 1)) { s.tv[n] = 0.0; s.uv[n] = 0.0; }
+  SYNC5();
+  const int np = (n + 1) >> 1;
+  for (int p = wid; p < np; p += NW) {
+    const int o0 = 2 * p * (p + 1), o1 = o0 + 2 * p + 2;
+    const bool has1 = 2 * p + 1 < n;
+    const double2 u = *reinterpret_cast<const double2 *>(s.uv + 2 * p);
+    for (int c = lane; c <= p; c += 32) {
+      const double2 t = *reinterpret_cast<const double2 *>(s.tv + 2 * c);
+      double2 *p0 = reinterpret_cast<double2 *>(s.T2 + o0 + 2 * c);
+      double2 x0 = *p0;
+      x0.x = fma(-u.x, t.x, x0.x); x0.y = fma(-u.x, t.y, x0.y);
+      *p0 = x0;
+      if (has1) {
+        double2 *p1 = reinterpret_cast<double2 *>(s.T2 + o1 + 2 * c);
+        double2 x1 = *p1;
+        x1.x = fma(-u.y, t.x, x1.x); x1.y = fma(-u.y, t.y, x1.y);
+        *p1 = x1;
+      }
+    }
+  }
+  SYNC5();
+  const double sgn = fwd ? 1.0 : -1.0;
+  for (int i = tid; i < n; i += T) {
+    const double val = i == k ? -dinv : sgn * s.uv[i];
+    if (i <= k) s.T2[offk + i] = val; else s.T2[off5(i) + k] = val;
+  }
+  SYNC5();
+}
+
+// T2 <- T1[Rb, Rb], then sweep the toggled window variables into their current state
+template <int T>
+__device__ __noinline__ void t2_rebuild(const Sh5 s, W5 &w) {
+  constexpr int NW = T / 32;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n = w.n;
+  for (int i = wid; i < n; i += NW) {
+    const double *row = w.T1 + (size_t)w.ld1 * s.rvar[i];
+    const int o = off5(i);
+    for (int j = lane; j <= i; j += 32) s.T2[o + j] = __ldcg(row + s.rvar[j]);
+    if (lane == 0 && !(i & 1)) s.T2[o + i + 1] = 0.0;          // pad element
+  }
+  SYNC5();
+  for (int k = 1; k < n; ++k) {
+    const unsigned char f = s.st[s.rvar[k]];
+    const bool pas = f & ST_PAS, ino = f & ST_INO;
+    if (pas != ino) { t2_sweep<T>(s, n, k, pas); w.n_sweep++; w.sum_p2 += (unsigned long long)(n * n) >> 2; }
+  }
+}
+
+// window <- {rhs} + the variables of the fast groups + every toggled variable (index order)
+__device__ __noinline__ void window_reset(const Sh5 s, W5 &w) {
+  const int tid = threadIdx.x;
+  const int Mp = w.Mp;
+  if (tid < 32) {
+    const int lane = tid;
+    if (lane == 0) s.rvar[0] = (short)Mp;
+    int base = 1;
+    for (int m0 = 0; m0 < Mp; m0 += 32) {
+      const int m = m0 + lane;
+      bool keep = false;
+      if (m < Mp) {
+        const unsigned char f = s.st[m];
+        keep = (w.gmask[m] & w.lowmask) != 0ull || (((f & ST_PAS) != 0) != ((f & ST_INO) != 0));
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      if (m < Mp) {
+        if (keep) { const int k = base + __popc(bal & ((1u << lane) - 1)); s.rvar[k] = (short)m; s.slot[m] = (short)k; }
+        else s.slot[m] = -1;
+      }
+      base += __popc(bal);
+    }
+    if (lane == 0) s.ctl[C_N] = base;
+  }
+  SYNC5();
+  w.n = s.ctl[C_N];
+}
+
+// ---- streaming pass ------------------------------------------------------------------------------------------
+// v = T1[rhs, :] - sum_{s toggled} e_s T2[s, rhs] T1[s, :].  Returns max |v[s]| over the toggled variables (the
+// residual of the S-system).  NQ = double2 pieces of a row per thread.
+template <int T, int NQ>
+__device__ __noinline__ double stream5(const Sh5 s, W5 &w) {
+  const int tid = threadIdx.x;
+  const int n = w.n, ld2 = w.ld1 >> 1;
+  constexpr int UB = 8;
+  if (tid < 32) {                                      // S list: variable -> lst, y -> yv
+    const int lane = tid;
+    int ns = 0;
+    for (int k0 = 1; k0 < n; k0 += 32) {
+      const int k = k0 + lane;
+      bool tg = false, pas = false; int m = 0;
+      if (k < n) { m = s.rvar[k]; const unsigned char f = s.st[m]; pas = f & ST_PAS; tg = pas != ((f & ST_INO) != 0); }
+      const unsigned bal = __ballot_sync(0xffffffffu, tg);
+      if (tg) { const int p = ns + __popc(bal & ((1u << lane) - 1)); s.lst[p] = (short)m; s.yv[p] = pas ? s.T2[off5(k)] : -s.T2[off5(k)]; }
+      ns += __popc(bal);
+    }
+    const int nsp = (ns + UB - 1) / UB * UB;
+    for (int p = ns + lane; p < nsp; p += 32) { s.lst[p] = (short)w.Mp; s.yv[p] = 0.0; }   // padding: the rhs row with weight 0
+    if (lane == 0) s.ctl[C_NS] = ns;
+  }
+  SYNC5();
+  const int ns = s.ctl[C_NS];
+  const int nsp = (ns + UB - 1) / UB * UB;
+  double2 acc[NQ];
+  const double2 *T1v = reinterpret_cast<const double2 *>(w.T1);
+  {
+    const double2 *r = T1v + (size_t)ld2 * w.Mp;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) acc[q] = (tid + T * q < ld2) ? __ldcg(r + tid + T * q) : make_double2(0.0, 0.0);
+  }
+  for (int p = 0; p < nsp; p += UB) {
+    double2 g[UB][NQ];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const double2 *r = T1v + (size_t)ld2 * s.lst[p + u];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) g[u][q] = (tid + T * q < ld2) ? __ldcg(r + tid + T * q) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const double y = s.yv[p + u];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) { acc[q].x = fma(-y, g[u][q].x, acc[q].x); acc[q].y = fma(-y, g[u][q].y, acc[q].y); }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+    if (tid + T * q < ld2) reinterpret_cast<double2 *>(s.v)[tid + T * q] = acc[q];
+  SYNC5();
+  double res = 0.0;
+  for (int p = tid; p < ns; p += T) res = fmax(res, fabs(s.v[s.lst[p]]));
+  res = bmax5<T>(s, res);
+  w.n_stream++; w.sum_s += ns;
+  return res;
+}
+
+// ---- a variable outside the window joins it (not toggled): new last row of T2 ------------------------------------
+//   row[j] = [slot j not toggled] T1[m, var_j] - sum_{s toggled} e_s T1[m, s] T2[s, j],   diag = T1[m, m] - sum_s e_s T1[m, s] row[s]
+template <int T>
+__device__ __noinline__ void join5(const Sh5 s, W5 &w, int m) {
+  const int tid = threadIdx.x;
+  const int n = w.n;
+  const double *row1 = w.T1 + (size_t)w.ld1 * m;
+  if (tid < 32) {                                      // toggled slots -> lstE, coefficients e_s T1[m, s] -> yv
+    const int lane = tid;
+    int ns = 0;
+    for (int k0 = 1; k0 < n; k0 += 32) {
+      const int k = k0 + lane;
+      bool tg = false, pas = false; int var = 0;
+      if (k < n) { var = s.rvar[k]; const unsigned char f = s.st[var]; pas = f & ST_PAS; tg = pas != ((f & ST_INO) != 0); }
+      const unsigned bal = __ballot_sync(0xffffffffu, tg);
+      if (tg) { const int p = ns + __popc(bal & ((1u << lane) - 1)); s.lstE[p] = (short)k; const double a = __ldcg(row1 + var); s.yv[p] = pas ? a : -a; }
+      if (k < n) s.uv[k] = tg ? 1.0 : 0.0;
+      ns += __popc(bal);
+    }
+    if (lane == 0) { s.uv[0] = 0.0; s.ctl[C_NS] = ns; }
+  }
+  SYNC5();
+  const int ns = s.ctl[C_NS];
+  for (int j = tid; j < n; j += T) {
+    double a = s.uv[j] != 0.0 ? 0.0 : __ldcg(row1 + s.rvar[j]);
+    const int oj = off5(j);
+    for (int p = 0; p < ns; ++p) {
+      const int k = s.lstE[p];
+      const double t = j <= k ? s.T2[off5(k) + j] : s.T2[oj + k];
+      a = fma(-s.yv[p], t, a);
+    }
+    s.tv[j] = a;
+  }
+  SYNC5();
+  const int on = off5(n);
+  for (int j = tid; j < n; j += T) s.T2[on + j] = s.tv[j];
+  if (tid < 32) {
+    double dg = 0.0;
+    for (int p = tid; p < ns; p += 32) dg = fma(s.yv[p], s.tv[s.lstE[p]], dg);
+    dg = wsum5(dg);
+    if (tid == 0) {
+      s.T2[on + n] = __ldcg(row1 + m) - dg; s.rvar[n] = (short)m; s.slot[m] = (short)n;
+      if (!(n & 1)) s.T2[on + n + 1] = 0.0;            // pad element
+    }
+  }
+  w.n = n + 1;
+  w.sum_p2 += (unsigned long long)(ns * n) >> 1;
+  SYNC5();
+}
+
+// ---- fold: the toggled slow window variables B (<= 8, swept-back ones first) are swept in T1 ----------------------
+// T1 -= P inv(D) P' off the B rows/columns (DMMA, lower tiles + mirrored store), T1[:, B_q] = e_q (P inv(D))[:, q],
+// T1[B, B] = -E inv(D) E.  Returns false (T1 untouched) if a pivot of D has the wrong sign / is too small.
+template <int T>
+__device__ __noinline__ bool fold_block5(const Sh5 s, W5 &w, const short *B, int nb) {
+  constexpr int NW = T / 32;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int ld1 = w.ld1;
+  double *Wp = s.T2;                                   // [ld1][8] panel W = P inv(D)  (T2 is rebuilt after the fold)
+  for (int q = 0; q < 8; ++q) {                        // P rows -> global scratch
+    const double *src = w.T1 + (size_t)ld1 * (q < nb ? B[q] : 0);
+    for (int j = tid; j < ld1; j += T) w.Pg[q * ld1 + j] = q < nb ? __ldcg(src + j) : 0.0;
+  }
+  for (int e = tid; e < 64; e += T) {                  // D -> shared
+    const int i = e >> 3, j = e & 7;
+    s.D[e] = (i < nb && j < nb) ? __ldcg(w.T1 + (size_t)ld1 * B[i] + B[j]) : (i == j ? 1.0 : 0.0);
+  }
+  SYNC5();
+  if (tid < 32) {
+    // Gauss-Jordan in the given order (swept-back variables first: pivots < 0; then entering ones: pivots > 0)
+    bool ok = true;
+    const int i = lane >> 2, j0 = (lane & 3) << 1;
+    double e0 = s.D[i * 8 + j0], e1 = s.D[i * 8 + j0 + 1];
+    for (int k = 0; k < nb; ++k) {
+      __syncwarp();
+      s.D[i * 8 + j0] = e0; s.D[i * 8 + j0 + 1] = e1;
+      __syncwarp();
+      const double pk0 = s.D[k * 8 + j0], pk1 = s.D[k * 8 + j0 + 1], cik = s.D[i * 8 + k], pkk = s.D[k * 8 + k];
+      const unsigned char f = s.st[B[k]];
+      if (f & ST_PAS) ok = ok && pkk > 1e-13 * __ldg(w.G + (size_t)w.ldg * B[k] + B[k]);     // enters O
+      else ok = ok && pkk < 0.0;                                                           // leaves O
+      const double d = 1.0 / pkk, fct = cik * d;
+      const bool rowk = i == k;
+      double n0 = rowk ? pk0 * d : fma(-fct, pk0, e0);
+      double n1 = rowk ? pk1 * d : fma(-fct, pk1, e1);
+      if (j0 == k) n0 = rowk ? d : -fct;
+      if (j0 + 1 == k) n1 = rowk ? d : -fct;
+      e0 = n0; e1 = n1;
+    }
+    __syncwarp();
+    s.D[i * 8 + j0] = e0; s.D[i * 8 + j0 + 1] = e1;
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) s.ctl[C_OK] = ok ? 1 : 0;
+  }
+  SYNC5();
+  if (!s.ctl[C_OK]) { SYNC5(); return false; }
+  for (int i = tid; i < ld1; i += T) {                 // W = P inv(D)
+    double p[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) p[r] = w.Pg[r * ld1 + i];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      double a = 0.0;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) a = fma(p[r], s.D[r * 8 + q], a);
+      Wp[i * 8 + q] = a;
+    }
+  }
+  SYNC5();
+  {                                                    // rank-8 update of the lower tiles, mirrored into the upper ones
+    const int fr = lane >> 2, fk = lane & 3;
+    const int nt = ld1 >> 3, ntl = (nt * (nt + 1)) >> 1;
+    constexpr int IFL = 4;
+    int q = (ntl * wid) / NW;
+    const int q1 = (ntl * (wid + 1)) / NW;
+    int ti = 0;
+    while (((ti + 1) * (ti + 2)) >> 1 <= q) ++ti;
+    int tj = q - ((ti * (ti + 1)) >> 1);
+    for (; q < q1; q += IFL) {
+      double2 c[IFL]; double a0[IFL], a1[IFL], b0[IFL], b1[IFL]; int ri[IFL], rj[IFL];
+#pragma unroll
+      for (int u = 0; u < IFL; ++u) {
+        ri[u] = ti; rj[u] = tj;
+        c[u] = __ldcg(reinterpret_cast<const double2 *>(w.T1 + (size_t)(ti * 8 + fr) * ld1 + tj * 8 + 2 * fk));
+        a0[u] = -Wp[(ti * 8 + fr) * 8 + fk]; a1[u] = -Wp[(ti * 8 + fr) * 8 + 4 + fk];
+        b0[u] = w.Pg[fk * ld1 + tj * 8 + fr]; b1[u] = w.Pg[(4 + fk) * ld1 + tj * 8 + fr];
+        if (q + u + 1 < q1) { if (++tj > ti) { ++ti; tj = 0; } }
+      }
+#pragma unroll
+      for (int u = 0; u < IFL; ++u) { dmma5(c[u].x, c[u].y, a0[u], b0[u]); dmma5(c[u].x, c[u].y, a1[u], b1[u]); }
+#pragma unroll
+      for (int u = 0; u < IFL; ++u) {
+        if (q + u < q1) {
+          __stcg(reinterpret_cast<double2 *>(w.T1 + (size_t)(ri[u] * 8 + fr) * ld1 + rj[u] * 8 + 2 * fk), c[u]);
+          if (ri[u] != rj[u]) {
+            double *mp = w.T1 + (size_t)(rj[u] * 8 + 2 * fk) * ld1 + ri[u] * 8 + fr;
+            __stcg(mp, c[u].x); __stcg(mp + ld1, c[u].y);
+          }
+        }
+      }
+    }
+  }
+  SYNC5();
+  for (int q = 0; q < nb; ++q) {                       // rows / columns of B
+    const double eq = (s.st[B[q]] & ST_PAS) ? 1.0 : -1.0;
+    double *rowq = w.T1 + (size_t)ld1 * B[q];
+    for (int i = tid; i < ld1; i += T) {
+      const double val = eq * Wp[i * 8 + q];
+      __stcg(rowq + i, val);
+      __stcg(w.T1 + (size_t)ld1 * i + B[q], val);
+    }
+  }
+  SYNC5();
+  for (int e = tid; e < 64; e += T) {
+    const int i = e >> 3, j = e & 7;
+    if (i < nb && j < nb) {
+      const double ei = (s.st[B[i]] & ST_PAS) ? 1.0 : -1.0, ej = (s.st[B[j]] & ST_PAS) ? 1.0 : -1.0;
+      __stcg(w.T1 + (size_t)ld1 * B[i] + B[j], -ei * ej * s.D[i * 8 + j]);
+    }
+  }
+  SYNC5();
+  if (tid < nb) { const int m = B[tid]; const unsigned char f = s.st[m]; s.st[m] = (f & ST_PAS) ? (unsigned char)(f | ST_INO) : (unsigned char)(f & ~ST_INO); }
+  SYNC5();
+  w.sum_p2 += 2ull * ld1 * ld1;
+  w.n_fold++;
+  return true;
+}
+
+// fold every toggled slow window variable, reset the window, rebuild T2.  Returns false if a block was refused.
+template <int T>
+__device__ __noinline__ bool fold5(const Sh5 s, W5 &w) {
+  const int tid = threadIdx.x;
+  const int n = w.n;
+  short *B = s.lstE;                                   // NR entries are enough: every listed variable is in the window
+  if (tid < 32) {                                      // swept-back (in O, now active) first, then entering; index order within each class
+    const int lane = tid;
+    int cnt = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int k0 = 1; k0 < n; k0 += 32) {
+        const int k = k0 + lane;
+        bool take = false; int m = 0;
+        if (k < n) {
+          m = s.rvar[k];
+          const unsigned char f = s.st[m];
+          const bool pas = f & ST_PAS, ino = f & ST_INO;
+          take = pas != ino && (w.gmask[m] & w.lowmask) == 0ull && (pass == 0 ? !pas : pas);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, take);
+        if (take) B[cnt + __popc(bal & ((1u << lane) - 1))] = (short)m;
+        cnt += __popc(bal);
+      }
+    }
+    if (lane == 0) s.ctl[C_CNT] = cnt;
+  }
+  SYNC5();
+  const int cnt = s.ctl[C_CNT];
+  bool ok = true;
+  for (int q0 = 0; q0 < cnt && ok; q0 += 8) ok = fold_block5<T>(s, w, B + q0, min(8, cnt - q0));
+  window_reset(s, w);
+  t2_rebuild<T>(s, w);
+  return ok;
+}
+
+// max KKT violation of the current point against the ORIGINAL system; s.v holds the streaming result
+// (weights of committed variables outside the window).  The full weight vector goes to the global scratch.
+template <int T>
+__device__ __noinline__ double verify5(const Sh5 s, W5 &w, const double *c) {
+  const int tid = threadIdx.x;
+  const int Mp = w.Mp;
+  double *wf = w.Pg;
+  if (tid < 32) {
+    const int lane = tid;
+    int np = 0;
+    for (int m0 = 0; m0 < Mp; m0 += 32) {
+      const int m = m0 + lane;
+      bool pas = false; double wv = 0.0;
+      if (m < Mp) {
+        pas = s.st[m] & ST_PAS;
+        if (pas) wv = s.slot[m] >= 0 ? s.T2[off5(s.slot[m])] : s.v[m];
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, pas);
+      if (pas) { const int p = np + __popc(bal & ((1u << lane) - 1)); s.lst[p] = (short)m; wf[p] = wv; }
+      np += __popc(bal);
+    }
+    if (lane == 0) s.ctl[C_NP] = np;
+  }
+  SYNC5();
+  const int np = s.ctl[C_NP];
+  double mx = 0.0;
+  for (int m = tid; m < Mp; m += T) {
+    double a0 = c[m], a1 = 0.0;
+    int t = 0;
+    for (; t + 1 < np; t += 2) {
+      a0 = fma(-w.G[(size_t)w.ldg * s.lst[t] + m], wf[t], a0);
+      a1 = fma(-w.G[(size_t)w.ldg * s.lst[t + 1] + m], wf[t + 1], a1);
+    }
+    if (t < np) a0 = fma(-w.G[(size_t)w.ldg * s.lst[t] + m], wf[t], a0);
+    const double rv = a0 + a1;
+    const int sg = s.sg[m];
+    const unsigned char f = s.st[m];
+    if (f & ST_PAS) mx = fmax(mx, fabs(rv));
+    else if (sg == SG_FREE5) mx = fmax(mx, fabs(rv));
+    else if (sg != 0 && !(f & ST_BLK)) mx = fmax(mx, (double)sg * rv);
+  }
+  return bmax5<T>(s, mx);
+}
+
+// ---- one orthant: block principal pivoting on the window + streaming checks.  Returns false on the iteration cap.
+template <int T, int NR, int NQ>
+__device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2_fresh) {
+  const int tid = threadIdx.x;
+  const int Mp = w.Mp;
+  const double told = 1e-12 * cmax;
+  int t_best = Mp + 1, pbar = 3, iters = 0, rebuilt = 0;
+  for (;;) {
+    // ---- block principal pivoting on the window (Judice-Pires / Kim-Park, Murty's backup rule)
+    for (;;) {
+      const int n = w.n;
+      if (tid < 32) {
+        const int lane = tid;
+        int nl = 0, ne = 0, mx = -1;
+        for (int k0 = 1; k0 < n; k0 += 32) {
+          const int k = k0 + lane;
+          int f = 0, m = -1;
+          if (k < n) {
+            m = s.rvar[k];
+            const double val = s.T2[off5(k)];
+            const int sg = s.sg[m];
+            const unsigned char fl = s.st[m];
+            if (fl & ST_PAS) { if (sg != SG_FREE5 && (sg == 0 || (double)sg * val < 0.0)) f = 1; }
+            else if (!(fl & ST_BLK) && sg != 0 && (sg == SG_FREE5 ? fabs(val) > told : (double)sg * val > told)) f = 2;
+          }
+          const unsigned bl = __ballot_sync(0xffffffffu, f == 1), be = __ballot_sync(0xffffffffu, f == 2);
+          const unsigned below = (1u << lane) - 1;
+          if (f == 1) s.lst[nl + __popc(bl & below)] = (short)k;
+          if (f == 2) s.lstE[ne + __popc(be & below)] = (short)k;
+          nl += __popc(bl); ne += __popc(be);
+          mx = max(mx, f ? m : -1);
+        }
+        mx = wmaxi5(mx);
+        if (lane == 0) { s.ctl[C_NL] = nl; s.ctl[C_NE] = ne; s.ctl[C_MX] = mx; }
+      }
+      SYNC5();
+      int nl = s.ctl[C_NL], ne = s.ctl[C_NE];
+      const int mx = s.ctl[C_MX];
+      const int nv = nl + ne;
+      if (nv == 0) break;
+      w.n_iter++;
+      if (++iters > 60 + 6 * Mp) return false;
+      bool single = false;
+      if (nv < t_best) { t_best = nv; pbar = 3; }
+      else if (pbar >= 1) --pbar;
+      else single = true;
+      if (single) {                                    // only the violator with the highest index moves
+        const int k = s.slot[mx];
+        const bool pas = s.st[mx] & ST_PAS;
+        nl = pas ? 1 : 0; ne = pas ? 0 : 1;
+        SYNC5();
+        if (tid == 0) { if (pas) s.lst[0] = (short)k; else s.lstE[0] = (short)k; }
+        SYNC5();
+      }
+      t2_fresh = false;
+      for (int q = 0; q < nl; ++q) {                   // leaving variables first: their pivots -inv(G_PP)_kk are safe
+        const int k = s.lst[q], m = s.rvar[k];
+        t2_sweep<T>(s, n, k, false);
+        if (tid == 0) s.st[m] &= (unsigned char)~ST_PAS;
+        w.n_sweep++; w.sum_p2 += (unsigned long long)(n * n) >> 2;
+      }
+      for (int q = 0; q < ne; ++q) {                   // entering variables behind a pivot test
+        const int k = s.lstE[q], m = s.rvar[k];
+        const double piv = s.T2[off5(k) + k];
+        if (piv > 1e-13 * __ldg(w.G + (size_t)w.ldg * m + m)) {
+          t2_sweep<T>(s, n, k, true);
+          if (tid == 0) s.st[m] |= ST_PAS;
+          w.n_sweep++; w.sum_p2 += (unsigned long long)(n * n) >> 2;
+        } else {
+          if (tid == 0) s.st[m] |= ST_BLK;
+          w.n_blk++;
+        }
+      }
+      SYNC5();
+    }
+    // ---- everything outside the window, and the accuracy of T2
+    const double res = stream5<T, NQ>(s, w);
+    if (res > 1e-12 * cmax) {                          // T2 lost digits: rebuild it from T1 and pivot again
+      if (res != res || (t2_fresh && res > 1e-9 * cmax) || ++rebuilt > 3) return false;
+      t2_rebuild<T>(s, w);
+      t2_fresh = true;
+      w.n_rebuild++;
+      continue;
+    }
+    if (tid < 32) {
+      const int lane = tid;
+      int nj = 0;
+      for (int m0 = 0; m0 < Mp; m0 += 32) {
+        const int m = m0 + lane;
+        bool f = false;
+        if (m < Mp && s.slot[m] < 0) {
+          const int sg = s.sg[m];
+          const unsigned char fl = s.st[m];
+          const double val = s.v[m];
+          if (fl & ST_INO) f = sg != SG_FREE5 && (sg == 0 ? val != 0.0 : (double)sg * val < 0.0);
+          else f = !(fl & ST_BLK) && sg != 0 && (sg == SG_FREE5 ? fabs(val) > told : (double)sg * val > told);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if (f) s.lst[nj + __popc(bal & ((1u << lane) - 1))] = (short)m;
+        nj += __popc(bal);
+      }
+      if (lane == 0) s.ctl[C_NJ] = nj;
+    }
+    SYNC5();
+    const int nj = s.ctl[C_NJ];
+    if (nj == 0) return true;
+    if (++iters > 60 + 6 * Mp) return false;
+    if (NR - w.n < nj) {                               // make room: fold the toggled slow variables, shrink the window
+      // the join list lives in lst, which the fold reuses; v is dead until the next streaming pass: park the list there
+      short *park = reinterpret_cast<short *>(s.v);
+      for (int p = tid; p < nj; p += T) park[p] = s.lst[p];
+      SYNC5();
+      if (!fold5<T>(s, w)) return false;
+      t2_fresh = true;
+      int room = NR - w.n;
+      if (room > nj) room = nj;
+      if (room <= 0) return false;                     // the fast groups alone fill the window (the host sized l to prevent this)
+      for (int p = 0; p < room; ++p) { const int m = park[p]; if (s.slot[m] < 0) join5<T>(s, w, m); }
+    } else {
+      for (int p = 0; p < nj; ++p) join5<T>(s, w, s.lst[p]);     // join5 uses lstE / yv / tv / uv, not lst
+    }
+    t_best = Mp + 1; pbar = 3;
+  }
+}
+
+template <int T, int NR, int NQ, int MINB>
+__global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
+  const int tid = threadIdx.x;
+  const int Mp = A.Mp, ld1 = A.cap;                    // ld1 = round_up(Mp + 1, 8): rows / row stride of T1
+  const Sh5 s = make_sh5(NR, ld1);
+  W5 w;
+  w.T1 = A.tab + (size_t)blockIdx.x * A.tabstride; w.ld1 = ld1;
+  w.Pg = w.T1 + (size_t)ld1 * ld1;
+  w.Mp = Mp; w.n = 1; w.lowmask = A.lowmask;
+  w.gmask = reinterpret_cast<const unsigned long long *>(A.gmask);
+  w.G = A.G; w.ldg = A.ldg;
+  w.n_sweep = w.n_stream = w.sum_s = w.sum_p2 = w.n_iter = w.n_blk = w.n_rebuild = w.n_fold = 0;
+  const double yy = A.scal[0], cmax = A.scal[1];
+  double best_obj = 0.0; long long best_b = -1;
+  int low_bits = 0;
+  while ((A.lowmask >> low_bits) & 1ull) ++low_bits;
+  const long long cnt = A.n_chains;
+  const long long i0 = cnt * (long long)blockIdx.x / (long long)gridDim.x;
+  const long long i1 = cnt * ((long long)blockIdx.x + 1) / (long long)gridDim.x;
+  bool cold = true, just_cold = false, t2_fresh = true;
+  int since_check = 0, check_every = A.verify_every;
+  double max_viol = 0.0;
+  unsigned long long n_drift = 0, n_noconv = 0;
+
+  for (long long i = i0; i < i1; ++i) {
+    if (cold) {
+      // T1 <- [G c; c' yy], zero padding (ld1 x ld1)
+      const int ld2 = ld1 >> 1;
+      for (int idx = tid; idx < ld1 * ld2; idx += T) {
+        const int row = idx / ld2, col = (idx - row * ld2) << 1;
+        double2 val = make_double2(0.0, 0.0);
+        if (row < Mp) {
+          const double *gr = A.G + (size_t)A.ldg * row;
+          val.x = col < Mp ? gr[col] : (col == Mp ? A.c[row] : 0.0);
+          val.y = col + 1 < Mp ? gr[col + 1] : (col + 1 == Mp ? A.c[row] : 0.0);
+        } else if (row == Mp) {
+          val.x = col < Mp ? A.c[col] : (col == Mp ? yy : 0.0);
+          val.y = col + 1 < Mp ? A.c[col + 1] : (col + 1 == Mp ? yy : 0.0);
+        }
+        __stcg(reinterpret_cast<double2 *>(w.T1 + (size_t)ld1 * row + col), val);
+      }
+      for (int m = tid; m < ld1; m += T) { s.st[m] = 0; s.slot[m] = -1; s.sg[m] = 0; }
+      SYNC5();
+      window_reset(s, w);
+      t2_rebuild<T>(s, w);
+      cold = false; just_cold = true; since_check = 0; t2_fresh = true;
+    }
+    const long long b = A.b_begin + (i ^ (i >> 1));
+    const int fb = i > 0 ? __ffsll(i) - 1 : 63;        // the group whose sign changed
+    for (int m = tid; m < Mp; m += T) {                // d_m = sum_k Po[m,k] (2 bit_k(b) - 1)   (Opt.jl:28-29)
+      const unsigned long long gm = w.gmask[m];
+      const int d = 2 * __popcll(gm & (unsigned long long)b) - __popcll(gm);
+      const bool fr = A.free_top && ((gm >> (A.Kp - 1)) & 1ull);
+      s.sg[m] = (signed char)(fr ? SG_FREE5 : (d > 0) - (d < 0));
+      s.st[m] &= (unsigned char)~ST_BLK;
+    }
+    SYNC5();
+
+    const bool ok = solve5<T, NR, NQ>(s, w, cmax, t2_fresh);
+    if (!ok) { cold = true; ++n_noconv; }
+
+    // ---- drift control: KKT conditions against the original G, c
+    ++since_check;
+    if (ok && (since_check >= check_every || i + 1 == i1)) {
+      since_check = 0;
+      const double viol = verify5<T>(s, w, A.c);
+      if (!just_cold) max_viol = fmax(max_viol, viol);
+      if (viol > 1e-13 * cmax && check_every > 8) check_every = 8;
+      if (viol > 1e-12 * cmax && !just_cold) { ++n_drift; cold = true; --i; continue; }
+    }
+    just_cold = false;
+
+    // ---- objective  sqrt(yy - c_P' w_P) = sqrt(v[rhs])  (= norm(Xa w - ya) at the KKT point, Opt.jl:90)
+    const double obj = ok ? sqrt(fmax(s.v[Mp], 0.0)) : __longlong_as_double(0x7ff8000000000000ll);
+    const long long rel = b - A.b_begin;
+    double w_top = 0.0;
+    if (A.free_top && (s.st[Mp - 1] & ST_PAS)) w_top = s.slot[Mp - 1] >= 0 ? s.T2[off5(s.slot[Mp - 1])] : s.v[Mp - 1];
+    const long long b_full = A.free_top ? (b | ((w_top > 0.0 ? 1ll : 0ll) << (A.Kp - 1))) : b;
+    if (A.all_obj && tid == 0) A.all_obj[rel] = obj;
+    const bool better = lex_better5(obj, b_full, best_obj, best_b);
+    if (better) { best_obj = obj; best_b = b_full; }
+    if (A.all_alpha || better) {
+      for (int m = tid; m < Mp; m += T) {
+        const unsigned long long gm = w.gmask[m];
+        const int d = 2 * __popcll(gm & (unsigned long long)b) - __popcll(gm);
+        double wv = 0.0;
+        if (ok && (s.st[m] & ST_PAS)) wv = s.slot[m] >= 0 ? s.T2[off5(s.slot[m])] : s.v[m];
+        const double al = s.sg[m] == SG_FREE5 ? fabs(wv) : (d != 0 ? fmax(wv / (double)d, 0.0) : 0.0);
+        if (A.all_alpha) A.all_alpha[(size_t)rel * Mp + m] = al;
+        if (better) A.cta_w[(size_t)blockIdx.x * Mp + m] = al;
+      }
+    }
+    // ---- fold: after a slow group moved, when the window is nearly full, or when a full block of toggled slow
+    //      variables has gathered
+    if (ok) {
+      if (tid < 32) {
+        int nslow = 0;
+        for (int k0 = 1; k0 < w.n; k0 += 32) {
+          const int k = k0 + tid;
+          bool t = false;
+          if (k < w.n) { const int m = s.rvar[k]; const unsigned char f = s.st[m]; t = (((f & ST_PAS) != 0) != ((f & ST_INO) != 0)) && (w.gmask[m] & w.lowmask) == 0ull; }
+          nslow += __popc(__ballot_sync(0xffffffffu, t));
+        }
+        if (tid == 0) s.ctl[C_NSLOW] = nslow;
+      }
+      SYNC5();
+      const int nslow = s.ctl[C_NSLOW];
+      if (fb >= low_bits || nslow >= 8 || w.n > NR - 8) {
+        if (!fold5<T>(s, w)) cold = true;             // refused block (near-singular pivot): restart cold
+        t2_fresh = true;
+      }
+    }
+    SYNC5();
+  }
+  if (tid == 0) {
+    A.cta_obj[blockIdx.x] = best_obj;
+    A.cta_b[blockIdx.x] = best_b;
+    atomicAdd(&A.counters[CNT_PIVOTS], w.n_sweep);
+    atomicAdd(&A.counters[CNT_GRAD], w.n_stream);
+    atomicAdd(&A.counters[CNT_SUMP], w.sum_s);
+    atomicAdd(&A.counters[CNT_SUMP2], w.sum_p2);
+    atomicAdd(&A.counters[CNT_ITERS], w.n_iter);
+    atomicAdd(&A.counters[CNT_REBUILDS], w.n_rebuild);
+    atomicAdd(&A.counters[CNT_BLOCKED], w.n_blk);
+    atomicAdd(&A.counters[CNT_NOCONV], n_noconv);
+    atomicAdd(&A.counters[CNT_SPILLS], n_drift);
+    atomicMax(&A.counters[CNT_NUM + 24], (unsigned long long)__double_as_longlong(max_viol / cmax));
+    atomicAdd(&A.counters[CNT_NUM + 1 + 20], w.n_fold);          // reported with the phase counters: fold passes
+  }
+}
+
+typedef void (*K5Fn)(const K2Args);
+struct Variant5 { int T, NR, NQ, minb; K5Fn fn; };
+const Variant5 kVariants5[] = {
+    {128, 72, 1, 8, k2v5_orthant_walks<128, 72, 1, 8>},     // M' + 1 <= 256
+    {128, 72, 2, 8, k2v5_orthant_walks<128, 72, 2, 8>},     // M' + 1 <= 328 (the fold's panel aliases T2)
+    {128, 96, 3, 5, k2v5_orthant_walks<128, 96, 3, 5>},     // M' + 1 <= 584
+    {64, 72, 2, 8, k2v5_orthant_walks<64, 72, 2, 8>},       // M' + 1 <= 256, 64 threads (PLS_K5_T=64)
+    {32, 72, 4, 8, k2v5_orthant_walks<32, 72, 4, 8>},       // M' + 1 <= 256, one warp (PLS_K5_T=32)
+};
+
+}  // namespace
+
+// Environment overrides for tuning / tests: PLS_K5_L (fast groups), PLS_K5_GRID (walks), PLS_K5_VERIFY, PLS_K5_T.
+// h_gmask: host copy of the group masks (sizes the window); n_bits: enumerated Gray bits.
+int k2v5_plan(int Mp, int n_bits, const uint64_t *h_gmask, K5Plan *pl) {
+  const int ld1 = (Mp + 1 + 7) & ~7;
+  const char *eT = getenv("PLS_K5_T");
+  const int wantT = eT ? atoi(eT) : 128;
+  const Variant5 *v = nullptr;
+  int vi = 0;
+  for (const Variant5 &c : kVariants5) {
+    const bool fits = c.T == wantT && ld1 <= 2 * c.T * c.NQ && (size_t)ld1 * 8 <= (size_t)t2_doubles(c.NR);
+    if (fits) { v = &c; break; }
+    ++vi;
+  }
+  if (!v || !h_gmask) return PLS_EUNSUPPORTED;
+  // fast groups: as many of the lowest Gray bits as leave >= 14 free window slots for variables that join
+  int l = 0;
+  for (int t = 1; t <= n_bits && t <= 10; ++t) {
+    int nf = 0;
+    const uint64_t mask = (1ull << t) - 1ull;
+    for (int m = 0; m < Mp; ++m) nf += (h_gmask[m] & mask) != 0ull;
+    if (nf + 1 + 14 <= v->NR) l = t; else break;
+  }
+  if (const char *eL = getenv("PLS_K5_L")) { const int t = atoi(eL); if (t >= 1 && t < l) l = t; }
+  if (l < 1) return PLS_EUNSUPPORTED;
+  int dev = 0, max_smem = 0;
+  PLS_CUDA_TRY(cudaGetDevice(&dev));
+  PLS_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const size_t sm = sh5_bytes(v->NR, ld1);
+  if (sm > (size_t)max_smem) return PLS_EUNSUPPORTED;
+  PLS_CUDA_TRY(cudaFuncSetAttribute(v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  int oc = 1;
+  PLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, v->fn, v->T, sm));
+  if (oc < 1) oc = 1;
+  if (const char *eO = getenv("PLS_K5_OCC")) { const int o = atoi(eO); if (o >= 1 && o < oc) oc = o; }
+  pl->variant = vi; pl->T = v->T; pl->NR = v->NR; pl->ld1 = ld1; pl->occ = oc; pl->smem = sm; pl->low_groups = l;
+  pl->tabstride = (size_t)ld1 * ld1 + 8 * (size_t)ld1 + 64;
+  const char *eV = getenv("PLS_K5_VERIFY");
+  pl->verify_every = eV ? atoi(eV) : 128;
+  if (pl->verify_every < 1) pl->verify_every = 1;
+  return PLS_OK;
+}
+
+int k2v5_launch(const K2Args &A, const K5Plan &pl, int grid, cudaStream_t st) {
+  kVariants5[pl.variant].fn<<<grid, pl.T, pl.smem, st>>>(A);
+  PLS_CUDA_TRY(cudaGetLastError());
+  return PLS_OK;
+}
+
+}  // namespace pls
