@@ -126,6 +126,7 @@ __device__ __forceinline__ Sh5 make_sh5(int NR, int ld1) {
 // walk state (CTA-uniform registers)
 struct W5 {
   double *T1; int ld1;      // this walk's tableau, row stride
+  int nr;                   // window capacity (slots incl. the rhs)
   double *Pg;               // [8][ld1] global scratch: the fold's P rows / the verify pass's weights
   int Mp;
   int n;                    // window size incl. slot 0 (rhs)
@@ -154,31 +155,35 @@ __device__ __forceinline__ double bmax5(const Sh5 &s, double v) {
 // same stored length 2p + 2: a warp takes a row pair, a lane a column pair (the pad element (2p, 2p+1) is updated
 // along -- it is never read).
 template <int T>
-__device__ __noinline__ void t2_sweep(const Sh5 s, int n, int k, bool fwd) {
+__device__ __noinline__ void t2_sweep(int nr, int ld1, int n, int k, bool fwd) {
+  const Sh5 s = make_sh5(nr, ld1);      // rebuilt here so that the compiler sees shared-memory pointers (LDS / STS, not generic accesses)
   constexpr int NW = T / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int offk = off5(k);
   const double dinv = 1.0 / s.T2[offk + k];
   for (int i = tid; i < n; i += T) { const double t = i <= k ? s.T2[offk + i] : s.T2[off5(i) + k]; s.tv[i] = t; s.uv[i] = t * dinv; }
-  if (tid == 0 && (n & 1)) { s.tv[n] = 0.0; s.uv[n] = 0.0; }
+  if (tid == 0 && (n & 1)) { s.tv[n] = 0.0; s.uv[n] = 0.0; }      // odd n: the pair's second row is a scratch row (u = 0)
   SYNC5();
+  const double2 *tv2 = reinterpret_cast<const double2 *>(s.tv), *uv2 = reinterpret_cast<const double2 *>(s.uv);
+  const double2 ta = tv2[lane];                        // this lane's column pair (2 lane, 2 lane + 1)
+  const double2 tb = n > 64 ? tv2[lane + 32] : make_double2(0.0, 0.0);
   const int np = (n + 1) >> 1;
+  double2 *T2v = reinterpret_cast<double2 *>(s.T2);
+#pragma unroll 2
   for (int p = wid; p < np; p += NW) {
-    const int o0 = 2 * p * (p + 1), o1 = o0 + 2 * p + 2;
-    const bool has1 = 2 * p + 1 < n;
-    const double2 u = *reinterpret_cast<const double2 *>(s.uv + 2 * p);
-    for (int c = lane; c <= p; c += 32) {
-      const double2 t = *reinterpret_cast<const double2 *>(s.tv + 2 * c);
-      double2 *p0 = reinterpret_cast<double2 *>(s.T2 + o0 + 2 * c);
-      double2 x0 = *p0;
-      x0.x = fma(-u.x, t.x, x0.x); x0.y = fma(-u.x, t.y, x0.y);
-      *p0 = x0;
-      if (has1) {
-        double2 *p1 = reinterpret_cast<double2 *>(s.T2 + o1 + 2 * c);
-        double2 x1 = *p1;
-        x1.x = fma(-u.y, t.x, x1.x); x1.y = fma(-u.y, t.y, x1.y);
-        *p1 = x1;
-      }
+    double2 *r0 = T2v + p * (p + 1), *r1 = r0 + p + 1;           // rows 2p and 2p + 1: p + 1 column pairs each
+    const double2 u = uv2[p];
+    if (lane <= p) {
+      double2 x0 = r0[lane], x1 = r1[lane];
+      x0.x = fma(-u.x, ta.x, x0.x); x0.y = fma(-u.x, ta.y, x0.y);
+      x1.x = fma(-u.y, ta.x, x1.x); x1.y = fma(-u.y, ta.y, x1.y);
+      r0[lane] = x0; r1[lane] = x1;
+    }
+    if (lane + 32 <= p) {
+      double2 x0 = r0[lane + 32], x1 = r1[lane + 32];
+      x0.x = fma(-u.x, tb.x, x0.x); x0.y = fma(-u.x, tb.y, x0.y);
+      x1.x = fma(-u.y, tb.x, x1.x); x1.y = fma(-u.y, tb.y, x1.y);
+      r0[lane + 32] = x0; r1[lane + 32] = x1;
     }
   }
   SYNC5();
@@ -192,7 +197,8 @@ __device__ __noinline__ void t2_sweep(const Sh5 s, int n, int k, bool fwd) {
 
 // T2 <- T1[Rb, Rb], then sweep the toggled window variables into their current state
 template <int T>
-__device__ __noinline__ void t2_rebuild(const Sh5 s, W5 &w) {
+__device__ __noinline__ void t2_rebuild(W5 &w) {
+  const Sh5 s = make_sh5(w.nr, w.ld1);
   constexpr int NW = T / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n = w.n;
@@ -206,12 +212,13 @@ __device__ __noinline__ void t2_rebuild(const Sh5 s, W5 &w) {
   for (int k = 1; k < n; ++k) {
     const unsigned char f = s.st[s.rvar[k]];
     const bool pas = f & ST_PAS, ino = f & ST_INO;
-    if (pas != ino) { t2_sweep<T>(s, n, k, pas); w.n_sweep++; w.sum_p2 += (unsigned long long)(n * n) >> 2; }
+    if (pas != ino) { t2_sweep<T>(w.nr, w.ld1, n, k, pas); w.n_sweep++; w.sum_p2 += (unsigned long long)(n * n) >> 2; }
   }
 }
 
 // window <- {rhs} + the variables of the fast groups + every toggled variable (index order)
-__device__ __noinline__ void window_reset(const Sh5 s, W5 &w) {
+__device__ __noinline__ void window_reset(W5 &w) {
+  const Sh5 s = make_sh5(w.nr, w.ld1);
   const int tid = threadIdx.x;
   const int Mp = w.Mp;
   if (tid < 32) {
@@ -242,7 +249,8 @@ __device__ __noinline__ void window_reset(const Sh5 s, W5 &w) {
 // v = T1[rhs, :] - sum_{s toggled} e_s T2[s, rhs] T1[s, :].  Returns max |v[s]| over the toggled variables (the
 // residual of the S-system).  NQ = double2 pieces of a row per thread.
 template <int T, int NQ>
-__device__ __noinline__ double stream5(const Sh5 s, W5 &w) {
+__device__ __noinline__ double stream5(W5 &w) {
+  const Sh5 s = make_sh5(w.nr, w.ld1);
   const int tid = threadIdx.x;
   const int n = w.n, ld2 = w.ld1 >> 1;
   constexpr int UB = 8;
@@ -300,7 +308,8 @@ __device__ __noinline__ double stream5(const Sh5 s, W5 &w) {
 // ---- a variable outside the window joins it (not toggled): new last row of T2 ------------------------------------
 //   row[j] = [slot j not toggled] T1[m, var_j] - sum_{s toggled} e_s T1[m, s] T2[s, j],   diag = T1[m, m] - sum_s e_s T1[m, s] row[s]
 template <int T>
-__device__ __noinline__ void join5(const Sh5 s, W5 &w, int m) {
+__device__ __noinline__ void join5(W5 &w, int m) {
+  const Sh5 s = make_sh5(w.nr, w.ld1);
   const int tid = threadIdx.x;
   const int n = w.n;
   const double *row1 = w.T1 + (size_t)w.ld1 * m;
@@ -351,7 +360,9 @@ __device__ __noinline__ void join5(const Sh5 s, W5 &w, int m) {
 // T1 -= P inv(D) P' off the B rows/columns (DMMA, lower tiles + mirrored store), T1[:, B_q] = e_q (P inv(D))[:, q],
 // T1[B, B] = -E inv(D) E.  Returns false (T1 untouched) if a pivot of D has the wrong sign / is too small.
 template <int T>
-__device__ __noinline__ bool fold_block5(const Sh5 s, W5 &w, const short *B, int nb) {
+__device__ __noinline__ bool fold_block5(W5 &w, int boff, int nb) {
+  const Sh5 s = make_sh5(w.nr, w.ld1);
+  const short *B = s.lstE + boff;
   constexpr int NW = T / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int ld1 = w.ld1;
@@ -467,7 +478,8 @@ __device__ __noinline__ bool fold_block5(const Sh5 s, W5 &w, const short *B, int
 
 // fold every toggled slow window variable, reset the window, rebuild T2.  Returns false if a block was refused.
 template <int T>
-__device__ __noinline__ bool fold5(const Sh5 s, W5 &w) {
+__device__ __noinline__ bool fold5(W5 &w) {
+  const Sh5 s = make_sh5(w.nr, w.ld1);
   const int tid = threadIdx.x;
   const int n = w.n;
   short *B = s.lstE;                                   // NR entries are enough: every listed variable is in the window
@@ -494,16 +506,17 @@ __device__ __noinline__ bool fold5(const Sh5 s, W5 &w) {
   SYNC5();
   const int cnt = s.ctl[C_CNT];
   bool ok = true;
-  for (int q0 = 0; q0 < cnt && ok; q0 += 8) ok = fold_block5<T>(s, w, B + q0, min(8, cnt - q0));
-  window_reset(s, w);
-  t2_rebuild<T>(s, w);
+  for (int q0 = 0; q0 < cnt && ok; q0 += 8) ok = fold_block5<T>(w, q0, min(8, cnt - q0));
+  window_reset(w);
+  t2_rebuild<T>(w);
   return ok;
 }
 
 // max KKT violation of the current point against the ORIGINAL system; s.v holds the streaming result
 // (weights of committed variables outside the window).  The full weight vector goes to the global scratch.
 template <int T>
-__device__ __noinline__ double verify5(const Sh5 s, W5 &w, const double *c) {
+__device__ __noinline__ double verify5(W5 &w, const double *c) {
+  const Sh5 s = make_sh5(w.nr, w.ld1);
   const int tid = threadIdx.x;
   const int Mp = w.Mp;
   double *wf = w.Pg;
@@ -601,7 +614,7 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
       t2_fresh = false;
       for (int q = 0; q < nl; ++q) {                   // leaving variables first: their pivots -inv(G_PP)_kk are safe
         const int k = s.lst[q], m = s.rvar[k];
-        t2_sweep<T>(s, n, k, false);
+        t2_sweep<T>(w.nr, w.ld1, n, k, false);
         if (tid == 0) s.st[m] &= (unsigned char)~ST_PAS;
         w.n_sweep++; w.sum_p2 += (unsigned long long)(n * n) >> 2;
       }
@@ -609,7 +622,7 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
         const int k = s.lstE[q], m = s.rvar[k];
         const double piv = s.T2[off5(k) + k];
         if (piv > 1e-13 * __ldg(w.G + (size_t)w.ldg * m + m)) {
-          t2_sweep<T>(s, n, k, true);
+          t2_sweep<T>(w.nr, w.ld1, n, k, true);
           if (tid == 0) s.st[m] |= ST_PAS;
           w.n_sweep++; w.sum_p2 += (unsigned long long)(n * n) >> 2;
         } else {
@@ -620,10 +633,10 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
       SYNC5();
     }
     // ---- everything outside the window, and the accuracy of T2
-    const double res = stream5<T, NQ>(s, w);
+    const double res = stream5<T, NQ>(w);
     if (res > 1e-12 * cmax) {                          // T2 lost digits: rebuild it from T1 and pivot again
       if (res != res || (t2_fresh && res > 1e-9 * cmax) || ++rebuilt > 3) return false;
-      t2_rebuild<T>(s, w);
+      t2_rebuild<T>(w);
       t2_fresh = true;
       w.n_rebuild++;
       continue;
@@ -656,14 +669,14 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
       short *park = reinterpret_cast<short *>(s.v);
       for (int p = tid; p < nj; p += T) park[p] = s.lst[p];
       SYNC5();
-      if (!fold5<T>(s, w)) return false;
+      if (!fold5<T>(w)) return false;
       t2_fresh = true;
       int room = NR - w.n;
       if (room > nj) room = nj;
       if (room <= 0) return false;                     // the fast groups alone fill the window (the host sized l to prevent this)
-      for (int p = 0; p < room; ++p) { const int m = park[p]; if (s.slot[m] < 0) join5<T>(s, w, m); }
+      for (int p = 0; p < room; ++p) { const int m = park[p]; if (s.slot[m] < 0) join5<T>(w, m); }
     } else {
-      for (int p = 0; p < nj; ++p) join5<T>(s, w, s.lst[p]);     // join5 uses lstE / yv / tv / uv, not lst
+      for (int p = 0; p < nj; ++p) join5<T>(w, s.lst[p]);     // join5 uses lstE / yv / tv / uv, not lst
     }
     t_best = Mp + 1; pbar = 3;
   }
@@ -677,7 +690,7 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
   W5 w;
   w.T1 = A.tab + (size_t)blockIdx.x * A.tabstride; w.ld1 = ld1;
   w.Pg = w.T1 + (size_t)ld1 * ld1;
-  w.Mp = Mp; w.n = 1; w.lowmask = A.lowmask;
+  w.Mp = Mp; w.n = 1; w.lowmask = A.lowmask; w.nr = NR;
   w.gmask = reinterpret_cast<const unsigned long long *>(A.gmask);
   w.G = A.G; w.ldg = A.ldg;
   w.n_sweep = w.n_stream = w.sum_s = w.sum_p2 = w.n_iter = w.n_blk = w.n_rebuild = w.n_fold = 0;
@@ -712,8 +725,8 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
       }
       for (int m = tid; m < ld1; m += T) { s.st[m] = 0; s.slot[m] = -1; s.sg[m] = 0; }
       SYNC5();
-      window_reset(s, w);
-      t2_rebuild<T>(s, w);
+      window_reset(w);
+      t2_rebuild<T>(w);
       cold = false; just_cold = true; since_check = 0; t2_fresh = true;
     }
     const long long b = A.b_begin + (i ^ (i >> 1));
@@ -734,7 +747,7 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
     ++since_check;
     if (ok && (since_check >= check_every || i + 1 == i1)) {
       since_check = 0;
-      const double viol = verify5<T>(s, w, A.c);
+      const double viol = verify5<T>(w, A.c);
       if (!just_cold) max_viol = fmax(max_viol, viol);
       if (viol > 1e-13 * cmax && check_every > 8) check_every = 8;
       if (viol > 1e-12 * cmax && !just_cold) { ++n_drift; cold = true; --i; continue; }
@@ -777,7 +790,7 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
       SYNC5();
       const int nslow = s.ctl[C_NSLOW];
       if (fb >= low_bits || nslow >= 8 || w.n > NR - 8) {
-        if (!fold5<T>(s, w)) cold = true;             // refused block (near-singular pivot): restart cold
+        if (!fold5<T>(w)) cold = true;             // refused block (near-singular pivot): restart cold
         t2_fresh = true;
       }
     }

@@ -17,17 +17,22 @@ RTOL = 1e-9
 
 K2_VARIANTS = {
     # name: environment of the K2 dispatcher (nnls.cu: k2_solve_range, nnls3.cu: k2v3_plan)
-    "v2": {"PLS_K2_IMPL": "v2"},                                        # inverse in shared memory, M' <= 208
     "v1": {"PLS_K2_IMPL": "v1"},                                        # rank-1 updates (any M')
     "v3g": {"PLS_K2_IMPL": "v3", "PLS_K3_QS": "0"},                     # inverse in L2 (global), T = 256
     "v3h": {"PLS_K2_IMPL": "v3", "PLS_K3_QS": "10"},                    # first 10 tiles shared, rest global
     "v3s512": {"PLS_K2_IMPL": "v3", "PLS_K3_QS": "-1", "PLS_K3_T": "512"},  # as much as fits shared, T = 512
-    # two-level path (nnls4.cu), forced onto small problems: few CTAs so that each walks a long piece of the Gray
-    # sequence (commits, reverse sweeps, compaction), frequent KKT checks against the original Gram system
+    # two-level paths, forced onto small problems: few CTAs so that each walks a long piece of the Gray sequence
+    # (commits / folds, reverse sweeps, joins, compaction), frequent KKT checks against the original Gram system
     "v4": {"PLS_K2_IMPL": "v4", "PLS_K4_GRID": "3", "PLS_K4_L": "2", "PLS_K4_VERIFY": "5"},
     "v4q": {"PLS_K2_IMPL": "v4", "PLS_K4_GRID": "2", "PLS_K4_L": "1", "PLS_K4_QS": "6", "PLS_K4_T": "256"},
+    # v5 (nnls5.cu, the default winner-only kernel): two swept tableaus per walk
+    "v5": {"PLS_K2_IMPL": "v5", "PLS_K5_GRID": "3", "PLS_K5_L": "2", "PLS_K5_VERIFY": "5"},
+    "v5w": {"PLS_K2_IMPL": "v5", "PLS_K5_GRID": "2", "PLS_K5_L": "1", "PLS_K5_T": "128"},
 }
-_K2_KEYS = ("PLS_K2_IMPL", "PLS_K3_QS", "PLS_K3_T", "PLS_K3_MINB", "PLS_K4_GRID", "PLS_K4_L", "PLS_K4_VERIFY", "PLS_K4_QS", "PLS_K4_T")
+_K2_KEYS = ("PLS_K2_IMPL", "PLS_K3_QS", "PLS_K3_T", "PLS_K3_MINB", "PLS_K4_GRID", "PLS_K4_L", "PLS_K4_VERIFY", "PLS_K4_QS", "PLS_K4_T",
+            "PLS_K5_GRID", "PLS_K5_L", "PLS_K5_VERIFY", "PLS_K5_T", "PLS_K2_NO_V5")
+# the kernel a winner-only fit of a long aligned range runs (pls_stats.k2_variant)
+DEFAULT_TWOLEVEL = 5
 
 
 @pytest.fixture(params=list(K2_VARIANTS))
@@ -150,8 +155,8 @@ def test_nnls_batch_hook_unaligned_range(ctx, oracle, k2impl):
 
 @pytest.mark.parametrize("M", [190, 230])
 def test_large_passive_sets(ctx, oracle, M, k2impl):
-    """Passive sets near M' (v2: every slot of the tile-packed inverse in use; v1: the inverse
-    outgrows shared memory and spills to global memory; M' > 208 always runs v1)."""
+    """Passive sets near M' (v1: the inverse outgrows shared memory and spills to global memory; the two-level
+    kernels do not take groups this large -- v5's window cannot hold one -- and hand over to the one-level kernel)."""
     o, oc = oracle
     N, K = 1200, 2
     X, y, P = o.make_synthetic(N, M, K, seed=4242, mixed_sign=False)
@@ -231,7 +236,8 @@ def test_full_size_config2_properties(ctx, oracle):
     eta = 1e-3
     r = ctx.opt_fit(X, y, P, eta=eta)
     st = r["stats"]
-    assert st["orthants"] == 2 ** 17 and st["rebuilds"] == 0
+    assert st["orthants"] == 2 ** 17 and st["rebuilds"] == 0 and st["nnls_problems"] == 2 ** 16
+    assert st["k2_variant"] == DEFAULT_TWOLEVEL and st["spills"] == 0 and st["k2_max_drift"] < 1e-12
     Xo, Po = o.homogeneous_coords(X, P)
     G = Xo.T @ Xo + eta * (Po @ Po.T); c = Xo.T @ y
     beta = o.index_to_beta(r["b_best"], 17)
@@ -460,19 +466,29 @@ def test_wide_long_chains_kkt(ctx, oracle):
 
 
 # ---- the two-level K2 path (nnls4.cu) on the edge cases ---------------------------------------------
-@pytest.fixture(params=["v4_few_ctas", "v4_one_cta", "v4_default_dispatch"])
+TWOLEVEL_ENVS = {
+    "v4_few_ctas": ({"PLS_K2_IMPL": "v4", "PLS_K4_GRID": "3", "PLS_K4_L": "2", "PLS_K4_VERIFY": "4"}, 4),
+    "v4_one_cta": ({"PLS_K2_IMPL": "v4", "PLS_K4_GRID": "1", "PLS_K4_L": "1", "PLS_K4_VERIFY": "4"}, 4),
+    "v5_few_walks": ({"PLS_K2_IMPL": "v5", "PLS_K5_GRID": "3", "PLS_K5_L": "2", "PLS_K5_VERIFY": "4"}, 5),
+    "v5_one_walk": ({"PLS_K2_IMPL": "v5", "PLS_K5_GRID": "1", "PLS_K5_L": "1", "PLS_K5_VERIFY": "4"}, 5),
+    "v5_one_warp": ({"PLS_K2_IMPL": "v5", "PLS_K5_GRID": "2", "PLS_K5_L": "3", "PLS_K5_T": "32"}, 5),
+    # per-orthant outputs through the default dispatcher: always the one-level kernel (every iterate is checked
+    # against the original Gram system)
+    "default_dispatch_one_level": ({}, 3),
+}
+
+
+@pytest.fixture(params=list(TWOLEVEL_ENVS))
 def twolevel(request):
-    """Forces the two-level kernel onto small problems: 3 CTAs / 1 CTA walking long pieces of the Gray
-    sequence with l = 2 / 1 fast groups and KKT checks every 4 orthants; the third setting leaves the
-    dispatcher alone (v4 only for ranges >= 64 orthants per SM)."""
-    env = {"v4_few_ctas": {"PLS_K2_IMPL": "v4", "PLS_K4_GRID": "3", "PLS_K4_L": "2", "PLS_K4_VERIFY": "4"},
-           "v4_one_cta": {"PLS_K2_IMPL": "v4", "PLS_K4_GRID": "1", "PLS_K4_L": "1", "PLS_K4_VERIFY": "4"},
-           "v4_default_dispatch": {}}[request.param]
+    """Forces the two-level kernels (v4: CTA per chain; v5: two swept tableaus per walk) onto small problems: 3 walks /
+    1 walk over long pieces of the Gray sequence with l = 2 / 1 fast groups and KKT checks every 4 orthants.  Yields
+    the kernel variant pls_stats.k2_variant must report."""
+    env, expect = TWOLEVEL_ENVS[request.param]
     old = {k: os.environ.get(k) for k in _K2_KEYS}
     for k in _K2_KEYS:
         os.environ.pop(k, None)
     os.environ.update(env)
-    yield request.param
+    yield expect
     for k, v in old.items():
         if v is None:
             os.environ.pop(k, None)
@@ -491,7 +507,7 @@ def test_twolevel_tableau_sizes(ctx, oracle, twolevel, M):
     assert np.allclose(r["objs"], ref["objs"], rtol=RTOL, atol=1e-6 * np.linalg.norm(y))
     scale = np.abs(ref["alphas"]).max(axis=1, keepdims=True)
     assert np.all(np.abs(r["alphas"] - ref["alphas"]) <= RTOL * scale + 1e-300)
-    assert r["stats"]["rebuilds"] == 0
+    assert r["stats"]["rebuilds"] == 0 and r["stats"]["k2_variant"] == twolevel
 
 
 def test_twolevel_edge_structures(ctx, oracle, twolevel):
@@ -502,6 +518,7 @@ def test_twolevel_edge_structures(ctx, oracle, twolevel):
     P[0, 1] = 1; P[0, 0] = 1; P[5, 3] = 1; P[5, 0] = 1          # two features in two groups each
     ref = oc.opt_fit(X, y, P, 1e-3)
     r = ctx.opt_fit(X, y, P, eta=1e-3, return_all=True)
+    assert r["stats"]["k2_variant"] == twolevel
     assert r["b_best"] == ref["b_best"] and abs(r["opt"] - ref["obj_best"]) <= RTOL * ref["obj_best"]
     assert np.allclose(r["objs"], ref["objs"], rtol=RTOL, atol=1e-6 * np.linalg.norm(y))
     scale = np.abs(ref["alphas"]).max(axis=1, keepdims=True)
@@ -516,14 +533,27 @@ def test_twolevel_edge_structures(ctx, oracle, twolevel):
     assert np.allclose(r["objs"], ref["objs"], rtol=1e-9, atol=1e-6 * np.linalg.norm(y2))
 
 
-def test_twolevel_long_walk_kkt_every_orthant(ctx, oracle):
-    """2^15 orthants at M' = 97 through the default dispatcher (v4, ~55 orthants per CTA), every orthant's
-    objective against a numpy active-set solve of a random sample, the winner against the C oracle."""
+@pytest.mark.parametrize("impl", ["v4", "v5"])
+def test_twolevel_long_walk_every_orthant(ctx, oracle, impl):
+    """2^15 orthants at M' = 97 on the two-level kernels with their production launch shape (full grid, default l, KKT
+    checks every 128 orthants; PLS_K2_IMPL only overrides the rule that per-orthant outputs run on the one-level
+    kernel): the objectives and alphas of a random sample of orthants, and the winner, against the C oracle."""
     o, oc = oracle
     N, M, K = 4000, 96, 14
     X, y, P = o.make_synthetic(N, M, K, seed=2024, mixed_sign=True, rho=0.2)
-    r = ctx.opt_fit(X, y, P, eta=1e-3, return_all=True)
-    assert r["stats"]["orthants"] == 2 ** 15 and r["stats"]["rebuilds"] == 0
+    old = {k: os.environ.get(k) for k in _K2_KEYS}
+    for k in _K2_KEYS:
+        os.environ.pop(k, None)
+    os.environ["PLS_K2_IMPL"] = impl
+    try:
+        r = ctx.opt_fit(X, y, P, eta=1e-3, return_all=True)
+    finally:
+        os.environ.pop("PLS_K2_IMPL", None)
+        for k, v in old.items():
+            if v is not None:
+                os.environ[k] = v
+    assert r["stats"]["k2_variant"] == int(impl[1]) and r["stats"]["k2_grid"] >= 148
+    assert r["stats"]["orthants"] == 2 ** 15 and r["stats"]["rebuilds"] == 0 and r["stats"]["spills"] == 0
     rng = np.random.default_rng(3)
     bl = np.unique(np.concatenate([rng.integers(0, 2 ** 15, size=40), [r["b_best"]]])).astype(np.int64)
     ref = oc.opt_fit(X, y, P, 1e-3, b_list=bl, nthreads=4)
@@ -532,6 +562,32 @@ def test_twolevel_long_walk_kkt_every_orthant(ctx, oracle):
         sc = max(np.abs(ref["alphas"][j]).max(), 1e-300)
         assert np.all(np.abs(ref["alphas"][j] - r["alphas"][b]) <= RTOL * sc)
     assert int(np.argmin(r["objs"])) == r["b_best"]
+
+
+def test_default_winner_only_path_against_oracle(ctx, pkg, oracle):
+    """The benchmark's exact path -- default dispatch, winner only, paired orthants, the two-level kernel -- at M' = 97,
+    K = 14 (2^14 NNLS problems): pls_stats must report that kernel, and b*, alpha, objective must equal the oracle's.
+    The oracle's argmin over all 2^15 orthants is found by solving, with the C oracle (data-space Lawson-Hanson), the
+    20 best orthants of the one-level kernel's literal enumeration plus 40 random ones (each of which must also agree
+    with that enumeration), so the candidate list is itself oracle-checked."""
+    o, oc = oracle
+    N, M, K = 4000, 96, 14
+    X, y, P = o.make_synthetic(N, M, K, seed=2025, mixed_sign=True, rho=0.2)
+    w = ctx.opt_fit(X, y, P, eta=1e-3)                                   # winner only: the default path
+    st = w["stats"]
+    assert st["k2_variant"] == DEFAULT_TWOLEVEL and st["nnls_problems"] == 2 ** K and st["orthants"] == 2 ** (K + 1)
+    assert st["rebuilds"] == 0 and st["spills"] == 0 and st["k2_max_drift"] < 1e-12
+    lit = ctx.opt_fit(X, y, P, eta=1e-3, return_all=True)               # one-level literal enumeration
+    assert lit["stats"]["k2_variant"] == 3
+    rng = np.random.default_rng(5)
+    bl = np.unique(np.concatenate([np.argsort(lit["objs"])[:20], rng.integers(0, 2 ** (K + 1), size=40)])).astype(np.int64)
+    ref = oc.opt_fit(X, y, P, 1e-3, b_list=bl, nthreads=4)
+    for j, b in enumerate(bl):
+        assert abs(ref["objs"][j] - lit["objs"][b]) <= RTOL * ref["objs"][j] + 1e-6 * np.linalg.norm(y)
+    jb = int(np.argmin(ref["objs"]))
+    assert w["b_best"] == int(bl[jb]) == lit["b_best"]
+    assert abs(w["opt"] - ref["objs"][jb]) <= RTOL * ref["objs"][jb]
+    assert np.all(np.abs(w["alpha_raw"] - ref["alphas"][jb]) <= RTOL * np.abs(ref["alphas"][jb]).max())
 
 
 def test_predict_resident(ctx, pkg, oracle):
