@@ -186,6 +186,11 @@ int pls_objective_finish_w(pls_ctx *ctx, const double *w, double ssq_total, doub
  * (host).  Works on one-GPU and multi-GPU contexts (every device predicts its row shard). */
 int pls_predict_resident(pls_ctx *ctx, const double *w, double *yhat);
 int pls_get_stats(pls_ctx *ctx, pls_stats *stats);
+/* y'y and max |Xo'y| of the finalised Gram system.  The argmin over orthants (Opt.jl:96) treats squared objectives
+ * closer than 1e-13 * y'y as equal and then takes the lower index -- the reference computes every orthant from scratch,
+ * so orthants that are the same problem (an empty group, an all-zero group at the optimum) tie exactly there; a caller
+ * that merges per-rank winners itself (dist.py) applies the same rule. */
+int pls_gram_scalars(pls_ctx *ctx, double *yy, double *cmax);
 
 /* ---- test / bench hooks ------------------------------------------------------------------------
  * pls_gram: K1 + finalize from host pointers; G is (M+1) x (M+1) column-major, c has M+1 entries.

@@ -76,12 +76,13 @@ lib.pls_residual_partial_w.argtypes = [_vp, _dp, _dp]
 lib.pls_predict_resident.argtypes = [_vp, _dp, _dp]
 lib.pls_objective_finish_w.argtypes = [_vp, _dp, C.c_double, _dp]
 lib.pls_get_stats.argtypes = [_vp, C.POINTER(PlsStats)]
+lib.pls_gram_scalars.argtypes = [_vp, _dp, _dp]
 lib.pls_gram.argtypes = [_vp, _dp, C.c_int64, C.c_int64, _dp, _ip, C.c_int64, C.c_double, _dp, _dp, _dp]
 lib.pls_nnls_batch.argtypes = [_vp, _dp, _dp, C.c_double, C.c_int64, C.POINTER(C.c_uint64), C.c_int64,
                                C.c_int64, C.c_int64, _dp, _dp]
 for _n in ("pls_create", "pls_opt_fit", "pls_bnb_fit", "pls_bnb_fit_resident", "pls_alt_fit", "pls_alt_fit_resident", "pls_residual_partial_w", "pls_predict_resident", "pls_objective_finish_w", "pls_load", "pls_opt_fit_resident", "pls_gram_build", "pls_gram_raw",
            "pls_gram_finalize", "pls_opt_solve_range", "pls_opt_solve_pairs", "pls_opt_residual_partial", "pls_opt_objective_finish",
-           "pls_get_stats", "pls_gram", "pls_nnls_batch"):
+           "pls_get_stats", "pls_gram_scalars", "pls_gram", "pls_nnls_batch"):
     getattr(lib, _n).restype = C.c_int
 
 
@@ -271,6 +272,12 @@ class Context:
         caller compares the ranks' bests and recomputes the winner's objective over all row shards."""
         return self.alt_fit(None, None, None, beta0_cols, eps=eps, T=T, resident=True,
                             flags=PLS_FLAG_NO_RECOMPUTE | PLS_FLAG_GRAM_READY)
+
+    def gram_scalars(self):
+        """(y'y, max |Xo'y|) of the finalised Gram system."""
+        yy = C.c_double(); cm = C.c_double()
+        _check(lib.pls_gram_scalars(self._h, C.byref(yy), C.byref(cm)))
+        return yy.value, cm.value
 
     def stats(self):
         st = PlsStats()

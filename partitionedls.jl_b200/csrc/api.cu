@@ -205,8 +205,9 @@ int fallback_if_stalled(pls_ctx *c, int64_t b_begin, int64_t b_count, bool want_
     bool better = best.empty();
     if (!better) {
       long long b1; memcpy(&b1, &best[Mp + 1], sizeof(b1));
-      const double o0 = c->h_pin[Mp], o1 = best[Mp];
-      better = (o0 != o0 && o1 == o1) || (o0 < o1) || (o0 == o1 && bb < b1);
+      double yy = 0.0;
+      PLS_CUDA_TRY(cudaMemcpy(&yy, c->pb.scal, sizeof(double), cudaMemcpyDeviceToHost));
+      better = opt_better(c->h_pin[Mp], bb, best[Mp], b1, PLS_TIE_REL * yy);
     }
     if (better) best.assign(c->h_pin, c->h_pin + Mp + 2);
   }
@@ -839,6 +840,17 @@ int pls_alt_fit(pls_ctx *c, const double *X, int64_t N, int64_t M, const double 
   rc = pls_alt_fit_resident(c, beta0, R, eps, T, flags, alpha, beta, obj, best_restart, iters, all_obj, stats);
   c->stats.ms_upload = 0.0;
   return rc;
+}
+
+int pls_gram_scalars(pls_ctx *c, double *yy, double *cmax) {
+  if (c && !c->subs.empty()) c = c->subs[0];
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!c->pb.gram_ready || !yy || !cmax) { set_error("Gram matrix not built or null pointer"); return PLS_EINVAL; }
+  double sc[2];
+  PLS_CUDA_TRY(cudaMemcpy(sc, c->pb.scal, sizeof(sc), cudaMemcpyDeviceToHost));
+  *yy = sc[0]; *cmax = sc[1];
+  return PLS_OK;
 }
 
 int pls_get_stats(pls_ctx *c, pls_stats *stats) {

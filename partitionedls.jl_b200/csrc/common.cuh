@@ -23,6 +23,27 @@ void set_error(const char *fmt, ...);
 
 static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
+// argmin rule of the orthant enumeration (Opt.jl:96: first minimum; NaN sorts lowest, as Julia's findmin does).
+// Objectives are Gram-space values sqrt(y'y - c'w) whose SQUARES carry rounding noise ~ eps * y'y that depends on
+// the order in which a warm-started solver reached the point.  The reference computes every orthant from scratch:
+// orthants that are the same problem (an empty group, a group whose weights are all zero at the optimum) tie
+// EXACTLY there and the lowest b wins.  To keep that outcome, squared objectives closer than tau = 1e-13 * y'y
+// count as equal and the lower index wins.
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+static inline bool opt_better(double oa, long long ba, double ob, long long bb, double tau) {
+  if (bb < 0) return ba >= 0;
+  if (ba < 0) return false;
+  const bool na = oa != oa, nb = ob != ob;
+  if (na != nb) return na;
+  if (na) return ba < bb;
+  const double diff = oa - ob;
+  if ((diff < 0 ? -diff : diff) * (oa + ob) <= tau) return ba < bb;
+  return oa < ob;
+}
+#define PLS_TIE_REL 1e-13
+
 // Solver work counters accumulated by K2 (device side, unsigned long long each).
 enum Counter {
   CNT_PIVOTS = 0, CNT_GRAD, CNT_SUMP, CNT_SUMP2, CNT_ITERS, CNT_SPILLS, CNT_REBUILDS, CNT_BLOCKED,

@@ -95,13 +95,6 @@ int multi_gram(pls_ctx *c) {
   });
 }
 
-bool lex_less(double oa, long long ba, double ob, long long bb) {   // Opt.jl:96: first minimum, NaN first
-  const bool na = oa != oa, nb = ob != ob;
-  if (na != nb) return na;
-  if (na) return ba < bb;
-  return oa < ob || (oa == ob && ba < bb);
-}
-
 void sum_stats(pls_ctx *c, pls_stats &s) {
   for (pls_ctx *d : c->subs) {
     const pls_stats &t = d->stats;
@@ -230,12 +223,20 @@ int multi_opt_fit_resident(pls_ctx *c, uint32_t flags, double *alpha_raw, int64_
     return PLS_OK;
   });
   if (rc) return rc;
+  double tau = 0.0;
+  {   // tie tolerance of the argmin rule: 1e-13 * y'y (common.cuh: opt_better)
+    pls_ctx *d0 = c->subs[0];
+    PLS_CUDA_TRY(cudaSetDevice(d0->dev));
+    double yy = 0.0;
+    PLS_CUDA_TRY(cudaMemcpy(&yy, d0->pb.scal, sizeof(double), cudaMemcpyDeviceToHost));
+    tau = PLS_TIE_REL * yy;
+  }
   int win = -1; double wo = 0.0; long long wb = -1;
   for (int g = 0; g < G; ++g) {
     if (!has[g]) continue;
     long long bb; memcpy(&bb, &rec[g][Mp + 1], sizeof(bb));
     if (bb < 0) continue;
-    if (win < 0 || lex_less(rec[g][Mp], bb, wo, wb)) { win = g; wo = rec[g][Mp]; wb = bb; }
+    if (win < 0 || opt_better(rec[g][Mp], bb, wo, wb, tau)) { win = g; wo = rec[g][Mp]; wb = bb; }
   }
   if (win < 0) { set_error("no orthant was solved"); return PLS_ENUMERIC; }
   memcpy(alpha_raw, rec[win].data(), sizeof(double) * Mp);

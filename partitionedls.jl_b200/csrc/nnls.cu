@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(T2, 1) k2_orthant_chains(const K2Args A) {
         A.all_alpha[(size_t)rel * Mp + m] = (s.pos[m] >= 0 && d != 0) ? fmax(s.w[m] / (double)d, 0.0) : 0.0;
       }
     }
-    const bool better = lex_better(obj, b, best_obj, best_b);
+    const bool better = opt_better(obj, b, best_obj, best_b, PLS_TIE_REL * yy);
     if (better) {
       best_obj = obj; best_b = b;
       for (int m = tid; m < Mp; m += T2) {
@@ -425,18 +425,19 @@ __global__ void __launch_bounds__(T2, 1) k2_orthant_chains(const K2Args A) {
 // K3: lexicographic (objective, b) minimum over the per-CTA winners; NaN sorts first (Julia
 // argmin semantics, Opt.jl:96).  One block.
 __global__ void __launch_bounds__(256) k3_select_winner(const double *cta_obj, const long long *cta_b,
-                                                        const double *cta_w, int n, int Mp, double *win) {
+                                                        const double *cta_w, int n, int Mp, double *win, const double *scal) {
+  const double tau = PLS_TIE_REL * scal[0];
   __shared__ double so[256];
   __shared__ long long sb[256];
   __shared__ int si[256];
   const int tid = threadIdx.x;
   double o = 0.0; long long b = -1; int idx = -1;
   for (int i = tid; i < n; i += 256)
-    if (lex_better(cta_obj[i], cta_b[i], o, b)) { o = cta_obj[i]; b = cta_b[i]; idx = i; }
+    if (opt_better(cta_obj[i], cta_b[i], o, b, tau)) { o = cta_obj[i]; b = cta_b[i]; idx = i; }
   so[tid] = o; sb[tid] = b; si[tid] = idx;
   __syncthreads();
   for (int st = 128; st; st >>= 1) {
-    if (tid < st && lex_better(so[tid + st], sb[tid + st], so[tid], sb[tid])) {
+    if (tid < st && opt_better(so[tid + st], sb[tid + st], so[tid], sb[tid], tau)) {
       so[tid] = so[tid + st]; sb[tid] = sb[tid + st]; si[tid] = si[tid + st];
     }
     __syncthreads();
@@ -615,7 +616,7 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
     PLS_CUDA_TRY(cudaGetLastError());
   }
   ++*launches;
-  k3_select_winner<<<1, 256, 0, st>>>(ws.cta_obj, ws.cta_b, ws.cta_w, (int)grid, Mp, ws.win);
+  k3_select_winner<<<1, 256, 0, st>>>(ws.cta_obj, ws.cta_b, ws.cta_w, (int)grid, Mp, ws.win, scal);
   PLS_CUDA_TRY(cudaGetLastError());
   ++*launches;
   return PLS_OK;

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(T, MINB) k2v3_orthant_chains(const K2Args A) {
           A.all_alpha[(size_t)rel * Mp + m] = (s.pos[m] >= 0 && d != 0) ? fmax(s.w[m] / (double)d, 0.0) : 0.0;
         }
       }
-      if (lex_better(obj, b_full, best_obj, best_b)) {
+      if (opt_better(obj, b_full, best_obj, best_b, PLS_TIE_REL * yy)) {
         best_obj = obj; best_b = b_full;
         for (int m = tid; m < Mp; m += T) {
           const int d = s.dd[m];

@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(T, MINB) k2v4_orthant_ranges(const K2Args A) {
         A.all_alpha[(size_t)rel * Mp + m] = d != 0 ? fmax(wv / (double)d, 0.0) : 0.0;
       }
     }
-    if (lex_better(obj, b_full, best_obj, best_b)) {
+    if (opt_better(obj, b_full, best_obj, best_b, PLS_TIE_REL * yy)) {
       best_obj = obj; best_b = b_full;
 #pragma unroll 1
       for (int m = tid; m < Mp; m += T) {

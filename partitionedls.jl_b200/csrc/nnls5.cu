@@ -69,46 +69,63 @@ __device__ __forceinline__ bool lex_better5(double oa, long long ba, double ob, 
   if (na) return ba < bb;
   return oa < ob || (oa == ob && ba < bb);
 }
-// packed lower triangle with rows padded to an even length: row i holds columns 0..i at off5(i);
-// rows 2p and 2p + 1 both take 2p + 2 doubles
-__device__ __forceinline__ int off5(int i) {
-  const int h = (i + 1) >> 1;
-  return (i & 1) ? 2 * h * h : 2 * h * (h + 1);
+// T2 storage: 8 x 8 tiles (row-major inside a tile), the lower triangle of tiles packed -- tile (ti, tj <= ti) at
+// ((ti (ti + 1)) >> 1) + tj -- and diagonal tiles holding both halves, so that a DMMA C fragment of any stored tile
+// is one 16-byte access per lane.  Window slot 0 is the right-hand side: T2(k, 0) is slot k's weight / gradient.
+__host__ __device__ constexpr int t2_doubles(int nr) { return ((nr / 8) * (nr / 8 + 1) / 2) * 64; }
+__device__ __forceinline__ int t2_idx(int i, int j) {          // i >= j
+  const int ti = i >> 3, tj = j >> 3;
+  return ((((ti * (ti + 1)) >> 1) + tj) << 6) + ((i & 7) << 3) + (j & 7);
 }
-__host__ __device__ constexpr int t2_doubles(int nr) { return 2 * (nr / 2) * (nr / 2 + 1); }
+__device__ __forceinline__ double t2_get(const double *T2, int i, int j) { return i >= j ? T2[t2_idx(i, j)] : T2[t2_idx(j, i)]; }
+__device__ __forceinline__ void t2_set(double *T2, int i, int j, double v) {
+  const int a = i > j ? i : j, b = i > j ? j : i;
+  const int x = t2_idx(a, b);
+  T2[x] = v;
+  if ((a >> 3) == (b >> 3)) T2[x - ((a & 7) << 3) - (b & 7) + ((b & 7) << 3) + (a & 7)] = v;
+}
+// n x 8 panels: element (row, col) with the column XOR-swizzled so that DMMA A / B fragment loads are conflict-free
+__device__ __forceinline__ int pan5(int row, int col) { return (row << 3) + (col ^ ((row & 2) << 1)); }
 
 struct Sh5 {
   double *T2;      // [t2_doubles(NR)]  (aliased by the fold's W panel: ld1 x 8)
   double *v;       // [ld1]   streaming result
-  double *tv, *uv; // [NR]    pivot column, pivot column / pivot
+  double *Pp, *Wp; // [NR x 8] block pivot: P = T2[:, B], W = P inv(D)   (Wp doubles as the join's scratch)
   double *yv;      // [NR]    y_s of the S list (stream), coefficients (join)
-  double *D;       // [64]    fold: D, then inv(D)
+  double *D;       // [64]    8 x 8 pivot block, then its inverse
+  double *gd;      // [8]     pivot references of the entering variables of a block
   double *red;     // [32]    block reductions
   int *ctl;        // [16]    broadcast slots
   short *slot;     // [ld1]   window slot of variable m, -1 outside
   short *rvar;     // [NR]    variable of window slot k (slot 0 = the right-hand side, variable index Mp)
-  short *lst;      // [ld1]   list scratch (S list / join list / fold list)
-  short *lstE;     // [NR]    entering list
+  short *lst;      // [ld1]   list scratch (leaving list / S list / join list)
+  short *lstE;     // [NR]    entering list / fold list
+  short *lstB;     // [8]     slots of the current block
+  unsigned short *tmap; // [NR/8 (NR/8 + 1) / 2] tile coordinates (ti << 8 | tj) of the packed tile sequence
   signed char *sg; // [ld1]
   unsigned char *st; // [ld1]
+  unsigned char *mk; // [NR]  block pivot: slot is in the current block
 };
-enum { C_NL = 0, C_NE, C_MX, C_NS, C_OK, C_CNT, C_N, C_NJ, C_NSLOW, C_NP };
+enum { C_NL = 0, C_NE, C_MX, C_NS, C_OK, C_CNT, C_N, C_NJ, C_NSLOW, C_NP, C_NLV };
 
 __host__ __device__ inline size_t sh5_bytes(int NR, int ld1) {
-  return sizeof(double) * ((size_t)t2_doubles(NR) + ld1 + 3 * (size_t)NR + 64 + 32) + sizeof(int) * 16 +
-         sizeof(short) * (2 * (size_t)ld1 + 2 * (size_t)NR) + 2 * (size_t)ld1 + 16;
+  const int ntl = (NR / 8) * (NR / 8 + 1) / 2;
+  return sizeof(double) * ((size_t)t2_doubles(NR) + ld1 + 16 * (size_t)NR + NR + 64 + 8 + 32) + sizeof(int) * 16 +
+         sizeof(short) * (2 * (size_t)ld1 + 2 * (size_t)NR + 8 + ((ntl + 3) & ~3)) + 2 * (size_t)ld1 + NR + 16;
 }
 
 __device__ __forceinline__ Sh5 make_sh5(int NR, int ld1) {
   extern __shared__ __align__(16) unsigned char smem_raw5[];
+  const int ntl = (NR / 8) * (NR / 8 + 1) / 2;
   Sh5 s;
   double *dp = reinterpret_cast<double *>(smem_raw5);
   s.T2 = dp; dp += t2_doubles(NR);
   s.v = dp; dp += ld1;
-  s.tv = dp; dp += NR;
-  s.uv = dp; dp += NR;
+  s.Pp = dp; dp += 8 * NR;
+  s.Wp = dp; dp += 8 * NR;
   s.yv = dp; dp += NR;
   s.D = dp; dp += 64;
+  s.gd = dp; dp += 8;
   s.red = dp; dp += 32;
   int *ip = reinterpret_cast<int *>(dp);
   s.ctl = ip; ip += 16;
@@ -117,9 +134,12 @@ __device__ __forceinline__ Sh5 make_sh5(int NR, int ld1) {
   s.rvar = sp; sp += NR;
   s.lst = sp; sp += ld1;
   s.lstE = sp; sp += NR;
+  s.lstB = sp; sp += 8;
+  s.tmap = reinterpret_cast<unsigned short *>(sp); sp += (ntl + 3) & ~3;
   signed char *cp = reinterpret_cast<signed char *>(sp);
   s.sg = cp; cp += ld1;
-  s.st = reinterpret_cast<unsigned char *>(cp);
+  s.st = reinterpret_cast<unsigned char *>(cp); cp += ld1;
+  s.mk = reinterpret_cast<unsigned char *>(cp);
   return s;
 }
 
@@ -150,70 +170,149 @@ __device__ __forceinline__ double bmax5(const Sh5 &s, double v) {
   return r;
 }
 
-// ---- T2: symmetric sweep on window slot k (fwd: the variable enters, else it leaves) ------------------------
-// T2[i,j] -= t_i t_j / d everywhere, then row / column k = +-t / d and T2[k,k] = -1/d.  Row pairs (2p, 2p+1) have the
-// same stored length 2p + 2: a warp takes a row pair, a lane a column pair (the pad element (2p, 2p+1) is updated
-// along -- it is never read).
+// ---- T2: block sweep ----------------------------------------------------------------------------------------------
+// Sweeps the window slots lstB[0..nb) in ONE pass: the first nlv leave the passive set (reverse sweep, e = -1), the
+// others enter it (forward sweep, e = +1; with `test` each behind the pivot test  pivot > 1e-13 G_mm):
+//     P = T2[:, B],  D = T2[B, B],  W = P inv(D)          (Gauss-Jordan in list order: leaving pivots < 0 first)
+//     T2 -= W P'  (lower tiles, DMMA),   T2[:, B_q] = e_q W[:, q],   T2[B, B] = -E inv(D) E
+// Returns nb on success (with `flip` the ST_PAS flags of the block are toggled); otherwise T2 is untouched and the
+// result is the block index (>= nlv) of the entering variable whose pivot failed, or -1 if a leaving pivot had the
+// wrong sign (T2 has lost its structure: the caller rebuilds it).
 template <int T>
-__device__ __noinline__ void t2_sweep(int nr, int ld1, int n, int k, bool fwd) {
-  const Sh5 s = make_sh5(nr, ld1);      // rebuilt here so that the compiler sees shared-memory pointers (LDS / STS, not generic accesses)
+__device__ __noinline__ int t2_block(W5 &w, int n, int nb, int nlv, bool test, bool flip) {
+  const Sh5 s = make_sh5(w.nr, w.ld1);
   constexpr int NW = T / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int offk = off5(k);
-  const double dinv = 1.0 / s.T2[offk + k];
-  for (int i = tid; i < n; i += T) { const double t = i <= k ? s.T2[offk + i] : s.T2[off5(i) + k]; s.tv[i] = t; s.uv[i] = t * dinv; }
-  if (tid == 0 && (n & 1)) { s.tv[n] = 0.0; s.uv[n] = 0.0; }      // odd n: the pair's second row is a scratch row (u = 0)
+  const int fr = lane >> 2, fk = lane & 3;
+  const int ntr = (n + 7) >> 3;
+  const short *B = s.lstB;
+  for (int idx = tid; idx < ntr * 64; idx += T) {
+    const int row = idx >> 3, q = idx & 7;
+    s.Pp[pan5(row, q)] = (row < n && q < nb) ? t2_get(s.T2, row, B[q]) : 0.0;
+  }
+  if (tid < 8) {
+    s.gd[tid] = (test && tid >= nlv && tid < nb) ? 1e-13 * __ldg(w.G + (size_t)w.ldg * s.rvar[B[tid]] + s.rvar[B[tid]]) : 0.0;
+    if (tid < nb) s.mk[B[tid]] = 1;
+  }
   SYNC5();
-  const double2 *tv2 = reinterpret_cast<const double2 *>(s.tv), *uv2 = reinterpret_cast<const double2 *>(s.uv);
-  const double2 ta = tv2[lane];                        // this lane's column pair (2 lane, 2 lane + 1)
-  const double2 tb = n > 64 ? tv2[lane + 32] : make_double2(0.0, 0.0);
-  const int np = (n + 1) >> 1;
-  double2 *T2v = reinterpret_cast<double2 *>(s.T2);
-#pragma unroll 2
-  for (int p = wid; p < np; p += NW) {
-    double2 *r0 = T2v + p * (p + 1), *r1 = r0 + p + 1;           // rows 2p and 2p + 1: p + 1 column pairs each
-    const double2 u = uv2[p];
-    if (lane <= p) {
-      double2 x0 = r0[lane], x1 = r1[lane];
-      x0.x = fma(-u.x, ta.x, x0.x); x0.y = fma(-u.x, ta.y, x0.y);
-      x1.x = fma(-u.y, ta.x, x1.x); x1.y = fma(-u.y, ta.y, x1.y);
-      r0[lane] = x0; r1[lane] = x1;
+  if (tid < 32) {
+    const int i = lane >> 2, j0 = (lane & 3) << 1;
+    double e0 = (i < nb && j0 < nb) ? s.Pp[pan5(B[i], j0)] : (i == j0 ? 1.0 : 0.0);
+    double e1 = (i < nb && j0 + 1 < nb) ? s.Pp[pan5(B[i], j0 + 1)] : (i == j0 + 1 ? 1.0 : 0.0);
+    int bad = nb;                                      // first failing pivot (nb = none)
+    for (int k = 0; k < nb; ++k) {
+      __syncwarp();
+      s.D[i * 8 + j0] = e0; s.D[i * 8 + j0 + 1] = e1;
+      __syncwarp();
+      const double pk0 = s.D[k * 8 + j0], pk1 = s.D[k * 8 + j0 + 1], cik = s.D[i * 8 + k], pkk = s.D[k * 8 + k];
+      const bool good = k < nlv ? pkk < 0.0 : (test ? pkk > s.gd[k] : pkk > 0.0);
+      if (!good && bad == nb) bad = k;
+      const double d = 1.0 / pkk, fct = cik * d;
+      const bool rowk = i == k;
+      double n0 = rowk ? pk0 * d : fma(-fct, pk0, e0);
+      double n1 = rowk ? pk1 * d : fma(-fct, pk1, e1);
+      if (j0 == k) n0 = rowk ? d : -fct;
+      if (j0 + 1 == k) n1 = rowk ? d : -fct;
+      e0 = n0; e1 = n1;
     }
-    if (lane + 32 <= p) {
-      double2 x0 = r0[lane + 32], x1 = r1[lane + 32];
-      x0.x = fma(-u.x, tb.x, x0.x); x0.y = fma(-u.x, tb.y, x0.y);
-      x1.x = fma(-u.y, tb.x, x1.x); x1.y = fma(-u.y, tb.y, x1.y);
-      r0[lane + 32] = x0; r1[lane + 32] = x1;
+    __syncwarp();
+    s.D[i * 8 + j0] = e0; s.D[i * 8 + j0 + 1] = e1;
+    if (lane == 0) s.ctl[C_OK] = bad == nb ? nb : (bad < nlv ? -1 : bad);
+  }
+  SYNC5();
+  const int res = s.ctl[C_OK];
+  if (res != nb) {
+    if (tid < nb) s.mk[B[tid]] = 0;
+    SYNC5();
+    return res;
+  }
+  for (int ti = wid; ti < ntr; ti += NW) {             // W = P inv(D)
+    double c0 = 0.0, c1 = 0.0;
+    dmma5(c0, c1, s.Pp[pan5(ti * 8 + fr, fk)], s.D[fk * 8 + fr]);
+    dmma5(c0, c1, s.Pp[pan5(ti * 8 + fr, 4 + fk)], s.D[(4 + fk) * 8 + fr]);
+    *reinterpret_cast<double2 *>(s.Wp + pan5(ti * 8 + fr, 2 * fk)) = make_double2(c0, c1);
+  }
+  SYNC5();
+  {                                                    // T2 -= W P' on the stored (lower) tiles
+    const int ntl = (ntr * (ntr + 1)) >> 1;
+    const int coff = fr * 8 + 2 * fk;
+    int q = wid;
+    for (; q + NW < ntl; q += 2 * NW) {
+      const int t0 = s.tmap[q], t1 = s.tmap[q + NW];
+      const int ra0 = (t0 >> 8) * 8 + fr, rb0 = (t0 & 255) * 8 + fr, ra1 = (t1 >> 8) * 8 + fr, rb1 = (t1 & 255) * 8 + fr;
+      double2 *cp0 = reinterpret_cast<double2 *>(s.T2 + (q << 6) + coff), *cp1 = reinterpret_cast<double2 *>(s.T2 + ((q + NW) << 6) + coff);
+      double2 c0 = *cp0, c1 = *cp1;
+      const double a00 = -s.Wp[pan5(ra0, fk)], a01 = -s.Wp[pan5(ra0, 4 + fk)], b00 = s.Pp[pan5(rb0, fk)], b01 = s.Pp[pan5(rb0, 4 + fk)];
+      const double a10 = -s.Wp[pan5(ra1, fk)], a11 = -s.Wp[pan5(ra1, 4 + fk)], b10 = s.Pp[pan5(rb1, fk)], b11 = s.Pp[pan5(rb1, 4 + fk)];
+      dmma5(c0.x, c0.y, a00, b00); dmma5(c1.x, c1.y, a10, b10);
+      dmma5(c0.x, c0.y, a01, b01); dmma5(c1.x, c1.y, a11, b11);
+      *cp0 = c0; *cp1 = c1;
+    }
+    if (q < ntl) {
+      const int t0 = s.tmap[q];
+      const int ra0 = (t0 >> 8) * 8 + fr, rb0 = (t0 & 255) * 8 + fr;
+      double2 *cp0 = reinterpret_cast<double2 *>(s.T2 + (q << 6) + coff);
+      double2 c0 = *cp0;
+      dmma5(c0.x, c0.y, -s.Wp[pan5(ra0, fk)], s.Pp[pan5(rb0, fk)]);
+      dmma5(c0.x, c0.y, -s.Wp[pan5(ra0, 4 + fk)], s.Pp[pan5(rb0, 4 + fk)]);
+      *cp0 = c0;
     }
   }
   SYNC5();
-  const double sgn = fwd ? 1.0 : -1.0;
-  for (int i = tid; i < n; i += T) {
-    const double val = i == k ? -dinv : sgn * s.uv[i];
-    if (i <= k) s.T2[offk + i] = val; else s.T2[off5(i) + k] = val;
+  for (int idx = tid; idx < n * 8; idx += T) {         // columns / rows of B outside the block
+    const int row = idx >> 3, q = idx & 7;
+    if (q < nb && !s.mk[row]) { const double val = s.Wp[pan5(row, q)]; t2_set(s.T2, row, B[q], q < nlv ? -val : val); }
+  }
+  for (int e = tid; e < 64; e += T) {                  // the block itself: -E inv(D) E
+    const int i = e >> 3, j = e & 7;
+    if (i < nb && j <= i) { const double val = s.D[i * 8 + j]; t2_set(s.T2, B[i], B[j], ((i < nlv) == (j < nlv)) ? -val : val); }
   }
   SYNC5();
+  if (tid < nb) {
+    s.mk[B[tid]] = 0;
+    if (flip) s.st[s.rvar[B[tid]]] ^= ST_PAS;
+  }
+  SYNC5();
+  w.n_sweep += nb; w.sum_p2 += ((unsigned long long)(n * n) * nb) >> 2;
+  return nb;
 }
 
-// T2 <- T1[Rb, Rb], then sweep the toggled window variables into their current state
+// T2 <- T1[Rb, Rb], then sweep the toggled window variables into their current state.  Returns false if a block
+// could not be swept (numerically broken state: the caller restarts cold).
 template <int T>
-__device__ __noinline__ void t2_rebuild(W5 &w) {
+__device__ __noinline__ bool t2_rebuild(W5 &w) {
   const Sh5 s = make_sh5(w.nr, w.ld1);
   constexpr int NW = T / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n = w.n;
   for (int i = wid; i < n; i += NW) {
     const double *row = w.T1 + (size_t)w.ld1 * s.rvar[i];
-    const int o = off5(i);
-    for (int j = lane; j <= i; j += 32) s.T2[o + j] = __ldcg(row + s.rvar[j]);
-    if (lane == 0 && !(i & 1)) s.T2[o + i + 1] = 0.0;          // pad element
+    for (int j = lane; j <= i; j += 32) t2_set(s.T2, i, j, __ldcg(row + s.rvar[j]));
+  }
+  if (tid < 32) {                                      // toggled slots: swept-back ones (in O, active now) first
+    int cnt = 0, nlv = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int k0 = 1; k0 < n; k0 += 32) {
+        const int k = k0 + lane;
+        bool take = false;
+        if (k < n) { const unsigned char f = s.st[s.rvar[k]]; const bool pas = f & ST_PAS, ino = f & ST_INO; take = pas != ino && (pass == 0 ? !pas : pas); }
+        const unsigned bal = __ballot_sync(0xffffffffu, take);
+        if (take) s.lst[cnt + __popc(bal & ((1u << lane) - 1))] = (short)k;
+        cnt += __popc(bal);
+      }
+      if (pass == 0) nlv = cnt;
+    }
+    if (lane == 0) { s.ctl[C_CNT] = cnt; s.ctl[C_NLV] = nlv; }
   }
   SYNC5();
-  for (int k = 1; k < n; ++k) {
-    const unsigned char f = s.st[s.rvar[k]];
-    const bool pas = f & ST_PAS, ino = f & ST_INO;
-    if (pas != ino) { t2_sweep<T>(w.nr, w.ld1, n, k, pas); w.n_sweep++; w.sum_p2 += (unsigned long long)(n * n) >> 2; }
+  const int cnt = s.ctl[C_CNT], nlv = s.ctl[C_NLV];
+  for (int q0 = 0; q0 < cnt; q0 += 8) {
+    const int nb = min(8, cnt - q0);
+    if (tid < nb) s.lstB[tid] = s.lst[q0 + tid];
+    SYNC5();
+    if (t2_block<T>(w, n, nb, max(0, min(nb, nlv - q0)), false, false) != nb) return false;
   }
+  return true;
 }
 
 // window <- {rhs} + the variables of the fast groups + every toggled variable (index order)
@@ -262,7 +361,7 @@ __device__ __noinline__ double stream5(W5 &w) {
       bool tg = false, pas = false; int m = 0;
       if (k < n) { m = s.rvar[k]; const unsigned char f = s.st[m]; pas = f & ST_PAS; tg = pas != ((f & ST_INO) != 0); }
       const unsigned bal = __ballot_sync(0xffffffffu, tg);
-      if (tg) { const int p = ns + __popc(bal & ((1u << lane) - 1)); s.lst[p] = (short)m; s.yv[p] = pas ? s.T2[off5(k)] : -s.T2[off5(k)]; }
+      if (tg) { const int p = ns + __popc(bal & ((1u << lane) - 1)); s.lst[p] = (short)m; { const double t = s.T2[t2_idx(k, 0)]; s.yv[p] = pas ? t : -t; } }
       ns += __popc(bal);
     }
     const int nsp = (ns + UB - 1) / UB * UB;
@@ -313,6 +412,7 @@ __device__ __noinline__ void join5(W5 &w, int m) {
   const int tid = threadIdx.x;
   const int n = w.n;
   const double *row1 = w.T1 + (size_t)w.ld1 * m;
+  double *rowv = s.Wp, *tog = s.Wp + w.nr;              // scratch: the new row, toggled marks
   if (tid < 32) {                                      // toggled slots -> lstE, coefficients e_s T1[m, s] -> yv
     const int lane = tid;
     int ns = 0;
@@ -322,34 +422,25 @@ __device__ __noinline__ void join5(W5 &w, int m) {
       if (k < n) { var = s.rvar[k]; const unsigned char f = s.st[var]; pas = f & ST_PAS; tg = pas != ((f & ST_INO) != 0); }
       const unsigned bal = __ballot_sync(0xffffffffu, tg);
       if (tg) { const int p = ns + __popc(bal & ((1u << lane) - 1)); s.lstE[p] = (short)k; const double a = __ldcg(row1 + var); s.yv[p] = pas ? a : -a; }
-      if (k < n) s.uv[k] = tg ? 1.0 : 0.0;
+      if (k < n) tog[k] = tg ? 1.0 : 0.0;
       ns += __popc(bal);
     }
-    if (lane == 0) { s.uv[0] = 0.0; s.ctl[C_NS] = ns; }
+    if (lane == 0) { tog[0] = 0.0; s.ctl[C_NS] = ns; }
   }
   SYNC5();
   const int ns = s.ctl[C_NS];
   for (int j = tid; j < n; j += T) {
-    double a = s.uv[j] != 0.0 ? 0.0 : __ldcg(row1 + s.rvar[j]);
-    const int oj = off5(j);
-    for (int p = 0; p < ns; ++p) {
-      const int k = s.lstE[p];
-      const double t = j <= k ? s.T2[off5(k) + j] : s.T2[oj + k];
-      a = fma(-s.yv[p], t, a);
-    }
-    s.tv[j] = a;
+    double a = tog[j] != 0.0 ? 0.0 : __ldcg(row1 + s.rvar[j]);
+    for (int p = 0; p < ns; ++p) a = fma(-s.yv[p], t2_get(s.T2, s.lstE[p], j), a);
+    rowv[j] = a;
   }
   SYNC5();
-  const int on = off5(n);
-  for (int j = tid; j < n; j += T) s.T2[on + j] = s.tv[j];
+  for (int j = tid; j < n; j += T) t2_set(s.T2, n, j, rowv[j]);
   if (tid < 32) {
     double dg = 0.0;
-    for (int p = tid; p < ns; p += 32) dg = fma(s.yv[p], s.tv[s.lstE[p]], dg);
+    for (int p = tid; p < ns; p += 32) dg = fma(s.yv[p], rowv[s.lstE[p]], dg);
     dg = wsum5(dg);
-    if (tid == 0) {
-      s.T2[on + n] = __ldcg(row1 + m) - dg; s.rvar[n] = (short)m; s.slot[m] = (short)n;
-      if (!(n & 1)) s.T2[on + n + 1] = 0.0;            // pad element
-    }
+    if (tid == 0) { t2_set(s.T2, n, n, __ldcg(row1 + m) - dg); s.rvar[n] = (short)m; s.slot[m] = (short)n; }
   }
   w.n = n + 1;
   w.sum_p2 += (unsigned long long)(ns * n) >> 1;
@@ -366,7 +457,7 @@ __device__ __noinline__ bool fold_block5(W5 &w, int boff, int nb) {
   constexpr int NW = T / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int ld1 = w.ld1;
-  double *Wp = s.T2;                                   // [ld1][8] panel W = P inv(D)  (T2 is rebuilt after the fold)
+  double *Wp = s.T2;                                   // [ld1][8] panel W = P inv(D): aliases T2, which is rebuilt after the fold
   for (int q = 0; q < 8; ++q) {                        // P rows -> global scratch
     const double *src = w.T1 + (size_t)ld1 * (q < nb ? B[q] : 0);
     for (int j = tid; j < ld1; j += T) w.Pg[q * ld1 + j] = q < nb ? __ldcg(src + j) : 0.0;
@@ -508,7 +599,7 @@ __device__ __noinline__ bool fold5(W5 &w) {
   bool ok = true;
   for (int q0 = 0; q0 < cnt && ok; q0 += 8) ok = fold_block5<T>(w, q0, min(8, cnt - q0));
   window_reset(w);
-  t2_rebuild<T>(w);
+  if (!t2_rebuild<T>(w)) ok = false;
   return ok;
 }
 
@@ -528,7 +619,7 @@ __device__ __noinline__ double verify5(W5 &w, const double *c) {
       bool pas = false; double wv = 0.0;
       if (m < Mp) {
         pas = s.st[m] & ST_PAS;
-        if (pas) wv = s.slot[m] >= 0 ? s.T2[off5(s.slot[m])] : s.v[m];
+        if (pas) wv = s.slot[m] >= 0 ? s.T2[t2_idx(s.slot[m], 0)] : s.v[m];
       }
       const unsigned bal = __ballot_sync(0xffffffffu, pas);
       if (pas) { const int p = np + __popc(bal & ((1u << lane) - 1)); s.lst[p] = (short)m; wf[p] = wv; }
@@ -576,7 +667,7 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
           int f = 0, m = -1;
           if (k < n) {
             m = s.rvar[k];
-            const double val = s.T2[off5(k)];
+            const double val = s.T2[t2_idx(k, 0)];
             const int sg = s.sg[m];
             const unsigned char fl = s.st[m];
             if (fl & ST_PAS) { if (sg != SG_FREE5 && (sg == 0 || (double)sg * val < 0.0)) f = 1; }
@@ -612,31 +703,35 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
         SYNC5();
       }
       t2_fresh = false;
-      for (int q = 0; q < nl; ++q) {                   // leaving variables first: their pivots -inv(G_PP)_kk are safe
-        const int k = s.lst[q], m = s.rvar[k];
-        t2_sweep<T>(w.nr, w.ld1, n, k, false);
-        if (tid == 0) s.st[m] &= (unsigned char)~ST_PAS;
-        w.n_sweep++; w.sum_p2 += (unsigned long long)(n * n) >> 2;
-      }
-      for (int q = 0; q < ne; ++q) {                   // entering variables behind a pivot test
-        const int k = s.lstE[q], m = s.rvar[k];
-        const double piv = s.T2[off5(k) + k];
-        if (piv > 1e-13 * __ldg(w.G + (size_t)w.ldg * m + m)) {
-          t2_sweep<T>(w.nr, w.ld1, n, k, true);
-          if (tid == 0) s.st[m] |= ST_PAS;
-          w.n_sweep++; w.sum_p2 += (unsigned long long)(n * n) >> 2;
-        } else {
-          if (tid == 0) s.st[m] |= ST_BLK;
-          w.n_blk++;
+      // leaving variables first (their pivots -inv(G_PP)_kk are safe), then the entering ones, in blocks of <= 8
+      int done = 0, tot = nl + ne;
+      bool broken = false;
+      while (done < tot) {
+        const int nb = min(8, tot - done), nlv = max(0, min(nb, nl - done));
+        if (tid < nb) s.lstB[tid] = done + tid < nl ? s.lst[done + tid] : s.lstE[done + tid - nl];
+        SYNC5();
+        const int r = t2_block<T>(w, n, nb, nlv, true, true);
+        if (r == nb) { done += nb; continue; }
+        if (r < 0) { broken = true; break; }
+        // the entering variable at block position r failed its pivot test: refuse it at this orthant, drop it from the list
+        const int pos = done + r - nl;                 // its position in lstE
+        if (tid == 0) {
+          s.st[s.rvar[s.lstE[pos]]] |= ST_BLK;
+          for (int q = pos; q + 1 < ne; ++q) s.lstE[q] = s.lstE[q + 1];
         }
+        --ne; --tot; w.n_blk++;
+        SYNC5();
       }
-      SYNC5();
+      if (broken) {                                    // a leaving pivot with the wrong sign: T2 lost its structure
+        if (++rebuilt > 3 || !t2_rebuild<T>(w)) return false;
+        t2_fresh = true; w.n_rebuild++;
+      }
     }
     // ---- everything outside the window, and the accuracy of T2
     const double res = stream5<T, NQ>(w);
     if (res > 1e-12 * cmax) {                          // T2 lost digits: rebuild it from T1 and pivot again
       if (res != res || (t2_fresh && res > 1e-9 * cmax) || ++rebuilt > 3) return false;
-      t2_rebuild<T>(w);
+      if (!t2_rebuild<T>(w)) return false;
       t2_fresh = true;
       w.n_rebuild++;
       continue;
@@ -694,6 +789,9 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
   w.gmask = reinterpret_cast<const unsigned long long *>(A.gmask);
   w.G = A.G; w.ldg = A.ldg;
   w.n_sweep = w.n_stream = w.sum_s = w.sum_p2 = w.n_iter = w.n_blk = w.n_rebuild = w.n_fold = 0;
+  for (int ti = tid; ti < NR / 8; ti += T)
+    for (int tj = 0; tj <= ti; ++tj) s.tmap[((ti * (ti + 1)) >> 1) + tj] = (unsigned short)((ti << 8) | tj);
+  for (int k = tid; k < NR; k += T) s.mk[k] = 0;
   const double yy = A.scal[0], cmax = A.scal[1];
   double best_obj = 0.0; long long best_b = -1;
   int low_bits = 0;
@@ -726,7 +824,7 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
       for (int m = tid; m < ld1; m += T) { s.st[m] = 0; s.slot[m] = -1; s.sg[m] = 0; }
       SYNC5();
       window_reset(w);
-      t2_rebuild<T>(w);
+      t2_rebuild<T>(w);                                // nothing is toggled: a plain copy
       cold = false; just_cold = true; since_check = 0; t2_fresh = true;
     }
     const long long b = A.b_begin + (i ^ (i >> 1));
@@ -758,17 +856,17 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
     const double obj = ok ? sqrt(fmax(s.v[Mp], 0.0)) : __longlong_as_double(0x7ff8000000000000ll);
     const long long rel = b - A.b_begin;
     double w_top = 0.0;
-    if (A.free_top && (s.st[Mp - 1] & ST_PAS)) w_top = s.slot[Mp - 1] >= 0 ? s.T2[off5(s.slot[Mp - 1])] : s.v[Mp - 1];
+    if (A.free_top && (s.st[Mp - 1] & ST_PAS)) w_top = s.slot[Mp - 1] >= 0 ? s.T2[t2_idx(s.slot[Mp - 1], 0)] : s.v[Mp - 1];
     const long long b_full = A.free_top ? (b | ((w_top > 0.0 ? 1ll : 0ll) << (A.Kp - 1))) : b;
     if (A.all_obj && tid == 0) A.all_obj[rel] = obj;
-    const bool better = lex_better5(obj, b_full, best_obj, best_b);
+    const bool better = opt_better(obj, b_full, best_obj, best_b, PLS_TIE_REL * yy);
     if (better) { best_obj = obj; best_b = b_full; }
     if (A.all_alpha || better) {
       for (int m = tid; m < Mp; m += T) {
         const unsigned long long gm = w.gmask[m];
         const int d = 2 * __popcll(gm & (unsigned long long)b) - __popcll(gm);
         double wv = 0.0;
-        if (ok && (s.st[m] & ST_PAS)) wv = s.slot[m] >= 0 ? s.T2[off5(s.slot[m])] : s.v[m];
+        if (ok && (s.st[m] & ST_PAS)) wv = s.slot[m] >= 0 ? s.T2[t2_idx(s.slot[m], 0)] : s.v[m];
         const double al = s.sg[m] == SG_FREE5 ? fabs(wv) : (d != 0 ? fmax(wv / (double)d, 0.0) : 0.0);
         if (A.all_alpha) A.all_alpha[(size_t)rel * Mp + m] = al;
         if (better) A.cta_w[(size_t)blockIdx.x * Mp + m] = al;
@@ -815,45 +913,52 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
 
 typedef void (*K5Fn)(const K2Args);
 struct Variant5 { int T, NR, NQ, minb; K5Fn fn; };
+#define V5(T, NR, NQ, MINB) {T, NR, NQ, MINB, k2v5_orthant_walks<T, NR, NQ, MINB>}
 const Variant5 kVariants5[] = {
-    {128, 72, 1, 8, k2v5_orthant_walks<128, 72, 1, 8>},     // M' + 1 <= 256
-    {128, 72, 2, 8, k2v5_orthant_walks<128, 72, 2, 8>},     // M' + 1 <= 328 (the fold's panel aliases T2)
-    {128, 96, 3, 5, k2v5_orthant_walks<128, 96, 3, 5>},     // M' + 1 <= 584
-    {64, 72, 2, 8, k2v5_orthant_walks<64, 72, 2, 8>},       // M' + 1 <= 256, 64 threads (PLS_K5_T=64)
-    {32, 72, 4, 8, k2v5_orthant_walks<32, 72, 4, 8>},       // M' + 1 <= 256, one warp (PLS_K5_T=32)
+    // M' + 1 <= 256 (NQ = row pieces per thread of the streaming pass: ld1 <= 2 T NQ)
+    V5(64, 72, 2, 6), V5(64, 56, 2, 8), V5(64, 64, 2, 7), V5(64, 80, 2, 5), V5(64, 96, 2, 4), V5(128, 56, 1, 8), V5(128, 64, 1, 7), V5(128, 72, 1, 6),
+    V5(128, 80, 1, 5), V5(128, 96, 1, 4), V5(32, 56, 4, 8), V5(32, 72, 4, 6),
+    // wider problems (the fold's ld1 x 8 panel aliases T2: ld1 * 8 <= t2_doubles(NR))
+    V5(128, 72, 2, 6), V5(128, 96, 3, 4),
 };
+#undef V5
 
 }  // namespace
 
-// Environment overrides for tuning / tests: PLS_K5_L (fast groups), PLS_K5_GRID (walks), PLS_K5_VERIFY, PLS_K5_T.
+// Environment overrides for tuning / tests: PLS_K5_T (threads per walk), PLS_K5_NR (window slots), PLS_K5_L (fast groups),
+// PLS_K5_GRID (walks), PLS_K5_VERIFY, PLS_K5_OCC.
 // h_gmask: host copy of the group masks (sizes the window); n_bits: enumerated Gray bits.
 int k2v5_plan(int Mp, int n_bits, const uint64_t *h_gmask, K5Plan *pl) {
+  if (!h_gmask) return PLS_EUNSUPPORTED;
   const int ld1 = (Mp + 1 + 7) & ~7;
-  const char *eT = getenv("PLS_K5_T");
-  const int wantT = eT ? atoi(eT) : 128;
-  const Variant5 *v = nullptr;
-  int vi = 0;
-  for (const Variant5 &c : kVariants5) {
-    const bool fits = c.T == wantT && ld1 <= 2 * c.T * c.NQ && (size_t)ld1 * 8 <= (size_t)t2_doubles(c.NR);
-    if (fits) { v = &c; break; }
-    ++vi;
-  }
-  if (!v || !h_gmask) return PLS_EUNSUPPORTED;
-  // fast groups: as many of the lowest Gray bits as leave >= 14 free window slots for variables that join
-  int l = 0;
-  for (int t = 1; t <= n_bits && t <= 10; ++t) {
-    int nf = 0;
-    const uint64_t mask = (1ull << t) - 1ull;
-    for (int m = 0; m < Mp; ++m) nf += (h_gmask[m] & mask) != 0ull;
-    if (nf + 1 + 14 <= v->NR) l = t; else break;
-  }
-  if (const char *eL = getenv("PLS_K5_L")) { const int t = atoi(eL); if (t >= 1 && t < l) l = t; }
-  if (l < 1) return PLS_EUNSUPPORTED;
+  const char *eT = getenv("PLS_K5_T"), *eN = getenv("PLS_K5_NR");
+  const int wantT = eT ? atoi(eT) : 0, wantNR = eN ? atoi(eN) : 0;
   int dev = 0, max_smem = 0;
   PLS_CUDA_TRY(cudaGetDevice(&dev));
   PLS_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const Variant5 *v = nullptr;
+  int vi = 0, l = 0;
+  const char *eM = getenv("PLS_K5_MARGIN");
+  const int margin = eM ? atoi(eM) : 14;
+  for (const Variant5 &c : kVariants5) {
+    const bool fits = (!wantT || c.T == wantT) && (!wantNR || c.NR == wantNR) && ld1 <= 2 * c.T * c.NQ &&
+                      (size_t)ld1 * 8 <= (size_t)t2_doubles(c.NR) && sh5_bytes(c.NR, ld1) <= (size_t)max_smem;
+    if (fits) {
+      // fast groups: as many of the lowest Gray bits as leave >= 14 free window slots for variables that join
+      l = 0;
+      for (int t = 1; t <= n_bits && t <= 10; ++t) {
+        int nf = 0;
+        const uint64_t mask = (1ull << t) - 1ull;
+        for (int m = 0; m < Mp; ++m) nf += (h_gmask[m] & mask) != 0ull;
+        if (nf + 1 + margin <= c.NR) l = t; else break;
+      }
+      if (l >= 1) { v = &c; break; }
+    }
+    ++vi;
+  }
+  if (!v) return PLS_EUNSUPPORTED;
+  if (const char *eL = getenv("PLS_K5_L")) { const int t = atoi(eL); if (t >= 1 && t < l) l = t; }
   const size_t sm = sh5_bytes(v->NR, ld1);
-  if (sm > (size_t)max_smem) return PLS_EUNSUPPORTED;
   PLS_CUDA_TRY(cudaFuncSetAttribute(v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   int oc = 1;
   PLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, v->fn, v->T, sm));

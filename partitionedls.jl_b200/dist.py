@@ -30,12 +30,27 @@ def shard_orthants(total: int, rank: int, world: int):
     return n * rank, n
 
 
-def pick_winner(records, Mp):
-    """records: array (world, Mp + 2) rows [alpha_raw (Mp), objective, b].  Lexicographic
-    (objective, b) minimum; NaN objectives sort first (Julia argmin semantics, Opt.jl:96)."""
+def pick_winner(records, Mp, tau=0.0):
+    """records: array (world, Mp + 2) rows [alpha_raw (Mp), objective, b].  The argmin rule of the orthant enumeration
+    (Opt.jl:96: first minimum, NaN objectives first -- Julia argmin semantics) with the library's tie tolerance: squared
+    objectives closer than tau = 1e-13 * y'y count as equal and the lower index wins (include/pls.h: pls_gram_scalars)."""
     rec = np.asarray(records, dtype=np.float64)
-    key = [(0 if np.isnan(r[Mp]) else 1, r[Mp] if not np.isnan(r[Mp]) else 0.0, r[Mp + 1]) for r in rec]
-    i = min(range(len(rec)), key=lambda q: key[q])
+
+    def better(a, c):
+        oa, ba, ob, bb = a[Mp], a[Mp + 1], c[Mp], c[Mp + 1]
+        na, nb = np.isnan(oa), np.isnan(ob)
+        if na != nb:
+            return bool(na)
+        if na:
+            return ba < bb
+        if abs(oa - ob) * (oa + ob) <= tau:
+            return ba < bb
+        return oa < ob
+
+    i = 0
+    for q in range(1, len(rec)):
+        if better(rec[q], rec[i]):
+            i = q
     return rec[i, :Mp].copy(), int(rec[i, Mp + 1]), float(rec[i, Mp]), i
 
 
@@ -97,7 +112,8 @@ def opt_fit_sharded(backend, comm, Mp: int, Kp: int, *, reload=None, pairs=None)
         b0, bn = shard_orthants(1 << Kp, comm.rank, comm.world)
         loc = backend.opt_solve_range(b0, bn)
     rec = np.concatenate([loc["alpha_raw"], [loc["obj_gram"], float(loc["b_best"])]])
-    alpha, b, _, _ = pick_winner(comm.allgather(rec), Mp)
+    tau = 1e-13 * backend.gram_scalars()[0] if hasattr(backend, "gram_scalars") else 0.0
+    alpha, b, _, _ = pick_winner(comm.allgather(rec), Mp, tau)
     ssq = comm.allreduce_sum(np.array([backend.residual_partial(alpha, b)]))[0]
     return b, backend.objective_finish(alpha, b, float(ssq)), alpha
 
