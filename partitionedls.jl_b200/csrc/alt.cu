@@ -53,7 +53,9 @@ __global__ void __launch_bounds__(T, MINB) k6_alt_restarts(const AltArgs A) {
   __shared__ double beta[64], cb[64], suma[64], rhs[64];
   __shared__ int cnt[64];
   __shared__ unsigned long long s_r;
-  __shared__ int s_fail;
+  __shared__ int s_fail, s_dead;
+  __shared__ double gdiag[64];
+  __shared__ unsigned char deadc[64];
   // scratch that is free between two solves: alpha | u in the first panel, Gb in the second
   double *alpha = s.Pa, *u = s.Pa + cap;
   double *Gb = A.gb_separate
@@ -100,6 +102,17 @@ __global__ void __launch_bounds__(T, MINB) k6_alt_restarts(const AltArgs A) {
       }
       __syncthreads();
       ok = bpp_solve3<T, 1>(cf, s, A.G, A.ldg, Mp, cmax, st);
+      if (!ok) {
+        // stalled block pivoting (nearly singular intermediate passive set): the alpha-step again from the empty
+        // passive set, one variable per step behind the pivot test -- the restart is not dropped
+        clear_state3<T, 1>(cf, max(st.nt_dirty, st.nt_cur));
+        st.nt_dirty = 0; st.hwm = 0; st.nt_cur = 0; st.r_valid = true;
+        for (int m = tid; m < cap; m += T) { s.w[m] = 0.0; s.r[m] = s.cs[m]; s.pos[m] = -1; s.vflag[m] = 0; }
+        __syncthreads();
+        ok = bpp_solve3<T, 1>(cf, s, A.G, A.ldg, Mp, cmax, st, true);
+        STAT_ADD3(ST_REBUILD, 1);
+        if (!ok) STAT_ADD3(ST_NOCONV, 1);
+      }
       if (!ok) break;
       for (int m = tid; m < Mp; m += T) {      // alpha = w ./ d  (>= 0 at the KKT point)
         uint64_t gm = s.gms[m];
@@ -166,16 +179,24 @@ __global__ void __launch_bounds__(T, MINB) k6_alt_restarts(const AltArgs A) {
         if (lane == 0) { cb[k] = a; rhs[k] = a; }
       }
       __syncthreads();
+      if (tid < Kp) { gdiag[tid] = Gb[tid * Kp + tid]; deadc[tid] = 0; }
+      __syncthreads();
       // Cholesky Gb = L L' (lower, in place), then L z = cb, L' beta = z
       for (int j = 0; j < Kp; ++j) {
         if (tid == 0) {
+          // A column of A = Po .* alpha that is zero (an empty group) or depends on the columns before it leaves a
+          // pivot that is not safely positive: the reference's `Xoa \ yo` (pivoted QR, Alt.jl:110) then gives that
+          // group beta_j = 0 (minimum norm for a zero column); here the row / column is taken out of the system.
           const double djj = Gb[j * Kp + j];
-          if (!(djj > 0.0)) s_fail = 1;
-          Gb[j * Kp + j] = sqrt(djj);
+          if (djj != djj) s_fail = 1;
+          s_dead = !(djj > 1e-13 * gdiag[j]);
+          Gb[j * Kp + j] = s_dead ? 1.0 : sqrt(djj);
+          deadc[j] = s_dead ? 1 : 0;
         }
         __syncthreads();
         const double ljj = Gb[j * Kp + j];
-        for (int i = j + 1 + tid; i < Kp; i += T) Gb[i * Kp + j] /= ljj;
+        const bool dead = s_dead;
+        for (int i = j + 1 + tid; i < Kp; i += T) Gb[i * Kp + j] = dead ? 0.0 : Gb[i * Kp + j] / ljj;
         __syncthreads();
         for (int e = tid; e < (Kp - j - 1) * (Kp - j - 1); e += T) {
           const int i = j + 1 + e / (Kp - j - 1), q = j + 1 + e % (Kp - j - 1);
@@ -185,14 +206,14 @@ __global__ void __launch_bounds__(T, MINB) k6_alt_restarts(const AltArgs A) {
       }
       if (wid == 0) {
         for (int j = 0; j < Kp; ++j) {          // forward substitution
-          const double z = rhs[j] / Gb[j * Kp + j];
+          const double z = deadc[j] ? 0.0 : rhs[j] / Gb[j * Kp + j];
           __syncwarp();
           if (lane == 0) rhs[j] = z;
           for (int i = j + 1 + lane; i < Kp; i += 32) rhs[i] -= Gb[i * Kp + j] * z;
           __syncwarp();
         }
         for (int j = Kp - 1; j >= 0; --j) {     // back substitution with L'
-          const double z = rhs[j] / Gb[j * Kp + j];
+          const double z = deadc[j] ? 0.0 : rhs[j] / Gb[j * Kp + j];
           __syncwarp();
           if (lane == 0) rhs[j] = z;
           for (int i = lane; i < j; i += 32) rhs[i] -= Gb[j * Kp + i] * z;

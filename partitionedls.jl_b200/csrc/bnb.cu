@@ -170,7 +170,18 @@ __global__ void __launch_bounds__(T, MINB) k5_bnb_expand(const BnbArgs A) {
         s.vflag[m] = 0;
       }
       __syncthreads();
-      const bool ok = bpp_solve3<T, 1>(cf, s, A.G, A.ldg, Mp, cmax, st);
+      bool ok = bpp_solve3<T, 1>(cf, s, A.G, A.ldg, Mp, cmax, st);
+      if (!ok) {
+        // block pivoting stalled on a nearly singular intermediate passive set (lower_bound, BnB.jl:69-92, always
+        // returns): solve this node again from the empty passive set, one variable per step behind the pivot test
+        clear_state3<T, 1>(cf, max(st.nt_dirty, st.nt_cur));
+        st.nt_dirty = 0; st.hwm = 0; st.nt_cur = 0; st.r_valid = true;
+        for (int m = tid; m < cap; m += T) { s.w[m] = 0.0; s.r[m] = s.cs[m]; s.pos[m] = -1; s.vflag[m] = 0; }
+        __syncthreads();
+        ok = bpp_solve3<T, 1>(cf, s, A.G, A.ldg, Mp, cmax, st, true);
+        STAT_ADD3(ST_REBUILD, 1);
+        if (!ok) STAT_ADD3(ST_NOCONV, 1);
+      }
       ++n_solved;
       double tot = 0.0;
 #pragma unroll

@@ -492,7 +492,9 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
     int n_bits = 0;
     while ((b_count >> (n_bits + 1)) > 0) ++n_bits;
     const int rc = k2v5_plan(Mp, n_bits, h_gmask, &plan5);
-    if (rc == PLS_OK && (force5 || b_count >= (long long)sm_count * plan5.occ * 16)) { variant = 5; cap = plan5.ld1; occ = plan5.occ; smem = plan5.smem; }
+    // measured crossover against v4 at M' = 201: ~2^15 problems (v5 pays ~3 ms per launch for its cold starts, then
+    // ~40 us per orthant and walk against v4's ~90)
+    if (rc == PLS_OK && (force5 || b_count >= (long long)sm_count * 192)) { variant = 5; cap = plan5.ld1; occ = plan5.occ; smem = plan5.smem; }
     else if (rc != PLS_OK && rc != PLS_EUNSUPPORTED) return rc;
   }
   if (variant == 4) {

@@ -893,10 +893,11 @@ __device__ __noinline__ void tab_unsweep3(const Cfg3 cf, const int *Bvar, int nb
 //     min w'Gw - 2c'w   s.t.  sg_m w_m >= 0  (sg_m = +-1),  w_m = 0 (sg_m = 0),  w_m free (SG_FREE)
 // (Judice-Pires / Kim-Park with Murty's single-pivot backup rule).  On return s.w / s.F / s.pos hold
 // the solution, s.r its gradient (st.r_valid), and s.red[0..NW) the partial sums of c_F'w_F.
-// Returns false if the iteration cap was hit or the inverse could not be rebuilt.
+// Returns false if the iteration cap was hit or the inverse could not be rebuilt.  ST_NOCONV is counted by the caller
+// (which may first retry in `safe` mode).
 template <int T, int MODE, bool TL = false>
 __device__ __forceinline__ bool bpp_solve3(const Cfg3 cf, const Sh3 &s, const double *G, int ldg, int Mp,
-                                           double cmax, Bpp3 &st) {
+                                           double cmax, Bpp3 &st, bool safe = false) {
   constexpr int NW = T / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int cap = cf.cap;
@@ -988,7 +989,10 @@ __device__ __forceinline__ bool bpp_solve3(const Cfg3 cf, const Sh3 &s, const do
     const int mxi = warp_max_i(lane < nvch ? s.pl[32 + lane] : -1);
     const int nv = nr + na;
     if (nv == 0) { st.r_valid = true; PH_TICK3(PH_PLAN); break; }   // KKT point; r stays valid for the next orthant
-    const bool single = !(nv < t_best) && pbar < 1;              // Murty's rule: only the highest index moves
+    // Murty's rule: only the highest index moves.  `safe`: from the first step on (the fallback of BnB nodes / Alt
+    // restarts whose block-pivoting solve passed through a nearly singular intermediate passive set: one variable per
+    // step behind the pivot test, as Lawson-Hanson, never forms such sets)
+    const bool single = safe || (!(nv < t_best) && pbar < 1);
     if (!single) {
       for (int ch = wid; ch < nvch; ch += NW) {
         const int m = (ch << 5) + lane;
@@ -1059,9 +1063,8 @@ __device__ __forceinline__ bool bpp_solve3(const Cfg3 cf, const Sh3 &s, const do
     PH_TICK3(PH_ADD);
     st.hwm = hw_after; st.nt_cur = (hw_after + 7) >> 3;
     STAT_ADD3(ST_ITER, 1);
-    if (++iters > 60 + 6 * Mp) { ok = false; break; }
+    if (++iters > (safe ? 200 + 40 * Mp : 60 + 6 * Mp)) { ok = false; break; }
   }
-  if (!ok) STAT_ADD3(ST_NOCONV, 1);
   return ok;
 }
 

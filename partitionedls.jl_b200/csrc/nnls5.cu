@@ -119,10 +119,10 @@ __device__ __forceinline__ Sh5 make_sh5(int NR, int ld1) {
   const int ntl = (NR / 8) * (NR / 8 + 1) / 2;
   Sh5 s;
   double *dp = reinterpret_cast<double *>(smem_raw5);
-  s.T2 = dp; dp += t2_doubles(NR);
-  s.v = dp; dp += ld1;
+  s.T2 = dp; dp += t2_doubles(NR);                    // T2 | Pp | Wp are contiguous: the fold's two ld1 x 8 panels alias them
   s.Pp = dp; dp += 8 * NR;
   s.Wp = dp; dp += 8 * NR;
+  s.v = dp; dp += ld1;
   s.yv = dp; dp += NR;
   s.D = dp; dp += 64;
   s.gd = dp; dp += 8;
@@ -456,30 +456,30 @@ __device__ __noinline__ bool fold_block5(W5 &w, int boff, int nb) {
   const short *B = s.lstE + boff;
   constexpr int NW = T / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int ld1 = w.ld1;
-  double *Wp = s.T2;                                   // [ld1][8] panel W = P inv(D): aliases T2, which is rebuilt after the fold
-  for (int q = 0; q < 8; ++q) {                        // P rows -> global scratch
-    const double *src = w.T1 + (size_t)ld1 * (q < nb ? B[q] : 0);
-    for (int j = tid; j < ld1; j += T) w.Pg[q * ld1 + j] = q < nb ? __ldcg(src + j) : 0.0;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int ld1 = w.ld1, nt = ld1 >> 3;
+  // panels P = T1[:, B] and W = P inv(D), both [ld1][8] (column XOR-swizzled): they alias T2 | Pp | Wp, which hold
+  // nothing that outlives a fold (T2 is rebuilt afterwards)
+  double *FP = s.T2, *FW = s.T2 + (size_t)ld1 * 8;
+  for (int idx = tid; idx < ld1 * 8; idx += T) {
+    const int j = idx >> 3, q = idx & 7;
+    FP[pan5(j, q)] = q < nb ? __ldcg(w.T1 + (size_t)ld1 * B[q] + j) : 0.0;
   }
-  for (int e = tid; e < 64; e += T) {                  // D -> shared
-    const int i = e >> 3, j = e & 7;
-    s.D[e] = (i < nb && j < nb) ? __ldcg(w.T1 + (size_t)ld1 * B[i] + B[j]) : (i == j ? 1.0 : 0.0);
-  }
+  if (tid < 8) s.gd[tid] = (tid < nb && (s.st[B[tid]] & ST_PAS)) ? 1e-13 * __ldg(w.G + (size_t)w.ldg * B[tid] + B[tid]) : 0.0;
   SYNC5();
   if (tid < 32) {
     // Gauss-Jordan in the given order (swept-back variables first: pivots < 0; then entering ones: pivots > 0)
     bool ok = true;
     const int i = lane >> 2, j0 = (lane & 3) << 1;
-    double e0 = s.D[i * 8 + j0], e1 = s.D[i * 8 + j0 + 1];
+    double e0 = (i < nb && j0 < nb) ? FP[pan5(B[i], j0)] : (i == j0 ? 1.0 : 0.0);
+    double e1 = (i < nb && j0 + 1 < nb) ? FP[pan5(B[i], j0 + 1)] : (i == j0 + 1 ? 1.0 : 0.0);
     for (int k = 0; k < nb; ++k) {
       __syncwarp();
       s.D[i * 8 + j0] = e0; s.D[i * 8 + j0 + 1] = e1;
       __syncwarp();
       const double pk0 = s.D[k * 8 + j0], pk1 = s.D[k * 8 + j0 + 1], cik = s.D[i * 8 + k], pkk = s.D[k * 8 + k];
-      const unsigned char f = s.st[B[k]];
-      if (f & ST_PAS) ok = ok && pkk > 1e-13 * __ldg(w.G + (size_t)w.ldg * B[k] + B[k]);     // enters O
-      else ok = ok && pkk < 0.0;                                                           // leaves O
+      if (s.st[B[k]] & ST_PAS) ok = ok && pkk > s.gd[k];     // enters O
+      else ok = ok && pkk < 0.0;                            // leaves O
       const double d = 1.0 / pkk, fct = cik * d;
       const bool rowk = i == k;
       double n0 = rowk ? pk0 * d : fma(-fct, pk0, e0);
@@ -495,40 +495,35 @@ __device__ __noinline__ bool fold_block5(W5 &w, int boff, int nb) {
   }
   SYNC5();
   if (!s.ctl[C_OK]) { SYNC5(); return false; }
-  for (int i = tid; i < ld1; i += T) {                 // W = P inv(D)
-    double p[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) p[r] = w.Pg[r * ld1 + i];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      double a = 0.0;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) a = fma(p[r], s.D[r * 8 + q], a);
-      Wp[i * 8 + q] = a;
-    }
+  for (int ti = wid; ti < nt; ti += NW) {              // W = P inv(D)
+    double c0 = 0.0, c1 = 0.0;
+    dmma5(c0, c1, FP[pan5(ti * 8 + fr, fk)], s.D[fk * 8 + fr]);
+    dmma5(c0, c1, FP[pan5(ti * 8 + fr, 4 + fk)], s.D[(4 + fk) * 8 + fr]);
+    *reinterpret_cast<double2 *>(FW + pan5(ti * 8 + fr, 2 * fk)) = make_double2(c0, c1);
   }
   SYNC5();
   {                                                    // rank-8 update of the lower tiles, mirrored into the upper ones
-    const int fr = lane >> 2, fk = lane & 3;
-    const int nt = ld1 >> 3, ntl = (nt * (nt + 1)) >> 1;
-    constexpr int IFL = 4;
+    const int ntl = (nt * (nt + 1)) >> 1;
+    constexpr int IFL = T <= 64 ? 8 : 4;               // tiles in flight per warp (global-memory latency)
     int q = (ntl * wid) / NW;
     const int q1 = (ntl * (wid + 1)) / NW;
     int ti = 0;
     while (((ti + 1) * (ti + 2)) >> 1 <= q) ++ti;
     int tj = q - ((ti * (ti + 1)) >> 1);
     for (; q < q1; q += IFL) {
-      double2 c[IFL]; double a0[IFL], a1[IFL], b0[IFL], b1[IFL]; int ri[IFL], rj[IFL];
+      double2 c[IFL]; int ri[IFL], rj[IFL];
 #pragma unroll
       for (int u = 0; u < IFL; ++u) {
         ri[u] = ti; rj[u] = tj;
         c[u] = __ldcg(reinterpret_cast<const double2 *>(w.T1 + (size_t)(ti * 8 + fr) * ld1 + tj * 8 + 2 * fk));
-        a0[u] = -Wp[(ti * 8 + fr) * 8 + fk]; a1[u] = -Wp[(ti * 8 + fr) * 8 + 4 + fk];
-        b0[u] = w.Pg[fk * ld1 + tj * 8 + fr]; b1[u] = w.Pg[(4 + fk) * ld1 + tj * 8 + fr];
         if (q + u + 1 < q1) { if (++tj > ti) { ++ti; tj = 0; } }
       }
 #pragma unroll
-      for (int u = 0; u < IFL; ++u) { dmma5(c[u].x, c[u].y, a0[u], b0[u]); dmma5(c[u].x, c[u].y, a1[u], b1[u]); }
+      for (int u = 0; u < IFL; ++u) {
+        const int ra = ri[u] * 8 + fr, rb = rj[u] * 8 + fr;
+        dmma5(c[u].x, c[u].y, -FW[pan5(ra, fk)], FP[pan5(rb, fk)]);
+        dmma5(c[u].x, c[u].y, -FW[pan5(ra, 4 + fk)], FP[pan5(rb, 4 + fk)]);
+      }
 #pragma unroll
       for (int u = 0; u < IFL; ++u) {
         if (q + u < q1) {
@@ -542,12 +537,11 @@ __device__ __noinline__ bool fold_block5(W5 &w, int boff, int nb) {
     }
   }
   SYNC5();
-  for (int q = 0; q < nb; ++q) {                       // rows / columns of B
-    const double eq = (s.st[B[q]] & ST_PAS) ? 1.0 : -1.0;
-    double *rowq = w.T1 + (size_t)ld1 * B[q];
-    for (int i = tid; i < ld1; i += T) {
-      const double val = eq * Wp[i * 8 + q];
-      __stcg(rowq + i, val);
+  for (int idx = tid; idx < ld1 * 8; idx += T) {       // rows / columns of B
+    const int i = idx >> 3, q = idx & 7;
+    if (q < nb) {
+      const double val = (s.st[B[q]] & ST_PAS) ? FW[pan5(i, q)] : -FW[pan5(i, q)];
+      __stcg(w.T1 + (size_t)ld1 * B[q] + i, val);
       __stcg(w.T1 + (size_t)ld1 * i + B[q], val);
     }
   }
@@ -777,6 +771,41 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
   }
 }
 
+// T1 <- [G c; c' yy] with zero padding (ld1 x ld1), every variable active and outside the window
+template <int T>
+__device__ __noinline__ void cold_init5(W5 &w, const double *c, double yy) {
+  const Sh5 s = make_sh5(w.nr, w.ld1);
+  const int tid = threadIdx.x, Mp = w.Mp, ld1 = w.ld1, ld2 = ld1 >> 1;
+  for (int idx = tid; idx < ld1 * ld2; idx += T) {
+    const int row = idx / ld2, col = (idx - row * ld2) << 1;
+    double2 val = make_double2(0.0, 0.0);
+    if (row < Mp) {
+      const double *gr = w.G + (size_t)w.ldg * row;
+      val.x = col < Mp ? gr[col] : (col == Mp ? c[row] : 0.0);
+      val.y = col + 1 < Mp ? gr[col + 1] : (col + 1 == Mp ? c[row] : 0.0);
+    } else if (row == Mp) {
+      val.x = col < Mp ? c[col] : (col == Mp ? yy : 0.0);
+      val.y = col + 1 < Mp ? c[col + 1] : (col + 1 == Mp ? yy : 0.0);
+    }
+    __stcg(reinterpret_cast<double2 *>(w.T1 + (size_t)ld1 * row + col), val);
+  }
+  for (int m = tid; m < ld1; m += T) { s.st[m] = 0; s.slot[m] = -1; s.sg[m] = 0; }
+  SYNC5();
+}
+
+// d_m = sum_k Po[m,k] (2 bit_k(b) - 1)   (Opt.jl:28-29) -> sign classes; clears the per-orthant refusal flags
+template <int T>
+__device__ __forceinline__ void set_signs5(const Sh5 &s, const W5 &w, long long b, int free_top, int Kp) {
+  for (int m = threadIdx.x; m < w.Mp; m += T) {
+    const unsigned long long gm = w.gmask[m];
+    const int d = 2 * __popcll(gm & (unsigned long long)b) - __popcll(gm);
+    const bool fr = free_top && ((gm >> (Kp - 1)) & 1ull);
+    s.sg[m] = (signed char)(fr ? SG_FREE5 : (d > 0) - (d < 0));
+    s.st[m] &= (unsigned char)~ST_BLK;
+  }
+  SYNC5();
+}
+
 template <int T, int NR, int NQ, int MINB>
 __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
   const int tid = threadIdx.x;
@@ -803,43 +832,24 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
   int since_check = 0, check_every = A.verify_every;
   double max_viol = 0.0;
   unsigned long long n_drift = 0, n_noconv = 0;
+  SYNC5();
 
   for (long long i = i0; i < i1; ++i) {
     if (cold) {
-      // T1 <- [G c; c' yy], zero padding (ld1 x ld1)
-      const int ld2 = ld1 >> 1;
-      for (int idx = tid; idx < ld1 * ld2; idx += T) {
-        const int row = idx / ld2, col = (idx - row * ld2) << 1;
-        double2 val = make_double2(0.0, 0.0);
-        if (row < Mp) {
-          const double *gr = A.G + (size_t)A.ldg * row;
-          val.x = col < Mp ? gr[col] : (col == Mp ? A.c[row] : 0.0);
-          val.y = col + 1 < Mp ? gr[col + 1] : (col + 1 == Mp ? A.c[row] : 0.0);
-        } else if (row == Mp) {
-          val.x = col < Mp ? A.c[col] : (col == Mp ? yy : 0.0);
-          val.y = col + 1 < Mp ? A.c[col + 1] : (col + 1 == Mp ? yy : 0.0);
-        }
-        __stcg(reinterpret_cast<double2 *>(w.T1 + (size_t)ld1 * row + col), val);
-      }
-      for (int m = tid; m < ld1; m += T) { s.st[m] = 0; s.slot[m] = -1; s.sg[m] = 0; }
-      SYNC5();
+      cold_init5<T>(w, A.c, yy);
+      // the cold solve runs with NO fast groups: the window starts empty and takes up to NR - 1 violators per round,
+      // all of which are folded into T1 in full blocks of 8 (~2 rounds instead of ~9 with the fast variables in the way)
+      w.lowmask = 0ull;
       window_reset(w);
       t2_rebuild<T>(w);                                // nothing is toggled: a plain copy
       cold = false; just_cold = true; since_check = 0; t2_fresh = true;
     }
     const long long b = A.b_begin + (i ^ (i >> 1));
     const int fb = i > 0 ? __ffsll(i) - 1 : 63;        // the group whose sign changed
-    for (int m = tid; m < Mp; m += T) {                // d_m = sum_k Po[m,k] (2 bit_k(b) - 1)   (Opt.jl:28-29)
-      const unsigned long long gm = w.gmask[m];
-      const int d = 2 * __popcll(gm & (unsigned long long)b) - __popcll(gm);
-      const bool fr = A.free_top && ((gm >> (A.Kp - 1)) & 1ull);
-      s.sg[m] = (signed char)(fr ? SG_FREE5 : (d > 0) - (d < 0));
-      s.st[m] &= (unsigned char)~ST_BLK;
-    }
-    SYNC5();
+    set_signs5<T>(s, w, b, A.free_top, A.Kp);
 
     const bool ok = solve5<T, NR, NQ>(s, w, cmax, t2_fresh);
-    if (!ok) { cold = true; ++n_noconv; }
+    if (!ok) { cold = true; ++n_noconv; w.lowmask = A.lowmask; }
 
     // ---- drift control: KKT conditions against the original G, c
     ++since_check;
@@ -887,9 +897,15 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
       }
       SYNC5();
       const int nslow = s.ctl[C_NSLOW];
-      if (fb >= low_bits || nslow >= 8 || w.n > NR - 8) {
+      const bool was_cold = w.lowmask != A.lowmask;   // first orthant after a cold start: fold everything, then bring the fast groups in
+      if (fb >= low_bits || nslow >= 8 || w.n > NR - 8 || was_cold) {
         if (!fold5<T>(w)) cold = true;             // refused block (near-singular pivot): restart cold
         t2_fresh = true;
+        if (was_cold && !cold) {
+          w.lowmask = A.lowmask;
+          window_reset(w);
+          if (!t2_rebuild<T>(w)) cold = true;
+        }
       }
     }
     SYNC5();
@@ -916,17 +932,17 @@ struct Variant5 { int T, NR, NQ, minb; K5Fn fn; };
 #define V5(T, NR, NQ, MINB) {T, NR, NQ, MINB, k2v5_orthant_walks<T, NR, NQ, MINB>}
 const Variant5 kVariants5[] = {
     // M' + 1 <= 256 (NQ = row pieces per thread of the streaming pass: ld1 <= 2 T NQ)
-    V5(64, 72, 2, 6), V5(64, 56, 2, 8), V5(64, 64, 2, 7), V5(64, 80, 2, 5), V5(64, 96, 2, 4), V5(128, 56, 1, 8), V5(128, 64, 1, 7), V5(128, 72, 1, 6),
-    V5(128, 80, 1, 5), V5(128, 96, 1, 4), V5(32, 56, 4, 8), V5(32, 72, 4, 6),
+    V5(128, 72, 1, 6), V5(128, 80, 1, 5), V5(128, 96, 1, 4), V5(64, 64, 2, 7), V5(64, 72, 2, 6), V5(64, 80, 2, 5), V5(64, 96, 2, 4),
+    V5(32, 72, 4, 6),
     // wider problems (the fold's ld1 x 8 panel aliases T2: ld1 * 8 <= t2_doubles(NR))
-    V5(128, 72, 2, 6), V5(128, 96, 3, 4),
+    V5(128, 96, 2, 4), V5(128, 128, 3, 3),
 };
 #undef V5
 
 }  // namespace
 
-// Environment overrides for tuning / tests: PLS_K5_T (threads per walk), PLS_K5_NR (window slots), PLS_K5_L (fast groups),
-// PLS_K5_GRID (walks), PLS_K5_VERIFY, PLS_K5_OCC.
+// Environment overrides for tuning / tests: PLS_K5_T (threads per walk), PLS_K5_NR (window slots), PLS_K5_MARGIN,
+// PLS_K5_L (fast groups), PLS_K5_GRID (walks), PLS_K5_VERIFY, PLS_K5_OCC.
 // h_gmask: host copy of the group masks (sizes the window); n_bits: enumerated Gray bits.
 int k2v5_plan(int Mp, int n_bits, const uint64_t *h_gmask, K5Plan *pl) {
   if (!h_gmask) return PLS_EUNSUPPORTED;
@@ -937,26 +953,32 @@ int k2v5_plan(int Mp, int n_bits, const uint64_t *h_gmask, K5Plan *pl) {
   PLS_CUDA_TRY(cudaGetDevice(&dev));
   PLS_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   const Variant5 *v = nullptr;
-  int vi = 0, l = 0;
+  int vi = -1, l = 0;
   const char *eM = getenv("PLS_K5_MARGIN");
-  const int margin = eM ? atoi(eM) : 14;
+  const int margin = eM ? atoi(eM) : 10;               // free window slots kept for variables that join
+  // Window size: a larger window holds more fast groups (a fold every 2^l orthants) but costs shared memory (walks
+  // per SM) and work per pivot.  Measured on M' = 201: l = 6 at NR = 72 beats NR = 96 (K = 20, groups of 10); with
+  // groups of 12-13 (K = 16) NR = 72 only reaches l = 4 and NR = 96 (l = 6) wins.  Rule: the first (smallest) window
+  // that reaches l >= 6 (or every enumerated bit but two), else the one with the most fast groups.
+  const int l_want = n_bits - 2 < 6 ? (n_bits - 2 < 1 ? 1 : n_bits - 2) : 6;
+  int ci = 0;
   for (const Variant5 &c : kVariants5) {
-    const bool fits = (!wantT || c.T == wantT) && (!wantNR || c.NR == wantNR) && ld1 <= 2 * c.T * c.NQ &&
-                      (size_t)ld1 * 8 <= (size_t)t2_doubles(c.NR) && sh5_bytes(c.NR, ld1) <= (size_t)max_smem;
+    const bool fits = c.T == (wantT ? wantT : 128) && (!wantNR || c.NR == wantNR) && ld1 <= 2 * c.T * c.NQ &&
+                      2 * (size_t)ld1 * 8 <= (size_t)t2_doubles(c.NR) + 16 * (size_t)c.NR && sh5_bytes(c.NR, ld1) <= (size_t)max_smem;
     if (fits) {
-      // fast groups: as many of the lowest Gray bits as leave >= 14 free window slots for variables that join
-      l = 0;
+      int lc = 0;
       for (int t = 1; t <= n_bits && t <= 10; ++t) {
         int nf = 0;
         const uint64_t mask = (1ull << t) - 1ull;
         for (int m = 0; m < Mp; ++m) nf += (h_gmask[m] & mask) != 0ull;
-        if (nf + 1 + margin <= c.NR) l = t; else break;
+        if (nf + 1 + margin <= c.NR) lc = t; else break;
       }
-      if (l >= 1) { v = &c; break; }
+      if (lc > l) { v = &c; vi = ci; l = lc; }
+      if (l >= l_want) break;
     }
-    ++vi;
+    ++ci;
   }
-  if (!v) return PLS_EUNSUPPORTED;
+  if (!v || l < 1) return PLS_EUNSUPPORTED;
   if (const char *eL = getenv("PLS_K5_L")) { const int t = atoi(eL); if (t >= 1 && t < l) l = t; }
   const size_t sm = sh5_bytes(v->NR, ld1);
   PLS_CUDA_TRY(cudaFuncSetAttribute(v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));

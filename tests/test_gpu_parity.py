@@ -27,10 +27,10 @@ K2_VARIANTS = {
     "v4q": {"PLS_K2_IMPL": "v4", "PLS_K4_GRID": "2", "PLS_K4_L": "1", "PLS_K4_QS": "6", "PLS_K4_T": "256"},
     # v5 (nnls5.cu, the default winner-only kernel): two swept tableaus per walk
     "v5": {"PLS_K2_IMPL": "v5", "PLS_K5_GRID": "3", "PLS_K5_L": "2", "PLS_K5_VERIFY": "5"},
-    "v5w": {"PLS_K2_IMPL": "v5", "PLS_K5_GRID": "2", "PLS_K5_L": "1", "PLS_K5_T": "128"},
+    "v5w": {"PLS_K2_IMPL": "v5", "PLS_K5_GRID": "2", "PLS_K5_L": "1", "PLS_K5_T": "64", "PLS_K5_NR": "64"},
 }
 _K2_KEYS = ("PLS_K2_IMPL", "PLS_K3_QS", "PLS_K3_T", "PLS_K3_MINB", "PLS_K4_GRID", "PLS_K4_L", "PLS_K4_VERIFY", "PLS_K4_QS", "PLS_K4_T",
-            "PLS_K5_GRID", "PLS_K5_L", "PLS_K5_VERIFY", "PLS_K5_T", "PLS_K2_NO_V5")
+            "PLS_K5_GRID", "PLS_K5_L", "PLS_K5_VERIFY", "PLS_K5_T", "PLS_K5_NR", "PLS_K5_MARGIN", "PLS_K2_NO_V5")
 # the kernel a winner-only fit of a long aligned range runs (pls_stats.k2_variant)
 DEFAULT_TWOLEVEL = 5
 
@@ -471,7 +471,7 @@ TWOLEVEL_ENVS = {
     "v4_one_cta": ({"PLS_K2_IMPL": "v4", "PLS_K4_GRID": "1", "PLS_K4_L": "1", "PLS_K4_VERIFY": "4"}, 4),
     "v5_few_walks": ({"PLS_K2_IMPL": "v5", "PLS_K5_GRID": "3", "PLS_K5_L": "2", "PLS_K5_VERIFY": "4"}, 5),
     "v5_one_walk": ({"PLS_K2_IMPL": "v5", "PLS_K5_GRID": "1", "PLS_K5_L": "1", "PLS_K5_VERIFY": "4"}, 5),
-    "v5_one_warp": ({"PLS_K2_IMPL": "v5", "PLS_K5_GRID": "2", "PLS_K5_L": "3", "PLS_K5_T": "32"}, 5),
+    "v5_64_threads": ({"PLS_K2_IMPL": "v5", "PLS_K5_GRID": "2", "PLS_K5_L": "3", "PLS_K5_T": "64", "PLS_K5_NR": "96"}, 5),
     # per-orthant outputs through the default dispatcher: always the one-level kernel (every iterate is checked
     # against the original Gram system)
     "default_dispatch_one_level": ({}, 3),
@@ -566,12 +566,12 @@ def test_twolevel_long_walk_every_orthant(ctx, oracle, impl):
 
 def test_default_winner_only_path_against_oracle(ctx, pkg, oracle):
     """The benchmark's exact path -- default dispatch, winner only, paired orthants, the two-level kernel -- at M' = 97,
-    K = 14 (2^14 NNLS problems): pls_stats must report that kernel, and b*, alpha, objective must equal the oracle's.
-    The oracle's argmin over all 2^15 orthants is found by solving, with the C oracle (data-space Lawson-Hanson), the
+    K = 15 (2^15 NNLS problems): pls_stats must report that kernel, and b*, alpha, objective must equal the oracle's.
+    The oracle's argmin over all 2^16 orthants is found by solving, with the C oracle (data-space Lawson-Hanson), the
     20 best orthants of the one-level kernel's literal enumeration plus 40 random ones (each of which must also agree
     with that enumeration), so the candidate list is itself oracle-checked."""
     o, oc = oracle
-    N, M, K = 4000, 96, 14
+    N, M, K = 4000, 96, 15
     X, y, P = o.make_synthetic(N, M, K, seed=2025, mixed_sign=True, rho=0.2)
     w = ctx.opt_fit(X, y, P, eta=1e-3)                                   # winner only: the default path
     st = w["stats"]

@@ -68,6 +68,20 @@ def big(ctx, name, reps=3):
     return 0 if same else 1
 
 
+def shard(ctx, name, nshard, reps=3):
+    """one rank's share of a strong-scaling run: the first 1/nshard of the sign patterns (pairs)"""
+    N, M, K, eta, seed, mixed = synth.CONFIGS[name]
+    X, y, P = synth.make_synthetic(N, M, K, seed, mixed_sign=mixed)
+    ctx.load(X, y, P, eta=eta); ctx.gram_build(); ctx.gram_finalize()
+    for label, e in (("v5", {}), ("v5_noseed", dict(PLS_K5_SEED=0)), ("v4", dict(PLS_K2_NO_V5=1))):
+        env(**e)
+        for _ in range(reps):
+            r = ctx.opt_solve_pairs(0, (1 << K) // nshard)
+        st = ctx.stats()
+        print(name, f"1/{nshard}", label, json.dumps(dict(variant=st["k2_variant"], ms_nnls=st["ms_nnls"], b=r["b_best"], sweeps=st["pivots"], grid=st["k2_grid"])), flush=True)
+    return 0
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     ctx = pkg.Context(0)
@@ -78,5 +92,17 @@ if __name__ == "__main__":
         bad += big(ctx, "cfg2")
     if what in ("k20", "all"):
         bad += big(ctx, "k20_m200")
+    if what == "cold":
+        N, M, K, eta, seed, mixed = synth.CONFIGS["k20_m200"]
+        X, y, P = synth.make_synthetic(N, M, K, seed, mixed_sign=mixed)
+        ctx.load(X, y, P, eta=eta); ctx.gram_build(); ctx.gram_finalize()
+        env(PLS_K2_IMPL="v5", PLS_K5_SEED=0)
+        for cnt in (1024, 2048, 4096, 8192, 16384, 32768, 65536):
+            for _ in range(3):
+                r = ctx.opt_solve_pairs(0, cnt)
+            st = ctx.stats()
+            print("cold", cnt, json.dumps(dict(ms=st["ms_nnls"], grid=st["k2_grid"], sweeps=st["pivots"], streams=st["grad_evals"], iters=st["bpp_iters"])), flush=True)
+    if what.startswith("shard"):
+        bad += shard(ctx, "k20_m200", int(what[5:]))
     print("RESULT", "ok" if bad == 0 else f"{bad} FAILED")
     sys.exit(1 if bad else 0)
