@@ -199,6 +199,12 @@ int pls_gram_scalars(pls_ctx *ctx, double *yy, double *cmax);
  * objective and raw alpha for b in [b_begin, b_begin + b_count). */
 int pls_gram(pls_ctx *ctx, const double *X, int64_t N, int64_t M, const double *y, const int64_t *P,
              int64_t K, double eta, double *G, double *c, double *yy);
+/* pls_bnb_lower_bounds: the relaxations of n <= 64 branch-and-bound nodes on the resident data set -- lower_bound(X, y,
+ * Sigma) of src/PartitionedLSBnB.jl:69-92 for Sigma = "every variable of the groups in pos_masks[i] >= 0, of the groups in
+ * neg_masks[i] <= 0" (bit k = group k, the intercept group is bit K).  lb_out[i] = norm(XX*aa - y) (Gram space),
+ * alpha_signed_out[i * (M+1) ...] = alpha_p - alpha_n.  Each node is solved cold by the K5 kernel. */
+int pls_bnb_lower_bounds(pls_ctx *ctx, const uint64_t *pos_masks, const uint64_t *neg_masks, int64_t n, double *lb_out,
+                         double *alpha_signed_out);
 int pls_nnls_batch(pls_ctx *ctx, const double *G, const double *c, double yy, int64_t Mp,
                    const uint64_t *gmask, int64_t Kp, int64_t b_begin, int64_t b_count,
                    double *obj_out, double *alpha_out);

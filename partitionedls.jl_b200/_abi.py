@@ -77,12 +77,13 @@ lib.pls_predict_resident.argtypes = [_vp, _dp, _dp]
 lib.pls_objective_finish_w.argtypes = [_vp, _dp, C.c_double, _dp]
 lib.pls_get_stats.argtypes = [_vp, C.POINTER(PlsStats)]
 lib.pls_gram_scalars.argtypes = [_vp, _dp, _dp]
+lib.pls_bnb_lower_bounds.argtypes = [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int64, _dp, _dp]
 lib.pls_gram.argtypes = [_vp, _dp, C.c_int64, C.c_int64, _dp, _ip, C.c_int64, C.c_double, _dp, _dp, _dp]
 lib.pls_nnls_batch.argtypes = [_vp, _dp, _dp, C.c_double, C.c_int64, C.POINTER(C.c_uint64), C.c_int64,
                                C.c_int64, C.c_int64, _dp, _dp]
 for _n in ("pls_create", "pls_opt_fit", "pls_bnb_fit", "pls_bnb_fit_resident", "pls_alt_fit", "pls_alt_fit_resident", "pls_residual_partial_w", "pls_predict_resident", "pls_objective_finish_w", "pls_load", "pls_opt_fit_resident", "pls_gram_build", "pls_gram_raw",
            "pls_gram_finalize", "pls_opt_solve_range", "pls_opt_solve_pairs", "pls_opt_residual_partial", "pls_opt_objective_finish",
-           "pls_get_stats", "pls_gram_scalars", "pls_gram", "pls_nnls_batch"):
+           "pls_get_stats", "pls_gram_scalars", "pls_bnb_lower_bounds", "pls_gram", "pls_nnls_batch"):
     getattr(lib, _n).restype = C.c_int
 
 
@@ -293,6 +294,16 @@ class Context:
         _check(lib.pls_gram(self._h, _d(X), N, M, _d(y), P.ctypes.data_as(_ip), P.shape[1], float(eta),
                             _d(G), _d(c), C.byref(yy)))
         return G, c, yy.value
+
+    def bnb_lower_bounds(self, pos_masks, neg_masks):
+        """pls_bnb_lower_bounds on the loaded data set: (lb[n], alpha_signed[n, M+1])."""
+        N, M, K = self._shape
+        pm = np.ascontiguousarray(pos_masks, dtype=np.uint64); nm = np.ascontiguousarray(neg_masks, dtype=np.uint64)
+        n = len(pm)
+        lb = np.zeros(n); al = np.zeros((n, M + 1))
+        u64 = C.POINTER(C.c_uint64)
+        _check(lib.pls_bnb_lower_bounds(self._h, pm.ctypes.data_as(u64), nm.ctypes.data_as(u64), n, _d(lb), _d(al)))
+        return lb, al
 
     def nnls_batch(self, G, c, yy, gmask, Kp, b_begin, b_count, want_alpha=True):
         G = np.asfortranarray(G, dtype=np.float64); c = np.ascontiguousarray(c, dtype=np.float64)

@@ -317,10 +317,18 @@ int pls_create(pls_ctx **out, const int *device_ids, int n_dev) {
   if (!c) { set_error("out of host memory"); return PLS_ENOMEM; }
   c->dev = dev; c->sm_count = prop.multiProcessorCount;
   memset(&c->stats, 0, sizeof(c->stats));
-  PLS_CUDA_TRY(cudaSetDevice(dev));
-  PLS_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  for (auto &ev : c->ev) PLS_CUDA_TRY(cudaEventCreate(&ev));
-  PLS_CUDA_TRY(cudaMalloc(&c->d_ssq, sizeof(double) * 2));
+  {
+    // a partially built context is safe to destroy: release it if any of the set-up calls fails
+    auto setup = [&]() -> int {
+      PLS_CUDA_TRY(cudaSetDevice(dev));
+      PLS_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+      for (auto &ev : c->ev) PLS_CUDA_TRY(cudaEventCreate(&ev));
+      PLS_CUDA_TRY(cudaMalloc(&c->d_ssq, sizeof(double) * 2));
+      return PLS_OK;
+    };
+    const int rc = setup();
+    if (rc) { pls_destroy(c); return rc; }
+  }
   *out = c;
   return PLS_OK;
 }
@@ -568,17 +576,10 @@ int pls_predict_resident(pls_ctx *c, const double *w, double *yhat) {
   if (!c || !c->pb.loaded || !w || !yhat) { set_error("no data set loaded or null pointer"); return PLS_EINVAL; }
   if (c->subs.empty()) return predict_dev(c, w, yhat);
   const int G = (int)c->subs.size();
-  std::vector<int> rcs(G, 0);
-  std::vector<std::string> msgs(G);
-  std::vector<std::thread> th;
-  for (int g = 0; g < G; ++g)
-    th.emplace_back([&, g] { rcs[g] = predict_dev(c->subs[g], w, yhat + c->row0[g]); if (rcs[g]) msgs[g] = pls_last_error(); });
-  for (auto &t : th) t.join();
+  const int rcp = multi_predict(c, w, yhat, predict_dev);
+  if (rcp) return rcp;
   double mx = 0.0;
-  for (int g = 0; g < G; ++g) {
-    if (rcs[g]) { set_error("device %d: %s", c->subs[g]->dev, msgs[g].c_str()); return rcs[g]; }
-    mx = std::fmax(mx, c->subs[g]->stats.ms_recompute);
-  }
+  for (int g = 0; g < G; ++g) mx = std::fmax(mx, c->subs[g]->stats.ms_recompute);
   c->stats.ms_recompute = mx;
   return PLS_OK;
 }
@@ -871,6 +872,36 @@ int pls_gram(pls_ctx *c, const double *X, int64_t N, int64_t M, const double *y,
   PLS_CUDA_TRY(cudaMemcpy2D(G, sizeof(double) * pb.Mp, pb.G, sizeof(double) * pb.ldg, sizeof(double) * pb.Mp, pb.Mp, cudaMemcpyDeviceToHost));
   PLS_CUDA_TRY(cudaMemcpy(cv, pb.c, sizeof(double) * pb.Mp, cudaMemcpyDeviceToHost));
   PLS_CUDA_TRY(cudaMemcpy(yy, pb.scal, sizeof(double), cudaMemcpyDeviceToHost));
+  return PLS_OK;
+}
+
+int pls_bnb_lower_bounds(pls_ctx *c, const uint64_t *pos_masks, const uint64_t *neg_masks, int64_t n, double *lb_out,
+                         double *alpha_signed_out) {
+  if (c && !c->subs.empty()) { set_error("test hooks need a one-GPU context"); return PLS_EUNSUPPORTED; }
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!c->pb.loaded) { set_error("no data set loaded"); return PLS_EINVAL; }
+  if (!pos_masks || !neg_masks || !lb_out || !alpha_signed_out || n < 1 || n > 64) { set_error("null pointer or n not in 1..64"); return PLS_EINVAL; }
+  Problem &pb = c->pb;
+  cudaStream_t st = c->stream;
+  if (!pb.gram_ready) {
+    rc = k1_gram_build(pb, st, &c->launches); if (rc) return rc;
+    rc = k1_gram_finalize(pb, st, &c->launches); if (rc) return rc;
+  }
+  PLS_CUDA_TRY(ensure_win(c->ws, pb.Mp + 2));
+  BnbShard sh;
+  sh.probe = true;
+  sh.root_pos.assign(pos_masks, pos_masks + n);
+  sh.root_neg.assign(neg_masks, neg_masks + n);
+  BnbReport rep;
+  rc = k5_bnb_run(pb, c->ws, c->sm_count, st, &c->launches, &rep, &sh);
+  if (rc) return rc;
+  if ((int64_t)sh.probe_lb.size() != n) { set_error("bnb probe: %zu of %lld nodes solved", sh.probe_lb.size(), (long long)n); return PLS_ECUDA; }
+  for (int64_t i = 0; i < n; ++i) {            // the wave builder takes the roots from the back of the list
+    const int64_t j = n - 1 - i;
+    lb_out[i] = sh.probe_lb[(size_t)j];
+    memcpy(alpha_signed_out + (size_t)i * pb.Mp, sh.probe_w.data() + (size_t)j * pb.Mp, sizeof(double) * pb.Mp);
+  }
   return PLS_OK;
 }
 

@@ -59,6 +59,7 @@ struct BnbArgs {
   unsigned long long *leaf_seq;                // global leaf counter: lower = found earlier
   BnbChild *out;                               // [n_items][2]
   unsigned long long *counters;
+  double *probe_w = nullptr;                   // test hook: [n_items][Mp] signed weights of every ROOT item's relaxation
 };
 
 // ---- pooled state: [H tiles | w (cap) | r (cap) | F (cap ints) | meta (8 ints)] -------------------
@@ -187,6 +188,8 @@ __global__ void __launch_bounds__(T, MINB) k5_bnb_expand(const BnbArgs A) {
 #pragma unroll
       for (int q = 0; q < NW; ++q) tot += s.red[q];
       const double lb = sqrt(fmax(yy - tot, 0.0));      // = norm(XX*aa - y), BnB.jl:91
+      if (A.probe_w && root)
+        for (int m = tid; m < Mp; m += T) A.probe_w[(size_t)it * Mp + m] = s.pos[m] >= 0 ? s.w[m] : 0.0;
       // nu_k (BnB.jl:42-57) as (sum of positive weights) * (sum of |negative weights|) per group
       for (int k = wid; k < Kp; k += NW) {
         double sp = 0.0, sn = 0.0;
@@ -317,7 +320,7 @@ int k5_bnb_run(const Problem &pb, SolveWs &ws, int sm_count, cudaStream_t st, in
   if (n_slots < 4) { set_error("bnb: not enough device memory for the state pool"); return PLS_ENOMEM; }
   const int wave_max = (int)std::min<size_t>((size_t)max_grid * 2, n_slots / 2);
 
-  double *pool = nullptr, *mu = nullptr;
+  double *pool = nullptr, *mu = nullptr, *d_probe = nullptr;
   BnbItem *d_items = nullptr; BnbChild *d_out = nullptr;
   unsigned long long *d_ctr = nullptr;
   int rc = PLS_OK;
@@ -384,6 +387,11 @@ int k5_bnb_run(const Problem &pb, SolveWs &ws, int sm_count, cudaStream_t st, in
     A.items = d_items; A.n_items = n; A.item_counter = d_ctr; A.mu = mu;
     A.cta_obj = ws.cta_obj; A.cta_b = ws.cta_b; A.cta_w = ws.cta_w; A.leaf_seq = d_ctr + 1;
     A.out = d_out; A.counters = ws.counters;
+    if (shard && shard->probe) {                 // test hook: the relaxations of the given roots, nothing else
+      if (!pending.empty()) { set_error("bnb probe: too many nodes for one wave (%d)", wave_max); rc = PLS_EINVAL; goto done; }
+      BNB_TRY(cudaMalloc(&d_probe, sizeof(double) * (size_t)n * Mp));
+      A.probe_w = d_probe;
+    }
     BNB_TRY(cudaMemcpyAsync(d_items, items.data(), sizeof(BnbItem) * n, cudaMemcpyHostToDevice, st));
     BNB_TRY(cudaMemsetAsync(d_ctr, 0, sizeof(unsigned long long), st));
     kern<<<std::min(n, max_grid), TB, smem, st>>>(A);
@@ -402,6 +410,17 @@ int k5_bnb_run(const Problem &pb, SolveWs &ws, int sm_count, cudaStream_t st, in
         BNB_TRY(cudaMemcpyAsync(mu, &h_mu, sizeof(double), cudaMemcpyHostToDevice, st));   // leaves only ever lower it further
         BNB_TRY(cudaStreamSynchronize(st));
       }
+    }
+    if (shard && shard->probe) {
+      shard->probe_lb.resize(n); shard->probe_w.resize((size_t)n * Mp);
+      BNB_TRY(cudaMemcpyAsync(shard->probe_w.data(), d_probe, sizeof(double) * (size_t)n * Mp, cudaMemcpyDeviceToHost, st));
+      BNB_TRY(cudaStreamSynchronize(st));
+      for (int i = 0; i < n; ++i) {
+        if (out[(size_t)2 * i].status == 3) { set_error("bnb: a node relaxation did not converge"); rc = PLS_ENUMERIC; goto done; }
+        shard->probe_lb[i] = out[(size_t)2 * i].lb;
+      }
+      visited = n; complete = false;
+      goto done;
     }
     for (int i = 0; i < n; ++i) {
       const BnbItem &itx = items[i];
@@ -472,7 +491,7 @@ int k5_bnb_run(const Problem &pb, SolveWs &ws, int sm_count, cudaStream_t st, in
     rep->complete = complete; rep->has_leaf = false;
   }
 done:
-  cudaFree(pool); cudaFree(mu); cudaFree(d_items); cudaFree(d_out); cudaFree(d_ctr);
+  cudaFree(pool); cudaFree(mu); cudaFree(d_items); cudaFree(d_out); cudaFree(d_ctr); cudaFree(d_probe);
   return rc;
 #undef BNB_TRY
 }

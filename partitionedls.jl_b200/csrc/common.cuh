@@ -172,6 +172,10 @@ struct BnbShard {
   std::atomic<unsigned long long> *shared_mu = nullptr;
   long long stop_waves = 0, stop_open = 0;
   std::vector<unsigned long long> open_pos, open_neg;
+  // test hook (pls_bnb_lower_bounds): solve the relaxations of the roots only and return them, in root order reversed
+  // by the wave builder -- see api.cu
+  bool probe = false;
+  std::vector<double> probe_lb, probe_w;
 };
 int k5_bnb_run(const Problem &pb, SolveWs &ws, int sm_count, cudaStream_t st, int *launches, BnbReport *rep,
                BnbShard *shard = nullptr);

@@ -23,6 +23,7 @@ struct pls_ctx {
   double *stage = nullptr;      // on subs[0]'s device: the other devices' raw Gram sums
   size_t stage_bytes = 0;
   std::vector<int64_t> row0;    // row shard boundaries (size subs.size() + 1)
+  void *pool = nullptr;         // multi.cu: one persistent host worker per device
 };
 
 namespace pls {
@@ -39,6 +40,7 @@ int residual_partial_w(pls_ctx *c, const double *w, double *ssq_out);
 double now_ms();
 // multi.cu
 int multi_create(pls_ctx *c, const int *device_ids, int n_dev);
+int multi_predict(pls_ctx *c, const double *w, double *yhat, int (*predict_dev)(pls_ctx *, const double *, double *));
 void multi_destroy(pls_ctx *c);
 int multi_load(pls_ctx *c, const double *X, int64_t N, int64_t ldx, int64_t M, const double *y, const int64_t *P,
                int64_t K, double eta);

@@ -21,6 +21,9 @@
 #include <atomic>
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 
@@ -37,37 +40,72 @@ __global__ void sum_parts(double *S, const double *stage, long long cnt, int npa
   S[i] = s;
 }
 
-// f(g, sub) on one host thread per device; first failure wins, its message is re-raised here
+// One persistent host worker per device (created with the context, joined when it is destroyed): a stage hands
+// every worker the same callable and waits for all of them -- no thread is spawned per stage or per fit.
+struct WorkerPool {
+  std::vector<std::thread> th;
+  std::mutex mu;
+  std::condition_variable cv_go, cv_done;
+  std::function<void(int)> job;
+  unsigned long long gen = 0;
+  int pending = 0;
+  bool stop = false;
+  explicit WorkerPool(int n) {
+    for (int g = 0; g < n; ++g)
+      th.emplace_back([this, g] {
+        unsigned long long seen = 0;
+        for (;;) {
+          std::function<void(int)> f;
+          {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_go.wait(lk, [&] { return stop || gen != seen; });
+            if (stop) return;
+            seen = gen; f = job;
+          }
+          f(g);
+          {
+            std::lock_guard<std::mutex> lk(mu);
+            if (--pending == 0) cv_done.notify_all();
+          }
+        }
+      });
+  }
+  void run(const std::function<void(int)> &f) {
+    std::unique_lock<std::mutex> lk(mu);
+    job = f; pending = (int)th.size(); ++gen;
+    cv_go.notify_all();
+    cv_done.wait(lk, [&] { return pending == 0; });
+  }
+  ~WorkerPool() {
+    { std::lock_guard<std::mutex> lk(mu); stop = true; }
+    cv_go.notify_all();
+    for (auto &t : th) t.join();
+  }
+};
+
+// f(g, sub) on the worker of every device; first failure wins, its message is re-raised here
 template <class F>
 int par_for(pls_ctx *c, F f) {
   const int G = (int)c->subs.size();
   std::vector<int> rcs(G, 0);
   std::vector<std::string> msgs(G);
-  std::vector<std::thread> th;
-  th.reserve(G);
-  for (int g = 0; g < G; ++g)
-    th.emplace_back([&, g] {
-      rcs[g] = f(g, c->subs[g]);
-      if (rcs[g]) msgs[g] = pls_last_error();
-    });
-  for (auto &t : th) t.join();
+  auto body = [&](int g) {
+    rcs[g] = f(g, c->subs[g]);
+    if (rcs[g]) msgs[g] = pls_last_error();
+  };
+  if (c->pool) static_cast<WorkerPool *>(c->pool)->run(body);
+  else for (int g = 0; g < G; ++g) body(g);
   for (int g = 0; g < G; ++g)
     if (rcs[g]) { set_error("device %d: %s", c->subs[g]->dev, msgs[g].c_str()); return rcs[g]; }
   return PLS_OK;
 }
 
-// K1 on every shard, then the peer-to-peer sum of the raw Gram sums and the per-device finalize
+// K1 on every shard, the peer-to-peer sum of the raw Gram sums and the per-device finalize.  Every device PUSHES its
+// sums to device 0's staging area on its own stream (the copies run in parallel over NVLink), device 0 adds them in a
+// fixed order (deterministic, bitwise-identical G everywhere) once all pushes have landed (events), and every device
+// PULLS the total on its own stream and finalises -- one host synchronisation per device at the very end.
 int multi_gram(pls_ctx *c) {
   const int G = (int)c->subs.size();
-  int rc = par_for(c, [](int, pls_ctx *s) -> int {
-    int r = check_ctx(s);
-    if (r) return r;
-    r = k1_gram_build(s->pb, s->stream, &s->launches);
-    if (r) return r;
-    PLS_CUDA_TRY(cudaStreamSynchronize(s->stream));
-    return PLS_OK;
-  });
-  if (rc) return rc;
   pls_ctx *d0 = c->subs[0];
   const long long cnt = (long long)d0->pb.zcols * d0->pb.zcols;
   const size_t bytes = sizeof(double) * (size_t)cnt;
@@ -77,17 +115,29 @@ int multi_gram(pls_ctx *c) {
     PLS_CUDA_TRY(cudaMalloc(&c->stage, bytes * (G - 1)));
     c->stage_bytes = bytes * (G - 1);
   }
-  for (int g = 1; g < G; ++g)
-    PLS_CUDA_TRY(cudaMemcpyPeerAsync(c->stage + (size_t)(g - 1) * cnt, d0->dev, c->subs[g]->pb.S, c->subs[g]->dev, bytes, d0->stream));
+  int rc = par_for(c, [&](int g, pls_ctx *s) -> int {
+    int r = check_ctx(s);
+    if (r) return r;
+    r = k1_gram_build(s->pb, s->stream, &s->launches);
+    if (r) return r;
+    if (g > 0) PLS_CUDA_TRY(cudaMemcpyPeerAsync(c->stage + (size_t)(g - 1) * cnt, d0->dev, s->pb.S, s->dev, bytes, s->stream));
+    PLS_CUDA_TRY(cudaEventRecord(s->ev[4], s->stream));
+    return PLS_OK;
+  });
+  if (rc) return rc;
+  PLS_CUDA_TRY(cudaSetDevice(d0->dev));
+  for (int g = 1; g < G; ++g) PLS_CUDA_TRY(cudaStreamWaitEvent(d0->stream, c->subs[g]->ev[4], 0));
   sum_parts<<<(unsigned)((cnt + 255) / 256), 256, 0, d0->stream>>>(d0->pb.S, c->stage, cnt, G - 1);
   PLS_CUDA_TRY(cudaGetLastError());
   ++d0->launches;
-  for (int g = 1; g < G; ++g)
-    PLS_CUDA_TRY(cudaMemcpyPeerAsync(c->subs[g]->pb.S, c->subs[g]->dev, d0->pb.S, d0->dev, bytes, d0->stream));
-  PLS_CUDA_TRY(cudaStreamSynchronize(d0->stream));
-  return par_for(c, [](int, pls_ctx *s) -> int {
+  PLS_CUDA_TRY(cudaEventRecord(d0->ev[5], d0->stream));
+  return par_for(c, [&](int g, pls_ctx *s) -> int {
     int r = check_ctx(s);
     if (r) return r;
+    if (g > 0) {
+      PLS_CUDA_TRY(cudaStreamWaitEvent(s->stream, d0->ev[5], 0));
+      PLS_CUDA_TRY(cudaMemcpyPeerAsync(s->pb.S, s->dev, d0->pb.S, d0->dev, bytes, s->stream));
+    }
     r = k1_gram_finalize(s->pb, s->stream, &s->launches);
     if (r) return r;
     PLS_CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -123,6 +173,7 @@ int multi_create(pls_ctx *c, const int *device_ids, int n_dev) {
   }
   c->dev = device_ids[0];
   c->sm_count = c->subs[0]->sm_count;
+  c->pool = new (std::nothrow) WorkerPool(n_dev);
   for (int g = 0; g < n_dev; ++g) {           // NVLink peer access where the topology allows it
     cudaSetDevice(device_ids[g]);
     for (int h = 0; h < n_dev; ++h) {
@@ -137,7 +188,12 @@ int multi_create(pls_ctx *c, const int *device_ids, int n_dev) {
   return PLS_OK;
 }
 
+int multi_predict(pls_ctx *c, const double *w, double *yhat, int (*predict_dev)(pls_ctx *, const double *, double *)) {
+  return par_for(c, [&](int g, pls_ctx *s) -> int { return predict_dev(s, w, yhat + c->row0[g]); });
+}
+
 void multi_destroy(pls_ctx *c) {
+  if (c->pool) { delete static_cast<WorkerPool *>(c->pool); c->pool = nullptr; }
   if (c->stage) { cudaSetDevice(c->subs.empty() ? c->dev : c->subs[0]->dev); cudaFree(c->stage); c->stage = nullptr; }
   for (pls_ctx *s : c->subs) pls_destroy(s);
   c->subs.clear();

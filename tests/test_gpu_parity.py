@@ -307,6 +307,96 @@ def test_bnb_equals_opt_and_small_pool(ctx, oracle):
     assert np.all(np.abs(r2["alpha_signed"] - r["alpha_signed"]) <= RTOL * np.abs(w_opt).max())
 
 
+def test_bnb_relaxations_at_baseline_width(ctx, oracle):
+    """BASELINE configs[4]'s width (M = 800, K = 32: M' = 801 runs the wide shared-memory plan of K5): the root
+    relaxation and the three relaxations below it that the reference's search would solve next (BnB.jl:117-124:
+    branch on k = argmax nu, positive child, then its own branching group both ways) against oracle.lower_bound
+    (data-space Lawson-Hanson on [Xp Xm], BnB.jl:69-92) -- same bound, same signed weights."""
+    o, _ = oracle
+    N, M, K, eta = 5000, 800, 32, 1e-3
+    X, y, P = o.make_synthetic(N, M, K, seed=77, mixed_sign=True)
+    Xo, Po = o.homogeneous_coords(X, P)
+    Xa, ya = o.regularize_problem(Xo, y, Po, eta)
+    ctx.load(X, y, P, eta=eta)
+
+    def sigma_of(pm, nm):
+        sg = []
+        for k in range(K + 1):
+            idx = [int(i) + 1 for i in np.flatnonzero(Po[:, k] == 1)]
+            if (pm >> k) & 1: sg += idx
+            if (nm >> k) & 1: sg += [-i for i in idx]
+        return sg
+
+    lb0, a0 = o.lower_bound(Xa, ya, [])
+    k0 = int(np.argmax(o.sum_max_0_ai_aj(Po, a0)))
+    lb1, a1 = o.lower_bound(Xa, ya, sigma_of(1 << k0, 0))
+    k1 = int(np.argmax(o.sum_max_0_ai_aj(Po, a1)))
+    nodes = [(0, 0), (1 << k0, 0), ((1 << k0) | (1 << k1), 0), (1 << k0, 1 << k1)]
+    refs = [(lb0, a0), (lb1, a1)] + [o.lower_bound(Xa, ya, sigma_of(pm, nm)) for pm, nm in nodes[2:]]
+    lb, al = ctx.bnb_lower_bounds([n[0] for n in nodes], [n[1] for n in nodes])
+    for i, (rl, ra) in enumerate(refs):
+        assert abs(lb[i] - rl) <= RTOL * rl, (i, lb[i], rl)
+        assert np.all(np.abs(al[i] - ra) <= RTOL * np.abs(ra).max()), i
+    assert int(np.argmax(o.sum_max_0_ai_aj(Po, al[0]))) == k0
+
+
+def test_alt_restarts_at_baseline_width(ctx, oracle):
+    """BASELINE configs[3]'s width (M = 1000, K = 50: M' = 1001, K' = 51 -- the 129 KB shared-memory plan of K6, one
+    CTA per SM): two restarts against oracle.fit_alt from the same beta_0 -- same loss, iteration count, alpha, beta."""
+    o, _ = oracle
+    N, M, K, eta = 5000, 1000, 50, 1e-3
+    X, y, P = o.make_synthetic(N, M, K, seed=78, mixed_sign=True)
+    rng = np.random.default_rng(78)
+    beta0 = (rng.random((K + 1, 2)) - 0.5) * 10.0
+    refs = [o.fit_alt(X, y, P, beta0[:, r], eta=eta, eps=1e-6, T=100) for r in range(2)]
+    r = ctx.alt_fit(X, y, P, beta0, eta=eta, eps=1e-6, T=100)
+    ref_objs = np.array([q["opt"] for q in refs])
+    assert np.allclose(r["all_obj"], ref_objs, rtol=1e-8)
+    best = int(np.argmin(ref_objs))
+    q = refs[best]
+    assert r["best_restart"] == best and r["iters"] == q["iters"]
+    assert abs(r["opt"] - q["opt"]) <= 1e-8 * q["opt"]
+    assert np.all(np.abs(r["alpha"] - q["alpha_full"]) <= 1e-7 * np.abs(q["alpha_full"]).max())
+    assert np.all(np.abs(r["beta"] - q["beta_full"]) <= 1e-7 * np.abs(q["beta_full"]).max())
+
+
+def test_stall_case_through_bnb_and_alt(ctx, pkg, oracle):
+    """The problem on which block pivoting stalls in Opt (N = 144, M' = 118, AR(1) columns with rho = 0.9; tools/v4_fuzz.py)
+    through fit(BnB) and fit(Alt): a stalled node relaxation / alpha-step is solved again with single pivots instead of
+    failing the fit (lower_bound and the Alt loop always return, BnB.jl:69-92, Alt.jl:77-117).  BnB against the Opt
+    optimum of the same problem (README.md:54), Alt restarts against oracle.fit_alt."""
+    o, oc = oracle
+    g = np.load(os.path.join(GOLD, "stall_n144_m117_rho09.npz"))
+    X, y, P, eta = np.asfortranarray(g["X"]), g["y"], np.asfortranarray(g["P"]), float(g["eta"])
+    ref = oc.opt_fit(X, y, P, eta)
+    rb = ctx.bnb_fit(X, y, P, eta=eta)
+    assert abs(rb["opt"] - ref["obj_best"]) <= RTOL * ref["obj_best"]
+    Xo, Po = o.homogeneous_coords(X, P)
+    w_opt = (Po @ o.index_to_beta(ref["b_best"], P.shape[1] + 1)) * ref["alpha_best"]
+    assert np.all(np.abs(rb["alpha_signed"] - w_opt) <= 1e-8 * np.abs(w_opt).max())
+    K = P.shape[1]
+    rng = np.random.default_rng(9)
+    beta0 = (rng.random((K + 1, 8)) - 0.5) * 10.0
+    ra = ctx.alt_fit(X, y, P, beta0, eta=eta, eps=1e-6, T=100)
+    refs = [o.fit_alt(X, y, P, beta0[:, r], eta=eta, eps=1e-6, T=100) for r in range(8)]
+    assert np.all(np.isfinite(ra["all_obj"]))
+    assert np.allclose(ra["all_obj"], [q["opt"] for q in refs], rtol=1e-7)
+
+
+def test_alt_empty_group_gives_beta_zero(ctx, oracle):
+    """A P with an empty group column: A = Po .* alpha has a zero column, the K' x K' normal equations are singular and the
+    reference's `Xoa \\ yo` (pivoted QR, minimum norm; Alt.jl:110) returns beta_k = 0 for it -- so does the library."""
+    o, _ = oracle
+    X, y, P = o.make_synthetic(500, 14, 4, seed=31, mixed_sign=True)
+    P = np.asfortranarray(np.hstack([P[:, :2], np.zeros((14, 1), dtype=np.int64), P[:, 2:]]))   # group 2 has no member
+    b0 = np.array([1.0, -2.0, 3.0, -1.0, 2.0, 0.5])
+    q = o.fit_alt(X, y, P, b0, eta=1e-3, eps=1e-6, T=100)
+    r = ctx.alt_fit(X, y, P, b0, eta=1e-3, eps=1e-6, T=100)
+    assert r["beta"][2] == 0.0 and abs(q["beta_full"][2]) <= 1e-12
+    assert abs(r["opt"] - q["opt"]) <= 1e-8 * q["opt"] and r["iters"] == q["iters"]
+    assert np.all(np.abs(r["beta"] - q["beta_full"]) <= 1e-7 * np.abs(q["beta_full"]).max())
+
+
 # ---- fit(Alt, ...)  (src/PartitionedLSAlt.jl) ----------------------------------------------------
 def test_alt_toy(pkg, oracle):
     """test/runtests.jl:41-69 with Optimizer=Alt: converges to opt ~ 0 from any start."""
