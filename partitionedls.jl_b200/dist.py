@@ -55,13 +55,26 @@ def pick_winner(records, Mp, tau=0.0):
 
 
 class TorchComm:
-    """Collectives over torch.distributed (NCCL for CUDA tensors, gloo for CPU tensors)."""
+    """Collectives over torch.distributed (NCCL for CUDA tensors, gloo for CPU tensors).  The two small exchanges of a
+    fit (winner records, winner residual) go through ONE preallocated pinned host buffer and ONE device buffer each, so
+    a fit costs one host->device copy, one collective and one device->host copy per exchange and no allocation."""
 
     def __init__(self, device=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist, self.device = torch, dist, device
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self._bufs = {}
+
+    def _buf(self, key, n):
+        """(pinned host tensor, device tensor or None) of n doubles, cached."""
+        b = self._bufs.get((key, n))
+        if b is None:
+            t = self.torch
+            host = t.empty(n, dtype=t.float64, pin_memory=self.device is not None)
+            dev = t.empty(n, dtype=t.float64, device=self.device) if self.device is not None else None
+            b = self._bufs[(key, n)] = (host, dev)
+        return b
 
     def allreduce_sum_inplace_dev(self, dev_ptr: int, count: int):
         """Sum a device buffer of `count` doubles across ranks, in place (zero-copy view)."""
@@ -74,26 +87,41 @@ class TorchComm:
         self.torch.cuda.synchronize(self.device)
 
     def allreduce_sum(self, arr: np.ndarray) -> np.ndarray:
-        t = self.torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64))
-        if self.device is not None:
-            t = t.to(self.device)
-        self.dist.all_reduce(t)
-        return t.cpu().numpy()
+        arr = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)
+        host, dev = self._buf("ar", arr.size)
+        host.numpy()[:] = arr
+        if dev is None:
+            self.dist.all_reduce(host)
+            return host.numpy().copy()
+        dev.copy_(host, non_blocking=True)
+        self.dist.all_reduce(dev)
+        host.copy_(dev)                      # blocking device->host copy: the one synchronisation of this exchange
+        return host.numpy().copy()
 
     def allgather(self, arr: np.ndarray) -> np.ndarray:
-        t = self.torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64))
-        if self.device is not None:
-            t = t.to(self.device)
-        out = [self.torch.empty_like(t) for _ in range(self.world)]
-        self.dist.all_gather(out, t)
-        return self.torch.stack(out).cpu().numpy()
+        arr = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)
+        host, dev = self._buf("ag_in", arr.size)
+        hout, dout = self._buf("ag_out", arr.size * self.world)
+        host.numpy()[:] = arr
+        if dev is None:
+            self.dist.all_gather_into_tensor(hout, host)
+            return hout.numpy().reshape(self.world, -1).copy()
+        dev.copy_(host, non_blocking=True)
+        self.dist.all_gather_into_tensor(dout, dev)
+        hout.copy_(dout)
+        return hout.numpy().reshape(self.world, -1).copy()
 
 
 def opt_fit_sharded(backend, comm, Mp: int, Kp: int, *, reload=None, pairs=None):
     """One Opt fit over `comm.world` ranks on data already loaded in `backend` (or loaded by the
     `reload()` callback first -- the end-to-end variant).  Returns (b*, objective, alpha_raw).
     pairs (default: whenever the backend offers it and the problem fits): shard the 2^K sign patterns of
-    the user groups and leave the intercept sign free -- each solve resolves two reference orthants."""
+    the user groups and leave the intercept sign free -- each solve resolves two reference orthants.
+
+    Exchanges per fit: the all-reduce of the raw Gram sums (in place, on the device), ONE all-gather of the ranks'
+    winner records and ONE all-reduce of the winner's squared residual over the row shards.  A rank whose local solve
+    fails does not leave the others waiting in a collective: it sends a record flagged as failed, and every rank raises
+    after the gather."""
     if reload is not None:
         reload()
     backend.gram_build()
@@ -105,15 +133,25 @@ def opt_fit_sharded(backend, comm, Mp: int, Kp: int, *, reload=None, pairs=None)
     backend.gram_finalize()
     if pairs is None:
         pairs = hasattr(backend, "opt_solve_pairs") and Mp <= 1024 and Kp >= 2 and (1 << (Kp - 1)) >= comm.world
-    if pairs:
-        b0, bn = shard_orthants(1 << (Kp - 1), comm.rank, comm.world)
-        loc = backend.opt_solve_pairs(b0, bn)
-    else:
-        b0, bn = shard_orthants(1 << Kp, comm.rank, comm.world)
-        loc = backend.opt_solve_range(b0, bn)
-    rec = np.concatenate([loc["alpha_raw"], [loc["obj_gram"], float(loc["b_best"])]])
+    rec = np.zeros(Mp + 3)
+    err = None
+    try:
+        if pairs:
+            b0, bn = shard_orthants(1 << (Kp - 1), comm.rank, comm.world)
+            loc = backend.opt_solve_pairs(b0, bn)
+        else:
+            b0, bn = shard_orthants(1 << Kp, comm.rank, comm.world)
+            loc = backend.opt_solve_range(b0, bn)
+        rec[:Mp], rec[Mp], rec[Mp + 1] = loc["alpha_raw"], loc["obj_gram"], float(loc["b_best"])
+    except Exception as e:                   # sentinel record: objective +inf, b = -1, error flag
+        err = e
+        rec[Mp], rec[Mp + 1], rec[Mp + 2] = np.inf, -1.0, 1.0
+    allrec = comm.allgather(rec)
+    if allrec[:, Mp + 2].any():
+        bad = [int(r) for r in np.flatnonzero(allrec[:, Mp + 2])]
+        raise RuntimeError(f"opt_fit_sharded: the local solve failed on rank(s) {bad}" + (f": {err}" if err is not None else ""))
     tau = 1e-13 * backend.gram_scalars()[0] if hasattr(backend, "gram_scalars") else 0.0
-    alpha, b, _, _ = pick_winner(comm.allgather(rec), Mp, tau)
+    alpha, b, _, _ = pick_winner(allrec[:, :Mp + 2], Mp, tau)
     ssq = comm.allreduce_sum(np.array([backend.residual_partial(alpha, b)]))[0]
     return b, backend.objective_finish(alpha, b, float(ssq)), alpha
 
@@ -143,9 +181,12 @@ def alt_fit_sharded(backend, comm, Po, beta0, eps=1e-6, T=100):
     rec = np.zeros(Mp + Kp + 3)
     rec[Mp + Kp], rec[Mp + Kp + 1] = np.inf, -1.0
     if r1 > r0:
-        loc = backend.alt_fit_shard(beta0[:, r0:r1], eps=eps, T=T)
-        rec[:Mp], rec[Mp:Mp + Kp] = loc["alpha"], loc["beta"]
-        rec[Mp + Kp], rec[Mp + Kp + 1], rec[Mp + Kp + 2] = loc["opt"], r0 + loc["best_restart"], loc["iters"]
+        try:
+            loc = backend.alt_fit_shard(beta0[:, r0:r1], eps=eps, T=T)
+            rec[:Mp], rec[Mp:Mp + Kp] = loc["alpha"], loc["beta"]
+            rec[Mp + Kp], rec[Mp + Kp + 1], rec[Mp + Kp + 2] = loc["opt"], r0 + loc["best_restart"], loc["iters"]
+        except Exception:                    # every restart of this shard failed: "no candidate" (as multi.cu does); the
+            pass                             # other ranks are not left waiting in the collective
     allrec = comm.allgather(rec)
     cand = [q for q in allrec if q[Mp + Kp + 1] >= 0]
     if not cand:

@@ -142,6 +142,50 @@ def test_two_rank_sharded_fit_matches_single_process(oracle):
         assert np.allclose(ra["alpha"], runs[ibest]["alpha_full"]) and np.allclose(ra["beta"], runs[ibest]["beta_full"])
 
 
+def _worker_fail(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    from importlib import import_module
+    g.load_package()
+    distmod = import_module(g.PKG_NAME + ".dist")
+    o, oc = g.load_oracle()
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        X, y, P = o.make_synthetic(200, 6, 2, seed=6, mixed_sign=True)
+        be = OracleBackend(o, oc, X, y, P, 1e-2, distmod.shard_rows(200, rank, world))
+        if rank == 1:
+            def boom(*a, **k):
+                raise ValueError("solver failed on this rank")
+            be.opt_solve_pairs = boom
+        comm = distmod.TorchComm(device=None)
+        try:
+            distmod.opt_fit_sharded(be, comm, Mp=7, Kp=3)
+            q.put((rank, "no error"))
+        except RuntimeError as e:
+            q.put((rank, str(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_rank_local_failure_raises_on_every_rank_instead_of_hanging():
+    """A local solve that fails on one rank must not leave the others blocked in the all-gather: the failing rank sends
+    a flagged record and every rank raises after the collective."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_fail, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert "rank(s) [1]" in res[0] and "rank(s) [1]" in res[1] and "solver failed on this rank" in res[1]
+
+
 def test_sharding_helpers(pkg):
     from importlib import import_module
     import __graft_entry__ as g
