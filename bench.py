@@ -53,7 +53,7 @@ K2_KERNELS = {
     1: "k2_orthant_chains (single-pivot active set, rank-1 updates of a dense inverse)",
     3: "k2v3_orthant_chains (one-level block principal pivoting, DMMA rank-8 updates of the packed inverse)",
     4: "k2v4_orthant_ranges (two-level: per-CTA swept tableau + block pivoting on the fast Gray groups, CTA per chain)",
-    5: "k2v5_orthant_walks (two-level: swept tableau in L2 + small swept tableau in shared memory, one warp-sized CTA per chain)",
+    5: "k2v5_orthant_walks (two swept tableaus per Gray walk: T1 in L2/HBM changed only by rank-8 DMMA folds, a small tile-packed T2 in shared memory swept by DMMA block pivots; one small CTA per walk)",
 }
 
 

@@ -955,10 +955,11 @@ int k2v5_plan(int Mp, int n_bits, const uint64_t *h_gmask, K5Plan *pl) {
   const Variant5 *v = nullptr;
   int vi = -1, l = 0;
   const char *eM = getenv("PLS_K5_MARGIN");
-  const int margin = eM ? atoi(eM) : 10;               // free window slots kept for variables that join
+  const int margin = eM ? atoi(eM) : 12;               // free window slots kept for variables that join
   // Window size: a larger window holds more fast groups (a fold every 2^l orthants) but costs shared memory (walks
-  // per SM) and work per pivot.  Measured on M' = 201: l = 6 at NR = 72 beats NR = 96 (K = 20, groups of 10); with
-  // groups of 12-13 (K = 16) NR = 72 only reaches l = 4 and NR = 96 (l = 6) wins.  Rule: the first (smallest) window
+  // per SM) and work per pivot.  Measured on M' = 201: K = 20 (groups of 10): l = 6 at NR = 80 (5 walks per SM) 43.0 ms,
+  // NR = 72 (6 per SM, 10 free slots) 44.4 ms, NR = 96 48.5 ms; K = 16 (groups of 12-13): NR = 72 only reaches l = 4
+  // (7.0 ms) and NR = 96 with l = 6 wins (5.1 ms).  Rule: the first (smallest) window
   // that reaches l >= 6 (or every enumerated bit but two), else the one with the most fast groups.
   const int l_want = n_bits - 2 < 6 ? (n_bits - 2 < 1 ? 1 : n_bits - 2) : 6;
   int ci = 0;

@@ -7,11 +7,12 @@ import __graft_entry__ as g
 pkg = g.load_package()
 from importlib import import_module
 synth = import_module(g.PKG_NAME + ".synth")
-KEYS = ("PLS_K2_IMPL", "PLS_K5_GRID", "PLS_K5_L", "PLS_K5_VERIFY", "PLS_K2_NO_V5", "PLS_K5_OCC")
+KEYS = ("PLS_K2_IMPL", "PLS_K2_NO_V5", "PLS_K5_SEED")
+SMALL_KEYS = ("PLS_K5_GRID", "PLS_K5_L", "PLS_K5_VERIFY")
 
 
 def env(**kw):
-    for k in KEYS:
+    for k in KEYS + (SMALL_KEYS if any(q in kw for q in SMALL_KEYS) or os.environ.get("_V5_SMALL") else ()):
         os.environ.pop(k, None)
     for k, v in kw.items():
         os.environ[k] = str(v)
@@ -19,6 +20,7 @@ def env(**kw):
 
 def small(ctx):
     bad = 0
+    os.environ["_V5_SMALL"] = "1"
     cases = [(900, 40, 6, 1e-3, True, 0.3, dict(PLS_K5_GRID=3, PLS_K5_L=2, PLS_K5_VERIFY=5)),
              (900, 40, 6, 1e-3, True, 0.3, dict(PLS_K5_GRID=1, PLS_K5_L=1, PLS_K5_VERIFY=4)),
              (2000, 64, 8, 1e-3, True, 0.0, dict(PLS_K5_GRID=5, PLS_K5_L=3)),
