@@ -117,11 +117,10 @@ __global__ void __launch_bounds__(T1) k1_gram_tiles(const double *__restrict__ Z
 // the diagonal are skipped (warp-uniform predicates).
 // ------------------------------------------------------------------------------------------------
 constexpr int KS = 16;            // rows per TMA box (128 B)
-constexpr int BOXES = 2;          // boxes per stage and side -> 32 rows per stage
-constexpr int STAGES = 2;
 constexpr int T1B = 160;          // 4 consumer warps + 1 producer warp
 constexpr int BOX_DOUBLES = BT * KS;                  // 1024 doubles = 8 KB
-constexpr int STAGE_DOUBLES = 2 * BOXES * BOX_DOUBLES; // A boxes then B boxes: 32 KB
+// STAGES x BOXES (boxes per stage and side: 16 BOXES rows per stage) are template parameters: a stage holds the A
+// boxes then the B boxes, 2 * BOXES * 8 KB
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -153,9 +152,11 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
 __device__ __forceinline__ int box_off(int c, int k) { return c * KS + ((((k >> 1) ^ (c & 7)) << 1) | (k & 1)); }
 __device__ __forceinline__ int perm8(int r) { return r < 4 ? 2 * r : 2 * (r - 4) + 1; }
 
+template <int STAGES, int BOXES>
 __global__ void __launch_bounds__(T1B) k1_gram_tiles_tma(const __grid_constant__ CUtensorMap zmap,
                                                          long long rows_per_chunk, long long n_rows_pad,
                                                          int n_tiles, int zcols, double *__restrict__ part) {
+  constexpr int STAGE_DOUBLES = 2 * BOXES * BOX_DOUBLES;
   extern __shared__ __align__(1024) unsigned char smem_k1[];
   double *stage_mem = reinterpret_cast<double *>(smem_k1);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_k1 + (size_t)STAGES * STAGE_DOUBLES * sizeof(double));
@@ -394,8 +395,9 @@ int k1_gram_build(Problem &pb, cudaStream_t st, int *launches) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // ~4 waves of CTAs (several CTAs fit per SM), chunks of whole stages
-  long long want_chunks = (2ll * 3 * sms + n_tiles - 1) / n_tiles;
+  // ~4 waves of CTAs at 3 CTAs per SM (measured: 1 / 2 / 4 waves = 19.2 / 22.5 / 24.5 TFLOP/s at the configs[2] shape), chunks of whole stages
+  const int waves = getenv("PLS_K1_WAVES") ? atoi(getenv("PLS_K1_WAVES")) : 4;
+  long long want_chunks = ((long long)waves * 3 * sms + n_tiles - 1) / n_tiles;
   long long max_chunks = n_rows_pad / (KB * 8);
   if (max_chunks < 1) max_chunks = 1;
   if (want_chunks > max_chunks) want_chunks = max_chunks;
@@ -413,9 +415,21 @@ int k1_gram_build(Problem &pb, cudaStream_t st, int *launches) {
   const char *impl = getenv("PLS_K1_IMPL");
   CUtensorMap zmap;
   if (!(impl && strcmp(impl, "v1") == 0) && make_zmap(pb, &zmap)) {
-    const size_t smem = (size_t)STAGES * STAGE_DOUBLES * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
-    PLS_CUDA_TRY(cudaFuncSetAttribute(k1_gram_tiles_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k1_gram_tiles_tma<<<grid, T1B, smem, st>>>(zmap, rows_per_chunk, n_rows_pad, n_tiles, pb.zcols, pb.part);
+    // pipeline shape (PLS_K1_PIPE = "stages x boxes" overrides).  Measured (profiles/r02_k1_pipe_sweep.txt): deeper rings
+    // do not help -- 2 stages of two 16-row boxes per side (64 KB, 3 CTAs per SM) beat 4 x 1, 6 x 1, 8 x 1 and 3 x 2 at
+    // every shape: the kernel is bound by DMMA issue, not by load latency.  More, shorter row chunks do help (4 waves).
+    int stages = 2, boxes = 2;
+    if (const char *ep = getenv("PLS_K1_PIPE")) sscanf(ep, "%dx%d", &stages, &boxes);
+    typedef void (*K1Fn)(const CUtensorMap, long long, long long, int, int, double *);
+    K1Fn fn = nullptr;
+    if (stages == 3 && boxes == 2) fn = k1_gram_tiles_tma<3, 2>;
+    else if (stages == 6 && boxes == 1) fn = k1_gram_tiles_tma<6, 1>;
+    else if (stages == 8 && boxes == 1) fn = k1_gram_tiles_tma<8, 1>;
+    else if (stages == 4 && boxes == 1) fn = k1_gram_tiles_tma<4, 1>;
+    else { stages = 2; boxes = 2; fn = k1_gram_tiles_tma<2, 2>; }
+    const size_t smem = (size_t)stages * 2 * boxes * BOX_DOUBLES * sizeof(double) + 2 * stages * sizeof(uint64_t);
+    PLS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fn<<<grid, T1B, smem, st>>>(zmap, rows_per_chunk, n_rows_pad, n_tiles, pb.zcols, pb.part);
   } else {
     k1_gram_tiles<<<grid, T1, 0, st>>>(pb.Z, pb.ldz, rows_per_chunk, n_rows_pad, n_tiles, pb.part);
   }
