@@ -301,6 +301,7 @@ __global__ void k6_weights(const double *win, const uint64_t *gmask, int Mp, int
 int k6_alt_run(const Problem &pb, SolveWs &ws, const std::vector<uint64_t> &h_gmask, const double *h_beta0, long long R,
                double eps, int Tmax, double *d_w, double *h_all_obj, int sm_count, cudaStream_t st, int *launches,
                double **d_win_out) {
+  NvtxRange nvtx("pls:K6 Alt restarts");
   const int Mp = pb.Mp, Kp = pb.Kp;
   if (Mp > CAP3MAX) { set_error("alt: M' = %d exceeds this build's limit (%d)", Mp, CAP3MAX); return PLS_EUNSUPPORTED; }
   if (Kp > 64) { set_error("alt: more than 63 groups"); return PLS_EUNSUPPORTED; }

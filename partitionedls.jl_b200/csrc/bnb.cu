@@ -288,6 +288,7 @@ struct OpenNode {
 // Host driver.  Leaves the winner (signed weights, objective, leaf sequence) in ws.win.
 int k5_bnb_run(const Problem &pb, SolveWs &ws, int sm_count, cudaStream_t st, int *launches, BnbReport *rep,
                BnbShard *shard) {
+  NvtxRange nvtx("pls:K5 BnB frontier waves");
   std::atomic<unsigned long long> *shared_mu = shard ? shard->shared_mu : nullptr;
   const int Mp = pb.Mp, Kp = pb.Kp;
   if (Mp > CAP3MAX) { set_error("bnb: M' = %d exceeds this build's limit (%d)", Mp, CAP3MAX); return PLS_EUNSUPPORTED; }

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <atomic>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>
 #include "../../include/pls.h"
 
 namespace pls {
@@ -22,6 +23,14 @@ void set_error(const char *fmt, ...);
   } while (0)
 
 static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// NVTX range around a stage (header-only NVTX 3: a no-op unless a profiler is attached)
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange &) = delete;
+  NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 // argmin rule of the orthant enumeration (Opt.jl:96: first minimum; NaN sorts lowest, as Julia's findmin does).
 // Objectives are Gram-space values sqrt(y'y - c'w) whose SQUARES carry rounding noise ~ eps * y'y that depends on

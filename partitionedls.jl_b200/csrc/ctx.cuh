@@ -16,6 +16,10 @@ struct pls_ctx {
   double *d_w = nullptr, *d_ssq = nullptr;
   double *h_pin = nullptr;   // pinned: winner record + ssq
   size_t z_bytes = 0;
+  // staging of PAGEABLE host input (a plain Julia Array): two pinned bounce buffers + the events of their DMAs
+  double *h_stage[2] = {nullptr, nullptr};
+  cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+  size_t h_stage_bytes = 0;
   int launches = 0, launch_mark = 0;
   // single-process multi-GPU (pls_create with n_dev > 1): one full context per device; this object only
   // orchestrates (multi.cu).  Empty for an ordinary one-GPU context.

@@ -389,6 +389,7 @@ __global__ void k1_finalize(const double *__restrict__ S, int zc, int Mp, double
 }  // namespace
 
 int k1_gram_build(Problem &pb, cudaStream_t st, int *launches) {
+  NvtxRange nvtx("pls:K1 gram build (TMA + DMMA)");
   const int nt = pb.zcols_pad / BT;
   const int n_tiles = nt * (nt + 1) / 2;
   const long long n_rows_pad = round_up(pb.N, KB);      // <= ldz (ldz % 32 == 0)
@@ -444,6 +445,7 @@ int k1_gram_build(Problem &pb, cudaStream_t st, int *launches) {
 }
 
 int k1_gram_finalize(Problem &pb, cudaStream_t st, int *launches) {
+  NvtxRange nvtx("pls:K1 gram finalize");
   const long long tot = (long long)pb.ldg * pb.Mp;
   PLS_CUDA_TRY(cudaMemsetAsync(pb.scal, 0, sizeof(double) * 4, st));
   k1_finalize<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(pb.S, pb.zcols, pb.Mp, pb.eta, pb.gmask,

@@ -460,6 +460,7 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
                    const uint64_t *gmask, int Mp, int Kp, SolveWs &ws, int64_t b_begin,
                    int64_t b_count, double *d_all_obj, double *d_all_alpha, int sm_count,
                    cudaStream_t st, int *launches, bool free_top, int force_variant, const uint64_t *h_gmask) {
+  NvtxRange nvtx("pls:K2 orthant NNLS + K3 argmin");
   if (b_count <= 0) { set_error("k2: empty orthant range"); return PLS_EINVAL; }
   if (free_top && (Mp > 1024 || d_all_obj || d_all_alpha)) { set_error("k2: paired orthants need M' <= 1024 and no per-orthant outputs"); return PLS_EUNSUPPORTED; }
   // variant (PLS_K2_IMPL = v1 | v2 | v3 overrides):

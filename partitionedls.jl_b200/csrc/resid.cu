@@ -114,6 +114,7 @@ static long long rows_grid(long long N, int sm_count) {
 // every column including the ones column and y, so it adds nothing.
 int k4_residual(const Problem &pb, SolveWs &ws, const double *d_w, double *d_ssq, int sm_count,
                 cudaStream_t st, int *launches) {
+  NvtxRange nvtx("pls:K4 winner recompute");
   if (pb.Mp > MAXNZ) { set_error("k4: M' = %d exceeds %d", pb.Mp, MAXNZ); return PLS_EUNSUPPORTED; }
   const long long blocks = rows_grid(pb.N, sm_count);
   const long long cap = (long long)sm_count * 8;
@@ -134,6 +135,7 @@ int k4_residual(const Problem &pb, SolveWs &ws, const double *d_w, double *d_ssq
 
 // d_w: device vector of signed weights (length Mp, intercept last); d_yhat: device vector of round_up(N, 2) doubles.
 int k7_predict(const Problem &pb, const double *d_w, double *d_yhat, int sm_count, cudaStream_t st, int *launches) {
+  NvtxRange nvtx("pls:K7 resident predict");
   if (pb.Mp > MAXNZ) { set_error("k7: M' = %d exceeds %d", pb.Mp, MAXNZ); return PLS_EUNSUPPORTED; }
   k47_rows<true><<<(unsigned)rows_grid(pb.N, sm_count), T4, 0, st>>>(pb.Z, pb.ldz, pb.N, pb.M + 1, d_w, pb.Mp, d_yhat);
   PLS_CUDA_TRY(cudaGetLastError());

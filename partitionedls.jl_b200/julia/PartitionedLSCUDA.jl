@@ -8,6 +8,16 @@
 # (Opt.jl:34-44), the BnB post-processing (BnB.jl:36-39), the RNG draws of Alt (Alt.jl:58-66),
 # `PartLSFitResult` (PartitionedLS.jl:29-49) and `predict` (:132-155) are the reference's own.
 #
+#
+# The GPU solvers are selected with their own marker types -- `fit(OptCUDA, X, y, P; η)`, `fit(BnBCUDA, ...)`,
+# `fit(AltCUDA, ...)` -- so this module adds methods to `PartitionedLS.fit` for types it owns: no method of the
+# reference is overwritten (no type piracy; safe to precompile next to the reference, whose @compile_workload runs
+# the CPU fits).  INTEGRATION.md shows the two-line change with which a maintainer routes `fit(Opt, ...)` itself
+# through the library.
+#
+# Devices: PLS_DEVICES="0,1,2,3" (or the older single PLS_DEVICE) -- with more than one device ONE process drives
+# all of them (pls_create with a device list: rows, sign patterns and restarts are sharded inside the library).
+#
 # NOTE: Julia is not installed in the build image, so this file has been reviewed by eye only; the
 # same C ABI is exercised end to end by the Python twin (partitionedls.jl_b200/_abi.py + tests/).
 module PartitionedLSCUDA
@@ -15,6 +25,13 @@ module PartitionedLSCUDA
 using PartitionedLS: PartLSFitResult, Opt, Alt, BnB, cleanupResult, homogeneousCoords
 using Random
 import PartitionedLS: fit
+
+export OptCUDA, AltCUDA, BnBCUDA, predict_resident
+
+"""Marker types of the GPU solvers: `fit(OptCUDA, X, y, P; η)` is `fit(Opt, X, y, P; η)` on libpls_cuda.so."""
+struct OptCUDA end
+struct AltCUDA end
+struct BnBCUDA end
 
 const libpls = get(ENV, "LIBPLS_CUDA", "libpls_cuda.so")
 
@@ -25,6 +42,7 @@ struct PlsStats            # mirrors `pls_stats` in include/pls.h
     bpp_iters::Int64; spills::Int64; rebuilds::Int64; blocked::Int64; kernel_launches::Int64
     gram_flops::Cdouble; nnls_flops::Cdouble; nnls_l2_bytes::Cdouble
     waves::Int64; max_open::Int64; nnls_problems::Int64
+    k2_variant::Int64; k2_threads::Int64; k2_ctas_per_sm::Int64; k2_grid::Int64; k2_max_drift::Cdouble
 end
 
 const _ctx = Ref{Ptr{Cvoid}}(C_NULL)      # created lazily: never ccall at precompile time
@@ -39,21 +57,21 @@ end
 
 function context()
     if _ctx[] == C_NULL
-        dev = Ref{Cint}(parse(Cint, get(ENV, "PLS_DEVICE", "0")))
-        _check(ccall((:pls_create, libpls), Cint, (Ref{Ptr{Cvoid}}, Ref{Cint}, Cint), _ctx, dev, 1))
+        devs = Cint[parse(Cint, strip(d)) for d in split(get(ENV, "PLS_DEVICES", get(ENV, "PLS_DEVICE", "0")), ',') if !isempty(strip(d))]
+        _check(ccall((:pls_create, libpls), Cint, (Ref{Ptr{Cvoid}}, Ptr{Cint}, Cint), _ctx, devs, length(devs)))
         atexit(() -> ccall((:pls_destroy, libpls), Cvoid, (Ptr{Cvoid},), _ctx[]))
     end
     _ctx[]
 end
 
 """
-    fit(Opt, X, y, P; η=0.0, nnlsalg=:nnls, returnAllSolutions=false)
+    fit(OptCUDA, X, y, P; η=0.0, nnlsalg=:nnls, returnAllSolutions=false)
 
 Same signature and return tuple as the reference (Opt.jl:73-74, :99-103).  `nnlsalg` is accepted
 and ignored: the GPU path has one Gram-space solver.  Float32 inputs are upcast (result fields are
 `Vector{AbstractFloat}`, PartitionedLS.jl:34,39).
 """
-function fit(::Type{Opt}, X::Array{<:AbstractFloat,2}, y::AbstractArray{<:AbstractFloat,1}, P::Array{Int,2};
+function fit(::Type{OptCUDA}, X::Array{<:AbstractFloat,2}, y::AbstractArray{<:AbstractFloat,1}, P::Array{Int,2};
              η=0.0, nnlsalg=:nnls, returnAllSolutions=false)
     Xd = convert(Matrix{Float64}, X); yd = convert(Vector{Float64}, y); Pd = convert(Matrix{Int64}, P)
     N, M = size(Xd); K = size(Pd, 2)
@@ -83,14 +101,14 @@ function fit(::Type{Opt}, X::Array{<:AbstractFloat,2}, y::AbstractArray{<:Abstra
 end
 
 """
-    fit(BnB, X, y, P; η=0.0, nnlsalg=:nnls)
+    fit(BnBCUDA, X, y, P; η=0.0, nnlsalg=:nnls)
 
 Same signature and return tuple as the reference (BnB.jl:30-40).  The library returns the signed
 weights α of the best feasible leaf (BnB.jl:84-89) and its objective; the post-processing of
 BnB.jl:36-39 runs here unchanged.  `nopen` counts the nodes visited by the batched traversal; it
 is traversal-order dependent and differs from the reference's depth-first count.
 """
-function fit(::Type{BnB}, X::Array{<:AbstractFloat,2}, y::AbstractArray{<:AbstractFloat,1}, P::Array{Int,2};
+function fit(::Type{BnBCUDA}, X::Array{<:AbstractFloat,2}, y::AbstractArray{<:AbstractFloat,1}, P::Array{Int,2};
              η=0.0, nnlsalg=:nnls)
     Xd = convert(Matrix{Float64}, X); yd = convert(Vector{Float64}, y); Pd = convert(Matrix{Int64}, P)
     N, M = size(Xd); K = size(Pd, 2)
@@ -108,7 +126,7 @@ function fit(::Type{BnB}, X::Array{<:AbstractFloat,2}, y::AbstractArray{<:Abstra
 end
 
 """
-    fit(Alt, X, y, P; η=0.0, ϵ=1e-6, T=100, nnlsalg=:nnls, rng=nothing, restarts=1)
+    fit(AltCUDA, X, y, P; η=0.0, ϵ=1e-6, T=100, nnlsalg=:nnls, rng=nothing, restarts=1)
 
 Same signature and return tuple as the reference (Alt.jl:50-51, :119) plus `restarts`: the
 initial values of every restart are drawn HERE exactly as Alt.jl:58-66 does (α₀ first -- dead
@@ -116,7 +134,7 @@ upstream but it keeps the stream aligned -- then β₀ = (rng(F, K') .- 0.5) .* 
 `rng` seed means what it means upstream; the library iterates all restarts as one batch and
 returns the best one.  `restarts = 1` is the reference's behaviour.
 """
-function fit(::Type{Alt}, X::Matrix{F}, y::Vector{F}, P::Array{Int,2};
+function fit(::Type{AltCUDA}, X::Matrix{F}, y::Vector{F}, P::Array{Int,2};
              η=0.0, ϵ=1e-6, T=100, nnlsalg=:nnls, rng=nothing, restarts::Int=1) where {F<:AbstractFloat}
     Xd = convert(Matrix{Float64}, X); yd = convert(Vector{Float64}, y); Pd = convert(Matrix{Int64}, P)
     N, M = size(Xd); K = size(Pd, 2)
