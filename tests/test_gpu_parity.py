@@ -361,7 +361,7 @@ def test_alt_restarts_at_baseline_width(ctx, oracle):
 
 
 def test_stall_case_through_bnb_and_alt(ctx, pkg, oracle):
-    """The problem on which block pivoting stalls in Opt (N = 144, M' = 118, AR(1) columns with rho = 0.9; tools/v4_fuzz.py)
+    """The problem on which block pivoting stalls in Opt (N = 144, M' = 118, AR(1) columns with rho = 0.9; tools/k2_fuzz.py)
     through fit(BnB) and fit(Alt): a stalled node relaxation / alpha-step is solved again with single pivots instead of
     failing the fit (lower_bound and the Alt loop always return, BnB.jl:69-92, Alt.jl:77-117).  BnB against the Opt
     optimum of the same problem (README.md:54), Alt restarts against oracle.fit_alt."""
@@ -703,12 +703,13 @@ def test_predict_resident(ctx, pkg, oracle):
 
 
 def test_twolevel_differential_fuzz():
-    """tools/v4_fuzz.py: random shapes / correlations (rho up to 0.9) / group layouts / CTA counts / fast-group
-    counts -- every orthant's objective and alpha of the two-level kernel against the one-level kernel."""
+    """tools/k2_fuzz.py: random shapes / correlations (rho up to 0.9) / group layouts / walk counts / fast-group counts --
+    every orthant's objective and alpha of the two-level kernels (v4, v5) against the one-level kernel, a sample of
+    orthants against the C oracle, and the winner-only fit against both."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "tools", "v4_fuzz.py"), "12", "3"], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "k2_fuzz.py"), "14", "3"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert '"result": "all equal"' in r.stdout
 
@@ -752,7 +753,7 @@ def test_paired_orthants_zero_intercept_ties(ctx, oracle):
 
 
 def test_stalled_block_pivoting_falls_back_to_single_pivots(ctx, oracle):
-    """N = 144, M' = 118, AR(1) columns with rho = 0.9 (found by tools/v4_fuzz.py): in two orthants block pivoting passes
+    """N = 144, M' = 118, AR(1) columns with rho = 0.9 (found by tools/k2_fuzz.py): in two orthants block pivoting passes
     through a nearly singular intermediate passive set (106 of 118 variables from 144 rows) and gives the solve up; the
     library re-solves the range with the single-pivot kernel.  Every orthant against the C oracle, both fit modes."""
     o, oc = oracle

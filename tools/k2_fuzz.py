@@ -1,0 +1,88 @@
+"""Differential fuzz of the two-level K2 kernels (v4: CTA per chain, nnls4.cu; v5: two swept tableaus per walk, nnls5.cu)
+on random problems -- shapes, correlations (rho up to 0.9), group layouts (overlaps, group-less features), eta, walk
+counts, fast-group counts, check intervals:
+  (a) every orthant's objective and alpha of a FORCED two-level run against the one-level kernel (v3);
+  (b) a sample of orthants and the winner of that run against the C ORACLE (data-space Lawson-Hanson);
+  (c) the winner-only fit under the same settings (paired orthants, polish / fallback guards) against (a)'s argmin.
+Bounds: 1e-9 relative (the parity tolerance) wherever the kernel's own KKT checks against the original Gram system
+stayed below 1e-13 max|c|; on the ill-conditioned cases where they did not (rho = 0.9: the kernel then re-checks every
+8 orthants and the library polishes the winner) the per-orthant outputs of the forced run are only a diagnostic (1e-6).
+   python tools/k2_fuzz.py [n_cases] [seed]"""
+import json, os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import __graft_entry__ as g
+pkg = g.load_package()
+o, oc = g.load_oracle()
+oc.build()
+from importlib import import_module
+synth = import_module(g.PKG_NAME + ".synth")
+n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+KEYS = ("PLS_K2_IMPL", "PLS_K4_GRID", "PLS_K4_L", "PLS_K4_VERIFY", "PLS_K4_T", "PLS_K4_QS",
+        "PLS_K5_GRID", "PLS_K5_L", "PLS_K5_VERIFY", "PLS_K5_T", "PLS_K5_NR", "PLS_K5_MARGIN")
+ctx = pkg.Context(0)
+worst = dict(obj=0.0, alpha=0.0, oracle_obj=0.0, oracle_alpha=0.0)
+n5 = 0
+for case in range(n_cases):
+    K = int(rng.integers(6, 13)); M = int(rng.integers(K + 2, 140)); N = int(rng.integers(M + 20, 4000))
+    rho = float(rng.choice([0.0, 0.3, 0.7, 0.9])); eta = float(rng.choice([0.0, 1e-3, 1e-1]))
+    mixed = bool(rng.integers(0, 2))
+    X, y, P = synth.make_synthetic(N, M, K, int(rng.integers(1, 1 << 30)), mixed_sign=mixed, rho=rho)
+    if rng.random() < 0.3:                      # overlapping groups / a group-less feature
+        P = P.copy(); P[int(rng.integers(0, M)), int(rng.integers(0, K))] = 1; P[int(rng.integers(0, M)), :] = 0
+        P = np.asfortranarray(P)
+    for k in KEYS: os.environ.pop(k, None)
+    os.environ["PLS_K2_IMPL"] = "v3"
+    a = ctx.opt_fit(X, y, P, eta=eta, return_all=True)
+    impl = "v5" if rng.random() < 0.6 else "v4"
+    os.environ["PLS_K2_IMPL"] = impl
+    if impl == "v4":
+        os.environ["PLS_K4_GRID"] = str(int(rng.choice([1, 2, 5, 37, 600])))
+        os.environ["PLS_K4_L"] = str(int(rng.integers(1, 7)))
+        os.environ["PLS_K4_VERIFY"] = str(int(rng.choice([1, 7, 128])))
+        if rng.random() < 0.3: os.environ["PLS_K4_T"] = str(int(rng.choice([64, 256])))
+        if rng.random() < 0.2: os.environ["PLS_K4_QS"] = str(int(rng.integers(1, 30)))
+    else:
+        os.environ["PLS_K5_GRID"] = str(int(rng.choice([1, 2, 5, 37, 900])))
+        os.environ["PLS_K5_L"] = str(int(rng.integers(1, 7)))
+        os.environ["PLS_K5_VERIFY"] = str(int(rng.choice([1, 7, 128])))
+        if rng.random() < 0.4: os.environ["PLS_K5_T"] = str(int(rng.choice([32, 64])))
+        if rng.random() < 0.4: os.environ["PLS_K5_NR"] = str(int(rng.choice([72, 80, 96])))
+        if rng.random() < 0.3: os.environ["PLS_K5_MARGIN"] = str(int(rng.choice([2, 6, 20])))
+    b = ctx.opt_fit(X, y, P, eta=eta, return_all=True)
+    ran = b["stats"]["k2_variant"]          # v5 hands over to v4 / v3 when its window cannot hold a group
+    n5 += ran == 5
+    drift = b["stats"]["k2_max_drift"]
+    tol = 1e-9 if drift <= 1e-13 else 1e-6
+    # winner-only fit under the same forced two-level settings: paired orthants (intercept free, 2^K problems) and,
+    # where the KKT checks saw the tableau lose digits, the winner polished by the one-level kernel -- against
+    # the one-level kernel's literal enumeration `a` at the parity tolerance
+    c = ctx.opt_fit(X, y, P, eta=eta)
+    # (an exact tie -- a group whose weights are all zero ties both of its signs -- is broken towards the lower index within
+    #  1e-13 y'y; beyond that rounding may pick either: the winner is then compared with the one-level kernel's solution of
+    #  the orthant it chose)
+    yn = float(np.linalg.norm(y))
+    cb = c["b_best"]
+    pair_ok = ((cb == a["b_best"] or abs(a["objs"][cb] - a["objs"][a["b_best"]]) <= 1e-10 * yn)
+               and abs(c["opt"] - a["opt"]) <= 1e-9 * max(a["opt"], 1e-300) + 1e-10 * yn
+               and np.all(np.abs(c["alpha_raw"] - a["alphas"][cb]) <= 1e-9 * max(np.abs(a["alphas"][cb]).max(), 1e-300))
+               and c["stats"]["nnls_problems"] * 2 == b["stats"]["nnls_problems"])
+    eo = float(np.abs(a["objs"] - b["objs"]).max() / yn)
+    sc = np.maximum(np.abs(a["alphas"]).max(axis=1, keepdims=True), 1e-300)
+    ea = float((np.abs(a["alphas"] - b["alphas"]) / sc).max())
+    near_tie = abs(a["objs"][a["b_best"]] - a["objs"][b["b_best"]]) <= 1e-10 * yn
+    # oracle leg: a sample of orthants and the winner, solved in data space by the C oracle
+    bl = np.unique(np.concatenate([rng.integers(0, 1 << (K + 1), size=6), [b["b_best"]]])).astype(np.int64)
+    ref = oc.opt_fit(X, y, P, eta, b_list=bl, nthreads=4)
+    eoo = float(max(abs(ref["objs"][j] - b["objs"][q]) for j, q in enumerate(bl)) / yn)
+    eao = float(max((np.abs(ref["alphas"][j] - b["alphas"][q]) / max(np.abs(ref["alphas"][j]).max(), 1e-300)).max() for j, q in enumerate(bl)))
+    ok = (a["b_best"] == b["b_best"] or near_tie) and eo <= tol and ea <= tol and eoo <= max(tol, 1e-9) + 1e-9 and eao <= tol and pair_ok
+    for key, val in (("obj", eo), ("alpha", ea), ("oracle_obj", eoo), ("oracle_alpha", eao)):
+        if drift <= 1e-13: worst[key] = max(worst[key], val)
+    print(json.dumps(dict(case=case, N=N, M=M, K=K, rho=rho, eta=eta, mixed=mixed, impl=impl, ran=ran, env={k: os.environ.get(k) for k in KEYS if os.environ.get(k)},
+                          obj_err=eo, alpha_err=ea, oracle_obj_err=eoo, oracle_alpha_err=eao, drift=drift, tol=tol, same_b=bool(a["b_best"] == b["b_best"]), pairs_equal=bool(pair_ok),
+                          rebuilds=b["stats"]["rebuilds"], drift_restarts=b["stats"]["spills"], v3_rebuilds=a["stats"]["rebuilds"], polished=c["stats"]["rebuilds"], ok=bool(ok))), flush=True)
+    if not ok:
+        sys.exit(1)
+print(json.dumps(dict(cases=n_cases, v5_cases=int(n5), worst_where_no_drift_was_flagged=worst, result="all equal")))
