@@ -561,8 +561,118 @@ __device__ __noinline__ bool fold_block5(W5 &w, int boff, int nb) {
   return true;
 }
 
-// fold every toggled slow window variable, reset the window, rebuild T2.  Returns false if a block was refused.
+// ---- fused fold: EVERY toggled window variable is swept in T1 in ONE pass (the cold solve: up to NR - 1 at once) ---------
+// With S = the toggled window slots, T2 = sweep(T1[Rb, Rb], S) already holds -E inv(T1[S, S]) E, so no block has to be
+// inverted.  With  P~[j, k] = e_k T1[var_k, j]  (k toggled, else 0; e_k = +1 entered / -1 left)  and  Z = P~ T2:
+//     T1[i, j] += sum_k Z[i, k] P~[j, k]            everywhere            (lower tiles + mirrored store, DMMA)
+//     T1[:, var_q] = T1[var_q, :] = -Z[:, q]        for the toggled q
+//     T1[Rb, Rb] = T2                               the window block (sweeps on S commute with the restriction to Rb)
+// One read + write of T1 instead of one per 8 variables; the two ld1 x NR panels live in this walk's global scratch.
 template <int T>
+__device__ __noinline__ void fold_fused5(W5 &w) {
+  const Sh5 s = make_sh5(w.nr, w.ld1);
+  constexpr int NW = T / 32;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int ld1 = w.ld1, nt = ld1 >> 3, n = w.n, NRp = w.nr;
+  const int ntr = (n + 7) >> 3, nk = ntr << 3;
+  double *PT = w.Pg + 8 * (size_t)ld1, *ZT = PT + (size_t)ld1 * NRp;       // [ld1][NR] each, row stride NR
+  // e_k per slot (0 = not toggled) -> yv
+  for (int k = tid; k < nk; k += T) {
+    double e = 0.0;
+    if (k >= 1 && k < n) { const unsigned char f = s.st[s.rvar[k]]; const bool pas = f & ST_PAS, ino = f & ST_INO; if (pas != ino) e = pas ? 1.0 : -1.0; }
+    s.yv[k] = e;
+  }
+  SYNC5();
+  for (int k = 0; k < nk; ++k) {                       // P~ (transposed copy of the toggled rows of T1)
+    const double e = s.yv[k];
+    const double *src = w.T1 + (size_t)ld1 * (e != 0.0 ? s.rvar[k] : 0);
+    for (int j = tid; j < ld1; j += T) PT[(size_t)j * NRp + k] = e != 0.0 ? e * __ldcg(src + j) : 0.0;
+  }
+  __threadfence_block();
+  SYNC5();
+  // Z = P~ T2  (T2 symmetric, tile-packed: tile (tk, tq) direct if tk >= tq, else the transposed tile (tq, tk)).  The
+  // k-tiles are taken three at a time: six global loads of A fragments in flight, then six DMMAs (small code, the
+  // latency of the panel loads is paid ~3 times per tile instead of 9 times).
+  constexpr int CH = 3;
+  for (int idx = wid; idx < nt * ntr; idx += NW) {
+    const int tj = idx / ntr, tq = idx - tj * ntr;
+    const double *pa = PT + (size_t)(tj * 8 + fr) * NRp + fk;
+    double c0 = 0.0, c1 = 0.0;
+#pragma unroll 1
+    for (int t0 = 0; t0 < ntr; t0 += CH) {
+      double a0[CH], a1[CH];
+#pragma unroll
+      for (int u = 0; u < CH; ++u) { const bool live = t0 + u < ntr; a0[u] = live ? pa[(t0 + u) * 8] : 0.0; a1[u] = live ? pa[(t0 + u) * 8 + 4] : 0.0; }
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        const int tk = t0 + u < ntr ? t0 + u : t0;     // dead k-tiles multiply zeros with a valid tile
+        double b0, b1;                                 // B[k][col] = T2(tk*8 + k, tq*8 + col), k = fk / fk + 4, col = fr
+        if (tk >= tq) { const double *tp = s.T2 + ((((tk * (tk + 1)) >> 1) + tq) << 6); b0 = tp[fk * 8 + fr]; b1 = tp[(4 + fk) * 8 + fr]; }
+        else { const double *tp = s.T2 + ((((tq * (tq + 1)) >> 1) + tk) << 6); b0 = tp[fr * 8 + fk]; b1 = tp[fr * 8 + 4 + fk]; }
+        dmma5(c0, c1, a0[u], b0); dmma5(c0, c1, a1[u], b1);
+      }
+    }
+    *reinterpret_cast<double2 *>(ZT + (size_t)(tj * 8 + fr) * NRp + tq * 8 + 2 * fk) = make_double2(c0, c1);
+  }
+  __threadfence_block();
+  SYNC5();
+  {                                                    // T1 += Z P~' on the lower tiles, mirrored into the upper ones
+    const int ntl = (nt * (nt + 1)) >> 1;
+    int q = (ntl * wid) / NW;
+    const int q1 = (ntl * (wid + 1)) / NW;
+    int ti = 0;
+    while (((ti + 1) * (ti + 2)) >> 1 <= q) ++ti;
+    int tj = q - ((ti * (ti + 1)) >> 1);
+    for (; q < q1; ++q) {
+      double2 c = __ldcg(reinterpret_cast<const double2 *>(w.T1 + (size_t)(ti * 8 + fr) * ld1 + tj * 8 + 2 * fk));
+      const double *za = ZT + (size_t)(ti * 8 + fr) * NRp + fk, *pb = PT + (size_t)(tj * 8 + fr) * NRp + fk;
+#pragma unroll 1
+      for (int t0 = 0; t0 < ntr; t0 += CH) {
+        double z0[CH], z1[CH], p0[CH], p1[CH];
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+          const bool live = t0 + u < ntr;
+          z0[u] = live ? za[(t0 + u) * 8] : 0.0; z1[u] = live ? za[(t0 + u) * 8 + 4] : 0.0;
+          p0[u] = live ? pb[(t0 + u) * 8] : 0.0; p1[u] = live ? pb[(t0 + u) * 8 + 4] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < CH; ++u) { dmma5(c.x, c.y, z0[u], p0[u]); dmma5(c.x, c.y, z1[u], p1[u]); }
+      }
+      __stcg(reinterpret_cast<double2 *>(w.T1 + (size_t)(ti * 8 + fr) * ld1 + tj * 8 + 2 * fk), c);
+      if (ti != tj) {
+        double *mp = w.T1 + (size_t)(tj * 8 + 2 * fk) * ld1 + ti * 8 + fr;
+        __stcg(mp, c.x); __stcg(mp + ld1, c.y);
+      }
+      if (++tj > ti) { ++ti; tj = 0; }
+    }
+  }
+  SYNC5();
+  for (int k = 1; k < n; ++k) {                        // rows / columns of the toggled variables: -Z[:, k]
+    if (s.yv[k] == 0.0) continue;
+    const int var = s.rvar[k];
+    for (int j = tid; j < ld1; j += T) {
+      const double val = -ZT[(size_t)j * NRp + k];
+      __stcg(w.T1 + (size_t)ld1 * var + j, val);
+      __stcg(w.T1 + (size_t)ld1 * j + var, val);
+    }
+  }
+  SYNC5();
+  for (int idx = tid; idx < n * n; idx += T) {         // the window block is T2 itself
+    const int a = idx / n, b = idx - a * n;
+    __stcg(w.T1 + (size_t)ld1 * s.rvar[a] + s.rvar[b], t2_get(s.T2, a, b));
+  }
+  SYNC5();
+  for (int k = tid; k < n; k += T) {
+    if (k >= 1 && s.yv[k] != 0.0) { const int m = s.rvar[k]; const unsigned char f = s.st[m]; s.st[m] = (f & ST_PAS) ? (unsigned char)(f | ST_INO) : (unsigned char)(f & ~ST_INO); }
+  }
+  SYNC5();
+  w.sum_p2 += 2ull * ld1 * ld1 * (unsigned long long)ntr / 8 + (unsigned long long)ld1 * nk * nk / 2;
+  w.n_fold++;
+}
+
+// fold every toggled slow window variable, reset the window, rebuild T2.  Returns false if a block was refused.
+template <int T, int NR>
 __device__ __noinline__ bool fold5(W5 &w) {
   const Sh5 s = make_sh5(w.nr, w.ld1);
   const int tid = threadIdx.x;
@@ -591,7 +701,8 @@ __device__ __noinline__ bool fold5(W5 &w) {
   SYNC5();
   const int cnt = s.ctl[C_CNT];
   bool ok = true;
-  for (int q0 = 0; q0 < cnt && ok; q0 += 8) ok = fold_block5<T>(w, q0, min(8, cnt - q0));
+  if (w.lowmask == 0ull && cnt > 8) fold_fused5<T>(w);          // cold solve: everything toggled goes in, one pass
+  else for (int q0 = 0; q0 < cnt && ok; q0 += 8) ok = fold_block5<T>(w, q0, min(8, cnt - q0));
   window_reset(w);
   if (!t2_rebuild<T>(w)) ok = false;
   return ok;
@@ -758,7 +869,7 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
       short *park = reinterpret_cast<short *>(s.v);
       for (int p = tid; p < nj; p += T) park[p] = s.lst[p];
       SYNC5();
-      if (!fold5<T>(w)) return false;
+      if (!fold5<T, NR>(w)) return false;
       t2_fresh = true;
       int room = NR - w.n;
       if (room > nj) room = nj;
@@ -821,6 +932,7 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
   for (int ti = tid; ti < NR / 8; ti += T)
     for (int tj = 0; tj <= ti; ++tj) s.tmap[((ti * (ti + 1)) >> 1) + tj] = (unsigned short)((ti << 8) | tj);
   for (int k = tid; k < NR; k += T) s.mk[k] = 0;
+  for (int e = tid; e < t2_doubles(NR); e += T) s.T2[e] = 0.0;      // unused entries of partly used tiles must stay finite (they meet zeros in DMMA products)
   const double yy = A.scal[0], cmax = A.scal[1];
   double best_obj = 0.0; long long best_b = -1;
   int low_bits = 0;
@@ -899,7 +1011,7 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
       const int nslow = s.ctl[C_NSLOW];
       const bool was_cold = w.lowmask != A.lowmask;   // first orthant after a cold start: fold everything, then bring the fast groups in
       if (fb >= low_bits || nslow >= 8 || w.n > NR - 8 || was_cold) {
-        if (!fold5<T>(w)) cold = true;             // refused block (near-singular pivot): restart cold
+        if (!fold5<T, NR>(w)) cold = true;             // refused block (near-singular pivot): restart cold
         t2_fresh = true;
         if (was_cold && !cold) {
           w.lowmask = A.lowmask;
@@ -988,7 +1100,8 @@ int k2v5_plan(int Mp, int n_bits, const uint64_t *h_gmask, K5Plan *pl) {
   if (oc < 1) oc = 1;
   if (const char *eO = getenv("PLS_K5_OCC")) { const int o = atoi(eO); if (o >= 1 && o < oc) oc = o; }
   pl->variant = vi; pl->T = v->T; pl->NR = v->NR; pl->ld1 = ld1; pl->occ = oc; pl->smem = sm; pl->low_groups = l;
-  pl->tabstride = (size_t)ld1 * ld1 + 8 * (size_t)ld1 + 64;
+  // per walk: T1 (ld1 x ld1), the verify pass's weight vector (8 ld1 reserved), and the fused fold's two ld1 x NR panels
+  pl->tabstride = (size_t)ld1 * ld1 + 8 * (size_t)ld1 + 2 * (size_t)ld1 * v->NR + 64;
   const char *eV = getenv("PLS_K5_VERIFY");
   pl->verify_every = eV ? atoi(eV) : 128;
   if (pl->verify_every < 1) pl->verify_every = 1;
