@@ -186,9 +186,21 @@ __device__ __noinline__ int t2_block(W5 &w, int n, int nb, int nlv, bool test, b
   const int fr = lane >> 2, fk = lane & 3;
   const int ntr = (n + 7) >> 3;
   const short *B = s.lstB;
-  for (int idx = tid; idx < ntr * 64; idx += T) {
-    const int row = idx >> 3, q = idx & 7;
-    s.Pp[pan5(row, q)] = (row < n && q < nb) ? t2_get(s.T2, row, B[q]) : 0.0;
+  // P = T2[:, B]: a thread takes a row and all 8 block columns; the row's tile-row base and in-tile offsets are
+  // computed once (rows >= the column: tile (tr, tc), element (r7, c7); rows below it: the transposed tile (tc, tr))
+  for (int row = tid; row < ntr * 8; row += T) {
+    const int tr = row >> 3, r7 = row & 7;
+    const int rbase = (((tr * (tr + 1)) >> 1) << 6) + (r7 << 3);
+    const int sw = (row & 2) << 1, pb = row << 3;
+#pragma unroll 1
+    for (int q = 0; q < 8; ++q) {
+      double val = 0.0;
+      if (row < n && q < nb) {
+        const int c = B[q], tc = c >> 3, c7 = c & 7;
+        val = row >= c ? s.T2[rbase + (tc << 6) + c7] : s.T2[((((tc * (tc + 1)) >> 1) + tr) << 6) + (c7 << 3) + r7];
+      }
+      s.Pp[pb + (q ^ sw)] = val;
+    }
   }
   if (tid < 8) {
     s.gd[tid] = (test && tid >= nlv && tid < nb) ? 1e-13 * __ldg(w.G + (size_t)w.ldg * s.rvar[B[tid]] + s.rvar[B[tid]]) : 0.0;
@@ -259,9 +271,22 @@ __device__ __noinline__ int t2_block(W5 &w, int n, int nb, int nlv, bool test, b
     }
   }
   SYNC5();
-  for (int idx = tid; idx < n * 8; idx += T) {         // columns / rows of B outside the block
-    const int row = idx >> 3, q = idx & 7;
-    if (q < nb && !s.mk[row]) { const double val = s.Wp[pan5(row, q)]; t2_set(s.T2, row, B[q], q < nlv ? -val : val); }
+  for (int row = tid; row < n; row += T) {             // columns / rows of B outside the block: e_q W[:, q]
+    if (s.mk[row]) continue;
+    const int tr = row >> 3, r7 = row & 7;
+    const int rbase = (((tr * (tr + 1)) >> 1) << 6) + (r7 << 3);
+    const int sw = (row & 2) << 1, pb = row << 3;
+#pragma unroll 1
+    for (int q = 0; q < nb; ++q) {
+      {
+        const int c = B[q], tc = c >> 3, c7 = c & 7;
+        const double w0 = s.Wp[pb + (q ^ sw)];
+        const double val = q < nlv ? -w0 : w0;
+        if (tr > tc) s.T2[rbase + (tc << 6) + c7] = val;
+        else if (tr < tc) s.T2[((((tc * (tc + 1)) >> 1) + tr) << 6) + (c7 << 3) + r7] = val;
+        else { const int d = (((tr * (tr + 1)) >> 1) + tr) << 6; s.T2[d + (r7 << 3) + c7] = val; s.T2[d + (c7 << 3) + r7] = val; }
+      }
+    }
   }
   for (int e = tid; e < 64; e += T) {                  // the block itself: -E inv(D) E
     const int i = e >> 3, j = e & 7;
