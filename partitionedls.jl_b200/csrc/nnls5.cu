@@ -248,19 +248,8 @@ __device__ __noinline__ int t2_block(W5 &w, int n, int nb, int nlv, bool test, b
   {                                                    // T2 -= W P' on the stored (lower) tiles
     const int ntl = (ntr * (ntr + 1)) >> 1;
     const int coff = fr * 8 + 2 * fk;
-    int q = wid;
-    for (; q + NW < ntl; q += 2 * NW) {
-      const int t0 = s.tmap[q], t1 = s.tmap[q + NW];
-      const int ra0 = (t0 >> 8) * 8 + fr, rb0 = (t0 & 255) * 8 + fr, ra1 = (t1 >> 8) * 8 + fr, rb1 = (t1 & 255) * 8 + fr;
-      double2 *cp0 = reinterpret_cast<double2 *>(s.T2 + (q << 6) + coff), *cp1 = reinterpret_cast<double2 *>(s.T2 + ((q + NW) << 6) + coff);
-      double2 c0 = *cp0, c1 = *cp1;
-      const double a00 = -s.Wp[pan5(ra0, fk)], a01 = -s.Wp[pan5(ra0, 4 + fk)], b00 = s.Pp[pan5(rb0, fk)], b01 = s.Pp[pan5(rb0, 4 + fk)];
-      const double a10 = -s.Wp[pan5(ra1, fk)], a11 = -s.Wp[pan5(ra1, 4 + fk)], b10 = s.Pp[pan5(rb1, fk)], b11 = s.Pp[pan5(rb1, 4 + fk)];
-      dmma5(c0.x, c0.y, a00, b00); dmma5(c1.x, c1.y, a10, b10);
-      dmma5(c0.x, c0.y, a01, b01); dmma5(c1.x, c1.y, a11, b11);
-      *cp0 = c0; *cp1 = c1;
-    }
-    if (q < ntl) {
+#pragma unroll 1
+    for (int q = wid; q < ntl; q += NW) {
       const int t0 = s.tmap[q];
       const int ra0 = (t0 >> 8) * 8 + fr, rb0 = (t0 & 255) * 8 + fr;
       double2 *cp0 = reinterpret_cast<double2 *>(s.T2 + (q << 6) + coff);
@@ -317,6 +306,7 @@ __device__ __noinline__ bool t2_rebuild(W5 &w) {
   if (tid < 32) {                                      // toggled slots: swept-back ones (in O, active now) first
     int cnt = 0, nlv = 0;
     for (int pass = 0; pass < 2; ++pass) {
+      #pragma unroll 1
       for (int k0 = 1; k0 < n; k0 += 32) {
         const int k = k0 + lane;
         bool take = false;
@@ -349,6 +339,7 @@ __device__ __noinline__ void window_reset(W5 &w) {
     const int lane = tid;
     if (lane == 0) s.rvar[0] = (short)Mp;
     int base = 1;
+    #pragma unroll 1
     for (int m0 = 0; m0 < Mp; m0 += 32) {
       const int m = m0 + lane;
       bool keep = false;
@@ -381,6 +372,7 @@ __device__ __noinline__ double stream5(W5 &w) {
   if (tid < 32) {                                      // S list: variable -> lst, y -> yv
     const int lane = tid;
     int ns = 0;
+    #pragma unroll 1
     for (int k0 = 1; k0 < n; k0 += 32) {
       const int k = k0 + lane;
       bool tg = false, pas = false; int m = 0;
@@ -441,6 +433,7 @@ __device__ __noinline__ void join5(W5 &w, int m) {
   if (tid < 32) {                                      // toggled slots -> lstE, coefficients e_s T1[m, s] -> yv
     const int lane = tid;
     int ns = 0;
+    #pragma unroll 1
     for (int k0 = 1; k0 < n; k0 += 32) {
       const int k = k0 + lane;
       bool tg = false, pas = false; int var = 0;
@@ -707,6 +700,7 @@ __device__ __noinline__ bool fold5(W5 &w) {
     const int lane = tid;
     int cnt = 0;
     for (int pass = 0; pass < 2; ++pass) {
+      #pragma unroll 1
       for (int k0 = 1; k0 < n; k0 += 32) {
         const int k = k0 + lane;
         bool take = false; int m = 0;
@@ -744,6 +738,7 @@ __device__ __noinline__ double verify5(W5 &w, const double *c) {
   if (tid < 32) {
     const int lane = tid;
     int np = 0;
+    #pragma unroll 1
     for (int m0 = 0; m0 < Mp; m0 += 32) {
       const int m = m0 + lane;
       bool pas = false; double wv = 0.0;
@@ -760,6 +755,7 @@ __device__ __noinline__ double verify5(W5 &w, const double *c) {
   SYNC5();
   const int np = s.ctl[C_NP];
   double mx = 0.0;
+  #pragma unroll 1
   for (int m = tid; m < Mp; m += T) {
     double a0 = c[m], a1 = 0.0;
     int t = 0;
@@ -792,6 +788,7 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
       if (tid < 32) {
         const int lane = tid;
         int nl = 0, ne = 0, mx = -1;
+        #pragma unroll 1
         for (int k0 = 1; k0 < n; k0 += 32) {
           const int k = k0 + lane;
           int f = 0, m = -1;
@@ -869,6 +866,7 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
     if (tid < 32) {
       const int lane = tid;
       int nj = 0;
+      #pragma unroll 1
       for (int m0 = 0; m0 < Mp; m0 += 32) {
         const int m = m0 + lane;
         bool f = false;
@@ -932,6 +930,7 @@ __device__ __noinline__ void cold_init5(W5 &w, const double *c, double yy) {
 // d_m = sum_k Po[m,k] (2 bit_k(b) - 1)   (Opt.jl:28-29) -> sign classes; clears the per-orthant refusal flags
 template <int T>
 __device__ __forceinline__ void set_signs5(const Sh5 &s, const W5 &w, long long b, int free_top, int Kp) {
+  #pragma unroll 1
   for (int m = threadIdx.x; m < w.Mp; m += T) {
     const unsigned long long gm = w.gmask[m];
     const int d = 2 * __popcll(gm & (unsigned long long)b) - __popcll(gm);
@@ -1009,6 +1008,7 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
     const bool better = opt_better(obj, b_full, best_obj, best_b, PLS_TIE_REL * yy);
     if (better) { best_obj = obj; best_b = b_full; }
     if (A.all_alpha || better) {
+      #pragma unroll 1
       for (int m = tid; m < Mp; m += T) {
         const unsigned long long gm = w.gmask[m];
         const int d = 2 * __popcll(gm & (unsigned long long)b) - __popcll(gm);
@@ -1024,6 +1024,7 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
     if (ok) {
       if (tid < 32) {
         int nslow = 0;
+        #pragma unroll 1
         for (int k0 = 1; k0 < w.n; k0 += 32) {
           const int k = k0 + tid;
           bool t = false;
