@@ -188,6 +188,7 @@ __device__ __noinline__ int t2_block(W5 &w, int n, int nb, int nlv, bool test, b
   const short *B = s.lstB;
   // P = T2[:, B]: a thread takes a row and all 8 block columns; the row's tile-row base and in-tile offsets are
   // computed once (rows >= the column: tile (tr, tc), element (r7, c7); rows below it: the transposed tile (tc, tr))
+  #pragma unroll 1
   for (int row = tid; row < ntr * 8; row += T) {
     const int tr = row >> 3, r7 = row & 7;
     const int rbase = (((tr * (tr + 1)) >> 1) << 6) + (r7 << 3);
@@ -212,6 +213,7 @@ __device__ __noinline__ int t2_block(W5 &w, int n, int nb, int nlv, bool test, b
     double e0 = (i < nb && j0 < nb) ? s.Pp[pan5(B[i], j0)] : (i == j0 ? 1.0 : 0.0);
     double e1 = (i < nb && j0 + 1 < nb) ? s.Pp[pan5(B[i], j0 + 1)] : (i == j0 + 1 ? 1.0 : 0.0);
     int bad = nb;                                      // first failing pivot (nb = none)
+    #pragma unroll 1
     for (int k = 0; k < nb; ++k) {
       __syncwarp();
       s.D[i * 8 + j0] = e0; s.D[i * 8 + j0 + 1] = e1;
@@ -238,6 +240,7 @@ __device__ __noinline__ int t2_block(W5 &w, int n, int nb, int nlv, bool test, b
     SYNC5();
     return res;
   }
+  #pragma unroll 1
   for (int ti = wid; ti < ntr; ti += NW) {             // W = P inv(D)
     double c0 = 0.0, c1 = 0.0;
     dmma5(c0, c1, s.Pp[pan5(ti * 8 + fr, fk)], s.D[fk * 8 + fr]);
@@ -260,6 +263,7 @@ __device__ __noinline__ int t2_block(W5 &w, int n, int nb, int nlv, bool test, b
     }
   }
   SYNC5();
+  #pragma unroll 1
   for (int row = tid; row < n; row += T) {             // columns / rows of B outside the block: e_q W[:, q]
     if (s.mk[row]) continue;
     const int tr = row >> 3, r7 = row & 7;
@@ -277,6 +281,7 @@ __device__ __noinline__ int t2_block(W5 &w, int n, int nb, int nlv, bool test, b
       }
     }
   }
+  #pragma unroll 1
   for (int e = tid; e < 64; e += T) {                  // the block itself: -E inv(D) E
     const int i = e >> 3, j = e & 7;
     if (i < nb && j <= i) { const double val = s.D[i * 8 + j]; t2_set(s.T2, B[i], B[j], ((i < nlv) == (j < nlv)) ? -val : val); }
@@ -299,12 +304,15 @@ __device__ __noinline__ bool t2_rebuild(W5 &w) {
   constexpr int NW = T / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n = w.n;
+  #pragma unroll 1
   for (int i = wid; i < n; i += NW) {
     const double *row = w.T1 + (size_t)w.ld1 * s.rvar[i];
+    #pragma unroll 1
     for (int j = lane; j <= i; j += 32) t2_set(s.T2, i, j, __ldcg(row + s.rvar[j]));
   }
   if (tid < 32) {                                      // toggled slots: swept-back ones (in O, active now) first
     int cnt = 0, nlv = 0;
+    #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
       #pragma unroll 1
       for (int k0 = 1; k0 < n; k0 += 32) {
@@ -321,6 +329,7 @@ __device__ __noinline__ bool t2_rebuild(W5 &w) {
   }
   SYNC5();
   const int cnt = s.ctl[C_CNT], nlv = s.ctl[C_NLV];
+  #pragma unroll 1
   for (int q0 = 0; q0 < cnt; q0 += 8) {
     const int nb = min(8, cnt - q0);
     if (tid < nb) s.lstB[tid] = s.lst[q0 + tid];
@@ -382,6 +391,7 @@ __device__ __noinline__ double stream5(W5 &w) {
       ns += __popc(bal);
     }
     const int nsp = (ns + UB - 1) / UB * UB;
+    #pragma unroll 1
     for (int p = ns + lane; p < nsp; p += 32) { s.lst[p] = (short)w.Mp; s.yv[p] = 0.0; }   // padding: the rhs row with weight 0
     if (lane == 0) s.ctl[C_NS] = ns;
   }
@@ -395,6 +405,7 @@ __device__ __noinline__ double stream5(W5 &w) {
 #pragma unroll
     for (int q = 0; q < NQ; ++q) acc[q] = (tid + T * q < ld2) ? __ldcg(r + tid + T * q) : make_double2(0.0, 0.0);
   }
+  #pragma unroll 1
   for (int p = 0; p < nsp; p += UB) {
     double2 g[UB][NQ];
 #pragma unroll
@@ -415,6 +426,7 @@ __device__ __noinline__ double stream5(W5 &w) {
     if (tid + T * q < ld2) reinterpret_cast<double2 *>(s.v)[tid + T * q] = acc[q];
   SYNC5();
   double res = 0.0;
+  #pragma unroll 1
   for (int p = tid; p < ns; p += T) res = fmax(res, fabs(s.v[s.lst[p]]));
   res = bmax5<T>(s, res);
   w.n_stream++; w.sum_s += ns;
@@ -447,15 +459,19 @@ __device__ __noinline__ void join5(W5 &w, int m) {
   }
   SYNC5();
   const int ns = s.ctl[C_NS];
+  #pragma unroll 1
   for (int j = tid; j < n; j += T) {
     double a = tog[j] != 0.0 ? 0.0 : __ldcg(row1 + s.rvar[j]);
+    #pragma unroll 1
     for (int p = 0; p < ns; ++p) a = fma(-s.yv[p], t2_get(s.T2, s.lstE[p], j), a);
     rowv[j] = a;
   }
   SYNC5();
+  #pragma unroll 1
   for (int j = tid; j < n; j += T) t2_set(s.T2, n, j, rowv[j]);
   if (tid < 32) {
     double dg = 0.0;
+    #pragma unroll 1
     for (int p = tid; p < ns; p += 32) dg = fma(s.yv[p], rowv[s.lstE[p]], dg);
     dg = wsum5(dg);
     if (tid == 0) { t2_set(s.T2, n, n, __ldcg(row1 + m) - dg); s.rvar[n] = (short)m; s.slot[m] = (short)n; }
@@ -479,6 +495,7 @@ __device__ __noinline__ bool fold_block5(W5 &w, int boff, int nb) {
   // panels P = T1[:, B] and W = P inv(D), both [ld1][8] (column XOR-swizzled): they alias T2 | Pp | Wp, which hold
   // nothing that outlives a fold (T2 is rebuilt afterwards)
   double *FP = s.T2, *FW = s.T2 + (size_t)ld1 * 8;
+  #pragma unroll 1
   for (int idx = tid; idx < ld1 * 8; idx += T) {
     const int j = idx >> 3, q = idx & 7;
     FP[pan5(j, q)] = q < nb ? __ldcg(w.T1 + (size_t)ld1 * B[q] + j) : 0.0;
@@ -491,6 +508,7 @@ __device__ __noinline__ bool fold_block5(W5 &w, int boff, int nb) {
     const int i = lane >> 2, j0 = (lane & 3) << 1;
     double e0 = (i < nb && j0 < nb) ? FP[pan5(B[i], j0)] : (i == j0 ? 1.0 : 0.0);
     double e1 = (i < nb && j0 + 1 < nb) ? FP[pan5(B[i], j0 + 1)] : (i == j0 + 1 ? 1.0 : 0.0);
+    #pragma unroll 1
     for (int k = 0; k < nb; ++k) {
       __syncwarp();
       s.D[i * 8 + j0] = e0; s.D[i * 8 + j0 + 1] = e1;
@@ -513,6 +531,7 @@ __device__ __noinline__ bool fold_block5(W5 &w, int boff, int nb) {
   }
   SYNC5();
   if (!s.ctl[C_OK]) { SYNC5(); return false; }
+  #pragma unroll 1
   for (int ti = wid; ti < nt; ti += NW) {              // W = P inv(D)
     double c0 = 0.0, c1 = 0.0;
     dmma5(c0, c1, FP[pan5(ti * 8 + fr, fk)], s.D[fk * 8 + fr]);
@@ -528,6 +547,7 @@ __device__ __noinline__ bool fold_block5(W5 &w, int boff, int nb) {
     int ti = 0;
     while (((ti + 1) * (ti + 2)) >> 1 <= q) ++ti;
     int tj = q - ((ti * (ti + 1)) >> 1);
+    #pragma unroll 1
     for (; q < q1; q += IFL) {
       double2 c[IFL]; int ri[IFL], rj[IFL];
 #pragma unroll
@@ -555,6 +575,7 @@ __device__ __noinline__ bool fold_block5(W5 &w, int boff, int nb) {
     }
   }
   SYNC5();
+  #pragma unroll 1
   for (int idx = tid; idx < ld1 * 8; idx += T) {       // rows / columns of B
     const int i = idx >> 3, q = idx & 7;
     if (q < nb) {
@@ -564,6 +585,7 @@ __device__ __noinline__ bool fold_block5(W5 &w, int boff, int nb) {
     }
   }
   SYNC5();
+  #pragma unroll 1
   for (int e = tid; e < 64; e += T) {
     const int i = e >> 3, j = e & 7;
     if (i < nb && j < nb) {
@@ -596,15 +618,18 @@ __device__ __noinline__ void fold_fused5(W5 &w) {
   const int ntr = (n + 7) >> 3, nk = ntr << 3;
   double *PT = w.Pg + 8 * (size_t)ld1, *ZT = PT + (size_t)ld1 * NRp;       // [ld1][NR] each, row stride NR
   // e_k per slot (0 = not toggled) -> yv
+  #pragma unroll 1
   for (int k = tid; k < nk; k += T) {
     double e = 0.0;
     if (k >= 1 && k < n) { const unsigned char f = s.st[s.rvar[k]]; const bool pas = f & ST_PAS, ino = f & ST_INO; if (pas != ino) e = pas ? 1.0 : -1.0; }
     s.yv[k] = e;
   }
   SYNC5();
+  #pragma unroll 1
   for (int k = 0; k < nk; ++k) {                       // P~ (transposed copy of the toggled rows of T1)
     const double e = s.yv[k];
     const double *src = w.T1 + (size_t)ld1 * (e != 0.0 ? s.rvar[k] : 0);
+    #pragma unroll 1
     for (int j = tid; j < ld1; j += T) PT[(size_t)j * NRp + k] = e != 0.0 ? e * __ldcg(src + j) : 0.0;
   }
   __threadfence_block();
@@ -613,6 +638,7 @@ __device__ __noinline__ void fold_fused5(W5 &w) {
   // k-tiles are taken three at a time: six global loads of A fragments in flight, then six DMMAs (small code, the
   // latency of the panel loads is paid ~3 times per tile instead of 9 times).
   constexpr int CH = 3;
+  #pragma unroll 1
   for (int idx = wid; idx < nt * ntr; idx += NW) {
     const int tj = idx / ntr, tq = idx - tj * ntr;
     const double *pa = PT + (size_t)(tj * 8 + fr) * NRp + fk;
@@ -642,6 +668,7 @@ __device__ __noinline__ void fold_fused5(W5 &w) {
     int ti = 0;
     while (((ti + 1) * (ti + 2)) >> 1 <= q) ++ti;
     int tj = q - ((ti * (ti + 1)) >> 1);
+    #pragma unroll 1
     for (; q < q1; ++q) {
       double2 c = __ldcg(reinterpret_cast<const double2 *>(w.T1 + (size_t)(ti * 8 + fr) * ld1 + tj * 8 + 2 * fk));
       const double *za = ZT + (size_t)(ti * 8 + fr) * NRp + fk, *pb = PT + (size_t)(tj * 8 + fr) * NRp + fk;
@@ -666,9 +693,11 @@ __device__ __noinline__ void fold_fused5(W5 &w) {
     }
   }
   SYNC5();
+  #pragma unroll 1
   for (int k = 1; k < n; ++k) {                        // rows / columns of the toggled variables: -Z[:, k]
     if (s.yv[k] == 0.0) continue;
     const int var = s.rvar[k];
+    #pragma unroll 1
     for (int j = tid; j < ld1; j += T) {
       const double val = -ZT[(size_t)j * NRp + k];
       __stcg(w.T1 + (size_t)ld1 * var + j, val);
@@ -676,11 +705,13 @@ __device__ __noinline__ void fold_fused5(W5 &w) {
     }
   }
   SYNC5();
+  #pragma unroll 1
   for (int idx = tid; idx < n * n; idx += T) {         // the window block is T2 itself
     const int a = idx / n, b = idx - a * n;
     __stcg(w.T1 + (size_t)ld1 * s.rvar[a] + s.rvar[b], t2_get(s.T2, a, b));
   }
   SYNC5();
+  #pragma unroll 1
   for (int k = tid; k < n; k += T) {
     if (k >= 1 && s.yv[k] != 0.0) { const int m = s.rvar[k]; const unsigned char f = s.st[m]; s.st[m] = (f & ST_PAS) ? (unsigned char)(f | ST_INO) : (unsigned char)(f & ~ST_INO); }
   }
@@ -699,6 +730,7 @@ __device__ __noinline__ bool fold5(W5 &w) {
   if (tid < 32) {                                      // swept-back (in O, now active) first, then entering; index order within each class
     const int lane = tid;
     int cnt = 0;
+    #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
       #pragma unroll 1
       for (int k0 = 1; k0 < n; k0 += 32) {
@@ -759,6 +791,7 @@ __device__ __noinline__ double verify5(W5 &w, const double *c) {
   for (int m = tid; m < Mp; m += T) {
     double a0 = c[m], a1 = 0.0;
     int t = 0;
+    #pragma unroll 1
     for (; t + 1 < np; t += 2) {
       a0 = fma(-w.G[(size_t)w.ldg * s.lst[t] + m], wf[t], a0);
       a1 = fma(-w.G[(size_t)w.ldg * s.lst[t + 1] + m], wf[t + 1], a1);
@@ -781,8 +814,10 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
   const int Mp = w.Mp;
   const double told = 1e-12 * cmax;
   int t_best = Mp + 1, pbar = 3, iters = 0, rebuilt = 0;
+  #pragma unroll 1
   for (;;) {
     // ---- block principal pivoting on the window (Judice-Pires / Kim-Park, Murty's backup rule)
+    #pragma unroll 1
     for (;;) {
       const int n = w.n;
       if (tid < 32) {
@@ -844,6 +879,7 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
         const int pos = done + r - nl;                 // its position in lstE
         if (tid == 0) {
           s.st[s.rvar[s.lstE[pos]]] |= ST_BLK;
+          #pragma unroll 1
           for (int q = pos; q + 1 < ne; ++q) s.lstE[q] = s.lstE[q + 1];
         }
         --ne; --tot; w.n_blk++;
@@ -890,6 +926,7 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
     if (NR - w.n < nj) {                               // make room: fold the toggled slow variables, shrink the window
       // the join list lives in lst, which the fold reuses; v is dead until the next streaming pass: park the list there
       short *park = reinterpret_cast<short *>(s.v);
+      #pragma unroll 1
       for (int p = tid; p < nj; p += T) park[p] = s.lst[p];
       SYNC5();
       if (!fold5<T, NR>(w)) return false;
@@ -897,8 +934,10 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
       int room = NR - w.n;
       if (room > nj) room = nj;
       if (room <= 0) return false;                     // the fast groups alone fill the window (the host sized l to prevent this)
+      #pragma unroll 1
       for (int p = 0; p < room; ++p) { const int m = park[p]; if (s.slot[m] < 0) join5<T>(w, m); }
     } else {
+      #pragma unroll 1
       for (int p = 0; p < nj; ++p) join5<T>(w, s.lst[p]);     // join5 uses lstE / yv / tv / uv, not lst
     }
     t_best = Mp + 1; pbar = 3;
@@ -910,6 +949,7 @@ template <int T>
 __device__ __noinline__ void cold_init5(W5 &w, const double *c, double yy) {
   const Sh5 s = make_sh5(w.nr, w.ld1);
   const int tid = threadIdx.x, Mp = w.Mp, ld1 = w.ld1, ld2 = ld1 >> 1;
+  #pragma unroll 1
   for (int idx = tid; idx < ld1 * ld2; idx += T) {
     const int row = idx / ld2, col = (idx - row * ld2) << 1;
     double2 val = make_double2(0.0, 0.0);
@@ -923,6 +963,7 @@ __device__ __noinline__ void cold_init5(W5 &w, const double *c, double yy) {
     }
     __stcg(reinterpret_cast<double2 *>(w.T1 + (size_t)ld1 * row + col), val);
   }
+  #pragma unroll 1
   for (int m = tid; m < ld1; m += T) { s.st[m] = 0; s.slot[m] = -1; s.sg[m] = 0; }
   SYNC5();
 }
@@ -953,9 +994,13 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
   w.gmask = reinterpret_cast<const unsigned long long *>(A.gmask);
   w.G = A.G; w.ldg = A.ldg;
   w.n_sweep = w.n_stream = w.sum_s = w.sum_p2 = w.n_iter = w.n_blk = w.n_rebuild = w.n_fold = 0;
+  #pragma unroll 1
   for (int ti = tid; ti < NR / 8; ti += T)
+    #pragma unroll 1
     for (int tj = 0; tj <= ti; ++tj) s.tmap[((ti * (ti + 1)) >> 1) + tj] = (unsigned short)((ti << 8) | tj);
+  #pragma unroll 1
   for (int k = tid; k < NR; k += T) s.mk[k] = 0;
+  #pragma unroll 1
   for (int e = tid; e < t2_doubles(NR); e += T) s.T2[e] = 0.0;      // unused entries of partly used tiles must stay finite (they meet zeros in DMMA products)
   const double yy = A.scal[0], cmax = A.scal[1];
   double best_obj = 0.0; long long best_b = -1;
@@ -970,6 +1015,7 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
   unsigned long long n_drift = 0, n_noconv = 0;
   SYNC5();
 
+  #pragma unroll 1
   for (long long i = i0; i < i1; ++i) {
     if (cold) {
       cold_init5<T>(w, A.c, yy);
