@@ -186,34 +186,37 @@ __device__ __noinline__ int t2_block(W5 &w, int n, int nb, int nlv, bool test, b
   const int fr = lane >> 2, fk = lane & 3;
   const int ntr = (n + 7) >> 3;
   const short *B = s.lstB;
-  // P = T2[:, B]: a thread takes a row and all 8 block columns; the row's tile-row base and in-tile offsets are
-  // computed once (rows >= the column: tile (tr, tc), element (r7, c7); rows below it: the transposed tile (tc, tr))
-  #pragma unroll 1
-  for (int row = tid; row < ntr * 8; row += T) {
-    const int tr = row >> 3, r7 = row & 7;
-    const int rbase = (((tr * (tr + 1)) >> 1) << 6) + (r7 << 3);
-    const int sw = (row & 2) << 1, pb = row << 3;
+  // Warp 0 inverts the pivot block D = T2[B, B] (read straight from the tiles) while the other warps gather the panel
+  // P = T2[:, B]: a thread takes a row and all 8 block columns; the row's tile-row base and in-tile offsets are computed
+  // once (rows >= the column: tile (tr, tc), element (r7, c7); rows below it: the transposed tile (tc, tr)).
+  if (tid >= 32 || T == 32) {
+    constexpr int TG = T == 32 ? 32 : T - 32;
 #pragma unroll 1
-    for (int q = 0; q < 8; ++q) {
-      double val = 0.0;
-      if (row < n && q < nb) {
-        const int c = B[q], tc = c >> 3, c7 = c & 7;
-        val = row >= c ? s.T2[rbase + (tc << 6) + c7] : s.T2[((((tc * (tc + 1)) >> 1) + tr) << 6) + (c7 << 3) + r7];
+    for (int row = T == 32 ? tid : tid - 32; row < ntr * 8; row += TG) {
+      const int tr = row >> 3, r7 = row & 7;
+      const int rbase = (((tr * (tr + 1)) >> 1) << 6) + (r7 << 3);
+      const int sw = (row & 2) << 1, pb = row << 3;
+#pragma unroll 1
+      for (int q = 0; q < 8; ++q) {
+        double val = 0.0;
+        if (row < n && q < nb) {
+          const int c = B[q], tc = c >> 3, c7 = c & 7;
+          val = row >= c ? s.T2[rbase + (tc << 6) + c7] : s.T2[((((tc * (tc + 1)) >> 1) + tr) << 6) + (c7 << 3) + r7];
+        }
+        s.Pp[pb + (q ^ sw)] = val;
       }
-      s.Pp[pb + (q ^ sw)] = val;
     }
   }
-  if (tid < 8) {
-    s.gd[tid] = (test && tid >= nlv && tid < nb) ? 1e-13 * __ldg(w.G + (size_t)w.ldg * s.rvar[B[tid]] + s.rvar[B[tid]]) : 0.0;
-    if (tid < nb) s.mk[B[tid]] = 1;
-  }
-  SYNC5();
   if (tid < 32) {
+    if (lane < 8) {
+      s.gd[lane] = (test && lane >= nlv && lane < nb) ? 1e-13 * __ldg(w.G + (size_t)w.ldg * s.rvar[B[lane]] + s.rvar[B[lane]]) : 0.0;
+      if (lane < nb) s.mk[B[lane]] = 1;
+    }
     const int i = lane >> 2, j0 = (lane & 3) << 1;
-    double e0 = (i < nb && j0 < nb) ? s.Pp[pan5(B[i], j0)] : (i == j0 ? 1.0 : 0.0);
-    double e1 = (i < nb && j0 + 1 < nb) ? s.Pp[pan5(B[i], j0 + 1)] : (i == j0 + 1 ? 1.0 : 0.0);
+    double e0 = (i < nb && j0 < nb) ? t2_get(s.T2, B[i], B[j0]) : (i == j0 ? 1.0 : 0.0);
+    double e1 = (i < nb && j0 + 1 < nb) ? t2_get(s.T2, B[i], B[j0 + 1]) : (i == j0 + 1 ? 1.0 : 0.0);
     int bad = nb;                                      // first failing pivot (nb = none)
-    #pragma unroll 1
+#pragma unroll 1
     for (int k = 0; k < nb; ++k) {
       __syncwarp();
       s.D[i * 8 + j0] = e0; s.D[i * 8 + j0 + 1] = e1;
@@ -899,10 +902,24 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
       w.n_rebuild++;
       continue;
     }
+    // anything outside the window that violates its condition?  All threads look (the usual answer is no); only then does
+    // warp 0 build the ordered list
+    bool mine = false;
+#pragma unroll 1
+    for (int m = tid; m < Mp; m += T) {
+      if (s.slot[m] < 0) {
+        const int sg = s.sg[m];
+        const unsigned char fl = s.st[m];
+        const double val = s.v[m];
+        if (fl & ST_INO) mine = mine || (sg != SG_FREE5 && (sg == 0 ? val != 0.0 : (double)sg * val < 0.0));
+        else mine = mine || (!(fl & ST_BLK) && sg != 0 && (sg == SG_FREE5 ? fabs(val) > told : (double)sg * val > told));
+      }
+    }
+    if (!__syncthreads_or(mine)) return true;
     if (tid < 32) {
       const int lane = tid;
       int nj = 0;
-      #pragma unroll 1
+#pragma unroll 1
       for (int m0 = 0; m0 < Mp; m0 += 32) {
         const int m = m0 + lane;
         bool f = false;
@@ -1068,19 +1085,13 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
     // ---- fold: after a slow group moved, when the window is nearly full, or when a full block of toggled slow
     //      variables has gathered
     if (ok) {
-      if (tid < 32) {
-        int nslow = 0;
-        #pragma unroll 1
-        for (int k0 = 1; k0 < w.n; k0 += 32) {
-          const int k = k0 + tid;
-          bool t = false;
-          if (k < w.n) { const int m = s.rvar[k]; const unsigned char f = s.st[m]; t = (((f & ST_PAS) != 0) != ((f & ST_INO) != 0)) && (w.gmask[m] & w.lowmask) == 0ull; }
-          nslow += __popc(__ballot_sync(0xffffffffu, t));
-        }
-        if (tid == 0) s.ctl[C_NSLOW] = nslow;
+      bool tslow = false;                            // toggled slow variables in the window (NR <= T: one slot per thread)
+#pragma unroll 1
+      for (int k = tid + 1; k < w.n; k += T) {
+        const int m = s.rvar[k]; const unsigned char f = s.st[m];
+        tslow = tslow || ((((f & ST_PAS) != 0) != ((f & ST_INO) != 0)) && (w.gmask[m] & w.lowmask) == 0ull);
       }
-      SYNC5();
-      const int nslow = s.ctl[C_NSLOW];
+      const int nslow = __syncthreads_count(tslow);
       const bool was_cold = w.lowmask != A.lowmask;   // first orthant after a cold start: fold everything, then bring the fast groups in
       if (fb >= low_bits || nslow >= 8 || w.n > NR - 8 || was_cold) {
         if (!fold5<T, NR>(w)) cold = true;             // refused block (near-singular pivot): restart cold
