@@ -106,7 +106,7 @@ struct Sh5 {
   unsigned char *st; // [ld1]
   unsigned char *mk; // [NR]  block pivot: slot is in the current block
 };
-enum { C_NL = 0, C_NE, C_MX, C_NS, C_OK, C_CNT, C_N, C_NJ, C_NSLOW, C_NP, C_NLV };
+enum { C_NL = 0, C_NE, C_MX, C_NS, C_OK, C_CNT, C_N, C_NJ, C_NSLOW, C_NP, C_NLV, C_FLAG };
 
 __host__ __device__ inline size_t sh5_bytes(int NR, int ld1) {
   const int ntl = (NR / 8) * (NR / 8 + 1) / 2;
@@ -210,7 +210,6 @@ __device__ __noinline__ int t2_block(W5 &w, int n, int nb, int nlv, bool test, b
   if (tid < 32) {
     if (lane < 8) {
       s.gd[lane] = (test && lane >= nlv && lane < nb) ? 1e-13 * __ldg(w.G + (size_t)w.ldg * s.rvar[B[lane]] + s.rvar[B[lane]]) : 0.0;
-      if (lane < nb) s.mk[B[lane]] = 1;
     }
     const int i = lane >> 2, j0 = (lane & 3) << 1;
     double e0 = (i < nb && j0 < nb) ? t2_get(s.T2, B[i], B[j0]) : (i == j0 ? 1.0 : 0.0);
@@ -238,11 +237,7 @@ __device__ __noinline__ int t2_block(W5 &w, int n, int nb, int nlv, bool test, b
   }
   SYNC5();
   const int res = s.ctl[C_OK];
-  if (res != nb) {
-    if (tid < nb) s.mk[B[tid]] = 0;
-    SYNC5();
-    return res;
-  }
+  if (res != nb) { SYNC5(); return res; }
   #pragma unroll 1
   for (int ti = wid; ti < ntr; ti += NW) {             // W = P inv(D)
     double c0 = 0.0, c1 = 0.0;
@@ -267,33 +262,31 @@ __device__ __noinline__ int t2_block(W5 &w, int n, int nb, int nlv, bool test, b
   }
   SYNC5();
   #pragma unroll 1
+#pragma unroll 1
   for (int row = tid; row < n; row += T) {             // columns / rows of B outside the block: e_q W[:, q]
-    if (s.mk[row]) continue;
+    bool inb = false;
+#pragma unroll 1
+    for (int q = 0; q < nb; ++q) inb = inb || row == B[q];
+    if (inb) continue;
     const int tr = row >> 3, r7 = row & 7;
     const int rbase = (((tr * (tr + 1)) >> 1) << 6) + (r7 << 3);
     const int sw = (row & 2) << 1, pb = row << 3;
 #pragma unroll 1
     for (int q = 0; q < nb; ++q) {
-      {
-        const int c = B[q], tc = c >> 3, c7 = c & 7;
-        const double w0 = s.Wp[pb + (q ^ sw)];
-        const double val = q < nlv ? -w0 : w0;
-        if (tr > tc) s.T2[rbase + (tc << 6) + c7] = val;
-        else if (tr < tc) s.T2[((((tc * (tc + 1)) >> 1) + tr) << 6) + (c7 << 3) + r7] = val;
-        else { const int d = (((tr * (tr + 1)) >> 1) + tr) << 6; s.T2[d + (r7 << 3) + c7] = val; s.T2[d + (c7 << 3) + r7] = val; }
-      }
+      const int c = B[q], tc = c >> 3, c7 = c & 7;
+      const double w0 = s.Wp[pb + (q ^ sw)];
+      const double val = q < nlv ? -w0 : w0;
+      if (tr > tc) s.T2[rbase + (tc << 6) + c7] = val;
+      else if (tr < tc) s.T2[((((tc * (tc + 1)) >> 1) + tr) << 6) + (c7 << 3) + r7] = val;
+      else { const int d = (((tr * (tr + 1)) >> 1) + tr) << 6; s.T2[d + (r7 << 3) + c7] = val; s.T2[d + (c7 << 3) + r7] = val; }
     }
   }
-  #pragma unroll 1
+#pragma unroll 1
   for (int e = tid; e < 64; e += T) {                  // the block itself: -E inv(D) E
     const int i = e >> 3, j = e & 7;
     if (i < nb && j <= i) { const double val = s.D[i * 8 + j]; t2_set(s.T2, B[i], B[j], ((i < nlv) == (j < nlv)) ? -val : val); }
   }
-  SYNC5();
-  if (tid < nb) {
-    s.mk[B[tid]] = 0;
-    if (flip) s.st[s.rvar[B[tid]]] ^= ST_PAS;
-  }
+  if (flip && tid < nb) s.st[s.rvar[B[tid]]] ^= ST_PAS;       // nothing in this phase reads the flags
   SYNC5();
   w.n_sweep += nb; w.sum_p2 += ((unsigned long long)(n * n) * nb) >> 2;
   return nb;
@@ -373,10 +366,10 @@ __device__ __noinline__ void window_reset(W5 &w) {
 }
 
 // ---- streaming pass ------------------------------------------------------------------------------------------
-// v = T1[rhs, :] - sum_{s toggled} e_s T2[s, rhs] T1[s, :].  Returns max |v[s]| over the toggled variables (the
-// residual of the S-system).  NQ = double2 pieces of a row per thread.
+// v = T1[rhs, :] - sum_{s toggled} e_s T2[s, rhs] T1[s, :]; the toggled variables stay listed in s.lst[0 .. ctl[C_NS])
+// (on their rows v is the residual of the S-system).  NQ = double2 pieces of a row per thread.
 template <int T, int NQ>
-__device__ __noinline__ double stream5(W5 &w) {
+__device__ __noinline__ void stream5(W5 &w) {
   const Sh5 s = make_sh5(w.nr, w.ld1);
   const int tid = threadIdx.x;
   const int n = w.n, ld2 = w.ld1 >> 1;
@@ -396,7 +389,7 @@ __device__ __noinline__ double stream5(W5 &w) {
     const int nsp = (ns + UB - 1) / UB * UB;
     #pragma unroll 1
     for (int p = ns + lane; p < nsp; p += 32) { s.lst[p] = (short)w.Mp; s.yv[p] = 0.0; }   // padding: the rhs row with weight 0
-    if (lane == 0) s.ctl[C_NS] = ns;
+    if (lane == 0) { s.ctl[C_NS] = ns; s.ctl[C_FLAG] = 0; }
   }
   SYNC5();
   const int ns = s.ctl[C_NS];
@@ -428,12 +421,7 @@ __device__ __noinline__ double stream5(W5 &w) {
   for (int q = 0; q < NQ; ++q)
     if (tid + T * q < ld2) reinterpret_cast<double2 *>(s.v)[tid + T * q] = acc[q];
   SYNC5();
-  double res = 0.0;
-  #pragma unroll 1
-  for (int p = tid; p < ns; p += T) res = fmax(res, fabs(s.v[s.lst[p]]));
-  res = bmax5<T>(s, res);
   w.n_stream++; w.sum_s += ns;
-  return res;
 }
 
 // ---- a variable outside the window joins it (not toggled): new last row of T2 ------------------------------------
@@ -894,28 +882,42 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
       }
     }
     // ---- everything outside the window, and the accuracy of T2
-    const double res = stream5<T, NQ>(w);
-    if (res > 1e-12 * cmax) {                          // T2 lost digits: rebuild it from T1 and pivot again
-      if (res != res || (t2_fresh && res > 1e-9 * cmax) || ++rebuilt > 3) return false;
-      if (!t2_rebuild<T>(w)) return false;
-      t2_fresh = true;
-      w.n_rebuild++;
-      continue;
-    }
-    // anything outside the window that violates its condition?  All threads look (the usual answer is no); only then does
-    // warp 0 build the ordered list
-    bool mine = false;
+    stream5<T, NQ>(w);
+    // One pass of all threads over v, one barrier: is the residual of the S-system too large (T2 lost digits), and does
+    // anything outside the window violate its condition?  The usual answer to both is no.
+    {
+      const int ns = s.ctl[C_NS];
+      int code = 0;
 #pragma unroll 1
-    for (int m = tid; m < Mp; m += T) {
-      if (s.slot[m] < 0) {
-        const int sg = s.sg[m];
-        const unsigned char fl = s.st[m];
-        const double val = s.v[m];
-        if (fl & ST_INO) mine = mine || (sg != SG_FREE5 && (sg == 0 ? val != 0.0 : (double)sg * val < 0.0));
-        else mine = mine || (!(fl & ST_BLK) && sg != 0 && (sg == SG_FREE5 ? fabs(val) > told : (double)sg * val > told));
+      for (int p = tid; p < ns; p += T) if (!(fabs(s.v[s.lst[p]]) <= 1e-12 * cmax)) code |= 2;
+#pragma unroll 1
+      for (int m = tid; m < Mp; m += T) {
+        if (s.slot[m] < 0) {
+          const int sg = s.sg[m];
+          const unsigned char fl = s.st[m];
+          const double val = s.v[m];
+          bool f;
+          if (fl & ST_INO) f = sg != SG_FREE5 && (sg == 0 ? val != 0.0 : (double)sg * val < 0.0);
+          else f = !(fl & ST_BLK) && sg != 0 && (sg == SG_FREE5 ? fabs(val) > told : (double)sg * val > told);
+          if (f) code |= 1;
+        }
       }
+      if (code) atomicOr(&s.ctl[C_FLAG], code);
+      SYNC5();
+      const int flags = s.ctl[C_FLAG];
+      if (flags & 2) {                                 // T2 lost digits: rebuild it from T1 and pivot again
+        double res = 0.0;
+#pragma unroll 1
+        for (int p = tid; p < ns; p += T) { const double r = fabs(s.v[s.lst[p]]); res = r == r ? fmax(res, r) : r; }
+        res = bmax5<T>(s, res);
+        if (res != res || (t2_fresh && res > 1e-9 * cmax) || ++rebuilt > 3) return false;
+        if (!t2_rebuild<T>(w)) return false;
+        t2_fresh = true;
+        w.n_rebuild++;
+        continue;
+      }
+      if (!(flags & 1)) return true;
     }
-    if (!__syncthreads_or(mine)) return true;
     if (tid < 32) {
       const int lane = tid;
       int nj = 0;
