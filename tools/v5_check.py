@@ -94,6 +94,8 @@ if __name__ == "__main__":
         bad += big(ctx, "cfg2")
     if what in ("k20", "all"):
         bad += big(ctx, "k20_m200")
+    if what in synth.CONFIGS and what not in ("cfg2",):
+        bad += big(ctx, what, reps=2)
     if what == "cold":
         N, M, K, eta, seed, mixed = synth.CONFIGS["k20_m200"]
         X, y, P = synth.make_synthetic(N, M, K, seed, mixed_sign=mixed)
