@@ -625,33 +625,39 @@ __device__ __noinline__ void fold_fused5(W5 &w) {
   }
   __threadfence_block();
   SYNC5();
-  // Z = P~ T2  (T2 symmetric, tile-packed: tile (tk, tq) direct if tk >= tq, else the transposed tile (tq, tk)).  The
-  // k-tiles are taken three at a time: six global loads of A fragments in flight, then six DMMAs (small code, the
-  // latency of the panel loads is paid ~3 times per tile instead of 9 times).
-  constexpr int CH = 3;
-  #pragma unroll 1
-  for (int idx = wid; idx < nt * ntr; idx += NW) {
-    const int tj = idx / ntr, tq = idx - tj * ntr;
-    const double *pa = PT + (size_t)(tj * 8 + fr) * NRp + fk;
-    double c0 = 0.0, c1 = 0.0;
+  // Z = P~ T2  (T2 symmetric, tile-packed: tile (tk, tq) direct if tk >= tq, else the transposed tile (tq, tk)).  A warp
+  // takes a row tile of P~ and keeps the accumulators of ALL its column tiles in registers: every A fragment is fetched
+  // from the global panel once (the next k-tile's while the current one is multiplied) and meets its B fragments in
+  // shared memory.
+  constexpr int NTQ = 12;                              // column tiles of Z held in registers (NR <= 96)
 #pragma unroll 1
-    for (int t0 = 0; t0 < ntr; t0 += CH) {
-      double a0[CH], a1[CH];
+  for (int tj = wid; tj < nt; tj += NW) {
+    const double *pa = PT + (size_t)(tj * 8 + fr) * NRp + fk;
+    double2 acc[NTQ];
 #pragma unroll
-      for (int u = 0; u < CH; ++u) { const bool live = t0 + u < ntr; a0[u] = live ? pa[(t0 + u) * 8] : 0.0; a1[u] = live ? pa[(t0 + u) * 8 + 4] : 0.0; }
+    for (int u = 0; u < NTQ; ++u) acc[u] = make_double2(0.0, 0.0);
+    double a0 = pa[0], a1 = pa[4];
+#pragma unroll 1
+    for (int tk = 0; tk < ntr; ++tk) {
+      const double n0 = tk + 1 < ntr ? pa[(tk + 1) * 8] : 0.0, n1 = tk + 1 < ntr ? pa[(tk + 1) * 8 + 4] : 0.0;
 #pragma unroll
-      for (int u = 0; u < CH; ++u) {
-        const int tk = t0 + u < ntr ? t0 + u : t0;     // dead k-tiles multiply zeros with a valid tile
-        double b0, b1;                                 // B[k][col] = T2(tk*8 + k, tq*8 + col), k = fk / fk + 4, col = fr
-        if (tk >= tq) { const double *tp = s.T2 + ((((tk * (tk + 1)) >> 1) + tq) << 6); b0 = tp[fk * 8 + fr]; b1 = tp[(4 + fk) * 8 + fr]; }
-        else { const double *tp = s.T2 + ((((tq * (tq + 1)) >> 1) + tk) << 6); b0 = tp[fr * 8 + fk]; b1 = tp[fr * 8 + 4 + fk]; }
-        dmma5(c0, c1, a0[u], b0); dmma5(c0, c1, a1[u], b1);
+      for (int tq = 0; tq < NTQ; ++tq) {
+        if (tq < ntr) {
+          double b0, b1;                               // B[k][col] = T2(tk*8 + k, tq*8 + col), k = fk / fk + 4, col = fr
+          if (tk >= tq) { const double *tp = s.T2 + ((((tk * (tk + 1)) >> 1) + tq) << 6); b0 = tp[fk * 8 + fr]; b1 = tp[(4 + fk) * 8 + fr]; }
+          else { const double *tp = s.T2 + ((((tq * (tq + 1)) >> 1) + tk) << 6); b0 = tp[fr * 8 + fk]; b1 = tp[fr * 8 + 4 + fk]; }
+          dmma5(acc[tq].x, acc[tq].y, a0, b0); dmma5(acc[tq].x, acc[tq].y, a1, b1);
+        }
       }
+      a0 = n0; a1 = n1;
     }
-    *reinterpret_cast<double2 *>(ZT + (size_t)(tj * 8 + fr) * NRp + tq * 8 + 2 * fk) = make_double2(c0, c1);
+#pragma unroll
+    for (int tq = 0; tq < NTQ; ++tq)
+      if (tq < ntr) *reinterpret_cast<double2 *>(ZT + (size_t)(tj * 8 + fr) * NRp + tq * 8 + 2 * fk) = acc[tq];
   }
   __threadfence_block();
   SYNC5();
+  constexpr int CH = 5;
   {                                                    // T1 += Z P~' on the lower tiles, mirrored into the upper ones
     const int ntl = (nt * (nt + 1)) >> 1;
     int q = (ntl * wid) / NW;
@@ -1132,7 +1138,7 @@ const Variant5 kVariants5[] = {
     V5(128, 72, 1, 6), V5(128, 80, 1, 5), V5(128, 96, 1, 4), V5(64, 64, 2, 7), V5(64, 72, 2, 6), V5(64, 80, 2, 5), V5(64, 96, 2, 4),
     V5(32, 72, 4, 6),
     // wider problems (the fold's ld1 x 8 panel aliases T2: ld1 * 8 <= t2_doubles(NR))
-    V5(128, 96, 2, 4), V5(128, 128, 3, 3),
+    V5(128, 96, 2, 4),                                  // (NR <= 96: the fused fold keeps 12 column tiles of Z in registers)
 };
 #undef V5
 
