@@ -472,7 +472,11 @@ int pls_gram_build(pls_ctx *c) {
   if (!c->pb.loaded) { set_error("no data set loaded"); return PLS_EINVAL; }
   c->pb.gram_ready = false;
   c->launch_mark = c->launches;
-  return k1_gram_build(c->pb, c->stream, &c->launches);
+  PLS_CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));           // stage-wise timing: ms_gram = build + finalize kernels
+  rc = k1_gram_build(c->pb, c->stream, &c->launches);
+  if (rc) return rc;
+  PLS_CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+  return PLS_OK;
 }
 
 int pls_gram_raw(pls_ctx *c, void **dev_ptr, int64_t *count) {
@@ -491,9 +495,15 @@ int pls_gram_finalize(pls_ctx *c) {
   int rc = check_ctx(c);
   if (rc) return rc;
   if (!c->pb.loaded) { set_error("no data set loaded"); return PLS_EINVAL; }
+  PLS_CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
   rc = k1_gram_finalize(c->pb, c->stream, &c->launches);
   if (rc) return rc;
+  PLS_CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
   PLS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  float m0 = 0.f, m1 = 0.f;
+  if (cudaEventElapsedTime(&m0, c->ev[0], c->ev[1]) != cudaSuccess) { cudaGetLastError(); m0 = 0.f; }
+  if (cudaEventElapsedTime(&m1, c->ev[4], c->ev[5]) != cudaSuccess) { cudaGetLastError(); m1 = 0.f; }
+  c->stats.ms_gram = m0 + m1;
   return PLS_OK;
 }
 
@@ -586,11 +596,15 @@ int pls_opt_residual_partial(pls_ctx *c, const double *alpha_raw, int64_t b, dou
   for (int m = 0; m < Mp; ++m) c->h_pin[m] = (double)host_d(c->h_gmask, m, b) * alpha_raw[m];
   cudaStream_t st = c->stream;
   PLS_CUDA_TRY(cudaMemcpyAsync(c->d_w, c->h_pin, sizeof(double) * Mp, cudaMemcpyHostToDevice, st));
+  PLS_CUDA_TRY(cudaEventRecord(c->ev[4], st));
   rc = k4_residual(c->pb, c->ws, c->d_w, c->d_ssq, c->sm_count, st, &c->launches);
   if (rc) return rc;
+  PLS_CUDA_TRY(cudaEventRecord(c->ev[5], st));
   PLS_CUDA_TRY(cudaMemcpyAsync(c->h_pin + Mp, c->d_ssq, sizeof(double), cudaMemcpyDeviceToHost, st));
   PLS_CUDA_TRY(cudaStreamSynchronize(st));
   *ssq_out = c->h_pin[Mp];
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->stats.ms_recompute = ms; else cudaGetLastError();
   return PLS_OK;
 }
 

@@ -207,6 +207,32 @@ def test_stagewise_equals_one_call_and_two_rank_split(ctx, oracle):
     assert res["b_best"] == one["b_best"] and np.array_equal(res["alpha_raw"], one["alpha_raw"])
 
 
+def test_context_reuse_with_a_wider_problem(pkg, oracle):
+    """One context, Opt on a small M, then Alt on a large M, then Opt / BnB on the large M: every per-context buffer that is
+    sized by M' -- the winner record first of all (it kept its 12 doubles after the Alt call had already moved
+    ws.Mp to 502) -- must follow the widest problem.  Results against the oracle on a fresh comparison."""
+    o, oc = oracle
+    c = pkg.Context(0)
+    try:
+        Xs, ys, Ps = o.make_synthetic(300, 10, 3, seed=1, mixed_sign=True)
+        r0 = c.opt_fit(Xs, ys, Ps, eta=1e-3)
+        assert r0["b_best"] == oc.opt_fit(Xs, ys, Ps, 1e-3)["b_best"]
+        Xl, yl, Pl = o.make_synthetic(1500, 500, 3, seed=2, mixed_sign=True)
+        b0 = np.array([[1.0, -2.0, 3.0, 0.5], [-1.0, 2.0, -3.0, 0.5]]).T
+        ra = c.alt_fit(Xl, yl, Pl, b0, eta=1e-3)
+        assert np.isfinite(ra["opt"])
+        ref = oc.opt_fit(Xl, yl, Pl, 1e-3)
+        r1 = c.opt_fit(Xl, yl, Pl, eta=1e-3)
+        assert r1["b_best"] == ref["b_best"] and abs(r1["opt"] - ref["obj_best"]) <= RTOL * ref["obj_best"]
+        assert np.all(np.abs(r1["alpha_raw"] - ref["alpha_best"]) <= RTOL * np.abs(ref["alpha_best"]).max())
+        rb = c.bnb_fit(Xl, yl, Pl, eta=1e-3)
+        assert abs(rb["opt"] - ref["obj_best"]) <= RTOL * ref["obj_best"]
+        r2 = c.opt_fit(Xs, ys, Ps, eta=1e-3)                      # and back to the small one
+        assert r2["b_best"] == r0["b_best"] and r2["opt"] == r0["opt"]
+    finally:
+        c.close()
+
+
 def test_error_behaviour(ctx, pkg, oracle):
     o, _ = oracle
     X, y, P = o.make_synthetic(50, 6, 2, seed=1)
