@@ -567,7 +567,8 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   if (variant == 3) hneed = (size_t)max_grid * plan3.hstride * sizeof(double);
   if (variant == 4 || variant == 5) {
     if (variant == 4) hneed = (size_t)max_grid * plan4.hstride * sizeof(double);
-    const size_t tneed = (size_t)max_grid * (variant == 4 ? plan4.tabstride : plan5.tabstride) * sizeof(double);
+    const size_t tneed = variant == 4 ? (size_t)max_grid * plan4.tabstride * sizeof(double)
+                                      : ((size_t)max_grid * plan5.tabstride + (size_t)plan5.ld1 * plan5.ld1) * sizeof(double);   // + the shared cold tableau T0
     if (tneed > ws.tab_bytes) {
       if (ws.tab) cudaFree(ws.tab);
       ws.tab = nullptr; ws.tab_bytes = 0;
@@ -602,7 +603,10 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   A.all_obj = d_all_obj; A.all_alpha = d_all_alpha; A.counters = ws.counters;
   if (variant == 5) {
     A.tab = ws.tab; A.tabstride = plan5.tabstride;
+    A.hglob = ws.tab + (size_t)max_grid * plan5.tabstride;        // T0 = [G c; c' yy], written by the launch's prologue kernel
+    ++*launches;
     A.lowmask = (1ull << plan5.low_groups) - 1ull; A.verify_every = plan5.verify_every;
+    A.qs = plan5.cold_cap; A.chain_log2 = plan5.cold_fused;   // (fields the v5 kernel does not use otherwise)
     const int rc = k2v5_launch(A, plan5, (int)grid, st);
     if (rc) return rc;
   } else if (variant == 4) {

@@ -95,6 +95,7 @@ struct Sh5 {
   double *D;       // [64]    8 x 8 pivot block, then its inverse
   double *gd;      // [8]     pivot references of the entering variables of a block
   double *red;     // [32]    block reductions
+  int4 *binfo;     // [8]     per column of the current block: slot c, T2 offsets of the column for rows >= c / rows < c
   int *ctl;        // [16]    broadcast slots
   short *slot;     // [ld1]   window slot of variable m, -1 outside
   short *rvar;     // [NR]    variable of window slot k (slot 0 = the right-hand side, variable index Mp)
@@ -104,13 +105,13 @@ struct Sh5 {
   unsigned short *tmap; // [NR/8 (NR/8 + 1) / 2] tile coordinates (ti << 8 | tj) of the packed tile sequence
   signed char *sg; // [ld1]
   unsigned char *st; // [ld1]
-  unsigned char *mk; // [NR]  block pivot: slot is in the current block
+  unsigned char *mk; // [NR]  block pivot: stamp of the last block this slot was in (== W5::gen: in the current block)
 };
 enum { C_NL = 0, C_NE, C_MX, C_NS, C_OK, C_CNT, C_N, C_NJ, C_NSLOW, C_NP, C_NLV, C_FLAG };
 
 __host__ __device__ inline size_t sh5_bytes(int NR, int ld1) {
   const int ntl = (NR / 8) * (NR / 8 + 1) / 2;
-  return sizeof(double) * ((size_t)t2_doubles(NR) + ld1 + 16 * (size_t)NR + NR + 64 + 8 + 32) + sizeof(int) * 16 +
+  return sizeof(double) * ((size_t)t2_doubles(NR) + ld1 + 16 * (size_t)NR + NR + 64 + 8 + 32 + 16) + sizeof(int) * 16 +
          sizeof(short) * (2 * (size_t)ld1 + 2 * (size_t)NR + 8 + ((ntl + 3) & ~3)) + 2 * (size_t)ld1 + NR + 16;
 }
 
@@ -127,6 +128,7 @@ __device__ __forceinline__ Sh5 make_sh5(int NR, int ld1) {
   s.D = dp; dp += 64;
   s.gd = dp; dp += 8;
   s.red = dp; dp += 32;
+  s.binfo = reinterpret_cast<int4 *>(dp); dp += 16;
   int *ip = reinterpret_cast<int *>(dp);
   s.ctl = ip; ip += 16;
   short *sp = reinterpret_cast<short *>(ip);
@@ -146,10 +148,14 @@ __device__ __forceinline__ Sh5 make_sh5(int NR, int ld1) {
 // walk state (CTA-uniform registers)
 struct W5 {
   double *T1; int ld1;      // this walk's tableau, row stride
+  const double *T1r;        // where T1 is READ: the launch's shared T0 = [G c; c' yy] from a cold start until the first fold
+                            // pass has written this walk's own copy, then T1 itself
   int nr;                   // window capacity (slots incl. the rhs)
   double *Pg;               // [8][ld1] global scratch: the fold's P rows / the verify pass's weights
   int Mp;
   int n;                    // window size incl. slot 0 (rhs)
+  int gen;                  // stamp of the current block (1 .. 255)
+  int cold_fused;           // cold solve: fold with the fused pass (else rank-8 block passes)
   unsigned long long lowmask;
   const unsigned long long *gmask;
   const double *G; int ldg;
@@ -168,6 +174,25 @@ __device__ __forceinline__ double bmax5(const Sh5 &s, double v) {
   for (int i = 1; i < NW; ++i) r = fmax(r, s.red[i]);
   SYNC5();
   return r;
+}
+
+// The block about to be swept: slot list, per-column T2 offsets, membership stamps.  `slot` is read for tid < nb; the
+// caller's barrier follows.  T2 element (row, c): rows >= c at  rbase(row) + y,  rows < c at  z + (tr << 6) + r7.
+template <int T>
+__device__ __forceinline__ void set_block5(const Sh5 &s, W5 &w, int nb, int slot) {
+  const int tid = threadIdx.x;
+  if (++w.gen == 256) {                                // stamps wrap: forget the old ones
+    #pragma unroll 1
+    for (int k = tid; k < w.nr; k += T) s.mk[k] = 0;
+    w.gen = 1;
+    SYNC5();
+  }
+  if (tid < nb) {
+    const int tc = slot >> 3, c7 = slot & 7;
+    s.lstB[tid] = (short)slot;
+    s.binfo[tid] = make_int4(slot, (tc << 6) + c7, (((tc * (tc + 1)) >> 1) << 6) + (c7 << 3), 0);
+    s.mk[slot] = (unsigned char)w.gen;
+  }
 }
 
 // ---- T2: block sweep ----------------------------------------------------------------------------------------------
@@ -194,15 +219,12 @@ __device__ __noinline__ int t2_block(W5 &w, int n, int nb, int nlv, bool test, b
 #pragma unroll 1
     for (int row = T == 32 ? tid : tid - 32; row < ntr * 8; row += TG) {
       const int tr = row >> 3, r7 = row & 7;
-      const int rbase = (((tr * (tr + 1)) >> 1) << 6) + (r7 << 3);
+      const int rbase = (((tr * (tr + 1)) >> 1) << 6) + (r7 << 3), rowt = (tr << 6) + r7;
       const int sw = (row & 2) << 1, pb = row << 3;
 #pragma unroll 1
       for (int q = 0; q < 8; ++q) {
         double val = 0.0;
-        if (row < n && q < nb) {
-          const int c = B[q], tc = c >> 3, c7 = c & 7;
-          val = row >= c ? s.T2[rbase + (tc << 6) + c7] : s.T2[((((tc * (tc + 1)) >> 1) + tr) << 6) + (c7 << 3) + r7];
-        }
+        if (row < n && q < nb) { const int4 bi = s.binfo[q]; val = s.T2[row >= bi.x ? rbase + bi.y : bi.z + rowt]; }
         s.Pp[pb + (q ^ sw)] = val;
       }
     }
@@ -247,38 +269,43 @@ __device__ __noinline__ int t2_block(W5 &w, int n, int nb, int nlv, bool test, b
   }
   SYNC5();
   {                                                    // T2 -= W P' on the stored (lower) tiles
+    // a warp takes a contiguous run of the packed tile sequence (row-major lower triangle): the A fragments (-W rows)
+    // change only when the tile row does, the B fragments (P rows) and the C tile advance by one tile per step
     const int ntl = (ntr * (ntr + 1)) >> 1;
-    const int coff = fr * 8 + 2 * fk;
+    int q = (ntl * wid) / NW;
+    const int q1 = (ntl * (wid + 1)) / NW;
+    const int t0 = s.tmap[q];
+    int ti = t0 >> 8, tj = t0 & 255;
+    const int la0 = pan5(fr, fk), la1 = pan5(fr, 4 + fk);          // lane offsets inside an 8-row tile of a panel
+    double2 *cp = reinterpret_cast<double2 *>(s.T2 + (q << 6) + fr * 8 + 2 * fk);
+    const double *pw = s.Wp + (ti << 6), *pp = s.Pp + (tj << 6);
+    double a0 = -pw[la0], a1 = -pw[la1];
 #pragma unroll 1
-    for (int q = wid; q < ntl; q += NW) {
-      const int t0 = s.tmap[q];
-      const int ra0 = (t0 >> 8) * 8 + fr, rb0 = (t0 & 255) * 8 + fr;
-      double2 *cp0 = reinterpret_cast<double2 *>(s.T2 + (q << 6) + coff);
-      double2 c0 = *cp0;
-      dmma5(c0.x, c0.y, -s.Wp[pan5(ra0, fk)], s.Pp[pan5(rb0, fk)]);
-      dmma5(c0.x, c0.y, -s.Wp[pan5(ra0, 4 + fk)], s.Pp[pan5(rb0, 4 + fk)]);
-      *cp0 = c0;
+    for (; q < q1; ++q) {
+      double2 c0 = *cp;
+      dmma5(c0.x, c0.y, a0, pp[la0]);
+      dmma5(c0.x, c0.y, a1, pp[la1]);
+      *cp = c0;
+      cp += 32; pp += 64;
+      if (++tj > ti) { ++ti; tj = 0; pp = s.Pp; pw += 64; a0 = -pw[la0]; a1 = -pw[la1]; }
     }
   }
   SYNC5();
   #pragma unroll 1
 #pragma unroll 1
   for (int row = tid; row < n; row += T) {             // columns / rows of B outside the block: e_q W[:, q]
-    bool inb = false;
-#pragma unroll 1
-    for (int q = 0; q < nb; ++q) inb = inb || row == B[q];
-    if (inb) continue;
+    if (s.mk[row] == (unsigned char)w.gen) continue;
     const int tr = row >> 3, r7 = row & 7;
-    const int rbase = (((tr * (tr + 1)) >> 1) << 6) + (r7 << 3);
+    const int rbase = (((tr * (tr + 1)) >> 1) << 6) + (r7 << 3), rowt = (tr << 6) + r7;
     const int sw = (row & 2) << 1, pb = row << 3;
 #pragma unroll 1
     for (int q = 0; q < nb; ++q) {
-      const int c = B[q], tc = c >> 3, c7 = c & 7;
+      const int4 bi = s.binfo[q];
+      const int tc = bi.x >> 3;
       const double w0 = s.Wp[pb + (q ^ sw)];
       const double val = q < nlv ? -w0 : w0;
-      if (tr > tc) s.T2[rbase + (tc << 6) + c7] = val;
-      else if (tr < tc) s.T2[((((tc * (tc + 1)) >> 1) + tr) << 6) + (c7 << 3) + r7] = val;
-      else { const int d = (((tr * (tr + 1)) >> 1) + tr) << 6; s.T2[d + (r7 << 3) + c7] = val; s.T2[d + (c7 << 3) + r7] = val; }
+      if (tr >= tc) s.T2[rbase + bi.y] = val;          // (a diagonal tile holds both halves)
+      if (tr <= tc) s.T2[bi.z + rowt] = val;
     }
   }
 #pragma unroll 1
@@ -302,7 +329,7 @@ __device__ __noinline__ bool t2_rebuild(W5 &w) {
   const int n = w.n;
   #pragma unroll 1
   for (int i = wid; i < n; i += NW) {
-    const double *row = w.T1 + (size_t)w.ld1 * s.rvar[i];
+    const double *row = w.T1r + (size_t)w.ld1 * s.rvar[i];
     #pragma unroll 1
     for (int j = lane; j <= i; j += 32) t2_set(s.T2, i, j, __ldcg(row + s.rvar[j]));
   }
@@ -328,7 +355,7 @@ __device__ __noinline__ bool t2_rebuild(W5 &w) {
   #pragma unroll 1
   for (int q0 = 0; q0 < cnt; q0 += 8) {
     const int nb = min(8, cnt - q0);
-    if (tid < nb) s.lstB[tid] = s.lst[q0 + tid];
+    set_block5<T>(s, w, nb, tid < nb ? s.lst[q0 + tid] : 0);
     SYNC5();
     if (t2_block<T>(w, n, nb, max(0, min(nb, nlv - q0)), false, false) != nb) return false;
   }
@@ -365,6 +392,60 @@ __device__ __noinline__ void window_reset(W5 &w) {
   w.n = s.ctl[C_N];
 }
 
+// ---- window compaction: slots that are neither toggled nor in a fast group leave the window --------------------------
+// T2 restricted to the remaining slots is still sweep(T1[R', R'], S): rows / columns are moved, nothing is recomputed.
+// (Out of place through this walk's global scratch: the fused fold's panel area.)
+template <int T>
+__device__ __noinline__ void t2_compact(W5 &w) {
+  const Sh5 s = make_sh5(w.nr, w.ld1);
+  const int tid = threadIdx.x;
+  const int n = w.n;
+  double *scr = w.Pg + 8 * (size_t)w.ld1;
+  short *old = s.lst;
+  if (tid < 32) {
+    const int lane = tid;
+    if (lane == 0) old[0] = 0;
+    int base = 1;
+    #pragma unroll 1
+    for (int k0 = 1; k0 < n; k0 += 32) {
+      const int k = k0 + lane;
+      bool keep = false; int m = 0;
+      if (k < n) {
+        m = s.rvar[k];
+        const unsigned char f = s.st[m];
+        keep = (w.gmask[m] & w.lowmask) != 0ull || (((f & ST_PAS) != 0) != ((f & ST_INO) != 0));
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      const int kn = base + __popc(bal & ((1u << lane) - 1));
+      __syncwarp();
+      if (k < n) {
+        if (keep) { old[kn] = (short)k; s.rvar[kn] = (short)m; s.slot[m] = (short)kn; }   // kn <= k: slots move down, in order
+        else s.slot[m] = -1;
+      }
+      __syncwarp();
+      base += __popc(bal);
+    }
+    if (lane == 0) s.ctl[C_N] = base;
+  }
+  SYNC5();
+  const int nn = s.ctl[C_N];
+  if (nn == n) return;
+  #pragma unroll 1
+  for (int idx = tid; idx < nn * nn; idx += T) {
+    const int a = idx / nn, b = idx - a * nn;
+    if (b <= a) __stcg(scr + idx, t2_get(s.T2, old[a], old[b]));
+  }
+  __threadfence_block();
+  SYNC5();
+  #pragma unroll 1
+  for (int idx = tid; idx < nn * nn; idx += T) {
+    const int a = idx / nn, b = idx - a * nn;
+    if (b <= a) t2_set(s.T2, a, b, __ldcg(scr + idx));
+  }
+  w.n = nn;
+  SYNC5();
+}
+
 // ---- streaming pass ------------------------------------------------------------------------------------------
 // v = T1[rhs, :] - sum_{s toggled} e_s T2[s, rhs] T1[s, :]; the toggled variables stay listed in s.lst[0 .. ctl[C_NS])
 // (on their rows v is the residual of the S-system).  NQ = double2 pieces of a row per thread.
@@ -395,7 +476,7 @@ __device__ __noinline__ void stream5(W5 &w) {
   const int ns = s.ctl[C_NS];
   const int nsp = (ns + UB - 1) / UB * UB;
   double2 acc[NQ];
-  const double2 *T1v = reinterpret_cast<const double2 *>(w.T1);
+  const double2 *T1v = reinterpret_cast<const double2 *>(w.T1r);
   {
     const double2 *r = T1v + (size_t)ld2 * w.Mp;
 #pragma unroll
@@ -431,7 +512,7 @@ __device__ __noinline__ void join5(W5 &w, int m) {
   const Sh5 s = make_sh5(w.nr, w.ld1);
   const int tid = threadIdx.x;
   const int n = w.n;
-  const double *row1 = w.T1 + (size_t)w.ld1 * m;
+  const double *row1 = w.T1r + (size_t)w.ld1 * m;
   double *rowv = s.Wp, *tog = s.Wp + w.nr;              // scratch: the new row, toggled marks
   if (tid < 32) {                                      // toggled slots -> lstE, coefficients e_s T1[m, s] -> yv
     const int lane = tid;
@@ -489,7 +570,7 @@ __device__ __noinline__ bool fold_block5(W5 &w, int boff, int nb) {
   #pragma unroll 1
   for (int idx = tid; idx < ld1 * 8; idx += T) {
     const int j = idx >> 3, q = idx & 7;
-    FP[pan5(j, q)] = q < nb ? __ldcg(w.T1 + (size_t)ld1 * B[q] + j) : 0.0;
+    FP[pan5(j, q)] = q < nb ? __ldcg(w.T1r + (size_t)ld1 * B[q] + j) : 0.0;
   }
   if (tid < 8) s.gd[tid] = (tid < nb && (s.st[B[tid]] & ST_PAS)) ? 1e-13 * __ldg(w.G + (size_t)w.ldg * B[tid] + B[tid]) : 0.0;
   SYNC5();
@@ -544,7 +625,7 @@ __device__ __noinline__ bool fold_block5(W5 &w, int boff, int nb) {
 #pragma unroll
       for (int u = 0; u < IFL; ++u) {
         ri[u] = ti; rj[u] = tj;
-        c[u] = __ldcg(reinterpret_cast<const double2 *>(w.T1 + (size_t)(ti * 8 + fr) * ld1 + tj * 8 + 2 * fk));
+        c[u] = __ldcg(reinterpret_cast<const double2 *>(w.T1r + (size_t)(ti * 8 + fr) * ld1 + tj * 8 + 2 * fk));
         if (q + u + 1 < q1) { if (++tj > ti) { ++ti; tj = 0; } }
       }
 #pragma unroll
@@ -587,6 +668,7 @@ __device__ __noinline__ bool fold_block5(W5 &w, int boff, int nb) {
   SYNC5();
   if (tid < nb) { const int m = B[tid]; const unsigned char f = s.st[m]; s.st[m] = (f & ST_PAS) ? (unsigned char)(f | ST_INO) : (unsigned char)(f & ~ST_INO); }
   SYNC5();
+  w.T1r = w.T1;                                        // every tile has been written
   w.sum_p2 += 2ull * ld1 * ld1;
   w.n_fold++;
   return true;
@@ -594,52 +676,62 @@ __device__ __noinline__ bool fold_block5(W5 &w, int boff, int nb) {
 
 // ---- fused fold: EVERY toggled window variable is swept in T1 in ONE pass (the cold solve: up to NR - 1 at once) ---------
 // With S = the toggled window slots, T2 = sweep(T1[Rb, Rb], S) already holds -E inv(T1[S, S]) E, so no block has to be
-// inverted.  With  P~[j, k] = e_k T1[var_k, j]  (k toggled, else 0; e_k = +1 entered / -1 left)  and  Z = P~ T2:
-//     T1[i, j] += sum_k Z[i, k] P~[j, k]            everywhere            (lower tiles + mirrored store, DMMA)
-//     T1[:, var_q] = T1[var_q, :] = -Z[:, q]        for the toggled q
+// inverted.  With  P~[j, k] = e_k T1[var_k, j]  (k toggled, else 0; e_k = +1 entered / -1 left),  Z = P~ T2  and
+// Z' = Z E (column k scaled by e_k):
+//     T1[i, j] += sum_k Z'[i, k] T1[var_k, j]       everywhere            (lower tiles + mirrored store, DMMA)
+//     T1[:, var_q] = T1[var_q, :] = -e_q Z'[:, q]   for the toggled q
 //     T1[Rb, Rb] = T2                               the window block (sweeps on S commute with the restriction to Rb)
-// One read + write of T1 instead of one per 8 variables; the two ld1 x NR panels live in this walk's global scratch.
+// One pass over T1 instead of one per 8 variables.  The rows T1[var_k, :] are read where they lie while T1 is still the
+// launch's shared T0 (the cold start: L2 hits for every walk, and this walk's own tableau is only written); once
+// T1 is this walk's own they are first copied to the global scratch (the tile updates would overwrite them).  Z' (ld1 x n)
+// lives in the global scratch.
 template <int T>
 __device__ __noinline__ void fold_fused5(W5 &w) {
   const Sh5 s = make_sh5(w.nr, w.ld1);
   constexpr int NW = T / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int fr = lane >> 2, fk = lane & 3;
-  const int ld1 = w.ld1, nt = ld1 >> 3, n = w.n, NRp = w.nr;
+  const int ld1 = w.ld1, nt = ld1 >> 3, n = w.n;
   const int ntr = (n + 7) >> 3, nk = ntr << 3;
-  double *PT = w.Pg + 8 * (size_t)ld1, *ZT = PT + (size_t)ld1 * NRp;       // [ld1][NR] each, row stride NR
+  double *PR = w.Pg + 8 * (size_t)ld1, *ZT = PR + (size_t)ld1 * w.nr;      // PR: [nk][ld1] row copies; ZT: [ld1][nk]
+  int *roff = reinterpret_cast<int *>(s.Wp);           // [nk] offset of slot k's row from `rows`
+  const bool own = w.T1r == w.T1;
+  const double *rows = own ? PR : w.T1r;
   // e_k per slot (0 = not toggled) -> yv
   #pragma unroll 1
   for (int k = tid; k < nk; k += T) {
     double e = 0.0;
     if (k >= 1 && k < n) { const unsigned char f = s.st[s.rvar[k]]; const bool pas = f & ST_PAS, ino = f & ST_INO; if (pas != ino) e = pas ? 1.0 : -1.0; }
     s.yv[k] = e;
+    roff[k] = e != 0.0 ? (own ? k : (int)s.rvar[k]) * ld1 : 0;          // untoggled: any finite row (it meets e = 0)
   }
   SYNC5();
-  #pragma unroll 1
-  for (int k = 0; k < nk; ++k) {                       // P~ (transposed copy of the toggled rows of T1)
-    const double e = s.yv[k];
-    const double *src = w.T1 + (size_t)ld1 * (e != 0.0 ? s.rvar[k] : 0);
+  if (own) {
     #pragma unroll 1
-    for (int j = tid; j < ld1; j += T) PT[(size_t)j * NRp + k] = e != 0.0 ? e * __ldcg(src + j) : 0.0;
+    for (int k = 0; k < n; ++k) {
+      if (k > 0 && s.yv[k] == 0.0) continue;           // (row 0 of the copy is the fallback row of untoggled slots)
+      const double *src = w.T1 + (size_t)ld1 * (s.yv[k] != 0.0 ? s.rvar[k] : 0);
+      #pragma unroll 1
+      for (int j = tid; j < ld1; j += T) PR[(size_t)k * ld1 + j] = __ldcg(src + j);
+    }
+    __threadfence_block();
+    SYNC5();
   }
-  __threadfence_block();
-  SYNC5();
-  // Z = P~ T2  (T2 symmetric, tile-packed: tile (tk, tq) direct if tk >= tq, else the transposed tile (tq, tk)).  A warp
+  // Z' = (P~ T2) E  (T2 symmetric, tile-packed: tile (tk, tq) direct if tk >= tq, else the transposed tile (tq, tk)).  A warp
   // takes a row tile of P~ and keeps the accumulators of ALL its column tiles in registers: every A fragment is fetched
-  // from the global panel once (the next k-tile's while the current one is multiplied) and meets its B fragments in
-  // shared memory.
+  // once (the next k-tile's while the current one is multiplied) and meets its B fragments in shared memory.
   constexpr int NTQ = 12;                              // column tiles of Z held in registers (NR <= 96)
 #pragma unroll 1
   for (int tj = wid; tj < nt; tj += NW) {
-    const double *pa = PT + (size_t)(tj * 8 + fr) * NRp + fk;
+    const double *pa = rows + tj * 8 + fr;
     double2 acc[NTQ];
 #pragma unroll
     for (int u = 0; u < NTQ; ++u) acc[u] = make_double2(0.0, 0.0);
-    double a0 = pa[0], a1 = pa[4];
+    double a0 = s.yv[fk] * __ldcg(pa + roff[fk]), a1 = s.yv[4 + fk] * __ldcg(pa + roff[4 + fk]);
 #pragma unroll 1
     for (int tk = 0; tk < ntr; ++tk) {
-      const double n0 = tk + 1 < ntr ? pa[(tk + 1) * 8] : 0.0, n1 = tk + 1 < ntr ? pa[(tk + 1) * 8 + 4] : 0.0;
+      double n0 = 0.0, n1 = 0.0;
+      if (tk + 1 < ntr) { const int k = (tk + 1) * 8 + fk; n0 = s.yv[k] * __ldcg(pa + roff[k]); n1 = s.yv[k + 4] * __ldcg(pa + roff[k + 4]); }
 #pragma unroll
       for (int tq = 0; tq < NTQ; ++tq) {
         if (tq < ntr) {
@@ -653,12 +745,15 @@ __device__ __noinline__ void fold_fused5(W5 &w) {
     }
 #pragma unroll
     for (int tq = 0; tq < NTQ; ++tq)
-      if (tq < ntr) *reinterpret_cast<double2 *>(ZT + (size_t)(tj * 8 + fr) * NRp + tq * 8 + 2 * fk) = acc[tq];
+      if (tq < ntr) {
+        const int k = tq * 8 + 2 * fk;
+        *reinterpret_cast<double2 *>(ZT + (size_t)(tj * 8 + fr) * nk + k) = make_double2(acc[tq].x * s.yv[k], acc[tq].y * s.yv[k + 1]);
+      }
   }
   __threadfence_block();
   SYNC5();
   constexpr int CH = 5;
-  {                                                    // T1 += Z P~' on the lower tiles, mirrored into the upper ones
+  {                                                    // T1 += Z' rows' on the lower tiles, mirrored into the upper ones
     const int ntl = (nt * (nt + 1)) >> 1;
     int q = (ntl * wid) / NW;
     const int q1 = (ntl * (wid + 1)) / NW;
@@ -667,16 +762,17 @@ __device__ __noinline__ void fold_fused5(W5 &w) {
     int tj = q - ((ti * (ti + 1)) >> 1);
     #pragma unroll 1
     for (; q < q1; ++q) {
-      double2 c = __ldcg(reinterpret_cast<const double2 *>(w.T1 + (size_t)(ti * 8 + fr) * ld1 + tj * 8 + 2 * fk));
-      const double *za = ZT + (size_t)(ti * 8 + fr) * NRp + fk, *pb = PT + (size_t)(tj * 8 + fr) * NRp + fk;
+      double2 c = __ldcg(reinterpret_cast<const double2 *>(w.T1r + (size_t)(ti * 8 + fr) * ld1 + tj * 8 + 2 * fk));
+      const double *za = ZT + (size_t)(ti * 8 + fr) * nk + fk, *pb = rows + tj * 8 + fr;
 #pragma unroll 1
       for (int t0 = 0; t0 < ntr; t0 += CH) {
         double z0[CH], z1[CH], p0[CH], p1[CH];
 #pragma unroll
         for (int u = 0; u < CH; ++u) {
           const bool live = t0 + u < ntr;
+          const int k = (t0 + u) * 8 + fk;
           z0[u] = live ? za[(t0 + u) * 8] : 0.0; z1[u] = live ? za[(t0 + u) * 8 + 4] : 0.0;
-          p0[u] = live ? pb[(t0 + u) * 8] : 0.0; p1[u] = live ? pb[(t0 + u) * 8 + 4] : 0.0;
+          p0[u] = live ? __ldcg(pb + roff[k]) : 0.0; p1[u] = live ? __ldcg(pb + roff[k + 4]) : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < CH; ++u) { dmma5(c.x, c.y, z0[u], p0[u]); dmma5(c.x, c.y, z1[u], p1[u]); }
@@ -692,11 +788,12 @@ __device__ __noinline__ void fold_fused5(W5 &w) {
   SYNC5();
   #pragma unroll 1
   for (int k = 1; k < n; ++k) {                        // rows / columns of the toggled variables: -Z[:, k]
-    if (s.yv[k] == 0.0) continue;
+    const double e = s.yv[k];
+    if (e == 0.0) continue;
     const int var = s.rvar[k];
     #pragma unroll 1
     for (int j = tid; j < ld1; j += T) {
-      const double val = -ZT[(size_t)j * NRp + k];
+      const double val = -e * ZT[(size_t)j * nk + k];
       __stcg(w.T1 + (size_t)ld1 * var + j, val);
       __stcg(w.T1 + (size_t)ld1 * j + var, val);
     }
@@ -713,6 +810,7 @@ __device__ __noinline__ void fold_fused5(W5 &w) {
     if (k >= 1 && s.yv[k] != 0.0) { const int m = s.rvar[k]; const unsigned char f = s.st[m]; s.st[m] = (f & ST_PAS) ? (unsigned char)(f | ST_INO) : (unsigned char)(f & ~ST_INO); }
   }
   SYNC5();
+  w.T1r = w.T1;
   w.sum_p2 += 2ull * ld1 * ld1 * (unsigned long long)ntr / 8 + (unsigned long long)ld1 * nk * nk / 2;
   w.n_fold++;
 }
@@ -722,6 +820,7 @@ template <int T, int NR>
 __device__ __noinline__ bool fold5(W5 &w) {
   const Sh5 s = make_sh5(w.nr, w.ld1);
   const int tid = threadIdx.x;
+  if (w.lowmask == 0ull) t2_compact<T>(w);             // cold solve: only toggled variables stay, the fused pass works on |S| columns
   const int n = w.n;
   short *B = s.lstE;                                   // NR entries are enough: every listed variable is in the window
   if (tid < 32) {                                      // swept-back (in O, now active) first, then entering; index order within each class
@@ -749,7 +848,7 @@ __device__ __noinline__ bool fold5(W5 &w) {
   SYNC5();
   const int cnt = s.ctl[C_CNT];
   bool ok = true;
-  if (w.lowmask == 0ull && cnt > 8) fold_fused5<T>(w);          // cold solve: everything toggled goes in, one pass
+  if (w.lowmask == 0ull && cnt > 8 && w.cold_fused) fold_fused5<T>(w);          // cold solve: everything toggled goes in, one pass
   else for (int q0 = 0; q0 < cnt && ok; q0 += 8) ok = fold_block5<T>(w, q0, min(8, cnt - q0));
   window_reset(w);
   if (!t2_rebuild<T>(w)) ok = false;
@@ -867,7 +966,7 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
       bool broken = false;
       while (done < tot) {
         const int nb = min(8, tot - done), nlv = max(0, min(nb, nl - done));
-        if (tid < nb) s.lstB[tid] = done + tid < nl ? s.lst[done + tid] : s.lstE[done + tid - nl];
+        set_block5<T>(s, w, nb, tid < nb ? (done + tid < nl ? s.lst[done + tid] : s.lstE[done + tid - nl]) : 0);
         SYNC5();
         const int r = t2_block<T>(w, n, nb, nlv, true, true);
         if (r == nb) { done += nb; continue; }
@@ -954,8 +1053,11 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
       #pragma unroll 1
       for (int p = tid; p < nj; p += T) park[p] = s.lst[p];
       SYNC5();
-      if (!fold5<T, NR>(w)) return false;
-      t2_fresh = true;
+      if (w.lowmask == 0ull) t2_compact<T>(w);         // cold solve: variables that went back to their T1 state just leave the window
+      if (NR - w.n < (nj < 8 ? nj : 8)) {
+        if (!fold5<T, NR>(w)) return false;
+        t2_fresh = true;
+      }
       int room = NR - w.n;
       if (room > nj) room = nj;
       if (room <= 0) return false;                     // the fast groups alone fill the window (the host sized l to prevent this)
@@ -969,28 +1071,27 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
   }
 }
 
-// T1 <- [G c; c' yy] with zero padding (ld1 x ld1), every variable active and outside the window
+// Cold start: T1 is READ from the launch's shared T0 = [G c; c' yy] (zero padded to ld1 x ld1, written once per launch by
+// k2v5_build_t0, L2-resident for every walk) until this walk's first fold pass writes its own tableau; every variable
+// active and outside the window.
 template <int T>
-__device__ __noinline__ void cold_init5(W5 &w, const double *c, double yy) {
+__device__ __noinline__ void cold_init5(W5 &w, const double *T0) {
   const Sh5 s = make_sh5(w.nr, w.ld1);
-  const int tid = threadIdx.x, Mp = w.Mp, ld1 = w.ld1, ld2 = ld1 >> 1;
-  #pragma unroll 1
-  for (int idx = tid; idx < ld1 * ld2; idx += T) {
-    const int row = idx / ld2, col = (idx - row * ld2) << 1;
-    double2 val = make_double2(0.0, 0.0);
-    if (row < Mp) {
-      const double *gr = w.G + (size_t)w.ldg * row;
-      val.x = col < Mp ? gr[col] : (col == Mp ? c[row] : 0.0);
-      val.y = col + 1 < Mp ? gr[col + 1] : (col + 1 == Mp ? c[row] : 0.0);
-    } else if (row == Mp) {
-      val.x = col < Mp ? c[col] : (col == Mp ? yy : 0.0);
-      val.y = col + 1 < Mp ? c[col + 1] : (col + 1 == Mp ? yy : 0.0);
-    }
-    __stcg(reinterpret_cast<double2 *>(w.T1 + (size_t)ld1 * row + col), val);
-  }
+  const int tid = threadIdx.x, ld1 = w.ld1;
+  w.T1r = T0;
   #pragma unroll 1
   for (int m = tid; m < ld1; m += T) { s.st[m] = 0; s.slot[m] = -1; s.sg[m] = 0; }
   SYNC5();
+}
+
+__global__ void __launch_bounds__(128) k2v5_build_t0(const double *G, int ldg, const double *c, const double *scal, int Mp, int ld1, double *T0) {
+  const int row = blockIdx.x;
+  for (int col = threadIdx.x; col < ld1; col += blockDim.x) {
+    double val = 0.0;
+    if (row < Mp) val = col < Mp ? G[(size_t)ldg * row + col] : (col == Mp ? c[row] : 0.0);
+    else if (row == Mp) val = col < Mp ? c[col] : (col == Mp ? scal[0] : 0.0);
+    T0[(size_t)ld1 * row + col] = val;
+  }
 }
 
 // d_m = sum_k Po[m,k] (2 bit_k(b) - 1)   (Opt.jl:28-29) -> sign classes; clears the per-orthant refusal flags
@@ -1013,9 +1114,9 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
   const int Mp = A.Mp, ld1 = A.cap;                    // ld1 = round_up(Mp + 1, 8): rows / row stride of T1
   const Sh5 s = make_sh5(NR, ld1);
   W5 w;
-  w.T1 = A.tab + (size_t)blockIdx.x * A.tabstride; w.ld1 = ld1;
+  w.T1 = A.tab + (size_t)blockIdx.x * A.tabstride; w.ld1 = ld1; w.T1r = A.hglob;
   w.Pg = w.T1 + (size_t)ld1 * ld1;
-  w.Mp = Mp; w.n = 1; w.lowmask = A.lowmask; w.nr = NR;
+  w.Mp = Mp; w.n = 1; w.lowmask = A.lowmask; w.nr = NR; w.cold_fused = A.chain_log2; w.gen = 0;
   w.gmask = reinterpret_cast<const unsigned long long *>(A.gmask);
   w.G = A.G; w.ldg = A.ldg;
   w.n_sweep = w.n_stream = w.sum_s = w.sum_p2 = w.n_iter = w.n_blk = w.n_rebuild = w.n_fold = 0;
@@ -1043,7 +1144,7 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
   #pragma unroll 1
   for (long long i = i0; i < i1; ++i) {
     if (cold) {
-      cold_init5<T>(w, A.c, yy);
+      cold_init5<T>(w, A.hglob);
       // the cold solve runs with NO fast groups: the window starts empty and takes up to NR - 1 violators per round,
       // all of which are folded into T1 in full blocks of 8 (~2 rounds instead of ~9 with the fast variables in the way)
       w.lowmask = 0ull;
@@ -1135,7 +1236,7 @@ struct Variant5 { int T, NR, NQ, minb; K5Fn fn; };
 #define V5(T, NR, NQ, MINB) {T, NR, NQ, MINB, k2v5_orthant_walks<T, NR, NQ, MINB>}
 const Variant5 kVariants5[] = {
     // M' + 1 <= 256 (NQ = row pieces per thread of the streaming pass: ld1 <= 2 T NQ)
-    V5(128, 72, 1, 6), V5(128, 80, 1, 5), V5(128, 96, 1, 4), V5(64, 64, 2, 7), V5(64, 72, 2, 6), V5(64, 80, 2, 5), V5(64, 96, 2, 4),
+    V5(128, 64, 1, 7), V5(128, 72, 1, 6), V5(128, 80, 1, 5), V5(128, 96, 1, 4), V5(64, 64, 2, 7), V5(64, 72, 2, 6), V5(64, 80, 2, 5), V5(64, 96, 2, 4),
     V5(32, 72, 4, 6),
     // wider problems (the fold's ld1 x 8 panel aliases T2: ld1 * 8 <= t2_doubles(NR))
     V5(128, 96, 2, 4),                                  // (NR <= 96: the fused fold keeps 12 column tiles of Z in registers)
@@ -1195,11 +1296,16 @@ int k2v5_plan(int Mp, int n_bits, const uint64_t *h_gmask, K5Plan *pl) {
   pl->tabstride = (size_t)ld1 * ld1 + 8 * (size_t)ld1 + 2 * (size_t)ld1 * v->NR + 64;
   const char *eV = getenv("PLS_K5_VERIFY");
   pl->verify_every = eV ? atoi(eV) : 128;
+  const char *eF = getenv("PLS_K5_FUSED");
+  pl->cold_cap = 0;
+  pl->cold_fused = eF ? atoi(eF) : 1;
   if (pl->verify_every < 1) pl->verify_every = 1;
   return PLS_OK;
 }
 
 int k2v5_launch(const K2Args &A, const K5Plan &pl, int grid, cudaStream_t st) {
+  k2v5_build_t0<<<pl.ld1, 128, 0, st>>>(A.G, A.ldg, A.c, A.scal, A.Mp, pl.ld1, A.hglob);   // A.hglob: the shared cold tableau T0
+  PLS_CUDA_TRY(cudaGetLastError());
   kVariants5[pl.variant].fn<<<grid, pl.T, pl.smem, st>>>(A);
   PLS_CUDA_TRY(cudaGetLastError());
   return PLS_OK;
