@@ -40,11 +40,21 @@ constexpr int SG_FREE5 = 2;
 constexpr unsigned char ST_INO = 1;   // variable is swept in T1 (committed)
 constexpr unsigned char ST_PAS = 2;   // variable is passive now
 constexpr unsigned char ST_BLK = 4;   // refused by the pivot test at this orthant
+constexpr unsigned char ST_FAST = 8;  // belongs to one of the fast Gray groups (never folded into T1); kept by set_lowmask5
 #define SYNC5() __syncthreads()
 
 __device__ __forceinline__ void dmma5(double &d0, double &d1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
       : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+// 1 / x to the last bits: hardware approximation + two Newton steps (the pivot-block inverse is a chain of 8 of these)
+__device__ __forceinline__ double rcp5(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
 }
 __device__ __forceinline__ double wsum5(double v) {
 #pragma unroll
@@ -105,6 +115,7 @@ struct Sh5 {
   unsigned short *tmap; // [NR/8 (NR/8 + 1) / 2] tile coordinates (ti << 8 | tj) of the packed tile sequence
   signed char *sg; // [ld1]
   unsigned char *st; // [ld1]
+  unsigned char *grp; // [ld1] the variable's only group (255: it belongs to several)
   unsigned char *mk; // [NR]  block pivot: stamp of the last block this slot was in (== W5::gen: in the current block)
 };
 enum { C_NL = 0, C_NE, C_MX, C_NS, C_OK, C_CNT, C_N, C_NJ, C_NSLOW, C_NP, C_NLV, C_FLAG };
@@ -112,7 +123,7 @@ enum { C_NL = 0, C_NE, C_MX, C_NS, C_OK, C_CNT, C_N, C_NJ, C_NSLOW, C_NP, C_NLV,
 __host__ __device__ inline size_t sh5_bytes(int NR, int ld1) {
   const int ntl = (NR / 8) * (NR / 8 + 1) / 2;
   return sizeof(double) * ((size_t)t2_doubles(NR) + ld1 + 16 * (size_t)NR + NR + 64 + 8 + 32 + 16) + sizeof(int) * 16 +
-         sizeof(short) * (2 * (size_t)ld1 + 2 * (size_t)NR + 8 + ((ntl + 3) & ~3)) + 2 * (size_t)ld1 + NR + 16;
+         sizeof(short) * (2 * (size_t)ld1 + 2 * (size_t)NR + 8 + ((ntl + 3) & ~3)) + 3 * (size_t)ld1 + NR + 16;
 }
 
 __device__ __forceinline__ Sh5 make_sh5(int NR, int ld1) {
@@ -141,6 +152,7 @@ __device__ __forceinline__ Sh5 make_sh5(int NR, int ld1) {
   signed char *cp = reinterpret_cast<signed char *>(sp);
   s.sg = cp; cp += ld1;
   s.st = reinterpret_cast<unsigned char *>(cp); cp += ld1;
+  s.grp = reinterpret_cast<unsigned char *>(cp); cp += ld1;
   s.mk = reinterpret_cast<unsigned char *>(cp);
   return s;
 }
@@ -245,7 +257,7 @@ __device__ __noinline__ int t2_block(W5 &w, int n, int nb, int nlv, bool test, b
       const double pk0 = s.D[k * 8 + j0], pk1 = s.D[k * 8 + j0 + 1], cik = s.D[i * 8 + k], pkk = s.D[k * 8 + k];
       const bool good = k < nlv ? pkk < 0.0 : (test ? pkk > s.gd[k] : pkk > 0.0);
       if (!good && bad == nb) bad = k;
-      const double d = 1.0 / pkk, fct = cik * d;
+      const double d = rcp5(pkk), fct = cik * d;
       const bool rowk = i == k;
       double n0 = rowk ? pk0 * d : fma(-fct, pk0, e0);
       double n1 = rowk ? pk1 * d : fma(-fct, pk1, e1);
@@ -377,7 +389,7 @@ __device__ __noinline__ void window_reset(W5 &w) {
       bool keep = false;
       if (m < Mp) {
         const unsigned char f = s.st[m];
-        keep = (w.gmask[m] & w.lowmask) != 0ull || (((f & ST_PAS) != 0) != ((f & ST_INO) != 0));
+        keep = (f & ST_FAST) || (((f & ST_PAS) != 0) != ((f & ST_INO) != 0));
       }
       const unsigned bal = __ballot_sync(0xffffffffu, keep);
       if (m < Mp) {
@@ -413,7 +425,7 @@ __device__ __noinline__ void t2_compact(W5 &w) {
       if (k < n) {
         m = s.rvar[k];
         const unsigned char f = s.st[m];
-        keep = (w.gmask[m] & w.lowmask) != 0ull || (((f & ST_PAS) != 0) != ((f & ST_INO) != 0));
+        keep = (f & ST_FAST) || (((f & ST_PAS) != 0) != ((f & ST_INO) != 0));
       }
       const unsigned bal = __ballot_sync(0xffffffffu, keep);
       const int kn = base + __popc(bal & ((1u << lane) - 1));
@@ -455,25 +467,32 @@ __device__ __noinline__ void stream5(W5 &w) {
   const int tid = threadIdx.x;
   const int n = w.n, ld2 = w.ld1 >> 1;
   constexpr int UB = 8;
-  if (tid < 32) {                                      // S list: variable -> lst, y -> yv
-    const int lane = tid;
-    int ns = 0;
+  // S list: variable -> lst, y -> yv, in slot order (every thread looks at one slot; per-warp counts meet in shared memory)
+  int ns = 0;
+  {
+    constexpr int NW = T / 32;
+    const int lane = tid & 31, wid = tid >> 5;
+    int *ri = reinterpret_cast<int *>(s.red);
     #pragma unroll 1
-    for (int k0 = 1; k0 < n; k0 += 32) {
-      const int k = k0 + lane;
+    for (int k0 = 1; k0 < n; k0 += T) {
+      const int k = k0 + tid;
       bool tg = false, pas = false; int m = 0;
       if (k < n) { m = s.rvar[k]; const unsigned char f = s.st[m]; pas = f & ST_PAS; tg = pas != ((f & ST_INO) != 0); }
       const unsigned bal = __ballot_sync(0xffffffffu, tg);
-      if (tg) { const int p = ns + __popc(bal & ((1u << lane) - 1)); s.lst[p] = (short)m; { const double t = s.T2[t2_idx(k, 0)]; s.yv[p] = pas ? t : -t; } }
-      ns += __popc(bal);
+      if (k0 > 1) SYNC5();
+      if (lane == 0) ri[wid] = __popc(bal);
+      SYNC5();
+      int off = ns;
+#pragma unroll
+      for (int w2 = 0; w2 < NW; ++w2) { const int c = ri[w2]; if (w2 < wid) off += c; ns += c; }
+      if (tg) { const int p = off + __popc(bal & ((1u << lane) - 1)); s.lst[p] = (short)m; const double t = s.T2[t2_idx(k, 0)]; s.yv[p] = pas ? t : -t; }
     }
     const int nsp = (ns + UB - 1) / UB * UB;
     #pragma unroll 1
-    for (int p = ns + lane; p < nsp; p += 32) { s.lst[p] = (short)w.Mp; s.yv[p] = 0.0; }   // padding: the rhs row with weight 0
-    if (lane == 0) { s.ctl[C_NS] = ns; s.ctl[C_FLAG] = 0; }
+    for (int p = ns + tid; p < nsp; p += T) { s.lst[p] = (short)w.Mp; s.yv[p] = 0.0; }   // padding: the rhs row with weight 0
+    if (tid == 0) { s.ctl[C_NS] = ns; s.ctl[C_FLAG] = 0; }
   }
   SYNC5();
-  const int ns = s.ctl[C_NS];
   const int nsp = (ns + UB - 1) / UB * UB;
   double2 acc[NQ];
   const double2 *T1v = reinterpret_cast<const double2 *>(w.T1r);
@@ -836,7 +855,7 @@ __device__ __noinline__ bool fold5(W5 &w) {
           m = s.rvar[k];
           const unsigned char f = s.st[m];
           const bool pas = f & ST_PAS, ino = f & ST_INO;
-          take = pas != ino && (w.gmask[m] & w.lowmask) == 0ull && (pass == 0 ? !pas : pas);
+          take = pas != ino && !(f & ST_FAST) && (pass == 0 ? !pas : pas);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, take);
         if (take) B[cnt + __popc(bal & ((1u << lane) - 1))] = (short)m;
@@ -916,12 +935,16 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
     #pragma unroll 1
     for (;;) {
       const int n = w.n;
-      if (tid < 32) {
-        const int lane = tid;
-        int nl = 0, ne = 0, mx = -1;
+      // every thread looks at one window slot; the violators are listed in slot order (leaving -> lst, entering -> lstE):
+      // warp ballots, the per-warp counts meet in shared memory, each warp adds the counts of the warps before it
+      int nl = 0, ne = 0, mx = -1;
+      {
+        constexpr int NW = T / 32;
+        const int lane = tid & 31, wid = tid >> 5;
+        int4 *ri = reinterpret_cast<int4 *>(s.red);
         #pragma unroll 1
-        for (int k0 = 1; k0 < n; k0 += 32) {
-          const int k = k0 + lane;
+        for (int k0 = 1; k0 < n; k0 += T) {
+          const int k = k0 + tid;
           int f = 0, m = -1;
           if (k < n) {
             m = s.rvar[k];
@@ -932,18 +955,23 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
             else if (!(fl & ST_BLK) && sg != 0 && (sg == SG_FREE5 ? fabs(val) > told : (double)sg * val > told)) f = 2;
           }
           const unsigned bl = __ballot_sync(0xffffffffu, f == 1), be = __ballot_sync(0xffffffffu, f == 2);
+          const int mw = __reduce_max_sync(0xffffffffu, f ? m : -1);
+          if (k0 > 1) SYNC5();                         // (the previous chunk's counts have been read)
+          if (lane == 0) ri[wid] = make_int4(__popc(bl), __popc(be), mw, 0);
+          SYNC5();
+          int ol = nl, oe = ne;
+#pragma unroll
+          for (int w2 = 0; w2 < NW; ++w2) {
+            const int4 r = ri[w2];
+            if (w2 < wid) { ol += r.x; oe += r.y; }
+            nl += r.x; ne += r.y; mx = max(mx, r.z);
+          }
           const unsigned below = (1u << lane) - 1;
-          if (f == 1) s.lst[nl + __popc(bl & below)] = (short)k;
-          if (f == 2) s.lstE[ne + __popc(be & below)] = (short)k;
-          nl += __popc(bl); ne += __popc(be);
-          mx = max(mx, f ? m : -1);
+          if (f == 1) s.lst[ol + __popc(bl & below)] = (short)k;
+          if (f == 2) s.lstE[oe + __popc(be & below)] = (short)k;
         }
-        mx = wmaxi5(mx);
-        if (lane == 0) { s.ctl[C_NL] = nl; s.ctl[C_NE] = ne; s.ctl[C_MX] = mx; }
       }
       SYNC5();
-      int nl = s.ctl[C_NL], ne = s.ctl[C_NE];
-      const int mx = s.ctl[C_MX];
       const int nv = nl + ne;
       if (nv == 0) break;
       w.n_iter++;
@@ -1094,15 +1122,34 @@ __global__ void __launch_bounds__(128) k2v5_build_t0(const double *G, int ldg, c
   }
 }
 
-// d_m = sum_k Po[m,k] (2 bit_k(b) - 1)   (Opt.jl:28-29) -> sign classes; clears the per-orthant refusal flags
+// the fast groups of the walk: w.lowmask and the ST_FAST flags (cold_init5 clears them: the cold solve has none)
 template <int T>
-__device__ __forceinline__ void set_signs5(const Sh5 &s, const W5 &w, long long b, int free_top, int Kp) {
+__device__ __forceinline__ void set_lowmask5(const Sh5 &s, W5 &w, unsigned long long mask) {
+  w.lowmask = mask;
   #pragma unroll 1
   for (int m = threadIdx.x; m < w.Mp; m += T) {
-    const unsigned long long gm = w.gmask[m];
-    const int d = 2 * __popcll(gm & (unsigned long long)b) - __popcll(gm);
-    const bool fr = free_top && ((gm >> (Kp - 1)) & 1ull);
-    s.sg[m] = (signed char)(fr ? SG_FREE5 : (d > 0) - (d < 0));
+    const unsigned char f = s.st[m];
+    s.st[m] = (w.gmask[m] & mask) ? (unsigned char)(f | ST_FAST) : (unsigned char)(f & ~ST_FAST);
+  }
+  SYNC5();
+}
+
+// d_m = sum_k Po[m,k] (2 bit_k(b) - 1)   (Opt.jl:28-29) -> sign classes; clears the per-orthant refusal flags.
+// fb >= 0: only the sign of group fb changed since the last call (a Gray step) -- a variable of that group alone flips
+// (s.grp: its only group, 255 = several), the others keep their class.
+template <int T>
+__device__ __forceinline__ void set_signs5(const Sh5 &s, const W5 &w, long long b, int free_top, int Kp, int fb) {
+  #pragma unroll 1
+  for (int m = threadIdx.x; m < w.Mp; m += T) {
+    const int g = s.grp[m];
+    if (fb >= 0 && g != 255) {
+      if (g == fb) s.sg[m] = (signed char)-s.sg[m];
+    } else if (fb < 0 || ((w.gmask[m] >> fb) & 1ull)) {
+      const unsigned long long gm = w.gmask[m];
+      const int d = 2 * __popcll(gm & (unsigned long long)b) - __popcll(gm);
+      const bool fr = free_top && ((gm >> (Kp - 1)) & 1ull);
+      s.sg[m] = (signed char)(fr ? SG_FREE5 : (d > 0) - (d < 0));
+    }
     s.st[m] &= (unsigned char)~ST_BLK;
   }
   SYNC5();
@@ -1126,6 +1173,8 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
     for (int tj = 0; tj <= ti; ++tj) s.tmap[((ti * (ti + 1)) >> 1) + tj] = (unsigned short)((ti << 8) | tj);
   #pragma unroll 1
   for (int k = tid; k < NR; k += T) s.mk[k] = 0;
+  #pragma unroll 1
+  for (int m = tid; m < Mp; m += T) { const unsigned long long gm = w.gmask[m]; s.grp[m] = (unsigned char)(__popcll(gm) == 1 ? __ffsll((long long)gm) - 1 : 255); }
   #pragma unroll 1
   for (int e = tid; e < t2_doubles(NR); e += T) s.T2[e] = 0.0;      // unused entries of partly used tiles must stay finite (they meet zeros in DMMA products)
   const double yy = A.scal[0], cmax = A.scal[1];
@@ -1154,7 +1203,7 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
     }
     const long long b = A.b_begin + (i ^ (i >> 1));
     const int fb = i > 0 ? __ffsll(i) - 1 : 63;        // the group whose sign changed
-    set_signs5<T>(s, w, b, A.free_top, A.Kp);
+    set_signs5<T>(s, w, b, A.free_top, A.Kp, (just_cold || i == i0) ? -1 : fb);
 
     const bool ok = solve5<T, NR, NQ>(s, w, cmax, t2_fresh);
     if (!ok) { cold = true; ++n_noconv; w.lowmask = A.lowmask; }
@@ -1198,7 +1247,7 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
 #pragma unroll 1
       for (int k = tid + 1; k < w.n; k += T) {
         const int m = s.rvar[k]; const unsigned char f = s.st[m];
-        tslow = tslow || ((((f & ST_PAS) != 0) != ((f & ST_INO) != 0)) && (w.gmask[m] & w.lowmask) == 0ull);
+        tslow = tslow || ((((f & ST_PAS) != 0) != ((f & ST_INO) != 0)) && !(f & ST_FAST));
       }
       const int nslow = __syncthreads_count(tslow);
       const bool was_cold = w.lowmask != A.lowmask;   // first orthant after a cold start: fold everything, then bring the fast groups in
@@ -1206,7 +1255,7 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
         if (!fold5<T, NR>(w)) cold = true;             // refused block (near-singular pivot): restart cold
         t2_fresh = true;
         if (was_cold && !cold) {
-          w.lowmask = A.lowmask;
+          set_lowmask5<T>(s, w, A.lowmask);
           window_reset(w);
           if (!t2_rebuild<T>(w)) cold = true;
         }
