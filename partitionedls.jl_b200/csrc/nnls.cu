@@ -489,14 +489,15 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
   K3Plan plan3;
   K4Plan plan4;
   K5Plan plan5;
-  // (wider problems stay on v4: at M' = 513, K = 20 v5 takes 619 ms against v4's 458 ms -- the folds stream 2.2 MB tableaus)
-  if (variant == 4 && !force4 && !no5 && h_gmask && (force5 || Mp + 1 <= 328)) {
+  // (M' + 1 > 328: one 512-thread walk per SM with a large window, worth it on long ranges; beyond M' + 1 = 640 untested -> v4)
+  const bool wide5 = Mp + 1 > 328;
+  if (variant == 4 && !force4 && !no5 && h_gmask && (force5 || Mp + 1 <= 640)) {
     int n_bits = 0;
     while ((b_count >> (n_bits + 1)) > 0) ++n_bits;
     const int rc = k2v5_plan(Mp, n_bits, h_gmask, &plan5);
     // measured crossover against v4 at M' = 201: ~2^15 problems (v5 pays ~3 ms per launch for its cold starts, then
     // ~40 us per orthant and walk against v4's ~90)
-    if (rc == PLS_OK && (force5 || b_count >= (long long)sm_count * 192)) { variant = 5; cap = plan5.ld1; occ = plan5.occ; smem = plan5.smem; }
+    if (rc == PLS_OK && (force5 || b_count >= (long long)sm_count * (wide5 ? 1024 : 192))) { variant = 5; cap = plan5.ld1; occ = plan5.occ; smem = plan5.smem; }
     else if (rc != PLS_OK && rc != PLS_EUNSUPPORTED) return rc;
   }
   if (variant == 4) {

@@ -1289,6 +1289,9 @@ const Variant5 kVariants5[] = {
     V5(32, 72, 4, 6),
     // wider problems (the fold's ld1 x 8 panel aliases T2: ld1 * 8 <= t2_doubles(NR))
     V5(128, 96, 2, 4),                                  // (NR <= 96: the fused fold keeps 12 column tiles of Z in registers)
+    // wide problems (M' + 1 > 328): ONE 512-thread walk per SM with a window of up to 207 variables (T2 up to 180 KB);
+    // cold folds in rank-8 passes.  Measured at M' = 513: K = 20 380 ms (v4: 456 ms), K = 16 47.5 ms (v4: 49.0 ms)
+    V5(512, 160, 1, 1), V5(512, 192, 1, 1), V5(512, 208, 1, 1),
 };
 #undef V5
 
@@ -1317,7 +1320,7 @@ int k2v5_plan(int Mp, int n_bits, const uint64_t *h_gmask, K5Plan *pl) {
   const int l_want = n_bits - 2 < 6 ? (n_bits - 2 < 1 ? 1 : n_bits - 2) : 6;
   int ci = 0;
   for (const Variant5 &c : kVariants5) {
-    const bool fits = c.T == (wantT ? wantT : 128) && (!wantNR || c.NR == wantNR) && ld1 <= 2 * c.T * c.NQ &&
+    const bool fits = c.T == (wantT ? wantT : (ld1 > 328 ? 512 : 128)) && (!wantNR || c.NR == wantNR) && ld1 <= 2 * c.T * c.NQ &&
                       2 * (size_t)ld1 * 8 <= (size_t)t2_doubles(c.NR) + 16 * (size_t)c.NR && sh5_bytes(c.NR, ld1) <= (size_t)max_smem;
     if (fits) {
       int lc = 0;
@@ -1347,7 +1350,7 @@ int k2v5_plan(int Mp, int n_bits, const uint64_t *h_gmask, K5Plan *pl) {
   pl->verify_every = eV ? atoi(eV) : 128;
   const char *eF = getenv("PLS_K5_FUSED");
   pl->cold_cap = 0;
-  pl->cold_fused = eF ? atoi(eF) : 1;
+  pl->cold_fused = v->NR > 96 ? 0 : (eF ? atoi(eF) : 1);
   if (pl->verify_every < 1) pl->verify_every = 1;
   return PLS_OK;
 }

@@ -16,6 +16,7 @@ CONFIGS = {
     "cfg3": (1_000_000, 512, 24, 0.0, 20240417, False),
     "m512_k16": (200_000, 512, 16, 0.0, 20240417, False),      # configs[2]'s width at a one-GPU orthant count
     "m512_k20": (200_000, 512, 20, 0.0, 20240417, False),
+    "m512_k24": (200_000, 512, 24, 0.0, 20240417, False),      # one rank's share of configs[2] is solved as a range of this
     "small": (20_000, 64, 10, 1e-3, 20240415, False),
 }
 

@@ -680,6 +680,68 @@ def test_twolevel_long_walk_every_orthant(ctx, oracle, impl):
     assert int(np.argmin(r["objs"])) == r["b_best"]
 
 
+def test_wide_window_walks_every_orthant(ctx, oracle):
+    """M' = 341 (> 327): the two-tableau kernel runs ONE 512-thread walk per SM with a window of up to 207 variables.  All
+    2^13 orthants forced onto it (per-orthant outputs normally run on the one-level kernel) against that kernel's
+    literal enumeration, a sample of them and the winner against the C oracle."""
+    o, oc = oracle
+    N, M, K = 1500, 340, 12
+    X, y, P = o.make_synthetic(N, M, K, seed=77, mixed_sign=True, rho=0.2)
+    old = {k: os.environ.get(k) for k in _K2_KEYS}
+    for k in _K2_KEYS:
+        os.environ.pop(k, None)
+    try:
+        os.environ["PLS_K2_IMPL"] = "v3"
+        lit = ctx.opt_fit(X, y, P, eta=1e-3, return_all=True)
+        os.environ["PLS_K2_IMPL"] = "v5"
+        r = ctx.opt_fit(X, y, P, eta=1e-3, return_all=True)
+    finally:
+        os.environ.pop("PLS_K2_IMPL", None)
+        for k, v in old.items():
+            if v is not None:
+                os.environ[k] = v
+    st = r["stats"]
+    assert st["k2_variant"] == 5 and st["k2_threads"] == 512 and st["k2_ctas_per_sm"] == 1, st
+    assert lit["stats"]["k2_variant"] == 3 and st["rebuilds"] == 0 and st["spills"] == 0
+    assert r["b_best"] == lit["b_best"] == int(np.argmin(r["objs"]))
+    assert np.allclose(r["objs"], lit["objs"], rtol=RTOL, atol=1e-6 * np.linalg.norm(y))
+    scale = np.abs(lit["alphas"]).max(axis=1, keepdims=True)
+    assert np.all(np.abs(r["alphas"] - lit["alphas"]) <= RTOL * scale + 1e-300)
+    rng = np.random.default_rng(5)
+    bl = np.unique(np.concatenate([rng.integers(0, 2 ** 13, size=6), [r["b_best"]]])).astype(np.int64)
+    ref = oc.opt_fit(X, y, P, 1e-3, b_list=bl, nthreads=4)
+    for j, b in enumerate(bl):
+        assert abs(ref["objs"][j] - r["objs"][b]) <= RTOL * ref["objs"][j] + 1e-6 * np.linalg.norm(y)
+        sc = max(np.abs(ref["alphas"][j]).max(), 1e-300)
+        assert np.all(np.abs(ref["alphas"][j] - r["alphas"][b]) <= RTOL * sc)
+
+
+def test_wide_default_dispatch_long_range(ctx, oracle):
+    """Default dispatch of a winner-only fit at M' = 331, K = 18 (2^18 NNLS problems): the wide two-tableau kernel runs;
+    same winner as round 1's two-level kernel, and that orthant agrees with the C oracle."""
+    o, oc = oracle
+    N, M, K = 1200, 330, 18
+    X, y, P = o.make_synthetic(N, M, K, seed=78, mixed_sign=True, rho=0.1)
+    old = {k: os.environ.get(k) for k in _K2_KEYS}
+    for k in _K2_KEYS:
+        os.environ.pop(k, None)
+    try:
+        a = ctx.opt_fit(X, y, P, eta=1e-3)
+        os.environ["PLS_K2_NO_V5"] = "1"
+        b = ctx.opt_fit(X, y, P, eta=1e-3)
+    finally:
+        os.environ.pop("PLS_K2_NO_V5", None)
+        for k, v in old.items():
+            if v is not None:
+                os.environ[k] = v
+    assert a["stats"]["k2_variant"] == 5 and a["stats"]["k2_threads"] == 512 and b["stats"]["k2_variant"] == 4
+    assert a["stats"]["nnls_problems"] == 1 << 18 and a["stats"]["spills"] == 0
+    assert a["b_best"] == b["b_best"] and abs(a["opt"] - b["opt"]) <= RTOL * b["opt"]
+    ref = oc.opt_fit(X, y, P, 1e-3, b_list=np.array([a["b_best"]], dtype=np.int64), nthreads=1)
+    assert abs(ref["objs"][0] - a["opt"]) <= RTOL * ref["objs"][0]
+    assert np.all(np.abs(ref["alphas"][0] - a["alpha_raw"]) <= RTOL * np.abs(ref["alphas"][0]).max())
+
+
 def test_default_winner_only_path_against_oracle(ctx, pkg, oracle):
     """The benchmark's exact path -- default dispatch, winner only, paired orthants, the two-level kernel -- at M' = 97,
     K = 15 (2^15 NNLS problems): pls_stats must report that kernel, and b*, alpha, objective must equal the oracle's.
