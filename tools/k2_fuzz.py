@@ -24,6 +24,7 @@ KEYS = ("PLS_K2_IMPL", "PLS_K4_GRID", "PLS_K4_L", "PLS_K4_VERIFY", "PLS_K4_T", "
 ctx = pkg.Context(0)
 worst = dict(obj=0.0, alpha=0.0, oracle_obj=0.0, oracle_alpha=0.0)
 n5 = 0
+n5w = 0
 for case in range(n_cases):
     K = int(rng.integers(6, 13)); M = int(rng.integers(K + 2, 140)); N = int(rng.integers(M + 20, 4000))
     rho = float(rng.choice([0.0, 0.3, 0.7, 0.9])); eta = float(rng.choice([0.0, 1e-3, 1e-1]))
@@ -47,12 +48,15 @@ for case in range(n_cases):
         os.environ["PLS_K5_GRID"] = str(int(rng.choice([1, 2, 5, 37, 900])))
         os.environ["PLS_K5_L"] = str(int(rng.integers(1, 7)))
         os.environ["PLS_K5_VERIFY"] = str(int(rng.choice([1, 7, 128])))
-        if rng.random() < 0.4: os.environ["PLS_K5_T"] = str(int(rng.choice([32, 64])))
+        if rng.random() < 0.5: os.environ["PLS_K5_T"] = str(int(rng.choice([32, 64, 512])))
         if rng.random() < 0.4: os.environ["PLS_K5_NR"] = str(int(rng.choice([72, 80, 96])))
+        if os.environ.get("PLS_K5_T") == "512":           # the wide-problem variants: one 512-thread walk per SM, large windows
+            os.environ["PLS_K5_NR"] = str(int(rng.choice([160, 192, 208])))
         if rng.random() < 0.3: os.environ["PLS_K5_MARGIN"] = str(int(rng.choice([2, 6, 20])))
     b = ctx.opt_fit(X, y, P, eta=eta, return_all=True)
     ran = b["stats"]["k2_variant"]          # v5 hands over to v4 / v3 when its window cannot hold a group
     n5 += ran == 5
+    n5w += ran == 5 and b["stats"]["k2_threads"] == 512
     drift = b["stats"]["k2_max_drift"]
     tol = 1e-9 if drift <= 1e-13 else 1e-6
     # winner-only fit under the same forced two-level settings: paired orthants (intercept free, 2^K problems) and,
@@ -85,4 +89,4 @@ for case in range(n_cases):
                           rebuilds=b["stats"]["rebuilds"], drift_restarts=b["stats"]["spills"], v3_rebuilds=a["stats"]["rebuilds"], polished=c["stats"]["rebuilds"], ok=bool(ok))), flush=True)
     if not ok:
         sys.exit(1)
-print(json.dumps(dict(cases=n_cases, v5_cases=int(n5), worst_where_no_drift_was_flagged=worst, result="all equal")))
+print(json.dumps(dict(cases=n_cases, v5_cases=int(n5), v5_512_thread_cases=int(n5w), worst_where_no_drift_was_flagged=worst, result="all equal")))
