@@ -36,6 +36,7 @@
 namespace pls {
 namespace {
 
+constexpr int H5_BYTES_ = 192;       // shared-memory header (struct H5) in front of the arrays
 constexpr int SG_FREE5 = 2;
 constexpr unsigned char ST_INO = 1;   // variable is swept in T1 (committed)
 constexpr unsigned char ST_PAS = 2;   // variable is passive now
@@ -116,13 +117,13 @@ struct Sh5 {
   signed char *sg; // [ld1]
   unsigned char *st; // [ld1]
   unsigned char *grp; // [ld1] the variable's only group (255: it belongs to several)
-  unsigned char *mk; // [NR]  block pivot: stamp of the last block this slot was in (== W5::gen: in the current block)
+  unsigned char *mk; // [NR]  block pivot: stamp of the last block this slot was in (== the block's stamp: in the current block)
 };
 enum { C_NL = 0, C_NE, C_MX, C_NS, C_OK, C_CNT, C_N, C_NJ, C_NSLOW, C_NP, C_NLV, C_FLAG };
 
 __host__ __device__ inline size_t sh5_bytes(int NR, int ld1) {
   const int ntl = (NR / 8) * (NR / 8 + 1) / 2;
-  return sizeof(double) * ((size_t)t2_doubles(NR) + ld1 + 16 * (size_t)NR + NR + 64 + 8 + 32 + 16) + sizeof(int) * 16 +
+  return H5_BYTES_ + sizeof(double) * ((size_t)t2_doubles(NR) + ld1 + 16 * (size_t)NR + NR + 64 + 8 + 32 + 16) + sizeof(int) * 16 +
          sizeof(short) * (2 * (size_t)ld1 + 2 * (size_t)NR + 8 + ((ntl + 3) & ~3)) + 3 * (size_t)ld1 + NR + 16;
 }
 
@@ -130,7 +131,7 @@ __device__ __forceinline__ Sh5 make_sh5(int NR, int ld1) {
   extern __shared__ __align__(16) unsigned char smem_raw5[];
   const int ntl = (NR / 8) * (NR / 8 + 1) / 2;
   Sh5 s;
-  double *dp = reinterpret_cast<double *>(smem_raw5);
+  double *dp = reinterpret_cast<double *>(smem_raw5 + H5_BYTES_);      // (after the H5 header)
   s.T2 = dp; dp += t2_doubles(NR);                    // T2 | Pp | Wp are contiguous: the fold's two ld1 x 8 panels alias them
   s.Pp = dp; dp += 8 * NR;
   s.Wp = dp; dp += 8 * NR;
@@ -157,23 +158,32 @@ __device__ __forceinline__ Sh5 make_sh5(int NR, int ld1) {
   return s;
 }
 
-// walk state (CTA-uniform registers)
-struct W5 {
-  double *T1; int ld1;      // this walk's tableau, row stride
+// Walk state that every function needs lives in a small HEADER at the start of the walk's shared memory (one copy per
+// walk; per-thread copies of it behind references end up in local memory, which the 5 x 43 KB of shared memory per SM
+// leave almost no L1 for).  Written by thread 0 only, always at least one barrier before anybody reads the new value.
+// The window size n and the cold-solve mode travel as by-value arguments / return values instead.
+struct H5 {
+  double *T1;               // this walk's tableau (row stride ld1)
   const double *T1r;        // where T1 is READ: the launch's shared T0 = [G c; c' yy] from a cold start until the first fold
                             // pass has written this walk's own copy, then T1 itself
-  int nr;                   // window capacity (slots incl. the rhs)
-  double *Pg;               // [8][ld1] global scratch: the fold's P rows / the verify pass's weights
-  int Mp;
-  int n;                    // window size incl. slot 0 (rhs)
-  int gen;                  // stamp of the current block (1 .. 255)
-  int cold_fused;           // cold solve: fold with the fused pass (else rank-8 block passes)
-  unsigned long long lowmask;
+  double *Pg;               // [8][ld1] global scratch (verify pass's weights), then the fused fold's panels
+  const double *G;
   const unsigned long long *gmask;
-  const double *G; int ldg;
-  // counters (thread 0's copy is reported)
-  unsigned long long n_sweep, n_stream, sum_s, sum_p2, n_iter, n_blk, n_rebuild, n_fold;
+  int ld1, nr, Mp, ldg;     // row stride of T1, window capacity (slots incl. the rhs), M', row stride of G
+  int cold_fused;           // cold solve: fold with the fused pass (else rank-8 block passes)
+  int gen;                  // stamp of the NEXT block pivot (1 .. 255), advanced inside t2_block
+  int pad0, pad1;
+  unsigned long long cnt[10]; // counters (thread 0)
+  double yy, cmax;          // y'y, max |c|
+  double max_viol;          // largest KKT violation the drift checks saw (thread 0)
 };
+enum { H_SWEEP = 0, H_STREAM, H_SUMS, H_SUMP2, H_ITER, H_BLK, H_REBUILD, H_FOLD, H_DRIFT, H_NOCONV };
+constexpr int H5_BYTES = H5_BYTES_;
+static_assert(sizeof(H5) <= H5_BYTES, "header size");
+__device__ __forceinline__ H5 &hdr5() {
+  extern __shared__ __align__(16) unsigned char smem_raw5[];
+  return *reinterpret_cast<H5 *>(smem_raw5);
+}
 
 template <int T>
 __device__ __forceinline__ double bmax5(const Sh5 &s, double v) {
@@ -191,19 +201,20 @@ __device__ __forceinline__ double bmax5(const Sh5 &s, double v) {
 // The block about to be swept: slot list, per-column T2 offsets, membership stamps.  `slot` is read for tid < nb; the
 // caller's barrier follows.  T2 element (row, c): rows >= c at  rbase(row) + y,  rows < c at  z + (tr << 6) + r7.
 template <int T>
-__device__ __forceinline__ void set_block5(const Sh5 &s, W5 &w, int nb, int slot) {
+__device__ __forceinline__ void set_block5(const Sh5 &s, int nb, int slot) {
   const int tid = threadIdx.x;
-  if (++w.gen == 256) {                                // stamps wrap: forget the old ones
+  const H5 &h = hdr5();
+  const int g = h.gen;                                 // (t2_block advances it, barriers away from every reader)
+  if (g == 1) {                                        // stamps wrapped (or the first block): forget the old ones
     #pragma unroll 1
-    for (int k = tid; k < w.nr; k += T) s.mk[k] = 0;
-    w.gen = 1;
+    for (int k = tid; k < h.nr; k += T) s.mk[k] = 0;
     SYNC5();
   }
   if (tid < nb) {
     const int tc = slot >> 3, c7 = slot & 7;
     s.lstB[tid] = (short)slot;
     s.binfo[tid] = make_int4(slot, (tc << 6) + c7, (((tc * (tc + 1)) >> 1) << 6) + (c7 << 3), 0);
-    s.mk[slot] = (unsigned char)w.gen;
+    s.mk[slot] = (unsigned char)g;
   }
 }
 
@@ -216,8 +227,10 @@ __device__ __forceinline__ void set_block5(const Sh5 &s, W5 &w, int nb, int slot
 // result is the block index (>= nlv) of the entering variable whose pivot failed, or -1 if a leaving pivot had the
 // wrong sign (T2 has lost its structure: the caller rebuilds it).
 template <int T>
-__device__ __noinline__ int t2_block(W5 &w, int n, int nb, int nlv, bool test, bool flip) {
-  const Sh5 s = make_sh5(w.nr, w.ld1);
+__device__ __noinline__ int t2_block(int n, int nb, int nlv, bool test, bool flip) {
+  H5 &h = hdr5();
+  const int gen = h.gen;
+  const Sh5 s = make_sh5(h.nr, h.ld1);
   constexpr int NW = T / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int fr = lane >> 2, fk = lane & 3;
@@ -243,7 +256,7 @@ __device__ __noinline__ int t2_block(W5 &w, int n, int nb, int nlv, bool test, b
   }
   if (tid < 32) {
     if (lane < 8) {
-      s.gd[lane] = (test && lane >= nlv && lane < nb) ? 1e-13 * __ldg(w.G + (size_t)w.ldg * s.rvar[B[lane]] + s.rvar[B[lane]]) : 0.0;
+      s.gd[lane] = (test && lane >= nlv && lane < nb) ? 1e-13 * __ldg(h.G + (size_t)h.ldg * s.rvar[B[lane]] + s.rvar[B[lane]]) : 0.0;
     }
     const int i = lane >> 2, j0 = (lane & 3) << 1;
     double e0 = (i < nb && j0 < nb) ? t2_get(s.T2, B[i], B[j0]) : (i == j0 ? 1.0 : 0.0);
@@ -271,6 +284,7 @@ __device__ __noinline__ int t2_block(W5 &w, int n, int nb, int nlv, bool test, b
   }
   SYNC5();
   const int res = s.ctl[C_OK];
+  if (tid == 0) h.gen = gen == 255 ? 1 : gen + 1;       // everyone read it before the barrier above; next read: the next block
   if (res != nb) { SYNC5(); return res; }
   #pragma unroll 1
   for (int ti = wid; ti < ntr; ti += NW) {             // W = P inv(D)
@@ -306,7 +320,7 @@ __device__ __noinline__ int t2_block(W5 &w, int n, int nb, int nlv, bool test, b
   #pragma unroll 1
 #pragma unroll 1
   for (int row = tid; row < n; row += T) {             // columns / rows of B outside the block: e_q W[:, q]
-    if (s.mk[row] == (unsigned char)w.gen) continue;
+    if (s.mk[row] == (unsigned char)gen) continue;
     const int tr = row >> 3, r7 = row & 7;
     const int rbase = (((tr * (tr + 1)) >> 1) << 6) + (r7 << 3), rowt = (tr << 6) + r7;
     const int sw = (row & 2) << 1, pb = row << 3;
@@ -327,21 +341,21 @@ __device__ __noinline__ int t2_block(W5 &w, int n, int nb, int nlv, bool test, b
   }
   if (flip && tid < nb) s.st[s.rvar[B[tid]]] ^= ST_PAS;       // nothing in this phase reads the flags
   SYNC5();
-  w.n_sweep += nb; w.sum_p2 += ((unsigned long long)(n * n) * nb) >> 2;
+  if (tid == 0) { h.cnt[H_SWEEP] += nb; h.cnt[H_SUMP2] += ((unsigned long long)(n * n) * nb) >> 2; }
   return nb;
 }
 
 // T2 <- T1[Rb, Rb], then sweep the toggled window variables into their current state.  Returns false if a block
 // could not be swept (numerically broken state: the caller restarts cold).
 template <int T>
-__device__ __noinline__ bool t2_rebuild(W5 &w) {
-  const Sh5 s = make_sh5(w.nr, w.ld1);
+__device__ __noinline__ bool t2_rebuild(int n) {
+  const H5 &h = hdr5();
+  const Sh5 s = make_sh5(h.nr, h.ld1);
   constexpr int NW = T / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int n = w.n;
   #pragma unroll 1
   for (int i = wid; i < n; i += NW) {
-    const double *row = w.T1r + (size_t)w.ld1 * s.rvar[i];
+    const double *row = h.T1r + (size_t)h.ld1 * s.rvar[i];
     #pragma unroll 1
     for (int j = lane; j <= i; j += 32) t2_set(s.T2, i, j, __ldcg(row + s.rvar[j]));
   }
@@ -367,18 +381,19 @@ __device__ __noinline__ bool t2_rebuild(W5 &w) {
   #pragma unroll 1
   for (int q0 = 0; q0 < cnt; q0 += 8) {
     const int nb = min(8, cnt - q0);
-    set_block5<T>(s, w, nb, tid < nb ? s.lst[q0 + tid] : 0);
+    set_block5<T>(s, nb, tid < nb ? s.lst[q0 + tid] : 0);
     SYNC5();
-    if (t2_block<T>(w, n, nb, max(0, min(nb, nlv - q0)), false, false) != nb) return false;
+    if (t2_block<T>(n, nb, max(0, min(nb, nlv - q0)), false, false) != nb) return false;
   }
   return true;
 }
 
 // window <- {rhs} + the variables of the fast groups + every toggled variable (index order)
-__device__ __noinline__ void window_reset(W5 &w) {
-  const Sh5 s = make_sh5(w.nr, w.ld1);
+__device__ __noinline__ int window_reset() {
+  const H5 &h = hdr5();
+  const Sh5 s = make_sh5(h.nr, h.ld1);
   const int tid = threadIdx.x;
-  const int Mp = w.Mp;
+  const int Mp = h.Mp;
   if (tid < 32) {
     const int lane = tid;
     if (lane == 0) s.rvar[0] = (short)Mp;
@@ -401,18 +416,18 @@ __device__ __noinline__ void window_reset(W5 &w) {
     if (lane == 0) s.ctl[C_N] = base;
   }
   SYNC5();
-  w.n = s.ctl[C_N];
+  return s.ctl[C_N];
 }
 
 // ---- window compaction: slots that are neither toggled nor in a fast group leave the window --------------------------
 // T2 restricted to the remaining slots is still sweep(T1[R', R'], S): rows / columns are moved, nothing is recomputed.
 // (Out of place through this walk's global scratch: the fused fold's panel area.)
 template <int T>
-__device__ __noinline__ void t2_compact(W5 &w) {
-  const Sh5 s = make_sh5(w.nr, w.ld1);
+__device__ __noinline__ int t2_compact(int n) {
+  const H5 &h = hdr5();
+  const Sh5 s = make_sh5(h.nr, h.ld1);
   const int tid = threadIdx.x;
-  const int n = w.n;
-  double *scr = w.Pg + 8 * (size_t)w.ld1;
+  double *scr = h.Pg + 8 * (size_t)h.ld1;
   short *old = s.lst;
   if (tid < 32) {
     const int lane = tid;
@@ -441,7 +456,7 @@ __device__ __noinline__ void t2_compact(W5 &w) {
   }
   SYNC5();
   const int nn = s.ctl[C_N];
-  if (nn == n) return;
+  if (nn == n) return n;
   #pragma unroll 1
   for (int idx = tid; idx < nn * nn; idx += T) {
     const int a = idx / nn, b = idx - a * nn;
@@ -454,18 +469,19 @@ __device__ __noinline__ void t2_compact(W5 &w) {
     const int a = idx / nn, b = idx - a * nn;
     if (b <= a) t2_set(s.T2, a, b, __ldcg(scr + idx));
   }
-  w.n = nn;
   SYNC5();
+  return nn;
 }
 
 // ---- streaming pass ------------------------------------------------------------------------------------------
 // v = T1[rhs, :] - sum_{s toggled} e_s T2[s, rhs] T1[s, :]; the toggled variables stay listed in s.lst[0 .. ctl[C_NS])
 // (on their rows v is the residual of the S-system).  NQ = double2 pieces of a row per thread.
 template <int T, int NQ>
-__device__ __noinline__ void stream5(W5 &w) {
-  const Sh5 s = make_sh5(w.nr, w.ld1);
+__device__ __noinline__ void stream5(int n) {
+  const H5 &h = hdr5();
+  const Sh5 s = make_sh5(h.nr, h.ld1);
   const int tid = threadIdx.x;
-  const int n = w.n, ld2 = w.ld1 >> 1;
+  const int ld2 = h.ld1 >> 1;
   constexpr int UB = 8;
   // S list: variable -> lst, y -> yv, in slot order (every thread looks at one slot; per-warp counts meet in shared memory)
   int ns = 0;
@@ -489,15 +505,15 @@ __device__ __noinline__ void stream5(W5 &w) {
     }
     const int nsp = (ns + UB - 1) / UB * UB;
     #pragma unroll 1
-    for (int p = ns + tid; p < nsp; p += T) { s.lst[p] = (short)w.Mp; s.yv[p] = 0.0; }   // padding: the rhs row with weight 0
+    for (int p = ns + tid; p < nsp; p += T) { s.lst[p] = (short)h.Mp; s.yv[p] = 0.0; }   // padding: the rhs row with weight 0
     if (tid == 0) { s.ctl[C_NS] = ns; s.ctl[C_FLAG] = 0; }
   }
   SYNC5();
   const int nsp = (ns + UB - 1) / UB * UB;
   double2 acc[NQ];
-  const double2 *T1v = reinterpret_cast<const double2 *>(w.T1r);
+  const double2 *T1v = reinterpret_cast<const double2 *>(h.T1r);
   {
-    const double2 *r = T1v + (size_t)ld2 * w.Mp;
+    const double2 *r = T1v + (size_t)ld2 * h.Mp;
 #pragma unroll
     for (int q = 0; q < NQ; ++q) acc[q] = (tid + T * q < ld2) ? __ldcg(r + tid + T * q) : make_double2(0.0, 0.0);
   }
@@ -521,18 +537,18 @@ __device__ __noinline__ void stream5(W5 &w) {
   for (int q = 0; q < NQ; ++q)
     if (tid + T * q < ld2) reinterpret_cast<double2 *>(s.v)[tid + T * q] = acc[q];
   SYNC5();
-  w.n_stream++; w.sum_s += ns;
+  if (tid == 0) { hdr5().cnt[H_STREAM]++; hdr5().cnt[H_SUMS] += ns; }
 }
 
 // ---- a variable outside the window joins it (not toggled): new last row of T2 ------------------------------------
 //   row[j] = [slot j not toggled] T1[m, var_j] - sum_{s toggled} e_s T1[m, s] T2[s, j],   diag = T1[m, m] - sum_s e_s T1[m, s] row[s]
 template <int T>
-__device__ __noinline__ void join5(W5 &w, int m) {
-  const Sh5 s = make_sh5(w.nr, w.ld1);
+__device__ __noinline__ void join5(int n, int m) {
+  const H5 &h = hdr5();
+  const Sh5 s = make_sh5(h.nr, h.ld1);
   const int tid = threadIdx.x;
-  const int n = w.n;
-  const double *row1 = w.T1r + (size_t)w.ld1 * m;
-  double *rowv = s.Wp, *tog = s.Wp + w.nr;              // scratch: the new row, toggled marks
+  const double *row1 = h.T1r + (size_t)h.ld1 * m;
+  double *rowv = s.Wp, *tog = s.Wp + h.nr;              // scratch: the new row, toggled marks
   if (tid < 32) {                                      // toggled slots -> lstE, coefficients e_s T1[m, s] -> yv
     const int lane = tid;
     int ns = 0;
@@ -567,8 +583,7 @@ __device__ __noinline__ void join5(W5 &w, int m) {
     dg = wsum5(dg);
     if (tid == 0) { t2_set(s.T2, n, n, __ldcg(row1 + m) - dg); s.rvar[n] = (short)m; s.slot[m] = (short)n; }
   }
-  w.n = n + 1;
-  w.sum_p2 += (unsigned long long)(ns * n) >> 1;
+  if (tid == 0) hdr5().cnt[H_SUMP2] += (unsigned long long)(ns * n) >> 1;
   SYNC5();
 }
 
@@ -576,22 +591,23 @@ __device__ __noinline__ void join5(W5 &w, int m) {
 // T1 -= P inv(D) P' off the B rows/columns (DMMA, lower tiles + mirrored store), T1[:, B_q] = e_q (P inv(D))[:, q],
 // T1[B, B] = -E inv(D) E.  Returns false (T1 untouched) if a pivot of D has the wrong sign / is too small.
 template <int T>
-__device__ __noinline__ bool fold_block5(W5 &w, int boff, int nb) {
-  const Sh5 s = make_sh5(w.nr, w.ld1);
+__device__ __noinline__ bool fold_block5(int boff, int nb) {
+  H5 &h = hdr5();
+  const Sh5 s = make_sh5(h.nr, h.ld1);
   const short *B = s.lstE + boff;
   constexpr int NW = T / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int fr = lane >> 2, fk = lane & 3;
-  const int ld1 = w.ld1, nt = ld1 >> 3;
+  const int ld1 = h.ld1, nt = ld1 >> 3;
   // panels P = T1[:, B] and W = P inv(D), both [ld1][8] (column XOR-swizzled): they alias T2 | Pp | Wp, which hold
   // nothing that outlives a fold (T2 is rebuilt afterwards)
   double *FP = s.T2, *FW = s.T2 + (size_t)ld1 * 8;
   #pragma unroll 1
   for (int idx = tid; idx < ld1 * 8; idx += T) {
     const int j = idx >> 3, q = idx & 7;
-    FP[pan5(j, q)] = q < nb ? __ldcg(w.T1r + (size_t)ld1 * B[q] + j) : 0.0;
+    FP[pan5(j, q)] = q < nb ? __ldcg(h.T1r + (size_t)ld1 * B[q] + j) : 0.0;
   }
-  if (tid < 8) s.gd[tid] = (tid < nb && (s.st[B[tid]] & ST_PAS)) ? 1e-13 * __ldg(w.G + (size_t)w.ldg * B[tid] + B[tid]) : 0.0;
+  if (tid < 8) s.gd[tid] = (tid < nb && (s.st[B[tid]] & ST_PAS)) ? 1e-13 * __ldg(h.G + (size_t)h.ldg * B[tid] + B[tid]) : 0.0;
   SYNC5();
   if (tid < 32) {
     // Gauss-Jordan in the given order (swept-back variables first: pivots < 0; then entering ones: pivots > 0)
@@ -644,7 +660,7 @@ __device__ __noinline__ bool fold_block5(W5 &w, int boff, int nb) {
 #pragma unroll
       for (int u = 0; u < IFL; ++u) {
         ri[u] = ti; rj[u] = tj;
-        c[u] = __ldcg(reinterpret_cast<const double2 *>(w.T1r + (size_t)(ti * 8 + fr) * ld1 + tj * 8 + 2 * fk));
+        c[u] = __ldcg(reinterpret_cast<const double2 *>(h.T1r + (size_t)(ti * 8 + fr) * ld1 + tj * 8 + 2 * fk));
         if (q + u + 1 < q1) { if (++tj > ti) { ++ti; tj = 0; } }
       }
 #pragma unroll
@@ -656,9 +672,9 @@ __device__ __noinline__ bool fold_block5(W5 &w, int boff, int nb) {
 #pragma unroll
       for (int u = 0; u < IFL; ++u) {
         if (q + u < q1) {
-          __stcg(reinterpret_cast<double2 *>(w.T1 + (size_t)(ri[u] * 8 + fr) * ld1 + rj[u] * 8 + 2 * fk), c[u]);
+          __stcg(reinterpret_cast<double2 *>(h.T1 + (size_t)(ri[u] * 8 + fr) * ld1 + rj[u] * 8 + 2 * fk), c[u]);
           if (ri[u] != rj[u]) {
-            double *mp = w.T1 + (size_t)(rj[u] * 8 + 2 * fk) * ld1 + ri[u] * 8 + fr;
+            double *mp = h.T1 + (size_t)(rj[u] * 8 + 2 * fk) * ld1 + ri[u] * 8 + fr;
             __stcg(mp, c[u].x); __stcg(mp + ld1, c[u].y);
           }
         }
@@ -671,8 +687,8 @@ __device__ __noinline__ bool fold_block5(W5 &w, int boff, int nb) {
     const int i = idx >> 3, q = idx & 7;
     if (q < nb) {
       const double val = (s.st[B[q]] & ST_PAS) ? FW[pan5(i, q)] : -FW[pan5(i, q)];
-      __stcg(w.T1 + (size_t)ld1 * B[q] + i, val);
-      __stcg(w.T1 + (size_t)ld1 * i + B[q], val);
+      __stcg(h.T1 + (size_t)ld1 * B[q] + i, val);
+      __stcg(h.T1 + (size_t)ld1 * i + B[q], val);
     }
   }
   SYNC5();
@@ -681,15 +697,13 @@ __device__ __noinline__ bool fold_block5(W5 &w, int boff, int nb) {
     const int i = e >> 3, j = e & 7;
     if (i < nb && j < nb) {
       const double ei = (s.st[B[i]] & ST_PAS) ? 1.0 : -1.0, ej = (s.st[B[j]] & ST_PAS) ? 1.0 : -1.0;
-      __stcg(w.T1 + (size_t)ld1 * B[i] + B[j], -ei * ej * s.D[i * 8 + j]);
+      __stcg(h.T1 + (size_t)ld1 * B[i] + B[j], -ei * ej * s.D[i * 8 + j]);
     }
   }
   SYNC5();
   if (tid < nb) { const int m = B[tid]; const unsigned char f = s.st[m]; s.st[m] = (f & ST_PAS) ? (unsigned char)(f | ST_INO) : (unsigned char)(f & ~ST_INO); }
+  if (tid == 0) { h.T1r = h.T1; h.cnt[H_SUMP2] += 2ull * ld1 * ld1; h.cnt[H_FOLD]++; }      // every tile has been written (nobody reads T1r in this phase)
   SYNC5();
-  w.T1r = w.T1;                                        // every tile has been written
-  w.sum_p2 += 2ull * ld1 * ld1;
-  w.n_fold++;
   return true;
 }
 
@@ -705,17 +719,18 @@ __device__ __noinline__ bool fold_block5(W5 &w, int boff, int nb) {
 // T1 is this walk's own they are first copied to the global scratch (the tile updates would overwrite them).  Z' (ld1 x n)
 // lives in the global scratch.
 template <int T>
-__device__ __noinline__ void fold_fused5(W5 &w) {
-  const Sh5 s = make_sh5(w.nr, w.ld1);
+__device__ __noinline__ void fold_fused5(int n) {
+  H5 &h = hdr5();
+  const Sh5 s = make_sh5(h.nr, h.ld1);
   constexpr int NW = T / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int fr = lane >> 2, fk = lane & 3;
-  const int ld1 = w.ld1, nt = ld1 >> 3, n = w.n;
+  const int ld1 = h.ld1, nt = ld1 >> 3;
   const int ntr = (n + 7) >> 3, nk = ntr << 3;
-  double *PR = w.Pg + 8 * (size_t)ld1, *ZT = PR + (size_t)ld1 * w.nr;      // PR: [nk][ld1] row copies; ZT: [ld1][nk]
+  double *PR = h.Pg + 8 * (size_t)ld1, *ZT = PR + (size_t)ld1 * h.nr;      // PR: [nk][ld1] row copies; ZT: [ld1][nk]
   int *roff = reinterpret_cast<int *>(s.Wp);           // [nk] offset of slot k's row from `rows`
-  const bool own = w.T1r == w.T1;
-  const double *rows = own ? PR : w.T1r;
+  const bool own = h.T1r == h.T1;
+  const double *rows = own ? PR : h.T1r;
   // e_k per slot (0 = not toggled) -> yv
   #pragma unroll 1
   for (int k = tid; k < nk; k += T) {
@@ -729,7 +744,7 @@ __device__ __noinline__ void fold_fused5(W5 &w) {
     #pragma unroll 1
     for (int k = 0; k < n; ++k) {
       if (k > 0 && s.yv[k] == 0.0) continue;           // (row 0 of the copy is the fallback row of untoggled slots)
-      const double *src = w.T1 + (size_t)ld1 * (s.yv[k] != 0.0 ? s.rvar[k] : 0);
+      const double *src = h.T1 + (size_t)ld1 * (s.yv[k] != 0.0 ? s.rvar[k] : 0);
       #pragma unroll 1
       for (int j = tid; j < ld1; j += T) PR[(size_t)k * ld1 + j] = __ldcg(src + j);
     }
@@ -781,7 +796,7 @@ __device__ __noinline__ void fold_fused5(W5 &w) {
     int tj = q - ((ti * (ti + 1)) >> 1);
     #pragma unroll 1
     for (; q < q1; ++q) {
-      double2 c = __ldcg(reinterpret_cast<const double2 *>(w.T1r + (size_t)(ti * 8 + fr) * ld1 + tj * 8 + 2 * fk));
+      double2 c = __ldcg(reinterpret_cast<const double2 *>(h.T1r + (size_t)(ti * 8 + fr) * ld1 + tj * 8 + 2 * fk));
       const double *za = ZT + (size_t)(ti * 8 + fr) * nk + fk, *pb = rows + tj * 8 + fr;
 #pragma unroll 1
       for (int t0 = 0; t0 < ntr; t0 += CH) {
@@ -796,9 +811,9 @@ __device__ __noinline__ void fold_fused5(W5 &w) {
 #pragma unroll
         for (int u = 0; u < CH; ++u) { dmma5(c.x, c.y, z0[u], p0[u]); dmma5(c.x, c.y, z1[u], p1[u]); }
       }
-      __stcg(reinterpret_cast<double2 *>(w.T1 + (size_t)(ti * 8 + fr) * ld1 + tj * 8 + 2 * fk), c);
+      __stcg(reinterpret_cast<double2 *>(h.T1 + (size_t)(ti * 8 + fr) * ld1 + tj * 8 + 2 * fk), c);
       if (ti != tj) {
-        double *mp = w.T1 + (size_t)(tj * 8 + 2 * fk) * ld1 + ti * 8 + fr;
+        double *mp = h.T1 + (size_t)(tj * 8 + 2 * fk) * ld1 + ti * 8 + fr;
         __stcg(mp, c.x); __stcg(mp + ld1, c.y);
       }
       if (++tj > ti) { ++ti; tj = 0; }
@@ -813,34 +828,32 @@ __device__ __noinline__ void fold_fused5(W5 &w) {
     #pragma unroll 1
     for (int j = tid; j < ld1; j += T) {
       const double val = -e * ZT[(size_t)j * nk + k];
-      __stcg(w.T1 + (size_t)ld1 * var + j, val);
-      __stcg(w.T1 + (size_t)ld1 * j + var, val);
+      __stcg(h.T1 + (size_t)ld1 * var + j, val);
+      __stcg(h.T1 + (size_t)ld1 * j + var, val);
     }
   }
   SYNC5();
   #pragma unroll 1
   for (int idx = tid; idx < n * n; idx += T) {         // the window block is T2 itself
     const int a = idx / n, b = idx - a * n;
-    __stcg(w.T1 + (size_t)ld1 * s.rvar[a] + s.rvar[b], t2_get(s.T2, a, b));
+    __stcg(h.T1 + (size_t)ld1 * s.rvar[a] + s.rvar[b], t2_get(s.T2, a, b));
   }
   SYNC5();
   #pragma unroll 1
   for (int k = tid; k < n; k += T) {
     if (k >= 1 && s.yv[k] != 0.0) { const int m = s.rvar[k]; const unsigned char f = s.st[m]; s.st[m] = (f & ST_PAS) ? (unsigned char)(f | ST_INO) : (unsigned char)(f & ~ST_INO); }
   }
+  if (tid == 0) { h.T1r = h.T1; h.cnt[H_SUMP2] += 2ull * ld1 * ld1 * (unsigned long long)ntr / 8 + (unsigned long long)ld1 * nk * nk / 2; h.cnt[H_FOLD]++; }
   SYNC5();
-  w.T1r = w.T1;
-  w.sum_p2 += 2ull * ld1 * ld1 * (unsigned long long)ntr / 8 + (unsigned long long)ld1 * nk * nk / 2;
-  w.n_fold++;
 }
 
 // fold every toggled slow window variable, reset the window, rebuild T2.  Returns false if a block was refused.
 template <int T, int NR>
-__device__ __noinline__ bool fold5(W5 &w) {
-  const Sh5 s = make_sh5(w.nr, w.ld1);
+__device__ __noinline__ int fold5(int n, bool cold_mode) {
+  const H5 &h = hdr5();
+  const Sh5 s = make_sh5(h.nr, h.ld1);
   const int tid = threadIdx.x;
-  if (w.lowmask == 0ull) t2_compact<T>(w);             // cold solve: only toggled variables stay, the fused pass works on |S| columns
-  const int n = w.n;
+  if (cold_mode) n = t2_compact<T>(n);                 // cold solve: only toggled variables stay, the fused pass works on |S| columns
   short *B = s.lstE;                                   // NR entries are enough: every listed variable is in the window
   if (tid < 32) {                                      // swept-back (in O, now active) first, then entering; index order within each class
     const int lane = tid;
@@ -867,21 +880,22 @@ __device__ __noinline__ bool fold5(W5 &w) {
   SYNC5();
   const int cnt = s.ctl[C_CNT];
   bool ok = true;
-  if (w.lowmask == 0ull && cnt > 8 && w.cold_fused) fold_fused5<T>(w);          // cold solve: everything toggled goes in, one pass
-  else for (int q0 = 0; q0 < cnt && ok; q0 += 8) ok = fold_block5<T>(w, q0, min(8, cnt - q0));
-  window_reset(w);
-  if (!t2_rebuild<T>(w)) ok = false;
-  return ok;
+  if (cold_mode && cnt > 8 && h.cold_fused) fold_fused5<T>(n);          // cold solve: everything toggled goes in, one pass
+  else for (int q0 = 0; q0 < cnt && ok; q0 += 8) ok = fold_block5<T>(q0, min(8, cnt - q0));
+  n = window_reset();
+  if (!t2_rebuild<T>(n)) ok = false;
+  return ok ? n : -1;
 }
 
 // max KKT violation of the current point against the ORIGINAL system; s.v holds the streaming result
 // (weights of committed variables outside the window).  The full weight vector goes to the global scratch.
 template <int T>
-__device__ __noinline__ double verify5(W5 &w, const double *c) {
-  const Sh5 s = make_sh5(w.nr, w.ld1);
+__device__ __noinline__ double verify5(const double *c) {
+  const H5 &h = hdr5();
+  const Sh5 s = make_sh5(h.nr, h.ld1);
   const int tid = threadIdx.x;
-  const int Mp = w.Mp;
-  double *wf = w.Pg;
+  const int Mp = h.Mp;
+  double *wf = h.Pg;
   if (tid < 32) {
     const int lane = tid;
     int np = 0;
@@ -908,10 +922,10 @@ __device__ __noinline__ double verify5(W5 &w, const double *c) {
     int t = 0;
     #pragma unroll 1
     for (; t + 1 < np; t += 2) {
-      a0 = fma(-w.G[(size_t)w.ldg * s.lst[t] + m], wf[t], a0);
-      a1 = fma(-w.G[(size_t)w.ldg * s.lst[t + 1] + m], wf[t + 1], a1);
+      a0 = fma(-h.G[(size_t)h.ldg * s.lst[t] + m], wf[t], a0);
+      a1 = fma(-h.G[(size_t)h.ldg * s.lst[t + 1] + m], wf[t + 1], a1);
     }
-    if (t < np) a0 = fma(-w.G[(size_t)w.ldg * s.lst[t] + m], wf[t], a0);
+    if (t < np) a0 = fma(-h.G[(size_t)h.ldg * s.lst[t] + m], wf[t], a0);
     const double rv = a0 + a1;
     const int sg = s.sg[m];
     const unsigned char f = s.st[m];
@@ -924,9 +938,11 @@ __device__ __noinline__ double verify5(W5 &w, const double *c) {
 
 // ---- one orthant: block principal pivoting on the window + streaming checks.  Returns false on the iteration cap.
 template <int T, int NR, int NQ>
-__device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2_fresh) {
+__device__ __forceinline__ bool solve5(const Sh5 s, int &n_win, bool cold_mode, bool &t2_fresh) {
   const int tid = threadIdx.x;
-  const int Mp = w.Mp;
+  H5 &h = hdr5();
+  const int Mp = h.Mp;
+  const double cmax = h.cmax;
   const double told = 1e-12 * cmax;
   int t_best = Mp + 1, pbar = 3, iters = 0, rebuilt = 0;
   #pragma unroll 1
@@ -934,7 +950,7 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
     // ---- block principal pivoting on the window (Judice-Pires / Kim-Park, Murty's backup rule)
     #pragma unroll 1
     for (;;) {
-      const int n = w.n;
+      const int n = n_win;
       // every thread looks at one window slot; the violators are listed in slot order (leaving -> lst, entering -> lstE):
       // warp ballots, the per-warp counts meet in shared memory, each warp adds the counts of the warps before it
       int nl = 0, ne = 0, mx = -1;
@@ -974,7 +990,7 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
       SYNC5();
       const int nv = nl + ne;
       if (nv == 0) break;
-      w.n_iter++;
+      if (tid == 0) h.cnt[H_ITER]++;
       if (++iters > 60 + 6 * Mp) return false;
       bool single = false;
       if (nv < t_best) { t_best = nv; pbar = 3; }
@@ -994,9 +1010,9 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
       bool broken = false;
       while (done < tot) {
         const int nb = min(8, tot - done), nlv = max(0, min(nb, nl - done));
-        set_block5<T>(s, w, nb, tid < nb ? (done + tid < nl ? s.lst[done + tid] : s.lstE[done + tid - nl]) : 0);
+        set_block5<T>(s, nb, tid < nb ? (done + tid < nl ? s.lst[done + tid] : s.lstE[done + tid - nl]) : 0);
         SYNC5();
-        const int r = t2_block<T>(w, n, nb, nlv, true, true);
+        const int r = t2_block<T>(n, nb, nlv, true, true);
         if (r == nb) { done += nb; continue; }
         if (r < 0) { broken = true; break; }
         // the entering variable at block position r failed its pivot test: refuse it at this orthant, drop it from the list
@@ -1006,16 +1022,16 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
           #pragma unroll 1
           for (int q = pos; q + 1 < ne; ++q) s.lstE[q] = s.lstE[q + 1];
         }
-        --ne; --tot; w.n_blk++;
+        --ne; --tot; if (tid == 0) h.cnt[H_BLK]++;
         SYNC5();
       }
       if (broken) {                                    // a leaving pivot with the wrong sign: T2 lost its structure
-        if (++rebuilt > 3 || !t2_rebuild<T>(w)) return false;
-        t2_fresh = true; w.n_rebuild++;
+        if (++rebuilt > 3 || !t2_rebuild<T>(n)) return false;
+        t2_fresh = true; if (tid == 0) h.cnt[H_REBUILD]++;
       }
     }
     // ---- everything outside the window, and the accuracy of T2
-    stream5<T, NQ>(w);
+    stream5<T, NQ>(n_win);
     // One pass of all threads over v, one barrier: is the residual of the S-system too large (T2 lost digits), and does
     // anything outside the window violate its condition?  The usual answer to both is no.
     {
@@ -1044,9 +1060,9 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
         for (int p = tid; p < ns; p += T) { const double r = fabs(s.v[s.lst[p]]); res = r == r ? fmax(res, r) : r; }
         res = bmax5<T>(s, res);
         if (res != res || (t2_fresh && res > 1e-9 * cmax) || ++rebuilt > 3) return false;
-        if (!t2_rebuild<T>(w)) return false;
+        if (!t2_rebuild<T>(n_win)) return false;
         t2_fresh = true;
-        w.n_rebuild++;
+        if (tid == 0) h.cnt[H_REBUILD]++;
         continue;
       }
       if (!(flags & 1)) return true;
@@ -1075,25 +1091,27 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
     const int nj = s.ctl[C_NJ];
     if (nj == 0) return true;
     if (++iters > 60 + 6 * Mp) return false;
-    if (NR - w.n < nj) {                               // make room: fold the toggled slow variables, shrink the window
+    if (NR - n_win < nj) {                               // make room: fold the toggled slow variables, shrink the window
       // the join list lives in lst, which the fold reuses; v is dead until the next streaming pass: park the list there
       short *park = reinterpret_cast<short *>(s.v);
       #pragma unroll 1
       for (int p = tid; p < nj; p += T) park[p] = s.lst[p];
       SYNC5();
-      if (w.lowmask == 0ull) t2_compact<T>(w);         // cold solve: variables that went back to their T1 state just leave the window
-      if (NR - w.n < (nj < 8 ? nj : 8)) {
-        if (!fold5<T, NR>(w)) return false;
+      if (cold_mode) n_win = t2_compact<T>(n_win);     // cold solve: variables that went back to their T1 state just leave the window
+      if (NR - n_win < (nj < 8 ? nj : 8)) {
+        const int nf = fold5<T, NR>(n_win, cold_mode);
+        if (nf < 0) return false;
+        n_win = nf;
         t2_fresh = true;
       }
-      int room = NR - w.n;
+      int room = NR - n_win;
       if (room > nj) room = nj;
       if (room <= 0) return false;                     // the fast groups alone fill the window (the host sized l to prevent this)
       #pragma unroll 1
-      for (int p = 0; p < room; ++p) { const int m = park[p]; if (s.slot[m] < 0) join5<T>(w, m); }
+      for (int p = 0; p < room; ++p) { const int m = park[p]; if (s.slot[m] < 0) { join5<T>(n_win, m); ++n_win; } }
     } else {
       #pragma unroll 1
-      for (int p = 0; p < nj; ++p) join5<T>(w, s.lst[p]);     // join5 uses lstE / yv / tv / uv, not lst
+      for (int p = 0; p < nj; ++p) { join5<T>(n_win, s.lst[p]); ++n_win; }     // join5 uses lstE / yv / tv / uv, not lst
     }
     t_best = Mp + 1; pbar = 3;
   }
@@ -1103,10 +1121,11 @@ __device__ __forceinline__ bool solve5(const Sh5 s, W5 &w, double cmax, bool &t2
 // k2v5_build_t0, L2-resident for every walk) until this walk's first fold pass writes its own tableau; every variable
 // active and outside the window.
 template <int T>
-__device__ __noinline__ void cold_init5(W5 &w, const double *T0) {
-  const Sh5 s = make_sh5(w.nr, w.ld1);
-  const int tid = threadIdx.x, ld1 = w.ld1;
-  w.T1r = T0;
+__device__ __noinline__ void cold_init5(const double *T0) {
+  H5 &h = hdr5();
+  const Sh5 s = make_sh5(h.nr, h.ld1);
+  const int tid = threadIdx.x, ld1 = h.ld1;
+  if (tid == 0) h.T1r = T0;                            // (the previous reader is a barrier away: the end of the orthant loop)
   #pragma unroll 1
   for (int m = tid; m < ld1; m += T) { s.st[m] = 0; s.slot[m] = -1; s.sg[m] = 0; }
   SYNC5();
@@ -1124,12 +1143,12 @@ __global__ void __launch_bounds__(128) k2v5_build_t0(const double *G, int ldg, c
 
 // the fast groups of the walk: w.lowmask and the ST_FAST flags (cold_init5 clears them: the cold solve has none)
 template <int T>
-__device__ __forceinline__ void set_lowmask5(const Sh5 &s, W5 &w, unsigned long long mask) {
-  w.lowmask = mask;
+__device__ __forceinline__ void set_lowmask5(const Sh5 &s, unsigned long long mask) {
+  const H5 &h = hdr5();
   #pragma unroll 1
-  for (int m = threadIdx.x; m < w.Mp; m += T) {
+  for (int m = threadIdx.x; m < h.Mp; m += T) {
     const unsigned char f = s.st[m];
-    s.st[m] = (w.gmask[m] & mask) ? (unsigned char)(f | ST_FAST) : (unsigned char)(f & ~ST_FAST);
+    s.st[m] = (h.gmask[m] & mask) ? (unsigned char)(f | ST_FAST) : (unsigned char)(f & ~ST_FAST);
   }
   SYNC5();
 }
@@ -1138,14 +1157,15 @@ __device__ __forceinline__ void set_lowmask5(const Sh5 &s, W5 &w, unsigned long 
 // fb >= 0: only the sign of group fb changed since the last call (a Gray step) -- a variable of that group alone flips
 // (s.grp: its only group, 255 = several), the others keep their class.
 template <int T>
-__device__ __forceinline__ void set_signs5(const Sh5 &s, const W5 &w, long long b, int free_top, int Kp, int fb) {
+__device__ __forceinline__ void set_signs5(const Sh5 &s, long long b, int free_top, int Kp, int fb) {
+  const H5 &h = hdr5();
   #pragma unroll 1
-  for (int m = threadIdx.x; m < w.Mp; m += T) {
+  for (int m = threadIdx.x; m < h.Mp; m += T) {
     const int g = s.grp[m];
     if (fb >= 0 && g != 255) {
       if (g == fb) s.sg[m] = (signed char)-s.sg[m];
-    } else if (fb < 0 || ((w.gmask[m] >> fb) & 1ull)) {
-      const unsigned long long gm = w.gmask[m];
+    } else if (fb < 0 || ((h.gmask[m] >> fb) & 1ull)) {
+      const unsigned long long gm = h.gmask[m];
       const int d = 2 * __popcll(gm & (unsigned long long)b) - __popcll(gm);
       const bool fr = free_top && ((gm >> (Kp - 1)) & 1ull);
       s.sg[m] = (signed char)(fr ? SG_FREE5 : (d > 0) - (d < 0));
@@ -1160,13 +1180,19 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
   const int tid = threadIdx.x;
   const int Mp = A.Mp, ld1 = A.cap;                    // ld1 = round_up(Mp + 1, 8): rows / row stride of T1
   const Sh5 s = make_sh5(NR, ld1);
-  W5 w;
-  w.T1 = A.tab + (size_t)blockIdx.x * A.tabstride; w.ld1 = ld1; w.T1r = A.hglob;
-  w.Pg = w.T1 + (size_t)ld1 * ld1;
-  w.Mp = Mp; w.n = 1; w.lowmask = A.lowmask; w.nr = NR; w.cold_fused = A.chain_log2; w.gen = 0;
-  w.gmask = reinterpret_cast<const unsigned long long *>(A.gmask);
-  w.G = A.G; w.ldg = A.ldg;
-  w.n_sweep = w.n_stream = w.sum_s = w.sum_p2 = w.n_iter = w.n_blk = w.n_rebuild = w.n_fold = 0;
+  H5 &h = hdr5();
+  if (tid == 0) {
+    h.T1 = A.tab + (size_t)blockIdx.x * A.tabstride; h.ld1 = ld1; h.T1r = A.hglob;
+    h.Pg = h.T1 + (size_t)ld1 * ld1;
+    h.Mp = Mp; h.nr = NR; h.cold_fused = A.chain_log2; h.gen = 1;
+    h.gmask = reinterpret_cast<const unsigned long long *>(A.gmask);
+    h.G = A.G; h.ldg = A.ldg;
+    #pragma unroll 1
+    for (int q = 0; q < 10; ++q) h.cnt[q] = 0;
+    h.yy = A.scal[0]; h.cmax = A.scal[1]; h.max_viol = 0.0;
+  }
+  int n_win = 1;                                       // window size incl. slot 0 (the right-hand side)
+  bool cold_mode = true;                               // the cold solve: no fast groups
   #pragma unroll 1
   for (int ti = tid; ti < NR / 8; ti += T)
     #pragma unroll 1
@@ -1174,10 +1200,9 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
   #pragma unroll 1
   for (int k = tid; k < NR; k += T) s.mk[k] = 0;
   #pragma unroll 1
-  for (int m = tid; m < Mp; m += T) { const unsigned long long gm = w.gmask[m]; s.grp[m] = (unsigned char)(__popcll(gm) == 1 ? __ffsll((long long)gm) - 1 : 255); }
+  for (int m = tid; m < Mp; m += T) { const unsigned long long gm = reinterpret_cast<const unsigned long long *>(A.gmask)[m]; s.grp[m] = (unsigned char)(__popcll(gm) == 1 ? __ffsll((long long)gm) - 1 : 255); }
   #pragma unroll 1
   for (int e = tid; e < t2_doubles(NR); e += T) s.T2[e] = 0.0;      // unused entries of partly used tiles must stay finite (they meet zeros in DMMA products)
-  const double yy = A.scal[0], cmax = A.scal[1];
   double best_obj = 0.0; long long best_b = -1;
   int low_bits = 0;
   while ((A.lowmask >> low_bits) & 1ull) ++low_bits;
@@ -1186,36 +1211,35 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
   const long long i1 = cnt * ((long long)blockIdx.x + 1) / (long long)gridDim.x;
   bool cold = true, just_cold = false, t2_fresh = true;
   int since_check = 0, check_every = A.verify_every;
-  double max_viol = 0.0;
-  unsigned long long n_drift = 0, n_noconv = 0;
   SYNC5();
 
   #pragma unroll 1
   for (long long i = i0; i < i1; ++i) {
     if (cold) {
-      cold_init5<T>(w, A.hglob);
+      cold_init5<T>(A.hglob);
       // the cold solve runs with NO fast groups: the window starts empty and takes up to NR - 1 violators per round,
       // all of which are folded into T1 in full blocks of 8 (~2 rounds instead of ~9 with the fast variables in the way)
-      w.lowmask = 0ull;
-      window_reset(w);
-      t2_rebuild<T>(w);                                // nothing is toggled: a plain copy
+      cold_mode = true;
+      n_win = window_reset();
+      t2_rebuild<T>(n_win);                            // nothing is toggled: a plain copy
       cold = false; just_cold = true; since_check = 0; t2_fresh = true;
     }
     const long long b = A.b_begin + (i ^ (i >> 1));
     const int fb = i > 0 ? __ffsll(i) - 1 : 63;        // the group whose sign changed
-    set_signs5<T>(s, w, b, A.free_top, A.Kp, (just_cold || i == i0) ? -1 : fb);
+    set_signs5<T>(s, b, A.free_top, A.Kp, (just_cold || i == i0) ? -1 : fb);
 
-    const bool ok = solve5<T, NR, NQ>(s, w, cmax, t2_fresh);
-    if (!ok) { cold = true; ++n_noconv; w.lowmask = A.lowmask; }
+    const bool ok = solve5<T, NR, NQ>(s, n_win, cold_mode, t2_fresh);
+    if (!ok) { cold = true; if (tid == 0) h.cnt[H_NOCONV]++; }
 
     // ---- drift control: KKT conditions against the original G, c
     ++since_check;
     if (ok && (since_check >= check_every || i + 1 == i1)) {
       since_check = 0;
-      const double viol = verify5<T>(w, A.c);
-      if (!just_cold) max_viol = fmax(max_viol, viol);
+      const double viol = verify5<T>(A.c);
+      const double cmax = h.cmax;
+      if (!just_cold && tid == 0) h.max_viol = fmax(h.max_viol, viol);
       if (viol > 1e-13 * cmax && check_every > 8) check_every = 8;
-      if (viol > 1e-12 * cmax && !just_cold) { ++n_drift; cold = true; --i; continue; }
+      if (viol > 1e-12 * cmax && !just_cold) { if (tid == 0) h.cnt[H_DRIFT]++; cold = true; --i; continue; }
     }
     just_cold = false;
 
@@ -1226,12 +1250,12 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
     if (A.free_top && (s.st[Mp - 1] & ST_PAS)) w_top = s.slot[Mp - 1] >= 0 ? s.T2[t2_idx(s.slot[Mp - 1], 0)] : s.v[Mp - 1];
     const long long b_full = A.free_top ? (b | ((w_top > 0.0 ? 1ll : 0ll) << (A.Kp - 1))) : b;
     if (A.all_obj && tid == 0) A.all_obj[rel] = obj;
-    const bool better = opt_better(obj, b_full, best_obj, best_b, PLS_TIE_REL * yy);
+    const bool better = opt_better(obj, b_full, best_obj, best_b, PLS_TIE_REL * h.yy);
     if (better) { best_obj = obj; best_b = b_full; }
     if (A.all_alpha || better) {
       #pragma unroll 1
       for (int m = tid; m < Mp; m += T) {
-        const unsigned long long gm = w.gmask[m];
+        const unsigned long long gm = h.gmask[m];
         const int d = 2 * __popcll(gm & (unsigned long long)b) - __popcll(gm);
         double wv = 0.0;
         if (ok && (s.st[m] & ST_PAS)) wv = s.slot[m] >= 0 ? s.T2[t2_idx(s.slot[m], 0)] : s.v[m];
@@ -1245,19 +1269,22 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
     if (ok) {
       bool tslow = false;                            // toggled slow variables in the window (NR <= T: one slot per thread)
 #pragma unroll 1
-      for (int k = tid + 1; k < w.n; k += T) {
+      for (int k = tid + 1; k < n_win; k += T) {
         const int m = s.rvar[k]; const unsigned char f = s.st[m];
         tslow = tslow || ((((f & ST_PAS) != 0) != ((f & ST_INO) != 0)) && !(f & ST_FAST));
       }
       const int nslow = __syncthreads_count(tslow);
-      const bool was_cold = w.lowmask != A.lowmask;   // first orthant after a cold start: fold everything, then bring the fast groups in
-      if (fb >= low_bits || nslow >= 8 || w.n > NR - 8 || was_cold) {
-        if (!fold5<T, NR>(w)) cold = true;             // refused block (near-singular pivot): restart cold
+      const bool was_cold = cold_mode;                // first orthant after a cold start: fold everything, then bring the fast groups in
+      if (fb >= low_bits || nslow >= 8 || n_win > NR - 8 || was_cold) {
+        const int nf = fold5<T, NR>(n_win, cold_mode);
+        if (nf < 0) cold = true;                       // refused block (near-singular pivot): restart cold
+        else n_win = nf;
         t2_fresh = true;
         if (was_cold && !cold) {
-          set_lowmask5<T>(s, w, A.lowmask);
-          window_reset(w);
-          if (!t2_rebuild<T>(w)) cold = true;
+          set_lowmask5<T>(s, A.lowmask);
+          cold_mode = false;
+          n_win = window_reset();
+          if (!t2_rebuild<T>(n_win)) cold = true;
         }
       }
     }
@@ -1266,17 +1293,17 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
   if (tid == 0) {
     A.cta_obj[blockIdx.x] = best_obj;
     A.cta_b[blockIdx.x] = best_b;
-    atomicAdd(&A.counters[CNT_PIVOTS], w.n_sweep);
-    atomicAdd(&A.counters[CNT_GRAD], w.n_stream);
-    atomicAdd(&A.counters[CNT_SUMP], w.sum_s);
-    atomicAdd(&A.counters[CNT_SUMP2], w.sum_p2);
-    atomicAdd(&A.counters[CNT_ITERS], w.n_iter);
-    atomicAdd(&A.counters[CNT_REBUILDS], w.n_rebuild);
-    atomicAdd(&A.counters[CNT_BLOCKED], w.n_blk);
-    atomicAdd(&A.counters[CNT_NOCONV], n_noconv);
-    atomicAdd(&A.counters[CNT_SPILLS], n_drift);
-    atomicMax(&A.counters[CNT_NUM + 24], (unsigned long long)__double_as_longlong(max_viol / cmax));
-    atomicAdd(&A.counters[CNT_NUM + 1 + 20], w.n_fold);          // reported with the phase counters: fold passes
+    atomicAdd(&A.counters[CNT_PIVOTS], h.cnt[H_SWEEP]);
+    atomicAdd(&A.counters[CNT_GRAD], h.cnt[H_STREAM]);
+    atomicAdd(&A.counters[CNT_SUMP], h.cnt[H_SUMS]);
+    atomicAdd(&A.counters[CNT_SUMP2], h.cnt[H_SUMP2]);
+    atomicAdd(&A.counters[CNT_ITERS], h.cnt[H_ITER]);
+    atomicAdd(&A.counters[CNT_REBUILDS], h.cnt[H_REBUILD]);
+    atomicAdd(&A.counters[CNT_BLOCKED], h.cnt[H_BLK]);
+    atomicAdd(&A.counters[CNT_NOCONV], h.cnt[H_NOCONV]);
+    atomicAdd(&A.counters[CNT_SPILLS], h.cnt[H_DRIFT]);
+    atomicMax(&A.counters[CNT_NUM + 24], (unsigned long long)__double_as_longlong(h.max_viol / h.cmax));
+    atomicAdd(&A.counters[CNT_NUM + 1 + 20], h.cnt[H_FOLD]);          // reported with the phase counters: fold passes
   }
 }
 
