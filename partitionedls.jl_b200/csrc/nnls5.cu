@@ -132,10 +132,11 @@ __device__ __forceinline__ Sh5 make_sh5(int NR, int ld1) {
   const int ntl = (NR / 8) * (NR / 8 + 1) / 2;
   Sh5 s;
   double *dp = reinterpret_cast<double *>(smem_raw5 + H5_BYTES_);      // (after the H5 header)
+  // arrays whose size depends on the window capacity only come first: in the kernel (NR a template constant) their
+  // addresses are immediates; the ld1-sized ones follow
   s.T2 = dp; dp += t2_doubles(NR);                    // T2 | Pp | Wp are contiguous: the fold's two ld1 x 8 panels alias them
   s.Pp = dp; dp += 8 * NR;
   s.Wp = dp; dp += 8 * NR;
-  s.v = dp; dp += ld1;
   s.yv = dp; dp += NR;
   s.D = dp; dp += 64;
   s.gd = dp; dp += 8;
@@ -144,17 +145,20 @@ __device__ __forceinline__ Sh5 make_sh5(int NR, int ld1) {
   int *ip = reinterpret_cast<int *>(dp);
   s.ctl = ip; ip += 16;
   short *sp = reinterpret_cast<short *>(ip);
-  s.slot = sp; sp += ld1;
   s.rvar = sp; sp += NR;
-  s.lst = sp; sp += ld1;
   s.lstE = sp; sp += NR;
   s.lstB = sp; sp += 8;
   s.tmap = reinterpret_cast<unsigned short *>(sp); sp += (ntl + 3) & ~3;
+  s.mk = reinterpret_cast<unsigned char *>(sp);       // NR bytes (a multiple of 8)
+  dp = reinterpret_cast<double *>(s.mk + NR);
+  s.v = dp; dp += ld1;
+  sp = reinterpret_cast<short *>(dp);
+  s.slot = sp; sp += ld1;
+  s.lst = sp; sp += ld1;
   signed char *cp = reinterpret_cast<signed char *>(sp);
   s.sg = cp; cp += ld1;
   s.st = reinterpret_cast<unsigned char *>(cp); cp += ld1;
-  s.grp = reinterpret_cast<unsigned char *>(cp); cp += ld1;
-  s.mk = reinterpret_cast<unsigned char *>(cp);
+  s.grp = reinterpret_cast<unsigned char *>(cp);
   return s;
 }
 
