@@ -124,7 +124,7 @@ enum { C_NL = 0, C_NE, C_MX, C_NS, C_OK, C_CNT, C_N, C_NJ, C_NSLOW, C_NP, C_NLV,
 __host__ __device__ inline size_t sh5_bytes(int NR, int ld1) {
   const int ntl = (NR / 8) * (NR / 8 + 1) / 2;
   return H5_BYTES_ + sizeof(double) * ((size_t)t2_doubles(NR) + ld1 + 16 * (size_t)NR + NR + 64 + 8 + 32 + 16) + sizeof(int) * 16 +
-         sizeof(short) * (2 * (size_t)ld1 + 2 * (size_t)NR + 8 + ((ntl + 3) & ~3)) + 3 * (size_t)ld1 + NR + 16;
+         sizeof(short) * (2 * (size_t)ld1 + 2 * (size_t)NR + 8 + ((ntl + 3) & ~3)) + 3 * (size_t)ld1 + NR + 16 + 16;
 }
 
 __device__ __forceinline__ Sh5 make_sh5(int NR, int ld1) {
@@ -149,8 +149,8 @@ __device__ __forceinline__ Sh5 make_sh5(int NR, int ld1) {
   s.lstE = sp; sp += NR;
   s.lstB = sp; sp += 8;
   s.tmap = reinterpret_cast<unsigned short *>(sp); sp += (ntl + 3) & ~3;
-  s.mk = reinterpret_cast<unsigned char *>(sp);       // NR bytes (a multiple of 8)
-  dp = reinterpret_cast<double *>(s.mk + NR);
+  s.mk = reinterpret_cast<unsigned char *>(sp);       // NR bytes; v (read as double2) starts at the next multiple of 16
+  dp = reinterpret_cast<double *>(smem_raw5 + ((static_cast<int>(s.mk - smem_raw5) + NR + 15) & ~15));
   s.v = dp; dp += ld1;
   sp = reinterpret_cast<short *>(dp);
   s.slot = sp; sp += ld1;

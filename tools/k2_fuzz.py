@@ -49,7 +49,7 @@ for case in range(n_cases):
         os.environ["PLS_K5_L"] = str(int(rng.integers(1, 7)))
         os.environ["PLS_K5_VERIFY"] = str(int(rng.choice([1, 7, 128])))
         if rng.random() < 0.5: os.environ["PLS_K5_T"] = str(int(rng.choice([32, 64, 512])))
-        if rng.random() < 0.4: os.environ["PLS_K5_NR"] = str(int(rng.choice([72, 80, 96])))
+        if rng.random() < 0.4: os.environ["PLS_K5_NR"] = str(int(rng.choice([64, 72, 80, 96])))
         if os.environ.get("PLS_K5_T") == "512":           # the wide-problem variants: one 512-thread walk per SM, large windows
             os.environ["PLS_K5_NR"] = str(int(rng.choice([160, 192, 208])))
         if rng.random() < 0.3: os.environ["PLS_K5_MARGIN"] = str(int(rng.choice([2, 6, 20])))
