@@ -1,20 +1,23 @@
-// K2, v5: two swept tableaus per Gray walk, one SMALL CTA (64 / 128 threads) per walk, 8 walks per SM
-// (default for winner-only Opt fits, M' <= 575).
+// K2, v5: two swept tableaus per Gray walk, one SMALL CTA (128 threads, 5 per SM) per walk -- the default for winner-only
+// Opt fits; M' <= 327 as described, 327 < M' <= 639 with ONE 512-thread walk per SM and a large window.
 //
 // Same subproblems, same KKT points and the same reference lines as the other K2 kernels
 // (src/PartitionedLSOpt.jl:85-96: one non-negative least-squares problem per sign pattern b, the residual
 // norm of each, first minimum).  What changes against nnls4.cu is where the per-orthant work lives:
 //
 //   T1 = sweep([G c; c' yy], O)      this walk's private (M'+1)^2 tableau in global memory (L2 where it is hot),
-//                                    changed only by FOLDS (rank-8 DMMA passes, ~2 per 2^l orthants);
+//                                    changed only by FOLDS (rank-8 DMMA passes, ~0.07 per orthant); until the first
+//                                    fold after a cold start it is READ from the launch's shared T0 = [G c; c' yy];
 //   T2 = sweep(T1[Rb, Rb], S)        a SMALL packed-symmetric tableau in shared memory over a window R of
 //                                    variables (the variables of the l fastest Gray groups plus whatever
 //                                    joined), S = the window variables toggled since T1 was last folded.
 //
 // The passive set is P = O xor S.  For a window variable the first column of its T2 row IS its weight (passive)
-// or its gradient (active): block principal pivoting reads it and TOGGLES violators by sweeping T2 -- a
-// warp-wide rank-1 update of ~60 x 60 / 2 doubles in shared memory, no barrier, no gradient evaluation, no 8 x 8
-// inverse.  Everything outside the window is checked once per converged orthant by ONE streaming pass
+// or its gradient (active): block principal pivoting reads it and TOGGLES violators by block sweeps of T2 -- up to 8
+// variables per pass: the 8 x 8 pivot block is inverted by warp 0 while the other warps gather the panel P = T2[:, B],
+// W = P inv(D) and T2 -= W P' are DMMA (mma.sync m8n8k4 f64) on the stored tiles; no gradient evaluation and no
+// global-memory access inside the pivoting loop.  Everything outside the window is checked once per converged
+// orthant by ONE streaming pass
 //       v = T1[rhs, :] - sum_{s in S} y_s T1[s, :],     y_s = e_s T2[s, rhs],  e_s = +1 (entered) / -1 (left)
 // which yields the implied weight of every committed variable, the gradient of every active one, the
 // objective (v[rhs] = y'y - c_P' w_P) and -- on the rows of S themselves -- the residual of the S-system, an
@@ -23,9 +26,10 @@
 // or when the window fills up, the toggled SLOW variables are folded into T1 (mixed forward / reverse block
 // sweep: T1 -= P inv(D) P', one DMMA pass per <= 8 variables) and the untoggled slow ones leave the window.
 //
-// A small CTA owns a walk; 8 CTAs per SM share the 227 KB of shared memory (T2 is 21 KB) and all of them execute the
-// same few KB of code.  A T2 sweep is 3 barriers apart and ~70 instructions per thread; there is no 8 x 8 inverse,
-// no gradient evaluation and no global-memory access inside the pivoting loop.
+// The kernel is latency-bound (a chain of short barrier-separated phases per block pivot): loops are NOT unrolled (the
+// instruction cache), shared-memory pointers are rebuilt inside every function (shared- instead of generic-space
+// accesses), and the walk's scalar state lives in a shared-memory header (H5), not in a per-thread struct behind a
+// reference (local memory: 5 x 43.7 KB of shared memory leave no L1 to cache it).
 //
 // Drift control as in nnls4.cu: every `verify_every` orthants (and at the end of the walk) the KKT conditions are
 // evaluated against the ORIGINAL G and c; above 1e-12 max|c| the walk restarts cold at that orthant.  T2 is
