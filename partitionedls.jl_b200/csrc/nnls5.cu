@@ -491,6 +491,10 @@ __device__ __noinline__ void stream5(int n) {
   const int tid = threadIdx.x;
   const int ld2 = h.ld1 >> 1;
   constexpr int UB = 8;
+  // 512-thread walks: the two halves of the CTA stream alternate rows (a row needs ld1 / 2 <= 320 threads' worth of
+  // double2 pieces, the other half would idle): twice the rows in flight
+  constexpr int NG = T >= 512 ? 2 : 1, TG = T / NG, NQE = NQ * NG, UBG = UB * NG;
+  const int grp = NG == 1 ? 0 : tid / TG, lt = NG == 1 ? tid : tid - grp * TG;
   // S list: variable -> lst, y -> yv, in slot order (every thread looks at one slot; per-warp counts meet in shared memory)
   int ns = 0;
   {
@@ -511,39 +515,53 @@ __device__ __noinline__ void stream5(int n) {
       for (int w2 = 0; w2 < NW; ++w2) { const int c = ri[w2]; if (w2 < wid) off += c; ns += c; }
       if (tg) { const int p = off + __popc(bal & ((1u << lane) - 1)); s.lst[p] = (short)m; const double t = s.T2[t2_idx(k, 0)]; s.yv[p] = pas ? t : -t; }
     }
-    const int nsp = (ns + UB - 1) / UB * UB;
+    const int nsp = (ns + UBG - 1) / UBG * UBG;
     #pragma unroll 1
     for (int p = ns + tid; p < nsp; p += T) { s.lst[p] = (short)h.Mp; s.yv[p] = 0.0; }   // padding: the rhs row with weight 0
     if (tid == 0) { s.ctl[C_NS] = ns; s.ctl[C_FLAG] = 0; }
   }
   SYNC5();
-  const int nsp = (ns + UB - 1) / UB * UB;
-  double2 acc[NQ];
+  const int nsp = (ns + UBG - 1) / UBG * UBG;
+  double2 acc[NQE];
   const double2 *T1v = reinterpret_cast<const double2 *>(h.T1r);
   {
     const double2 *r = T1v + (size_t)ld2 * h.Mp;
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) acc[q] = (tid + T * q < ld2) ? __ldcg(r + tid + T * q) : make_double2(0.0, 0.0);
+    for (int q = 0; q < NQE; ++q) acc[q] = (grp == 0 && lt + TG * q < ld2) ? __ldcg(r + lt + TG * q) : make_double2(0.0, 0.0);
   }
   #pragma unroll 1
-  for (int p = 0; p < nsp; p += UB) {
-    double2 g[UB][NQ];
+  for (int p = 0; p < nsp; p += UBG) {
+    double2 g[UB][NQE];
 #pragma unroll
     for (int u = 0; u < UB; ++u) {
-      const double2 *r = T1v + (size_t)ld2 * s.lst[p + u];
+      const double2 *r = T1v + (size_t)ld2 * s.lst[p + u * NG + grp];
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) g[u][q] = (tid + T * q < ld2) ? __ldcg(r + tid + T * q) : make_double2(0.0, 0.0);
+      for (int q = 0; q < NQE; ++q) g[u][q] = (lt + TG * q < ld2) ? __ldcg(r + lt + TG * q) : make_double2(0.0, 0.0);
     }
 #pragma unroll
     for (int u = 0; u < UB; ++u) {
-      const double y = s.yv[p + u];
+      const double y = s.yv[p + u * NG + grp];
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) { acc[q].x = fma(-y, g[u][q].x, acc[q].x); acc[q].y = fma(-y, g[u][q].y, acc[q].y); }
+      for (int q = 0; q < NQE; ++q) { acc[q].x = fma(-y, g[u][q].x, acc[q].x); acc[q].y = fma(-y, g[u][q].y, acc[q].y); }
     }
   }
+  if (NG > 1) {                                        // the second half's partial sums meet the first half's in shared memory
+    double2 *scr = reinterpret_cast<double2 *>(s.Wp);
+    if (grp == 1) {
 #pragma unroll
-  for (int q = 0; q < NQ; ++q)
-    if (tid + T * q < ld2) reinterpret_cast<double2 *>(s.v)[tid + T * q] = acc[q];
+      for (int q = 0; q < NQE; ++q) if (lt + TG * q < ld2) scr[lt + TG * q] = acc[q];
+    }
+    SYNC5();
+    if (grp == 0) {
+#pragma unroll
+      for (int q = 0; q < NQE; ++q) if (lt + TG * q < ld2) { const double2 o = scr[lt + TG * q]; acc[q].x += o.x; acc[q].y += o.y; }
+    }
+  }
+  if (grp == 0) {
+#pragma unroll
+    for (int q = 0; q < NQE; ++q)
+      if (lt + TG * q < ld2) reinterpret_cast<double2 *>(s.v)[lt + TG * q] = acc[q];
+  }
   SYNC5();
   if (tid == 0) { hdr5().cnt[H_STREAM]++; hdr5().cnt[H_SUMS] += ns; }
 }
@@ -557,23 +575,30 @@ __device__ __noinline__ void join5(int n, int m) {
   const int tid = threadIdx.x;
   const double *row1 = h.T1r + (size_t)h.ld1 * m;
   double *rowv = s.Wp, *tog = s.Wp + h.nr;              // scratch: the new row, toggled marks
-  if (tid < 32) {                                      // toggled slots -> lstE, coefficients e_s T1[m, s] -> yv
-    const int lane = tid;
-    int ns = 0;
+  // toggled slots -> lstE, coefficients e_s T1[m, s] -> yv, in slot order (all threads; per-warp counts through shared memory)
+  int ns = 0;
+  {
+    constexpr int NW = T / 32;
+    const int lane = tid & 31, wid = tid >> 5;
+    int *ri = reinterpret_cast<int *>(s.red);
     #pragma unroll 1
-    for (int k0 = 1; k0 < n; k0 += 32) {
-      const int k = k0 + lane;
+    for (int k0 = 1; k0 < n; k0 += T) {
+      const int k = k0 + tid;
       bool tg = false, pas = false; int var = 0;
       if (k < n) { var = s.rvar[k]; const unsigned char f = s.st[var]; pas = f & ST_PAS; tg = pas != ((f & ST_INO) != 0); }
       const unsigned bal = __ballot_sync(0xffffffffu, tg);
-      if (tg) { const int p = ns + __popc(bal & ((1u << lane) - 1)); s.lstE[p] = (short)k; const double a = __ldcg(row1 + var); s.yv[p] = pas ? a : -a; }
+      if (k0 > 1) SYNC5();
+      if (lane == 0) ri[wid] = __popc(bal);
+      SYNC5();
+      int off = ns;
+#pragma unroll
+      for (int w2 = 0; w2 < NW; ++w2) { const int c = ri[w2]; if (w2 < wid) off += c; ns += c; }
+      if (tg) { const int p = off + __popc(bal & ((1u << lane) - 1)); s.lstE[p] = (short)k; const double a = __ldcg(row1 + var); s.yv[p] = pas ? a : -a; }
       if (k < n) tog[k] = tg ? 1.0 : 0.0;
-      ns += __popc(bal);
     }
-    if (lane == 0) { tog[0] = 0.0; s.ctl[C_NS] = ns; }
+    if (tid == 0) tog[0] = 0.0;
   }
   SYNC5();
-  const int ns = s.ctl[C_NS];
   #pragma unroll 1
   for (int j = tid; j < n; j += T) {
     double a = tog[j] != 0.0 ? 0.0 : __ldcg(row1 + s.rvar[j]);
@@ -656,7 +681,7 @@ __device__ __noinline__ bool fold_block5(int boff, int nb) {
   SYNC5();
   {                                                    // rank-8 update of the lower tiles, mirrored into the upper ones
     const int ntl = (nt * (nt + 1)) >> 1;
-    constexpr int IFL = T <= 64 ? 8 : 4;               // tiles in flight per warp (global-memory latency)
+    constexpr int IFL = (T <= 64 || T >= 512) ? 8 : 4; // tiles in flight per warp (global-memory latency; 128-thread walks are register-bound)
     int q = (ntl * wid) / NW;
     const int q1 = (ntl * (wid + 1)) / NW;
     int ti = 0;
