@@ -234,11 +234,11 @@ __device__ __forceinline__ void set_block5(const Sh5 &s, int nb, int slot) {
 // Returns nb on success (with `flip` the ST_PAS flags of the block are toggled); otherwise T2 is untouched and the
 // result is the block index (>= nlv) of the entering variable whose pivot failed, or -1 if a leaving pivot had the
 // wrong sign (T2 has lost its structure: the caller rebuilds it).
-template <int T>
+template <int T, int NR>
 __device__ __noinline__ int t2_block(int n, int nb, int nlv, bool test, bool flip) {
   H5 &h = hdr5();
   const int gen = h.gen;
-  const Sh5 s = make_sh5(h.nr, h.ld1);
+  const Sh5 s = make_sh5(NR, h.ld1);                   // (NR a constant: the window-sized arrays sit at immediate addresses)
   constexpr int NW = T / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int fr = lane >> 2, fk = lane & 3;
@@ -355,10 +355,10 @@ __device__ __noinline__ int t2_block(int n, int nb, int nlv, bool test, bool fli
 
 // T2 <- T1[Rb, Rb], then sweep the toggled window variables into their current state.  Returns false if a block
 // could not be swept (numerically broken state: the caller restarts cold).
-template <int T>
+template <int T, int NR>
 __device__ __noinline__ bool t2_rebuild(int n) {
   const H5 &h = hdr5();
-  const Sh5 s = make_sh5(h.nr, h.ld1);
+  const Sh5 s = make_sh5(NR, h.ld1);
   constexpr int NW = T / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   #pragma unroll 1
@@ -391,15 +391,16 @@ __device__ __noinline__ bool t2_rebuild(int n) {
     const int nb = min(8, cnt - q0);
     set_block5<T>(s, nb, tid < nb ? s.lst[q0 + tid] : 0);
     SYNC5();
-    if (t2_block<T>(n, nb, max(0, min(nb, nlv - q0)), false, false) != nb) return false;
+    if (t2_block<T, NR>(n, nb, max(0, min(nb, nlv - q0)), false, false) != nb) return false;
   }
   return true;
 }
 
 // window <- {rhs} + the variables of the fast groups + every toggled variable (index order)
+template <int NR>
 __device__ __noinline__ int window_reset() {
   const H5 &h = hdr5();
-  const Sh5 s = make_sh5(h.nr, h.ld1);
+  const Sh5 s = make_sh5(NR, h.ld1);
   const int tid = threadIdx.x;
   const int Mp = h.Mp;
   if (tid < 32) {
@@ -430,10 +431,10 @@ __device__ __noinline__ int window_reset() {
 // ---- window compaction: slots that are neither toggled nor in a fast group leave the window --------------------------
 // T2 restricted to the remaining slots is still sweep(T1[R', R'], S): rows / columns are moved, nothing is recomputed.
 // (Out of place through this walk's global scratch: the fused fold's panel area.)
-template <int T>
+template <int T, int NR>
 __device__ __noinline__ int t2_compact(int n) {
   const H5 &h = hdr5();
-  const Sh5 s = make_sh5(h.nr, h.ld1);
+  const Sh5 s = make_sh5(NR, h.ld1);
   const int tid = threadIdx.x;
   double *scr = h.Pg + 8 * (size_t)h.ld1;
   short *old = s.lst;
@@ -484,10 +485,10 @@ __device__ __noinline__ int t2_compact(int n) {
 // ---- streaming pass ------------------------------------------------------------------------------------------
 // v = T1[rhs, :] - sum_{s toggled} e_s T2[s, rhs] T1[s, :]; the toggled variables stay listed in s.lst[0 .. ctl[C_NS])
 // (on their rows v is the residual of the S-system).  NQ = double2 pieces of a row per thread.
-template <int T, int NQ>
+template <int T, int NQ, int NR>
 __device__ __noinline__ void stream5(int n) {
   const H5 &h = hdr5();
-  const Sh5 s = make_sh5(h.nr, h.ld1);
+  const Sh5 s = make_sh5(NR, h.ld1);
   const int tid = threadIdx.x;
   const int ld2 = h.ld1 >> 1;
   constexpr int UB = 8;
@@ -568,13 +569,13 @@ __device__ __noinline__ void stream5(int n) {
 
 // ---- a variable outside the window joins it (not toggled): new last row of T2 ------------------------------------
 //   row[j] = [slot j not toggled] T1[m, var_j] - sum_{s toggled} e_s T1[m, s] T2[s, j],   diag = T1[m, m] - sum_s e_s T1[m, s] row[s]
-template <int T>
+template <int T, int NR>
 __device__ __noinline__ void join5(int n, int m) {
   const H5 &h = hdr5();
-  const Sh5 s = make_sh5(h.nr, h.ld1);
+  const Sh5 s = make_sh5(NR, h.ld1);
   const int tid = threadIdx.x;
   const double *row1 = h.T1r + (size_t)h.ld1 * m;
-  double *rowv = s.Wp, *tog = s.Wp + h.nr;              // scratch: the new row, toggled marks
+  double *rowv = s.Wp, *tog = s.Wp + NR;              // scratch: the new row, toggled marks
   // toggled slots -> lstE, coefficients e_s T1[m, s] -> yv, in slot order (all threads; per-warp counts through shared memory)
   int ns = 0;
   {
@@ -623,10 +624,10 @@ __device__ __noinline__ void join5(int n, int m) {
 // ---- fold: the toggled slow window variables B (<= 8, swept-back ones first) are swept in T1 ----------------------
 // T1 -= P inv(D) P' off the B rows/columns (DMMA, lower tiles + mirrored store), T1[:, B_q] = e_q (P inv(D))[:, q],
 // T1[B, B] = -E inv(D) E.  Returns false (T1 untouched) if a pivot of D has the wrong sign / is too small.
-template <int T>
+template <int T, int NR>
 __device__ __noinline__ bool fold_block5(int boff, int nb) {
   H5 &h = hdr5();
-  const Sh5 s = make_sh5(h.nr, h.ld1);
+  const Sh5 s = make_sh5(NR, h.ld1);
   const short *B = s.lstE + boff;
   constexpr int NW = T / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -751,10 +752,10 @@ __device__ __noinline__ bool fold_block5(int boff, int nb) {
 // launch's shared T0 (the cold start: L2 hits for every walk, and this walk's own tableau is only written); once
 // T1 is this walk's own they are first copied to the global scratch (the tile updates would overwrite them).  Z' (ld1 x n)
 // lives in the global scratch.
-template <int T>
+template <int T, int NR>
 __device__ __noinline__ void fold_fused5(int n) {
   H5 &h = hdr5();
-  const Sh5 s = make_sh5(h.nr, h.ld1);
+  const Sh5 s = make_sh5(NR, h.ld1);
   constexpr int NW = T / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int fr = lane >> 2, fk = lane & 3;
@@ -884,9 +885,9 @@ __device__ __noinline__ void fold_fused5(int n) {
 template <int T, int NR>
 __device__ __noinline__ int fold5(int n, bool cold_mode) {
   const H5 &h = hdr5();
-  const Sh5 s = make_sh5(h.nr, h.ld1);
+  const Sh5 s = make_sh5(NR, h.ld1);
   const int tid = threadIdx.x;
-  if (cold_mode) n = t2_compact<T>(n);                 // cold solve: only toggled variables stay, the fused pass works on |S| columns
+  if (cold_mode) n = t2_compact<T, NR>(n);                 // cold solve: only toggled variables stay, the fused pass works on |S| columns
   short *B = s.lstE;                                   // NR entries are enough: every listed variable is in the window
   if (tid < 32) {                                      // swept-back (in O, now active) first, then entering; index order within each class
     const int lane = tid;
@@ -913,19 +914,19 @@ __device__ __noinline__ int fold5(int n, bool cold_mode) {
   SYNC5();
   const int cnt = s.ctl[C_CNT];
   bool ok = true;
-  if (cold_mode && cnt > 8 && h.cold_fused) fold_fused5<T>(n);          // cold solve: everything toggled goes in, one pass
-  else for (int q0 = 0; q0 < cnt && ok; q0 += 8) ok = fold_block5<T>(q0, min(8, cnt - q0));
-  n = window_reset();
-  if (!t2_rebuild<T>(n)) ok = false;
+  if (cold_mode && cnt > 8 && h.cold_fused) fold_fused5<T, NR>(n);          // cold solve: everything toggled goes in, one pass
+  else for (int q0 = 0; q0 < cnt && ok; q0 += 8) ok = fold_block5<T, NR>(q0, min(8, cnt - q0));
+  n = window_reset<NR>();
+  if (!t2_rebuild<T, NR>(n)) ok = false;
   return ok ? n : -1;
 }
 
 // max KKT violation of the current point against the ORIGINAL system; s.v holds the streaming result
 // (weights of committed variables outside the window).  The full weight vector goes to the global scratch.
-template <int T>
+template <int T, int NR>
 __device__ __noinline__ double verify5(const double *c) {
   const H5 &h = hdr5();
-  const Sh5 s = make_sh5(h.nr, h.ld1);
+  const Sh5 s = make_sh5(NR, h.ld1);
   const int tid = threadIdx.x;
   const int Mp = h.Mp;
   double *wf = h.Pg;
@@ -1045,7 +1046,7 @@ __device__ __forceinline__ bool solve5(const Sh5 s, int &n_win, bool cold_mode, 
         const int nb = min(8, tot - done), nlv = max(0, min(nb, nl - done));
         set_block5<T>(s, nb, tid < nb ? (done + tid < nl ? s.lst[done + tid] : s.lstE[done + tid - nl]) : 0);
         SYNC5();
-        const int r = t2_block<T>(n, nb, nlv, true, true);
+        const int r = t2_block<T, NR>(n, nb, nlv, true, true);
         if (r == nb) { done += nb; continue; }
         if (r < 0) { broken = true; break; }
         // the entering variable at block position r failed its pivot test: refuse it at this orthant, drop it from the list
@@ -1059,12 +1060,12 @@ __device__ __forceinline__ bool solve5(const Sh5 s, int &n_win, bool cold_mode, 
         SYNC5();
       }
       if (broken) {                                    // a leaving pivot with the wrong sign: T2 lost its structure
-        if (++rebuilt > 3 || !t2_rebuild<T>(n)) return false;
+        if (++rebuilt > 3 || !t2_rebuild<T, NR>(n)) return false;
         t2_fresh = true; if (tid == 0) h.cnt[H_REBUILD]++;
       }
     }
     // ---- everything outside the window, and the accuracy of T2
-    stream5<T, NQ>(n_win);
+    stream5<T, NQ, NR>(n_win);
     // One pass of all threads over v, one barrier: is the residual of the S-system too large (T2 lost digits), and does
     // anything outside the window violate its condition?  The usual answer to both is no.
     {
@@ -1093,7 +1094,7 @@ __device__ __forceinline__ bool solve5(const Sh5 s, int &n_win, bool cold_mode, 
         for (int p = tid; p < ns; p += T) { const double r = fabs(s.v[s.lst[p]]); res = r == r ? fmax(res, r) : r; }
         res = bmax5<T>(s, res);
         if (res != res || (t2_fresh && res > 1e-9 * cmax) || ++rebuilt > 3) return false;
-        if (!t2_rebuild<T>(n_win)) return false;
+        if (!t2_rebuild<T, NR>(n_win)) return false;
         t2_fresh = true;
         if (tid == 0) h.cnt[H_REBUILD]++;
         continue;
@@ -1130,7 +1131,7 @@ __device__ __forceinline__ bool solve5(const Sh5 s, int &n_win, bool cold_mode, 
       #pragma unroll 1
       for (int p = tid; p < nj; p += T) park[p] = s.lst[p];
       SYNC5();
-      if (cold_mode) n_win = t2_compact<T>(n_win);     // cold solve: variables that went back to their T1 state just leave the window
+      if (cold_mode) n_win = t2_compact<T, NR>(n_win);     // cold solve: variables that went back to their T1 state just leave the window
       if (NR - n_win < (nj < 8 ? nj : 8)) {
         const int nf = fold5<T, NR>(n_win, cold_mode);
         if (nf < 0) return false;
@@ -1141,10 +1142,10 @@ __device__ __forceinline__ bool solve5(const Sh5 s, int &n_win, bool cold_mode, 
       if (room > nj) room = nj;
       if (room <= 0) return false;                     // the fast groups alone fill the window (the host sized l to prevent this)
       #pragma unroll 1
-      for (int p = 0; p < room; ++p) { const int m = park[p]; if (s.slot[m] < 0) { join5<T>(n_win, m); ++n_win; } }
+      for (int p = 0; p < room; ++p) { const int m = park[p]; if (s.slot[m] < 0) { join5<T, NR>(n_win, m); ++n_win; } }
     } else {
       #pragma unroll 1
-      for (int p = 0; p < nj; ++p) { join5<T>(n_win, s.lst[p]); ++n_win; }     // join5 uses lstE / yv / tv / uv, not lst
+      for (int p = 0; p < nj; ++p) { join5<T, NR>(n_win, s.lst[p]); ++n_win; }     // join5 uses lstE / yv / tv / uv, not lst
     }
     t_best = Mp + 1; pbar = 3;
   }
@@ -1153,10 +1154,10 @@ __device__ __forceinline__ bool solve5(const Sh5 s, int &n_win, bool cold_mode, 
 // Cold start: T1 is READ from the launch's shared T0 = [G c; c' yy] (zero padded to ld1 x ld1, written once per launch by
 // k2v5_build_t0, L2-resident for every walk) until this walk's first fold pass writes its own tableau; every variable
 // active and outside the window.
-template <int T>
+template <int T, int NR>
 __device__ __noinline__ void cold_init5(const double *T0) {
   H5 &h = hdr5();
-  const Sh5 s = make_sh5(h.nr, h.ld1);
+  const Sh5 s = make_sh5(NR, h.ld1);
   const int tid = threadIdx.x, ld1 = h.ld1;
   if (tid == 0) h.T1r = T0;                            // (the previous reader is a barrier away: the end of the orthant loop)
   #pragma unroll 1
@@ -1249,12 +1250,12 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
   #pragma unroll 1
   for (long long i = i0; i < i1; ++i) {
     if (cold) {
-      cold_init5<T>(A.hglob);
+      cold_init5<T, NR>(A.hglob);
       // the cold solve runs with NO fast groups: the window starts empty and takes up to NR - 1 violators per round,
       // all of which are folded into T1 in full blocks of 8 (~2 rounds instead of ~9 with the fast variables in the way)
       cold_mode = true;
-      n_win = window_reset();
-      t2_rebuild<T>(n_win);                            // nothing is toggled: a plain copy
+      n_win = window_reset<NR>();
+      t2_rebuild<T, NR>(n_win);                            // nothing is toggled: a plain copy
       cold = false; just_cold = true; since_check = 0; t2_fresh = true;
     }
     const long long b = A.b_begin + (i ^ (i >> 1));
@@ -1268,7 +1269,7 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
     ++since_check;
     if (ok && (since_check >= check_every || i + 1 == i1)) {
       since_check = 0;
-      const double viol = verify5<T>(A.c);
+      const double viol = verify5<T, NR>(A.c);
       const double cmax = h.cmax;
       if (!just_cold && tid == 0) h.max_viol = fmax(h.max_viol, viol);
       if (viol > 1e-13 * cmax && check_every > 8) check_every = 8;
@@ -1316,8 +1317,8 @@ __global__ void __launch_bounds__(T, MINB) k2v5_orthant_walks(const K2Args A) {
         if (was_cold && !cold) {
           set_lowmask5<T>(s, A.lowmask);
           cold_mode = false;
-          n_win = window_reset();
-          if (!t2_rebuild<T>(n_win)) cold = true;
+          n_win = window_reset<NR>();
+          if (!t2_rebuild<T, NR>(n_win)) cold = true;
         }
       }
     }
