@@ -227,7 +227,9 @@ def run_native(args, rank, world, local_rank):
         bar = barrier if collective else torch.cuda.synchronize
         for _ in range(warmup):
             fn()
-        sampler = ClockSampler(local_rank) if sample_clocks else None
+        # one sampler for the job (rank 0's GPU): NVML queries from every rank at once contend with the CUDA driver calls of the
+        # timed steps (an 8-rank run lost > 1 ms per step to them)
+        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
         per_step, host_step, last = [], [], None
         bar()
         if sampler:
