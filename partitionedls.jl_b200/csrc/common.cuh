@@ -167,7 +167,7 @@ int k2v4_launch(const K2Args &A, const K4Plan &pl, int grid, cudaStream_t st);
 int k2v4_plan_prof(int Mp, int Kp, K4Plan *pl, long long per_sm = 0);      // nnls4p.cu: same kernels with phase counters
 int k2v4_launch_prof(const K2Args &A, const K4Plan &pl, int grid, cudaStream_t st);
 // v5 = two swept tableaus per Gray walk, one warp per walk (nnls5.cu)
-struct K5Plan { int variant, T, NR, ld1, occ, low_groups, verify_every, cold_cap, cold_fused; size_t smem, tabstride; };
+struct K5Plan { int variant, T, NR, ld1, occ, low_groups, verify_every, cold_fused; size_t smem, tabstride; };
 int k2v5_plan(int Mp, int n_bits, const uint64_t *h_gmask, K5Plan *pl);
 int k2v5_launch(const K2Args &A, const K5Plan &pl, int grid, cudaStream_t st);
 // K5: branch and bound with batched frontier expansion (bnb.cu); winner left in ws.win

@@ -607,7 +607,7 @@ int k2_solve_range(const Problem &, const double *G, int ldg, const double *c, c
     A.hglob = ws.tab + (size_t)max_grid * plan5.tabstride;        // T0 = [G c; c' yy], written by the launch's prologue kernel
     ++*launches;
     A.lowmask = (1ull << plan5.low_groups) - 1ull; A.verify_every = plan5.verify_every;
-    A.qs = plan5.cold_cap; A.chain_log2 = plan5.cold_fused;   // (fields the v5 kernel does not use otherwise)
+    A.chain_log2 = plan5.cold_fused;                           // (a field the v5 kernel does not use otherwise)
     const int rc = k2v5_launch(A, plan5, (int)grid, st);
     if (rc) return rc;
   } else if (variant == 4) {

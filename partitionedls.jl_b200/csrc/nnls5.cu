@@ -1359,7 +1359,7 @@ const Variant5 kVariants5[] = {
 }  // namespace
 
 // Environment overrides for tuning / tests: PLS_K5_T (threads per walk), PLS_K5_NR (window slots), PLS_K5_MARGIN,
-// PLS_K5_L (fast groups), PLS_K5_GRID (walks), PLS_K5_VERIFY, PLS_K5_OCC.
+// PLS_K5_L (fast groups), PLS_K5_GRID (walks), PLS_K5_VERIFY, PLS_K5_OCC (walks per SM), PLS_K5_FUSED (0: cold folds in rank-8 passes).
 // h_gmask: host copy of the group masks (sizes the window); n_bits: enumerated Gray bits.
 int k2v5_plan(int Mp, int n_bits, const uint64_t *h_gmask, K5Plan *pl) {
   if (!h_gmask) return PLS_EUNSUPPORTED;
@@ -1410,7 +1410,6 @@ int k2v5_plan(int Mp, int n_bits, const uint64_t *h_gmask, K5Plan *pl) {
   const char *eV = getenv("PLS_K5_VERIFY");
   pl->verify_every = eV ? atoi(eV) : 128;
   const char *eF = getenv("PLS_K5_FUSED");
-  pl->cold_cap = 0;
   pl->cold_fused = v->NR > 96 ? 0 : (eF ? atoi(eF) : 1);
   if (pl->verify_every < 1) pl->verify_every = 1;
   return PLS_OK;
