@@ -109,11 +109,49 @@ class V5:
         self.R = [m for m in self.R if self.fast[m]]
         self.rebuild_T2()
 
-    def weights(self):
-        w = np.zeros(self.Mp)
-        return w
+    def compact(self):
+        """window variables that are neither toggled nor in a fast group leave the window: rows / columns of T2 are
+        dropped, nothing is recomputed (T2 restricted to the rest is still sweep(T1[R', R'], S)) -- nnls5.cu: t2_compact"""
+        keep = [m for m in self.R if self.fast[m] or m in self.tog]
+        if len(keep) == len(self.R):
+            return
+        idx = [self.R.index(m) for m in keep] + [len(self.R)]
+        self.T2 = self.T2[np.ix_(idx, idx)].copy()
+        self.R = keep
+        self.stat["compactions"] = self.stat.get("compactions", 0) + 1
 
-    def solve(self, sigma):
+    def fold_fused(self):
+        """EVERY toggled window variable into T1 in ONE pass (nnls5.cu: fold_fused5).  T2 already holds
+        -E inv(T1[S,S]) E on its S block, so with P~[j,k] = e_k T1[var_k, j] and Z' = (P~ T2[S,S]) E:
+            T1 += Z' T1[S,:];   T1[:, S] = T1[S, :]' = -Z' E;   T1[Rb, Rb] = T2"""
+        S = [m for m in self.R if m in self.tog]
+        if S:
+            ks = [self.R.index(m) for m in S]
+            e = np.array([float(self.tog[m]) for m in S])
+            rows = self.T1[S, :].copy()
+            Zp = ((rows.T * e) @ self.T2[np.ix_(ks, ks)]) * e
+            T1 = self.T1 + Zp @ rows
+            for q, m in enumerate(S):
+                T1[:, m] = -e[q] * Zp[:, q]
+                T1[m, :] = T1[:, m]
+            idx = self.R + [self.Mp]
+            T1[np.ix_(idx, idx)] = self.T2
+            self.T1 = T1
+            for m in S:
+                self.inO[m] = self.tog[m] > 0
+            self.tog = {}
+        self.stat["fused_folds"] = self.stat.get("fused_folds", 0) + 1
+        self.R = [m for m in self.R if self.fast[m]]
+        self.rebuild_T2()
+
+    def set_fast(self, l):
+        """the walk's fast groups (the cold solve runs with none)"""
+        self.low = (1 << l) - 1
+        self.fast = (self.gmask & self.low) != 0
+        self.R = sorted(set(m for m in range(self.Mp) if self.fast[m]) | set(self.tog))
+        self.rebuild_T2()
+
+    def solve(self, sigma, cold=False):
         Mp = self.Mp
         told = 1e-12 * self.scale
         blocked = set()
@@ -167,7 +205,13 @@ class V5:
             rounds += 1
             room = self.capR - len(self.R)
             if room < len(J):
-                self.fold()
+                if cold:                                  # cold solve: evict first, fold (fused) only if that is not enough
+                    self.compact()
+                    room = self.capR - len(self.R)
+                    if room < min(len(J), 8):
+                        self.fold_fused()
+                else:
+                    self.fold()
                 room = self.capR - len(self.R)
             for m in J[:room]:
                 self.join(m)
