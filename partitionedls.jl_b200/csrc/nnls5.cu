@@ -71,19 +71,6 @@ __device__ __forceinline__ double wmax5(double v) {
   for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-__device__ __forceinline__ int wmaxi5(int v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-__device__ __forceinline__ bool lex_better5(double oa, long long ba, double ob, long long bb) {
-  if (bb < 0) return ba >= 0;
-  if (ba < 0) return false;
-  const bool na = oa != oa, nb = ob != ob;
-  if (na != nb) return na;
-  if (na) return ba < bb;
-  return oa < ob || (oa == ob && ba < bb);
-}
 // T2 storage: 8 x 8 tiles (row-major inside a tile), the lower triangle of tiles packed -- tile (ti, tj <= ti) at
 // ((ti (ti + 1)) >> 1) + tj -- and diagonal tiles holding both halves, so that a DMMA C fragment of any stored tile
 // is one 16-byte access per lane.  Window slot 0 is the right-hand side: T2(k, 0) is slot k's weight / gradient.
@@ -123,7 +110,7 @@ struct Sh5 {
   unsigned char *grp; // [ld1] the variable's only group (255: it belongs to several)
   unsigned char *mk; // [NR]  block pivot: stamp of the last block this slot was in (== the block's stamp: in the current block)
 };
-enum { C_NL = 0, C_NE, C_MX, C_NS, C_OK, C_CNT, C_N, C_NJ, C_NSLOW, C_NP, C_NLV, C_FLAG };
+enum { C_NS = 0, C_OK, C_CNT, C_N, C_NJ, C_NP, C_NLV, C_FLAG };
 
 __host__ __device__ inline size_t sh5_bytes(int NR, int ld1) {
   const int ntl = (NR / 8) * (NR / 8 + 1) / 2;
@@ -325,7 +312,6 @@ __device__ __noinline__ int t2_block(int n, int nb, int nlv, bool test, bool fli
     }
   }
   SYNC5();
-  #pragma unroll 1
 #pragma unroll 1
   for (int row = tid; row < n; row += T) {             // columns / rows of B outside the block: e_q W[:, q]
     if (s.mk[row] == (unsigned char)gen) continue;
